@@ -1,0 +1,239 @@
+/*
+ * dspmap_c.h — C ABI of the B200-native particle occupancy-map update engine.
+ *
+ * This is the drop-in boundary for the per-frame hot path of tud-amr/semantic_dsp_map
+ * (SemanticDSPMap::update -> generateLabeledPointCloud -> subObjectLevelUpdate).  The
+ * reference has no FFI layer of its own: its "operator API" is the public section of
+ * class SemanticDSPMap (reference include/semantic_dsp_map.h:23-251).  Every entry
+ * point below names the reference interface it replaces.  Plain pointers and sizes
+ * only; no C++/torch types cross this boundary; no exceptions; rc 0 = ok, <0 = error.
+ *
+ * All host pointers are caller-owned and only read during the call, unless stated.
+ * One handle = one map (the reference allows exactly one map per process because its
+ * store is a namespace-scope global, include/mc_ring/buffer.h:86; handles lift that).
+ * A handle is not thread-safe (same as the reference: single ROS spinner thread).
+ */
+#ifndef DSPMAP_C_H
+#define DSPMAP_C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dspmap dspmap_t;
+
+/* ---- error codes -------------------------------------------------------- */
+enum {
+    DSPMAP_OK = 0,
+    DSPMAP_ERR_INVALID_ARG = -1, /* null pointer, bad enum, bad size                          */
+    DSPMAP_ERR_CONFIG = -2,      /* e.g. index bits > 31 (reference exit(-1), operations.h:55) */
+    DSPMAP_ERR_IMAGE_SIZE = -3,  /* depth/mask size != configured size (reference: silent OOB,
+                                    semantic_dsp_map.h:212-221 vs :974-979)                    */
+    DSPMAP_ERR_CUDA = -4,        /* a CUDA call failed; see dspmap_last_error()               */
+    DSPMAP_ERR_CAPACITY = -5,    /* a device work list overflowed its configured capacity      */
+    DSPMAP_ERR_NO_DEVICE = -6,   /* no CUDA device: there is NO CPU fallback                   */
+    DSPMAP_ERR_UNSUPPORTED = -7, /* option the engine does not implement (stated in DESIGN.md) */
+    DSPMAP_ERR_COMM = -8         /* NCCL failure in a sharded map                              */
+};
+
+/* ---- configuration (compile-time constants of the reference made runtime) ---- */
+typedef struct dspmap_config {
+    /* grid: reference include/settings/settings.h:32-119, include/mc_ring/buffer.h:28-41 */
+    int32_t voxel_bits_x;      /* C_VOXEL_NUM_AXIS_X_N                                  */
+    int32_t voxel_bits_y;      /* C_VOXEL_NUM_AXIS_Y_N                                  */
+    int32_t voxel_bits_z;      /* C_VOXEL_NUM_AXIS_Z_N                                  */
+    int32_t slot_bits;         /* C_MAX_PARTICLE_NUM_PER_VOXEL_N (slot 0 = time particle) */
+    float   voxel_size;        /* C_VOXEL_SIZE [m]                                      */
+    /* camera as delivered by the sensor (the g_camera_*_set constants) */
+    float   fx, fy, cx, cy;
+    int32_t image_width;       /* g_image_width_set                                     */
+    int32_t image_height;      /* g_image_height_set                                    */
+    int32_t boost_mode;        /* BOOST_MODE: 1 = internal image is the nearest 1/2 downsample
+                                  (settings.h:25-29,136-143; pointcloud_tools.h:1104-1133) */
+    float   depth_min;         /* g_depth_range_min                                     */
+    float   depth_max;         /* g_depth_range_max                                     */
+    int32_t consider_instance; /* g_consider_instance                                   */
+    int32_t zed2_filters;      /* the "#if SETTING == 3" blocks of generateLabeledPointCloud:
+                                  sky rejection + 3-D bbox gate (pointcloud_tools.h:234-273) */
+    int32_t window_half;       /* update window half size; 0 = reference default
+                                  (3 when boost_mode else 5, semantic_dsp_map.h:964-970)  */
+    /* sharding: the map's storage-z slabs are split over shard_count ranks */
+    int32_t shard_rank;        /* 0..shard_count-1                                      */
+    int32_t shard_count;       /* 1 = whole map on this GPU                             */
+    int32_t device;            /* CUDA device ordinal                                   */
+    uint32_t max_visible;      /* capacity of the per-frame visible-particle list, 0 = auto */
+    uint32_t reserved0;
+} dspmap_config;
+
+/* runtime parameters: reference setMapParameters / setMapOptions /
+ * setDepthNoiseModelParameters (semantic_dsp_map.h:101-166) */
+typedef struct dspmap_params {
+    float   detection_probability;     /* Pd                                   */
+    float   noise_number;              /* kappa                                */
+    int32_t nb_ptc_num_per_point;      /* newborn particles per point          */
+    float   occupancy_threshold;
+    float   forgetting_rate;
+    int32_t max_forget_count;          /* <= 5 (table size, basic_algorithms.h:33) */
+    float   id_transition_probability;
+    float   depth_noise_first_order;   /* n1 */
+    float   depth_noise_zero_order;    /* n0 */
+    int32_t consider_depth_noise;      /* g_if_consider_depth_noise            */
+    int32_t use_independent_filter;    /* g_if_use_independent_filter          */
+    int32_t zero_center;               /* visualize_with_zero_center_ (output positions minus camera) */
+} dspmap_params;
+
+/* one segmentation mask: reference MaskKpts (utils/tracking_result_handler.h:15-26),
+ * with the string/keypoint logic pre-evaluated by the host adapter */
+typedef struct dspmap_mask {
+    const uint8_t* data;   /* MONO8, image_height x image_width (input resolution)      */
+    int32_t row_stride;    /* bytes between rows                                        */
+    int32_t is_static;     /* MaskKpts.label == "static": pixel value v -> class v+1    */
+    int32_t track_id;      /* MaskKpts.track_id after the wrap of semantic_dsp_map.h:179-186 */
+    int32_t label_id;      /* g_label_id_map_default[MaskKpts.label]                    */
+    double  bbox_min[3];   /* min over kpts_current - 1 m (pointcloud_tools.h:178-199)  */
+    double  bbox_max[3];   /* max over kpts_current + 1 m; used only when zed2_filters  */
+} dspmap_mask;
+
+/* rigid motion of one tracked object for this frame: what objectLevelUpdate (host,
+ * semantic_dsp_map.h:306-566) leaves in rigidbody_tmatrix_vec[0] and what
+ * subObjectLevelUpdate feeds to moveParticlesInSetsByTransformations
+ * (semantic_dsp_map.h:588-699; mc_ring/operations.h:321-362) */
+typedef struct dspmap_object_move {
+    int32_t track_id;
+    float   t[16];         /* row-major 4x4, float (reference casts Matrix4d -> Matrix4f) */
+} dspmap_object_move;
+
+/* result view: occupied (state 1), guessed-occupied (state 2) voxels in ascending
+ * storage index, as getOccupancyResult emits them (semantic_dsp_map.h:1239-1383) */
+typedef struct dspmap_result {
+    uint32_t  count;          /* number of entries                                     */
+    uint32_t  free_count;     /* entries in the free-space view (0 unless requested)   */
+    const uint32_t* voxel_index;   /* storage voxel index                              */
+    const float*    xyz;           /* 3 floats per entry: voxel min corner, global frame
+                                      (minus camera position when zero_center)         */
+    const float*    weight_sum;    /* sum of particle weights of the voxel             */
+    const uint16_t* track_id;      /* fused instance id                                */
+    const uint8_t*  label_id;      /* fused semantic label                             */
+    const int8_t*   state;         /* 1 occupied, 2 guessed occupied                   */
+    const uint32_t* free_voxel_index;
+    const float*    free_xyz;
+} dspmap_result;
+
+/* per-frame counters (also the inputs of the roofline accounting) */
+typedef struct dspmap_frame_stats {
+    uint32_t time_stamp;        /* global_time_stamp after this frame                  */
+    uint32_t n_swept_voxels;    /* voxels visited by the frustum sweep                 */
+    uint32_t n_swept_nonempty;  /* ... of which held at least one particle             */
+    uint32_t n_visible;         /* particles binned to pixels (updated this frame)     */
+    uint32_t n_valid_points;    /* valid pixels of the labelled point image            */
+    uint32_t n_born;            /* particles born                                       */
+    uint32_t n_birth_voxels;    /* distinct voxels touched by births                   */
+    uint32_t n_resampled;       /* voxels resampled                                    */
+    uint32_t n_occupied;        /* result entries                                      */
+    uint32_t n_nonempty_voxels; /* voxels with >=1 non-vacant particle at extraction    */
+    uint32_t n_moved;           /* particles moved by object transforms                */
+    uint32_t n_removed;         /* particles deleted by track removal                  */
+    float    ms_stage[8];       /* device time per stage when profiling is on: project, shift,
+                                   predict, visibility, update, birth, occupancy, total */
+} dspmap_frame_stats;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+
+/* replaces: SemanticDSPMap() + RingBufferOperations() ctor chain
+ * (semantic_dsp_map.h:25-67; mc_ring/operations.h:44-64,684-767) */
+int  dspmap_create(const dspmap_config* cfg, dspmap_t** out);
+void dspmap_destroy(dspmap_t* h);
+/* replaces: SemanticDSPMap::clear (semantic_dsp_map.h:74-81) */
+int  dspmap_clear(dspmap_t* h);
+/* human-readable text of the last error on this handle (never NULL) */
+const char* dspmap_last_error(const dspmap_t* h);
+/* library/ABI version, e.g. 100 = 1.0.0 */
+int  dspmap_version(void);
+
+/* ---- setters ------------------------------------------------------------ */
+
+/* replaces: setMapParameters + setMapOptions + setVisualizeOptions(zero_center) +
+ * setDepthNoiseModelParameters + setOccupancyThreshold (semantic_dsp_map.h:101-166) */
+int dspmap_set_params(dspmap_t* h, const dspmap_params* p);
+
+/* replaces: the label globals of utils/data_base.h:108-212 as rewritten by
+ * ObjectInfoHandler::readObjectInfo (utils/object_info_handler.h:28-91).
+ *   static_value_to_track[v] = g_label_to_instance_id_map_default[g_label_id_map_reversed[v+1]]
+ *                              evaluated with std::unordered_map::operator[] semantics
+ *                              (a missing key yields 0), pointcloud_tools.h:137-138
+ *   static_tracks[i] -> static_labels[i]  : g_label_id_map_static[g_instance_id_to_label_map_default[t]]
+ *   max_movable_track                     : g_max_movable_object_instance_id
+ *   sky_track                             : g_label_to_instance_id_map_default["Sky"] (pointcloud_tools.h:236) */
+int dspmap_set_label_luts(dspmap_t* h, const uint16_t static_value_to_track[256],
+                          const uint16_t* static_tracks, const uint8_t* static_labels,
+                          int32_t n_static, uint16_t max_movable_track, uint16_t sky_track);
+
+/* replaces: the std::random_device-seeded table of
+ * GaussianRandomCalculator::calculateGaussianTable (utils/basic_algorithms.h:394-401);
+ * injecting it makes runs reproducible.  n must be >= 1. */
+int dspmap_set_random_table(dspmap_t* h, const float* table, uint32_t n);
+
+/* ---- the per-frame hot path ---------------------------------------------- */
+
+/* replaces: SemanticDSPMap::update (semantic_dsp_map.h:170-251) minus the host-side
+ * objectLevelUpdate, whose outputs arrive as `moves` / `remove_tracks`.
+ * depth: CV_32FC1 metres, rows x cols, row_stride in floats; HOST memory. */
+int dspmap_update(dspmap_t* h, const float* depth, int32_t rows, int32_t cols,
+                  int32_t row_stride, const dspmap_mask* masks, int32_t n_masks,
+                  const double position[3], const double orientation_wxyz[4],
+                  const dspmap_object_move* moves, int32_t n_moves,
+                  const int32_t* remove_tracks, int32_t n_remove,
+                  int32_t want_freespace);
+
+/* same, with depth and mask data already resident in DEVICE memory (bench `value`
+ * arm; pointers inside `masks` are device pointers); results stay on the device */
+int dspmap_update_device(dspmap_t* h, const float* d_depth, int32_t rows, int32_t cols,
+                         int32_t row_stride, const dspmap_mask* masks, int32_t n_masks,
+                         const double position[3], const double orientation_wxyz[4],
+                         const dspmap_object_move* moves, int32_t n_moves,
+                         const int32_t* remove_tracks, int32_t n_remove,
+                         int32_t want_freespace);
+
+/* result of the last update: host view (pinned buffers owned by the handle, valid until
+ * the next update) — what the reference push_backs into the caller's clouds */
+int dspmap_get_result(dspmap_t* h, dspmap_result* out);
+/* device view of the same (valid after dspmap_update_device too) */
+int dspmap_get_result_device(dspmap_t* h, dspmap_result* out);
+int dspmap_get_stats(dspmap_t* h, dspmap_frame_stats* out);
+/* enable per-stage CUDA-event timing (the reference's VERBOSE_MODE stage timers,
+ * semantic_dsp_map.h:912-953) */
+int dspmap_set_profiling(dspmap_t* h, int32_t on);
+
+/* number of live particles carrying `track_id` (device-side replacement of
+ * ObjectParticleHashMap::indices_map[track].size(), object_layer.h:20-52) */
+int dspmap_object_particle_count(dspmap_t* h, int32_t track_id, uint32_t* count);
+
+/* ---- sharded maps (one process per GPU) ------------------------------------ */
+/* unique id bytes come from dspmap_comm_unique_id on rank 0 and are broadcast by the
+ * caller's own plumbing (torch.distributed in bench.py) */
+#define DSPMAP_COMM_ID_BYTES 128
+int dspmap_comm_unique_id(uint8_t id[DSPMAP_COMM_ID_BYTES]);
+int dspmap_comm_init(dspmap_t* h, const uint8_t id[DSPMAP_COMM_ID_BYTES]);
+
+/* ---- parity / debug dumps (tests only) ------------------------------------- */
+enum {
+    DSPMAP_DUMP_POINTS = 1,   /* Hi*Wi records of 20 B: float x,y,z,sigma; u16 track; u8 label; u8 valid
+                                 (LabeledPoint, utils/data_base.h:78-92)                  */
+    DSPMAP_DUMP_PARTICLES = 2,/* N records of 24 B in the reference AoS layout (buffer.h:57-79) */
+    DSPMAP_DUMP_PIXEL_OFFSETS = 3, /* Hi*Wi+1 u32: CSR offsets of the per-pixel particle lists */
+    DSPMAP_DUMP_PIXEL_LISTS = 4,   /* n_visible u32 particle indices, pixel-major, ascending  */
+    DSPMAP_DUMP_CK = 5,       /* Hi*Wi f32: ck*Pd+kappa, 0 where the pixel is invalid     */
+    DSPMAP_DUMP_RING = 6,     /* ring state: 3 i32 moved steps, 3 i32 equivalent steps, 3 f32 map centre,
+                                 then stamps x,y,z as u32                                  */
+    DSPMAP_DUMP_VOXEL_STATE = 7 /* V i8: -1 unknown, 0 free, 1 occupied, 2 guessed          */
+};
+/* copies at most cap bytes to dst (host); *n_bytes = full size of the dump */
+int dspmap_dump(dspmap_t* h, int32_t what, void* dst, size_t cap, size_t* n_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSPMAP_C_H */
