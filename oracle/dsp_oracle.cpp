@@ -244,7 +244,9 @@ struct Oracle {
     // basic_algorithms.h:417-422
     inline float query_pdf(float x, float mu, float sigma) const {
         const float corrected_x = (x - mu) / sigma;
-        if (corrected_x > 9.9f || corrected_x < -9.9f) return 1e-9f;
+        // DEFINED UB: a NaN argument (0/0 when sigma == 0 and x == mu) indexes the table out of range in the
+        // reference; it is defined here as the tail value.
+        if (corrected_x > 9.9f || corrected_x < -9.9f || corrected_x != corrected_x) return 1e-9f;
         return pdf_lut[static_cast<int>(corrected_x * 1000 + 10000)];
     }
 

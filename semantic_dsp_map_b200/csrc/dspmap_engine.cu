@@ -1,0 +1,872 @@
+// dspmap_engine.cu — host side of the B200 particle-map engine and its C ABI (include/dspmap_c.h).
+//
+// The host keeps exactly what the reference keeps in scalar globals — ring offsets, slab stamps, the time stamp,
+// the camera matrices (mc_ring/buffer.h:97-120, utils/data_base.h:22) — and drives one stream of kernels per
+// frame.  Every large array lives in HBM; nothing here computes on particles, pixels or voxels on the CPU and
+// there is no CPU fallback: without a CUDA device dspmap_create fails with DSPMAP_ERR_NO_DEVICE.
+#include "../../include/dspmap_c.h"
+#include "dspmap_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace dspk;
+
+namespace {
+
+#define CU_TRY(h, expr)                                                                            \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) return (h)->fail(DSPMAP_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- small fixed-size linear algebra, evaluation order pinned (no FMA: host flags -ffp-contract=off) ----------
+// Eigen::Quaternion::toRotationMatrix, row-major
+template <typename T>
+void quat_to_rot(const T q[4], T R[9]) {
+    const T w = q[0], x = q[1], y = q[2], z = q[3];
+    const T tx = T(2) * x, ty = T(2) * y, tz = T(2) * z;
+    const T twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = T(1) - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+    R[3] = txy + twz; R[4] = T(1) - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy; R[7] = tyz + twx; R[8] = T(1) - (txx + tyy);
+}
+// fixed 3x3 inverse: cofactors * (1/det)
+void inverse3d(const double m[9], double o[9]) {
+    auto cof = [&](int i, int j) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        return m[i1 * 3 + j1] * m[i2 * 3 + j2] - m[i1 * 3 + j2] * m[i2 * 3 + j1];
+    };
+    const double det = (cof(0, 0) * m[0] + cof(1, 0) * m[3]) + cof(2, 0) * m[6];
+    const double invdet = 1.0 / det;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) o[r * 3 + c] = cof(c, r) * invdet;
+}
+// fixed 4x4 float inverse: adjugate / determinant
+void inverse4f(const float m[16], float o[16]) {
+    auto M = [&](int r, int c) { return m[r * 4 + c]; };
+    auto d3 = [&](int i1, int i2, int i3, int j1, int j2, int j3) { return M(i1, j1) * (M(i2, j2) * M(i3, j3) - M(i2, j3) * M(i3, j2)); };
+    float adj[16];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            const int i1 = (i + 1) % 4, i2 = (i + 2) % 4, i3 = (i + 3) % 4, j1 = (j + 1) % 4, j2 = (j + 2) % 4, j3 = (j + 3) % 4;
+            const float c = (d3(i1, i2, i3, j1, j2, j3) + d3(i2, i3, i1, j1, j2, j3)) + d3(i3, i1, i2, j1, j2, j3);
+            adj[j * 4 + i] = ((i + j) & 1) ? -c : c;
+        }
+    const float det = ((M(0, 0) * adj[0] + M(1, 0) * adj[1]) + M(2, 0) * adj[2]) + M(3, 0) * adj[3];
+    for (int k = 0; k < 16; ++k) o[k] = adj[k] / det;
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        return count ? cudaMalloc(&p, count * sizeof(T)) : cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+template <typename T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t reserve(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = std::max(count, n + n / 2);
+        return cudaMallocHost(&p, n * sizeof(T));
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct dspmap {
+    dspmap_config cfg{};
+    dspmap_params prm{};
+    FrameParams fp{};
+    std::string err = "";
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+
+    // host ring state (mc_ring/buffer.h:97-120)
+    std::vector<uint32_t> stamps[3];
+    int moved[3]{}, equiv[3]{};
+    float map_center[3]{}, ego_center[3]{}, last_pos[3]{};
+    uint32_t T = 0;
+    bool forgetting_init = false;
+    float forget_tab[5]{};
+    bool stamps_dirty = true;
+
+    // label tables
+    uint16_t h_static_track[256];
+    std::vector<uint8_t> h_static_label;  // 65536
+    uint32_t max_movable = 65523, sky_track = 65533;
+    uint32_t rand_n = 1;
+
+    // device: store (allocated for this shard's slabs; pointers are biased so the global particle index applies)
+    DevBuf<float> sx, sy, sz, sw;
+    DevBuf<uint64_t> smeta;
+    Store st{};
+    size_t n_slots_local = 0, slot_lo = 0;
+    uint32_t v_local = 0;
+    DevBuf<uint32_t> d_stamps;  // x | y | z
+    DevBuf<float> d_lut, d_randoms;
+    DevBuf<uint16_t> d_static_track;
+    DevBuf<uint8_t> d_static_label;
+    DevBuf<FrameParams> d_fp;
+    DevBuf<Counters> d_cnt;
+    DevBuf<Persist> d_persist;
+    DevBuf<MaskDesc> d_masks;
+    DevBuf<MoveTable> d_moves;
+    // images
+    DevBuf<float> d_depth_in, d_depth_int, d_ck;
+    DevBuf<uint8_t> d_mask_in;
+    DevBuf<float4> d_cloud_pos;
+    DevBuf<uint32_t> d_cloud_meta, d_pix_count, d_pix_offset, d_scan_block;
+    // visibility
+    DevBuf<uint32_t> d_vmask;
+    uint32_t words_per_row = 0, n_vwords = 0;
+    DevBuf<uint2> d_pairs;
+    DevBuf<uint32_t> d_csr_idx, d_vis_pix, d_vis_meta;
+    DevBuf<float4> d_vis_pos;
+    // ordered insertion
+    DevBuf<uint32_t> d_keys, d_ranks;
+    // object moves
+    DevBuf<uint32_t> d_sel_idx, d_sel_move, d_sel_seq;
+    DevBuf<float4> d_mov_pos;
+    DevBuf<uint64_t> d_mov_meta;
+    uint32_t sel_cap = 0;
+    // occupancy
+    DevBuf<uint64_t> d_lb_occ, d_lb_sel;
+    DevBuf<uint32_t> r_idx, r_free_idx;
+    DevBuf<float> r_xyz, r_w, r_free_xyz;
+    DevBuf<uint16_t> r_track;
+    DevBuf<uint8_t> r_label;
+    DevBuf<int8_t> r_state, d_voxel_state;
+    bool want_state = false;
+
+    // pinned staging
+    PinBuf<float> p_depth;
+    PinBuf<uint8_t> p_masks;
+    PinBuf<Counters> p_cnt;
+    PinBuf<FrameParams> p_fp;
+    PinBuf<uint32_t> p_stamps;
+    PinBuf<MaskDesc> p_maskdesc;
+    PinBuf<MoveTable> p_moves;
+    PinBuf<uint32_t> hr_idx, hr_free_idx;
+    PinBuf<float> hr_xyz, hr_w, hr_free_xyz;
+    PinBuf<uint16_t> hr_track;
+    PinBuf<uint8_t> hr_label;
+    PinBuf<int8_t> hr_state;
+    bool host_result_valid = false;
+
+    Counters last{};
+    dspmap_frame_stats stats{};
+    bool profiling = false;
+    cudaEvent_t ev[9]{};
+
+    int fail(int rc, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return rc;
+    }
+
+    // ---- ring shift: RingBufferOperations::updateEgoCenterPos / updateRingbufferIndexParams
+    //      (mc_ring/operations.h:68-96, 1111-1230) — O(slabs moved) scalar work, stays on the host ----
+    uint32_t axis_n(int a) const { return a == 0 ? fp.NX : (a == 1 ? fp.NY : fp.NZ); }
+    uint32_t wrap(int idx, int a) const {
+        const int n = (int)axis_n(a);
+        return idx < 0 ? (uint32_t)(idx + n) : (idx >= n ? (uint32_t)(idx - n) : (uint32_t)idx);
+    }
+    void ring_params() {
+        int center[3];
+        for (int a = 0; a < 3; ++a) {
+            center[a] = static_cast<int>(ego_center[a] * fp.voxel_recip);
+            map_center[a] = static_cast<float>(center[a]) * fp.voxel;
+        }
+        for (int a = 0; a < 3; ++a) {
+            const int n = (int)axis_n(a), d = center[a] - moved[a];
+            for (int i = 0; i < d; ++i) { stamps[a][wrap(i + equiv[a], a)] = T; stamps_dirty = true; }
+            for (int i = 0; i < -d; ++i) { stamps[a][wrap(n - 1 - i + equiv[a], a)] = T; stamps_dirty = true; }
+        }
+        for (int a = 0; a < 3; ++a) {
+            const int n = (int)axis_n(a);
+            moved[a] = center[a];
+            equiv[a] = moved[a] > 0 ? moved[a] % n : (moved[a] < 0 ? -(-moved[a] % n) : 0);
+        }
+    }
+    void ring_shift(const float pos[3]) {
+        const float lim = std::min(std::min((1 << (fp.Xb - 2)) * fp.voxel, (1 << (fp.Yb - 2)) * fp.voxel), (1 << (fp.Zb - 2)) * fp.voxel);
+        float mv[3] = {pos[0] - last_pos[0], pos[1] - last_pos[1], pos[2] - last_pos[2]};
+        const float sq = (mv[0] * mv[0] + mv[1] * mv[1]) + mv[2] * mv[2];
+        float unit[3] = {mv[0], mv[1], mv[2]};
+        if (sq > 0.f) { const float nn = sqrtf(sq); for (int a = 0; a < 3; ++a) unit[a] = mv[a] / nn; }
+        float dist = sqrtf(sq);
+        float np[3] = {last_pos[0], last_pos[1], last_pos[2]};
+        while (dist > lim) {
+            for (int a = 0; a < 3; ++a) np[a] = np[a] + unit[a] * lim;
+            for (int a = 0; a < 3; ++a) ego_center[a] = np[a];
+            ring_params();
+            for (int a = 0; a < 3; ++a) mv[a] = pos[a] - np[a];
+            dist = sqrtf((mv[0] * mv[0] + mv[1] * mv[1]) + mv[2] * mv[2]);
+        }
+        for (int a = 0; a < 3; ++a) ego_center[a] = pos[a];
+        ring_params();
+        for (int a = 0; a < 3; ++a) last_pos[a] = pos[a];
+    }
+
+    void reset_host_state() {
+        T = 0;
+        for (int a = 0; a < 3; ++a) std::fill(stamps[a].begin(), stamps[a].end(), 0u);
+        stamps_dirty = true;
+    }
+
+    void release_all() {
+        sx.release(); sy.release(); sz.release(); sw.release(); smeta.release(); d_stamps.release(); d_lut.release(); d_randoms.release();
+        d_static_track.release(); d_static_label.release(); d_fp.release(); d_cnt.release(); d_persist.release(); d_masks.release(); d_moves.release();
+        d_depth_in.release(); d_depth_int.release(); d_ck.release(); d_mask_in.release(); d_cloud_pos.release(); d_cloud_meta.release();
+        d_pix_count.release(); d_pix_offset.release(); d_scan_block.release(); d_vmask.release(); d_pairs.release(); d_csr_idx.release();
+        d_vis_pix.release(); d_vis_meta.release(); d_vis_pos.release(); d_keys.release(); d_ranks.release(); d_sel_idx.release();
+        d_sel_move.release(); d_sel_seq.release(); d_mov_pos.release(); d_mov_meta.release(); d_lb_occ.release(); d_lb_sel.release();
+        r_idx.release(); r_free_idx.release(); r_xyz.release(); r_w.release(); r_free_xyz.release(); r_track.release(); r_label.release();
+        r_state.release(); d_voxel_state.release();
+        p_depth.release(); p_masks.release(); p_cnt.release(); p_fp.release(); p_stamps.release(); p_maskdesc.release(); p_moves.release();
+        hr_idx.release(); hr_free_idx.release(); hr_xyz.release(); hr_w.release(); hr_free_xyz.release(); hr_track.release(); hr_label.release(); hr_state.release();
+        for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+        if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+    }
+
+    int init(const dspmap_config& c);
+    int clear_device();
+    int apply_params();
+    int run_moves(const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove);
+    int frame(const float* d_depth, int rows, int cols, int stride, const dspmap_mask* masks, int n_masks, const double pos[3],
+              const double quat[4], const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove,
+              int want_free);
+    int fetch_result_to_host();
+};
+
+// ------------------------------------------------------------------------------------------------------------
+int dspmap::init(const dspmap_config& c) {
+    cfg = c;
+    // runSystemChecking, mc_ring/operations.h:54-58
+    if (c.voxel_bits_x < 2 || c.voxel_bits_y < 2 || c.voxel_bits_z < 2 || c.slot_bits < 1 ||
+        c.voxel_bits_x + c.voxel_bits_y + c.voxel_bits_z + c.slot_bits > 31)
+        return fail(DSPMAP_ERR_CONFIG, "grid bits (%d,%d,%d)+%d must each be >= 2 (slots >= 1) and sum to <= 31", c.voxel_bits_x, c.voxel_bits_y, c.voxel_bits_z, c.slot_bits);
+    if ((1 << c.slot_bits) > MAX_P) return fail(DSPMAP_ERR_CONFIG, "at most %d slots per voxel", MAX_P);
+    if (!(c.voxel_size > 0.f) || c.image_width < 2 || c.image_height < 2 || !(c.fx > 0.f) || !(c.fy > 0.f) || !(c.depth_max > c.depth_min))
+        return fail(DSPMAP_ERR_CONFIG, "bad voxel size / image size / intrinsics / depth range");
+    if (c.shard_count < 1 || c.shard_rank < 0 || c.shard_rank >= c.shard_count || ((1 << c.voxel_bits_z) % c.shard_count) != 0)
+        return fail(DSPMAP_ERR_CONFIG, "shard_count must divide the storage-z extent and shard_rank must be in range");
+    if (c.shard_count > 1) return fail(DSPMAP_ERR_UNSUPPORTED, "sharded maps are not implemented yet");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(DSPMAP_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+    }
+    if (c.device < 0 || c.device >= ndev) return fail(DSPMAP_ERR_INVALID_ARG, "device %d of %d", c.device, ndev);
+    device = c.device;
+    CU_TRY(this, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(this, cudaGetDeviceProperties(&prop, device));
+    sm_count = prop.multiProcessorCount;
+    CU_TRY(this, cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (auto& e : ev) CU_TRY(this, cudaEventCreate(&e));
+
+    FrameParams& f = fp;
+    memset(&f, 0, sizeof f);
+    f.Xb = c.voxel_bits_x; f.Yb = c.voxel_bits_y; f.Zb = c.voxel_bits_z; f.Pb = c.slot_bits;
+    f.NX = 1u << f.Xb; f.NY = 1u << f.Yb; f.NZ = 1u << f.Zb; f.P = 1u << f.Pb;
+    f.V = f.NX * f.NY * f.NZ;
+    f.voxel = c.voxel_size;
+    f.voxel_recip = 1.f / f.voxel;                               // operations.h:766
+    f.pmax[0] = (f.NX >> 1) * f.voxel; f.pmax[1] = (f.NY >> 1) * f.voxel; f.pmax[2] = (f.NZ >> 1) * f.voxel;  // :735-741
+    for (int a = 0; a < 3; ++a) f.pmin[a] = -f.pmax[a];
+    if (c.boost_mode) {                                          // settings.h:136-143
+        const float s = 0.5f;
+        f.fx = s * c.fx; f.fy = s * c.fy; f.cx = s * c.cx; f.cy = s * c.cy;
+        f.W = (int)(s * c.image_width); f.H = (int)(s * c.image_height);
+    } else {
+        f.fx = c.fx; f.fy = c.fy; f.cx = c.cx; f.cy = c.cy; f.W = c.image_width; f.H = c.image_height;
+    }
+    f.in_W = c.image_width; f.in_H = c.image_height; f.boost = c.boost_mode ? 1 : 0;
+    f.depth_min = c.depth_min; f.depth_max = c.depth_max;
+    f.dmin = (double)c.depth_min; f.dmax = (double)c.depth_max;
+    f.tan_hx = (float)tan(atan2(f.W / 2.0, (double)f.fx));      // operations.h:1249-1250
+    f.tan_hy = (float)tan(atan2(f.H / 2.0, (double)f.fy));
+    f.win_r = c.window_half > 0 ? c.window_half : (c.boost_mode ? 3 : 5);   // semantic_dsp_map.h:964-970
+    f.zed2_filters = c.zed2_filters ? 1 : 0;
+    f.consider_instance = c.consider_instance ? 1 : 0;
+    const uint32_t slabs = f.NZ / (uint32_t)c.shard_count;
+    f.z_lo = slabs * (uint32_t)c.shard_rank; f.z_hi = f.z_lo + slabs;
+    f.topk = 2 * f.P - 1;
+    const double Km[9] = {(double)f.fx, 0, (double)f.cx, 0, (double)f.fy, (double)f.cy, 0, 0, 1};   // pointcloud_tools.h:113
+    inverse3d(Km, f.Kinv);
+
+    // defaults of the SemanticDSPMap constructor (semantic_dsp_map.h:25-43)
+    prm.detection_probability = 0.95f; prm.noise_number = 0.1f; prm.nb_ptc_num_per_point = 3; prm.occupancy_threshold = 0.2f;
+    prm.forgetting_rate = 1.0f; prm.max_forget_count = 5; prm.id_transition_probability = 0.1f; prm.depth_noise_first_order = 0.0f;
+    prm.depth_noise_zero_order = 0.1f; prm.consider_depth_noise = 0; prm.use_independent_filter = 0; prm.zero_center = 0;
+
+    const size_t npix = (size_t)f.W * f.H, npix_in = (size_t)f.in_W * f.in_H;
+    v_local = slabs << (f.Xb + f.Yb);
+    n_slots_local = (size_t)v_local << f.Pb;
+    slot_lo = ((size_t)f.z_lo << (f.Xb + f.Yb)) << f.Pb;
+    CU_TRY(this, sx.alloc(n_slots_local)); CU_TRY(this, sy.alloc(n_slots_local)); CU_TRY(this, sz.alloc(n_slots_local));
+    CU_TRY(this, sw.alloc(n_slots_local)); CU_TRY(this, smeta.alloc(n_slots_local));
+    st.x = sx.p - slot_lo; st.y = sy.p - slot_lo; st.z = sz.p - slot_lo; st.w = sw.p - slot_lo; st.meta = smeta.p - slot_lo;
+
+    for (int a = 0; a < 3; ++a) stamps[a].assign(axis_n(a), 0u);
+    CU_TRY(this, d_stamps.alloc(f.NX + f.NY + f.NZ));
+    CU_TRY(this, d_lut.alloc(PDF_NUM));
+    CU_TRY(this, d_randoms.alloc(1));
+    CU_TRY(this, cudaMemset(d_randoms.p, 0, sizeof(float)));
+    rand_n = 1;
+    CU_TRY(this, d_static_track.alloc(256)); CU_TRY(this, d_static_label.alloc(65536));
+    for (int i = 0; i < 256; ++i) h_static_track[i] = 65535;
+    h_static_label.assign(65536, 0);
+    CU_TRY(this, cudaMemcpy(d_static_track.p, h_static_track, sizeof h_static_track, cudaMemcpyHostToDevice));
+    CU_TRY(this, cudaMemset(d_static_label.p, 0, 65536));
+    CU_TRY(this, d_fp.alloc(1)); CU_TRY(this, d_cnt.alloc(1)); CU_TRY(this, d_persist.alloc(1)); CU_TRY(this, d_moves.alloc(1));
+    CU_TRY(this, d_masks.alloc(64));
+    CU_TRY(this, d_depth_in.alloc(npix_in)); CU_TRY(this, d_depth_int.alloc(npix)); CU_TRY(this, d_ck.alloc(npix));
+    CU_TRY(this, d_cloud_pos.alloc(npix)); CU_TRY(this, d_cloud_meta.alloc(npix));
+    CU_TRY(this, d_pix_count.alloc(npix)); CU_TRY(this, d_pix_offset.alloc(npix + 1));
+    CU_TRY(this, d_scan_block.alloc((npix + SCAN_BLOCK - 1) / SCAN_BLOCK));
+    words_per_row = (f.NX + 1 + 31) / 32;
+    n_vwords = words_per_row * (f.NY + 1) * (f.NZ + 1);
+    CU_TRY(this, d_vmask.alloc(n_vwords));
+
+    const size_t usable = n_slots_local - v_local;
+    f.vis_cap = (uint32_t)std::min<size_t>(usable, c.max_visible ? (size_t)c.max_visible : (size_t)16 << 20);
+    CU_TRY(this, d_pairs.alloc(f.vis_cap)); CU_TRY(this, d_csr_idx.alloc(f.vis_cap)); CU_TRY(this, d_vis_pix.alloc(f.vis_cap));
+    CU_TRY(this, d_vis_meta.alloc(f.vis_cap)); CU_TRY(this, d_vis_pos.alloc(f.vis_cap));
+
+    sel_cap = (uint32_t)std::min<size_t>(usable, (size_t)4 << 20);
+    CU_TRY(this, d_sel_idx.alloc(sel_cap)); CU_TRY(this, d_sel_move.alloc(sel_cap)); CU_TRY(this, d_sel_seq.alloc(sel_cap));
+    CU_TRY(this, d_mov_pos.alloc(sel_cap)); CU_TRY(this, d_mov_meta.alloc(sel_cap));
+
+    // hash table for ordered insertion: >= 2x the larger candidate population (pixels, moved particles)
+    size_t want = 2 * std::max<size_t>(npix, sel_cap);
+    uint32_t cap = 1024, bits = 10;
+    while (cap < want) { cap <<= 1; ++bits; }
+    f.hash_cap = cap; f.hash_shift = 32 - bits;
+    CU_TRY(this, d_keys.alloc(cap)); CU_TRY(this, d_ranks.alloc((size_t)cap * f.topk));
+
+    CU_TRY(this, d_lb_occ.alloc((v_local + OCC_BLOCK - 1) / OCC_BLOCK));
+    CU_TRY(this, d_lb_sel.alloc((n_slots_local + SEL_BLOCK - 1) / SEL_BLOCK));
+    CU_TRY(this, r_idx.alloc(v_local)); CU_TRY(this, r_xyz.alloc(3 * (size_t)v_local)); CU_TRY(this, r_w.alloc(v_local));
+    CU_TRY(this, r_track.alloc(v_local)); CU_TRY(this, r_label.alloc(v_local)); CU_TRY(this, r_state.alloc(v_local));
+
+    CU_TRY(this, p_cnt.reserve(1)); CU_TRY(this, p_fp.reserve(1)); CU_TRY(this, p_stamps.reserve(f.NX + f.NY + f.NZ));
+    CU_TRY(this, p_maskdesc.reserve(64)); CU_TRY(this, p_moves.reserve(1));
+
+    // Gaussian PDF LUT (utils/basic_algorithms.h:403-407, 455-459): (1/sqrt(2*M_PI_2f32)) * exp(-v^2/2), v=(i-10000)*0.001
+    {
+        std::vector<float> lut(PDF_NUM);
+        const float half_pi_f32 = 1.57079632679489661923f;
+        for (int i = 0; i < PDF_NUM; ++i) {
+            const float value = (float)(i - PDF_NUM / 2) * 0.001f;
+            lut[i] = (1.f / (sqrtf(2.f * half_pi_f32))) * expf(-(value * value) / (2));
+        }
+        CU_TRY(this, cudaMemcpy(d_lut.p, lut.data(), PDF_NUM * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    CU_TRY(this, cudaFuncSetAttribute(k_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, PDF_NUM * (int)sizeof(float)));
+    CU_TRY(this, cudaFuncSetAttribute(k_weight_update, cudaFuncAttributeMaxDynamicSharedMemorySize, PDF_NUM * (int)sizeof(float)));
+
+    for (int a = 0; a < 3; ++a) { moved[a] = 0; equiv[a] = 0; map_center[a] = 0.f; ego_center[a] = 0.f; last_pos[a] = 0.f; }
+    return clear_device();
+}
+
+// RingBufferOperations::clear (mc_ring/operations.h:684-723) + SemanticDSPMap::clear (semantic_dsp_map.h:74-81)
+int dspmap::clear_device() {
+    reset_host_state();
+    k_clear_store<<<sm_count * 8, 256, 0, stream>>>(Store{sx.p, sy.p, sz.p, sw.p, smeta.p}, n_slots_local, fp.P - 1);
+    k_fill_u32<<<sm_count * 4, 256, 0, stream>>>(d_keys.p, d_keys.n, EMPTY_KEY);
+    k_fill_u32<<<sm_count * 4, 256, 0, stream>>>(d_ranks.p, d_ranks.n, NO_RANK);
+    CU_TRY(this, cudaMemsetAsync(d_pix_count.p, 0, d_pix_count.n * sizeof(uint32_t), stream));
+    CU_TRY(this, cudaMemsetAsync(d_pix_offset.p, 0, d_pix_offset.n * sizeof(uint32_t), stream));
+    CU_TRY(this, cudaMemsetAsync(d_cnt.p, 0, sizeof(Counters), stream));
+    CU_TRY(this, cudaGetLastError());
+    CU_TRY(this, cudaStreamSynchronize(stream));
+    memset(&last, 0, sizeof last);
+    memset(&stats, 0, sizeof stats);
+    host_result_valid = false;
+    return DSPMAP_OK;
+}
+
+int dspmap::apply_params() {
+    FrameParams& f = fp;
+    f.Pd = prm.detection_probability; f.kappa = prm.noise_number; f.tau = prm.id_transition_probability;
+    f.occ_thr = prm.occupancy_threshold; f.max_forget = prm.max_forget_count;
+    f.depth_noise = prm.consider_depth_noise ? 1 : 0; f.indep = prm.use_independent_filter ? 1 : 0;
+    f.n0 = prm.depth_noise_zero_order; f.n1 = prm.depth_noise_first_order;
+    f.sigma_invalid = prm.consider_depth_noise ? prm.depth_noise_zero_order : 0.1f;
+    f.zero_center = prm.zero_center ? 1 : 0;
+    f.nb_ptc = prm.nb_ptc_num_per_point;
+    return DSPMAP_OK;
+}
+
+// moveParticlesInSetsByTransformations + removeObjectByTrackID (mc_ring/operations.h:321-362; object_layer.h:414-425)
+int dspmap::run_moves(const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove) {
+    if (n_moves > MAX_MOVES || n_remove > MAX_MOVES) return fail(DSPMAP_ERR_CAPACITY, "at most %d moves and %d removals per frame", MAX_MOVES, MAX_MOVES);
+    MoveTable& mt = *p_moves.p;
+    memset(&mt, 0, sizeof mt);
+    mt.n_moves = n_moves; mt.n_remove = n_remove;
+    for (int i = 0; i < n_moves; ++i) { mt.move_track[i] = moves[i].track_id; memcpy(mt.t[i], moves[i].t, 12 * sizeof(float)); }
+    for (int i = 0; i < n_remove; ++i) mt.remove_track[i] = remove_tracks[i];
+    CU_TRY(this, cudaMemcpyAsync(d_moves.p, &mt, sizeof mt, cudaMemcpyHostToDevice, stream));
+    CU_TRY(this, cudaMemsetAsync(d_lb_sel.p, 0, d_lb_sel.n * sizeof(uint64_t), stream));
+    k_select_tracks<<<(unsigned)d_lb_sel.n, SEL_BLOCK, 0, stream>>>(d_fp.p, st, d_moves.p, d_sel_idx.p, d_sel_move.p, d_lb_sel.p, d_cnt.p, sel_cap);
+    if (n_moves > 0) {
+        k_move_sequence<<<1, 1024, 0, stream>>>(d_cnt.p, d_moves.p, d_sel_move.p, d_sel_seq.p, sel_cap);
+        k_move_apply<<<sm_count * 4, 256, 0, stream>>>(d_fp.p, d_cnt.p, st, d_moves.p, d_randoms.p, d_persist.p, d_sel_idx.p, d_sel_move.p,
+                                                     d_sel_seq.p, d_mov_pos.p, d_mov_meta.p, d_keys.p, d_ranks.p, sel_cap);
+        k_advance_cursor<<<1, 1, 0, stream>>>(d_cnt.p, d_persist.p, rand_n, sel_cap);
+        k_move_replay<<<sm_count * 8, 128, 0, stream>>>(d_fp.p, st, d_stamps.p, d_stamps.p + fp.NX, d_stamps.p + fp.NX + fp.NY, d_mov_pos.p,
+                                                      d_mov_meta.p, d_keys.p, d_ranks.p, d_cnt.p);
+    }
+    CU_TRY(this, cudaGetLastError());
+    return DSPMAP_OK;
+}
+
+// SemanticDSPMap::update (semantic_dsp_map.h:170-251) -> subObjectLevelUpdate (:576-955)
+int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const dspmap_mask* masks, int n_masks, const double pos[3],
+                  const double quat[4], const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove,
+                  int want_free) {
+    FrameParams& f = fp;
+    if (prm.consider_depth_noise && prm.nb_ptc_num_per_point != 1)
+        return fail(DSPMAP_ERR_UNSUPPORTED, "nb_ptc_num_per_point != 1 with the depth-noise model is not implemented");
+    host_result_valid = false;
+    T += 1;                                                       // :173
+    f.T = T;
+    apply_params();
+    if (!forgetting_init) {                                       // utils/basic_algorithms.h:32-48, built once
+        for (int i = 0; i < 5; ++i) forget_tab[i] = (float)pow(2.5, -i / prm.forgetting_rate);
+        forgetting_init = true;
+    }
+    memcpy(f.forget_tab, forget_tab, sizeof forget_tab);
+
+    // camera matrices: double for the projection (pointcloud_tools.h:105-110), float for the map (:744-747)
+    quat_to_rot<double>(quat, f.R);
+    for (int a = 0; a < 3; ++a) f.t[a] = pos[a];
+    const float posf[3] = {(float)pos[0], (float)pos[1], (float)pos[2]};
+    const float qf[4] = {(float)quat[0], (float)quat[1], (float)quat[2], (float)quat[3]};
+    float Rf[9];
+    quat_to_rot<float>(qf, Rf);
+    const float c2g[16] = {Rf[0], Rf[1], Rf[2], posf[0], Rf[3], Rf[4], Rf[5], posf[1], Rf[6], Rf[7], Rf[8], posf[2], 0.f, 0.f, 0.f, 1.f};
+    inverse4f(c2g, f.ext);
+    float inv_ext[16];
+    inverse4f(f.ext, inv_ext);
+    f.cam[0] = inv_ext[3]; f.cam[1] = inv_ext[7]; f.cam[2] = inv_ext[11];   // :1241
+
+    ring_shift(posf);                                             // :584-585
+    for (int a = 0; a < 3; ++a) { f.equiv[a] = equiv[a]; f.map_center[a] = map_center[a]; f.vox_off[a] = map_center[a] + f.pmin[a]; }
+
+    // BFS start vertex (operations.h:1312-1338), clamped into the lattice
+    {
+        const float sg[3] = {(inv_ext[0] * 0.f + inv_ext[1] * 0.f + inv_ext[2] * 1.f) + inv_ext[3],
+                             (inv_ext[4] * 0.f + inv_ext[5] * 0.f + inv_ext[6] * 1.f) + inv_ext[7],
+                             (inv_ext[8] * 0.f + inv_ext[9] * 0.f + inv_ext[10] * 1.f) + inv_ext[11]};
+        int sv[3];
+        for (int a = 0; a < 3; ++a) {
+            sv[a] = static_cast<int>(((sg[a] - map_center[a]) + f.pmax[a]) * f.voxel_recip);
+            sv[a] = std::min(std::max(sv[a], 0), (int)axis_n(a));
+        }
+        const float vx = (float)sv[0] * f.voxel + f.vox_off[0], vy = (float)sv[1] * f.voxel + f.vox_off[1], vz = (float)sv[2] * f.voxel + f.vox_off[2];
+        const float c0 = ((f.ext[0] * vx + f.ext[1] * vy) + f.ext[2] * vz) + f.ext[3] * 1.0f;
+        const float c1 = ((f.ext[4] * vx + f.ext[5] * vy) + f.ext[6] * vz) + f.ext[7] * 1.0f;
+        const float c2 = ((f.ext[8] * vx + f.ext[9] * vy) + f.ext[10] * vz) + f.ext[11] * 1.0f;
+        f.start_in = !(c2 < f.depth_min || c2 > f.depth_max) && !(std::abs(c0) > c2 * f.tan_hx) && !(std::abs(c1) > c2 * f.tan_hy);
+    }
+    f.n_masks = n_masks;
+    f.max_movable = max_movable; f.sky_track = sky_track;
+    f.want_free = want_free ? 1 : 0; f.want_state = want_state ? 1 : 0;
+    f.rand_n = rand_n;
+
+    if (want_free && !r_free_idx.p) { CU_TRY(this, r_free_idx.alloc(v_local)); CU_TRY(this, r_free_xyz.alloc(3 * (size_t)v_local)); }
+    if (want_state && !d_voxel_state.p) CU_TRY(this, d_voxel_state.alloc(v_local));
+
+    // ---- uploads -------------------------------------------------------------------------------------------
+    if ((size_t)n_masks > d_masks.n) { CU_TRY(this, d_masks.alloc(n_masks)); }
+    CU_TRY(this, p_maskdesc.reserve(std::max(n_masks, 1)));
+    for (int m = 0; m < n_masks; ++m) {
+        MaskDesc& md = p_maskdesc.p[m];
+        md.data = masks[m].data; md.row_stride = masks[m].row_stride; md.is_static = masks[m].is_static;
+        md.track_id = masks[m].track_id; md.label_id = masks[m].label_id;
+        for (int a = 0; a < 3; ++a) { md.bbox_min[a] = masks[m].bbox_min[a]; md.bbox_max[a] = masks[m].bbox_max[a]; }
+    }
+    if (n_masks) CU_TRY(this, cudaMemcpyAsync(d_masks.p, p_maskdesc.p, n_masks * sizeof(MaskDesc), cudaMemcpyHostToDevice, stream));
+    *p_fp.p = f;
+    CU_TRY(this, cudaMemcpyAsync(d_fp.p, p_fp.p, sizeof(FrameParams), cudaMemcpyHostToDevice, stream));
+    if (stamps_dirty) {
+        uint32_t* s = p_stamps.p;
+        for (int a = 0; a < 3; ++a) { memcpy(s, stamps[a].data(), stamps[a].size() * 4); s += stamps[a].size(); }
+        CU_TRY(this, cudaMemcpyAsync(d_stamps.p, p_stamps.p, (f.NX + f.NY + f.NZ) * 4, cudaMemcpyHostToDevice, stream));
+        stamps_dirty = false;
+    }
+    CU_TRY(this, cudaMemsetAsync(d_cnt.p, 0, sizeof(Counters), stream));
+    CU_TRY(this, cudaMemsetAsync(d_lb_occ.p, 0, d_lb_occ.n * sizeof(uint64_t), stream));
+    const uint32_t* stx = d_stamps.p;
+    const uint32_t* sty = d_stamps.p + f.NX;
+    const uint32_t* stz = d_stamps.p + f.NX + f.NY;
+    const int npix = f.W * f.H;
+    const size_t lut_bytes = PDF_NUM * sizeof(float);
+
+    if (profiling) cudaEventRecord(ev[0], stream);
+    // ---- K1 projection ---------------------------------------------------------------------------------------
+    k_project<<<(npix + 255) / 256, 256, 0, stream>>>(d_fp.p, d_depth, stride, d_masks.p, d_static_track.p, d_static_label.p,
+                                                     d_depth_int.p, d_cloud_pos.p, d_cloud_meta.p, d_cnt.p);
+    if (profiling) { cudaEventRecord(ev[1], stream); cudaEventRecord(ev[2], stream); }
+    // ---- P2/P3 object predict / prune ---------------------------------------------------------------------------
+    if (n_moves > 0 || n_remove > 0) {
+        // a track that is both moved and removed is removed AFTER its move (the reference order)
+        std::vector<int32_t> rm_now, rm_after;
+        for (int i = 0; i < n_remove; ++i) {
+            bool also_moved = false;
+            for (int k = 0; k < n_moves; ++k) also_moved |= moves[k].track_id == remove_tracks[i];
+            (also_moved ? rm_after : rm_now).push_back(remove_tracks[i]);
+        }
+        int rc = run_moves(moves, n_moves, rm_now.data(), (int)rm_now.size());
+        if (rc != DSPMAP_OK) return rc;
+        if (!rm_after.empty()) {
+            CU_TRY(this, cudaStreamSynchronize(stream));   // the move table staging buffer is reused
+            CU_TRY(this, cudaMemsetAsync(&d_cnt.p->ticket_sel, 0, sizeof(uint32_t), stream));
+            rc = run_moves(nullptr, 0, rm_after.data(), (int)rm_after.size());
+            if (rc != DSPMAP_OK) return rc;
+        }
+    }
+    if (profiling) cudaEventRecord(ev[3], stream);
+    // ---- U2 visibility ---------------------------------------------------------------------------------------------
+    if (f.start_in) {
+        k_vertex_mask<<<(n_vwords * 32 + 127) / 128, 128, 0, stream>>>(d_fp.p, d_vmask.p, words_per_row, n_vwords);
+        k_sweep<<<(v_local + 255) / 256, 256, 0, stream>>>(d_fp.p, st, stx, sty, stz, d_vmask.p, words_per_row, d_depth_int.p,
+                                                         d_pix_count.p, d_pairs.p, d_cnt.p);
+    }
+    const int nsb = (npix + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    k_scan_blocksum<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p);
+    k_scan_apply<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p, d_pix_offset.p);
+    k_fill<<<sm_count * 4, 256, 0, stream>>>(d_fp.p, d_cnt.p, d_pairs.p, d_pix_offset.p, d_pix_count.p, d_csr_idx.p, d_vis_pix.p);
+    k_sort_lists<<<(npix + 255) / 256, 256, 0, stream>>>(d_fp.p, d_pix_offset.p, d_csr_idx.p);
+    k_gather_visible<<<sm_count * 4, 256, 0, stream>>>(d_fp.p, d_cnt.p, st, d_csr_idx.p, d_vis_pos.p, d_vis_meta.p);
+    if (profiling) cudaEventRecord(ev[4], stream);
+    // ---- U3 weight update --------------------------------------------------------------------------------------------
+    k_ck<<<sm_count * 2, 512, lut_bytes, stream>>>(d_fp.p, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_pix_offset.p, d_vis_pos.p, d_vis_meta.p, d_ck.p);
+    k_weight_update<<<sm_count * 2, 512, lut_bytes, stream>>>(d_fp.p, d_cnt.p, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_ck.p, d_csr_idx.p,
+                                                             d_vis_pix.p, d_vis_pos.p, d_vis_meta.p, st);
+    if (profiling) cudaEventRecord(ev[5], stream);
+    // ---- B1 birth + resample -----------------------------------------------------------------------------------------
+    k_birth_bin<<<(npix + 255) / 256, 256, 0, stream>>>(d_fp.p, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_cnt.p);
+    k_birth_replay<<<sm_count * 8, 128, 0, stream>>>(d_fp.p, st, stx, sty, stz, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_cnt.p);
+    if (profiling) cudaEventRecord(ev[6], stream);
+    // ---- O1 occupancy -------------------------------------------------------------------------------------------------
+    ResultArrays out{r_idx.p, r_xyz.p, r_w.p, r_track.p, r_label.p, r_state.p, r_free_idx.p, r_free_xyz.p};
+    k_occupancy<<<(unsigned)d_lb_occ.n, OCC_BLOCK, 0, stream>>>(d_fp.p, st, stx, sty, stz, out, d_voxel_state.p, d_lb_occ.p, d_cnt.p);
+    if (profiling) cudaEventRecord(ev[7], stream);
+    CU_TRY(this, cudaMemcpyAsync(p_cnt.p, d_cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+    CU_TRY(this, cudaGetLastError());
+    CU_TRY(this, cudaStreamSynchronize(stream));
+    last = *p_cnt.p;
+
+    stats.time_stamp = T;
+    stats.n_swept_voxels = last.n_swept_voxels; stats.n_swept_nonempty = last.n_swept_nonempty;
+    stats.n_visible = std::min(last.n_pairs, f.vis_cap); stats.n_valid_points = last.n_valid_points;
+    stats.n_born = last.n_born; stats.n_birth_voxels = last.n_birth_voxels; stats.n_resampled = last.n_resampled;
+    stats.n_occupied = last.n_occupied; stats.n_nonempty_voxels = last.n_nonempty_voxels;
+    stats.n_moved = last.n_moved; stats.n_removed = last.n_removed;
+    if (profiling) {
+        for (int k = 0; k < 7; ++k) cudaEventElapsedTime(&stats.ms_stage[k], ev[k], ev[k + 1]);
+        cudaEventElapsedTime(&stats.ms_stage[7], ev[0], ev[7]);
+    }
+    if (last.n_pairs > f.vis_cap) return fail(DSPMAP_ERR_CAPACITY, "visible-particle list overflow: %u > max_visible %u", last.n_pairs, f.vis_cap);
+    if (last.n_selected > sel_cap) return fail(DSPMAP_ERR_CAPACITY, "moved-particle list overflow: %u > %u", last.n_selected, sel_cap);
+    if (last.hash_overflow) return fail(DSPMAP_ERR_CAPACITY, "insertion hash table overflow");
+    return DSPMAP_OK;
+}
+
+int dspmap::fetch_result_to_host() {
+    if (host_result_valid) return DSPMAP_OK;
+    const size_t n = last.n_occupied, nf = fp.want_free ? last.n_free : 0;
+    CU_TRY(this, hr_idx.reserve(std::max<size_t>(n, 1))); CU_TRY(this, hr_xyz.reserve(std::max<size_t>(3 * n, 1)));
+    CU_TRY(this, hr_w.reserve(std::max<size_t>(n, 1))); CU_TRY(this, hr_track.reserve(std::max<size_t>(n, 1)));
+    CU_TRY(this, hr_label.reserve(std::max<size_t>(n, 1))); CU_TRY(this, hr_state.reserve(std::max<size_t>(n, 1)));
+    if (n) {
+        CU_TRY(this, cudaMemcpyAsync(hr_idx.p, r_idx.p, n * 4, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(this, cudaMemcpyAsync(hr_xyz.p, r_xyz.p, n * 12, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(this, cudaMemcpyAsync(hr_w.p, r_w.p, n * 4, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(this, cudaMemcpyAsync(hr_track.p, r_track.p, n * 2, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(this, cudaMemcpyAsync(hr_label.p, r_label.p, n, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(this, cudaMemcpyAsync(hr_state.p, r_state.p, n, cudaMemcpyDeviceToHost, stream));
+    }
+    if (nf) {
+        CU_TRY(this, hr_free_idx.reserve(nf)); CU_TRY(this, hr_free_xyz.reserve(3 * nf));
+        CU_TRY(this, cudaMemcpyAsync(hr_free_idx.p, r_free_idx.p, nf * 4, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(this, cudaMemcpyAsync(hr_free_xyz.p, r_free_xyz.p, nf * 12, cudaMemcpyDeviceToHost, stream));
+    }
+    CU_TRY(this, cudaStreamSynchronize(stream));
+    host_result_valid = true;
+    return DSPMAP_OK;
+}
+
+// =================================================== C ABI ===================================================
+extern "C" {
+
+int dspmap_version(void) { return 100; }
+
+int dspmap_create(const dspmap_config* cfg, dspmap_t** out) {
+    if (!cfg || !out) return DSPMAP_ERR_INVALID_ARG;
+    *out = nullptr;
+    dspmap* h = new (std::nothrow) dspmap();
+    if (!h) return DSPMAP_ERR_INVALID_ARG;
+    const int rc = h->init(*cfg);
+    if (rc != DSPMAP_OK) {
+        fprintf(stderr, "dspmap_create: %s\n", h->err.c_str());
+        h->release_all();
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return DSPMAP_OK;
+}
+
+void dspmap_destroy(dspmap_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->release_all();
+    delete h;
+}
+
+int dspmap_clear(dspmap_t* h) {
+    if (!h) return DSPMAP_ERR_INVALID_ARG;
+    CU_TRY(h, cudaSetDevice(h->device));
+    return h->clear_device();
+}
+
+const char* dspmap_last_error(const dspmap_t* h) { return h ? h->err.c_str() : "null handle"; }
+
+int dspmap_set_params(dspmap_t* h, const dspmap_params* p) {
+    if (!h || !p) return DSPMAP_ERR_INVALID_ARG;
+    if (p->max_forget_count > 5 || p->max_forget_count < 0 || p->nb_ptc_num_per_point < 1)
+        return h->fail(DSPMAP_ERR_INVALID_ARG, "max_forget_count must be in 0..5 and nb_ptc_num_per_point >= 1");
+    h->prm = *p;
+    return DSPMAP_OK;
+}
+
+int dspmap_set_label_luts(dspmap_t* h, const uint16_t static_value_to_track[256], const uint16_t* static_tracks,
+                          const uint8_t* static_labels, int32_t n_static, uint16_t max_movable_track, uint16_t sky_track) {
+    if (!h || !static_value_to_track || n_static < 0 || (n_static > 0 && (!static_tracks || !static_labels))) return DSPMAP_ERR_INVALID_ARG;
+    CU_TRY(h, cudaSetDevice(h->device));
+    memcpy(h->h_static_track, static_value_to_track, 256 * sizeof(uint16_t));
+    std::fill(h->h_static_label.begin(), h->h_static_label.end(), (uint8_t)0);
+    for (int i = 0; i < n_static; ++i) h->h_static_label[static_tracks[i]] = static_labels[i];
+    h->max_movable = max_movable_track;
+    h->sky_track = sky_track;
+    CU_TRY(h, cudaMemcpy(h->d_static_track.p, h->h_static_track, 256 * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(h->d_static_label.p, h->h_static_label.data(), 65536, cudaMemcpyHostToDevice));
+    return DSPMAP_OK;
+}
+
+int dspmap_set_random_table(dspmap_t* h, const float* table, uint32_t n) {
+    if (!h || !table || n < 1) return DSPMAP_ERR_INVALID_ARG;
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, h->d_randoms.alloc(n));
+    CU_TRY(h, cudaMemcpy(h->d_randoms.p, table, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    h->rand_n = n;
+    return DSPMAP_OK;
+}
+
+static int check_frame_args(dspmap_t* h, const float* depth, int32_t rows, int32_t cols, int32_t row_stride, const dspmap_mask* masks,
+                            int32_t n_masks, const double* position, const double* orientation, const dspmap_object_move* moves,
+                            int32_t n_moves, const int32_t* remove_tracks, int32_t n_remove) {
+    if (!h) return DSPMAP_ERR_INVALID_ARG;
+    if (!depth || !position || !orientation || n_masks < 0 || n_moves < 0 || n_remove < 0 || (n_masks && !masks) || (n_moves && !moves) ||
+        (n_remove && !remove_tracks))
+        return h->fail(DSPMAP_ERR_INVALID_ARG, "null pointer or negative count");
+    // the reference indexes with the compile-time size and reads out of bounds otherwise (semantic_dsp_map.h:212-221 vs :974-979)
+    if (rows != h->cfg.image_height || cols != h->cfg.image_width || row_stride < cols)
+        return h->fail(DSPMAP_ERR_IMAGE_SIZE, "depth is %dx%d (stride %d), map is configured for %dx%d", rows, cols, row_stride, h->cfg.image_height, h->cfg.image_width);
+    for (int m = 0; m < n_masks; ++m)
+        if (!masks[m].data || masks[m].row_stride < cols) return h->fail(DSPMAP_ERR_IMAGE_SIZE, "mask %d: null data or stride < width", m);
+    return DSPMAP_OK;
+}
+
+int dspmap_update_device(dspmap_t* h, const float* d_depth, int32_t rows, int32_t cols, int32_t row_stride, const dspmap_mask* masks,
+                         int32_t n_masks, const double position[3], const double orientation_wxyz[4], const dspmap_object_move* moves,
+                         int32_t n_moves, const int32_t* remove_tracks, int32_t n_remove, int32_t want_freespace) {
+    int rc = check_frame_args(h, d_depth, rows, cols, row_stride, masks, n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove);
+    if (rc != DSPMAP_OK) return rc;
+    CU_TRY(h, cudaSetDevice(h->device));
+    return h->frame(d_depth, rows, cols, row_stride, masks, n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove, want_freespace);
+}
+
+int dspmap_update(dspmap_t* h, const float* depth, int32_t rows, int32_t cols, int32_t row_stride, const dspmap_mask* masks,
+                  int32_t n_masks, const double position[3], const double orientation_wxyz[4], const dspmap_object_move* moves,
+                  int32_t n_moves, const int32_t* remove_tracks, int32_t n_remove, int32_t want_freespace) {
+    int rc = check_frame_args(h, depth, rows, cols, row_stride, masks, n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove);
+    if (rc != DSPMAP_OK) return rc;
+    CU_TRY(h, cudaSetDevice(h->device));
+    // stage the caller's (pageable) images through pinned memory, dense rows
+    const size_t npix = (size_t)rows * cols;
+    CU_TRY(h, h->p_depth.reserve(npix));
+    for (int r = 0; r < rows; ++r) memcpy(h->p_depth.p + (size_t)r * cols, depth + (size_t)r * row_stride, (size_t)cols * sizeof(float));
+    CU_TRY(h, cudaMemcpyAsync(h->d_depth_in.p, h->p_depth.p, npix * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    std::vector<dspmap_mask> dm(masks, masks + n_masks);
+    if (n_masks) {
+        CU_TRY(h, h->p_masks.reserve(npix * n_masks));
+        if (h->d_mask_in.n < npix * n_masks) CU_TRY(h, h->d_mask_in.alloc(npix * n_masks));
+        for (int m = 0; m < n_masks; ++m) {
+            uint8_t* dst = h->p_masks.p + (size_t)m * npix;
+            for (int r = 0; r < rows; ++r) memcpy(dst + (size_t)r * cols, masks[m].data + (size_t)r * masks[m].row_stride, cols);
+            dm[m].data = h->d_mask_in.p + (size_t)m * npix;
+            dm[m].row_stride = cols;
+        }
+        CU_TRY(h, cudaMemcpyAsync(h->d_mask_in.p, h->p_masks.p, npix * n_masks, cudaMemcpyHostToDevice, h->stream));
+    }
+    rc = h->frame(h->d_depth_in.p, rows, cols, cols, dm.data(), n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove, want_freespace);
+    if (rc != DSPMAP_OK) return rc;
+    return h->fetch_result_to_host();
+}
+
+int dspmap_get_result(dspmap_t* h, dspmap_result* out) {
+    if (!h || !out) return DSPMAP_ERR_INVALID_ARG;
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int rc = h->fetch_result_to_host();
+    if (rc != DSPMAP_OK) return rc;
+    out->count = h->last.n_occupied;
+    out->free_count = h->fp.want_free ? h->last.n_free : 0;
+    out->voxel_index = h->hr_idx.p; out->xyz = h->hr_xyz.p; out->weight_sum = h->hr_w.p; out->track_id = h->hr_track.p;
+    out->label_id = h->hr_label.p; out->state = h->hr_state.p; out->free_voxel_index = h->hr_free_idx.p; out->free_xyz = h->hr_free_xyz.p;
+    return DSPMAP_OK;
+}
+
+int dspmap_get_result_device(dspmap_t* h, dspmap_result* out) {
+    if (!h || !out) return DSPMAP_ERR_INVALID_ARG;
+    out->count = h->last.n_occupied;
+    out->free_count = h->fp.want_free ? h->last.n_free : 0;
+    out->voxel_index = h->r_idx.p; out->xyz = h->r_xyz.p; out->weight_sum = h->r_w.p; out->track_id = h->r_track.p;
+    out->label_id = h->r_label.p; out->state = h->r_state.p; out->free_voxel_index = h->r_free_idx.p; out->free_xyz = h->r_free_xyz.p;
+    return DSPMAP_OK;
+}
+
+int dspmap_get_stats(dspmap_t* h, dspmap_frame_stats* out) {
+    if (!h || !out) return DSPMAP_ERR_INVALID_ARG;
+    *out = h->stats;
+    return DSPMAP_OK;
+}
+
+int dspmap_set_profiling(dspmap_t* h, int32_t on) {
+    if (!h) return DSPMAP_ERR_INVALID_ARG;
+    h->profiling = on != 0;
+    return DSPMAP_OK;
+}
+
+int dspmap_object_particle_count(dspmap_t* h, int32_t track_id, uint32_t* count) {
+    if (!h || !count) return DSPMAP_ERR_INVALID_ARG;
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaMemsetAsync(&h->d_cnt.p->pad[0], 0, sizeof(uint32_t), h->stream));
+    k_count_track<<<h->sm_count * 8, 256, 0, h->stream>>>(Store{h->sx.p, h->sy.p, h->sz.p, h->sw.p, h->smeta.p}, h->n_slots_local, h->fp.P - 1, (uint32_t)track_id & 0xffffu, &h->d_cnt.p->pad[0]);
+    CU_TRY(h, cudaMemcpyAsync(count, &h->d_cnt.p->pad[0], sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return DSPMAP_OK;
+}
+
+int dspmap_comm_unique_id(uint8_t id[DSPMAP_COMM_ID_BYTES]) {
+    if (!id) return DSPMAP_ERR_INVALID_ARG;
+    memset(id, 0, DSPMAP_COMM_ID_BYTES);
+    return DSPMAP_ERR_UNSUPPORTED;
+}
+
+int dspmap_comm_init(dspmap_t* h, const uint8_t id[DSPMAP_COMM_ID_BYTES]) {
+    if (!h || !id) return DSPMAP_ERR_INVALID_ARG;
+    return h->fail(DSPMAP_ERR_UNSUPPORTED, "sharded maps are not implemented yet");
+}
+
+int dspmap_dump(dspmap_t* h, int32_t what, void* dst, size_t cap, size_t* n_bytes) {
+    if (!h) return DSPMAP_ERR_INVALID_ARG;
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    const FrameParams& f = h->fp;
+    const size_t npix = (size_t)f.W * f.H;
+    std::vector<uint8_t> tmp;
+    auto pull = [&](void* host, const void* dev, size_t bytes) { return cudaMemcpy(host, dev, bytes, cudaMemcpyDeviceToHost); };
+    switch (what) {
+        case DSPMAP_DUMP_POINTS: {
+            std::vector<float4> pos(npix);
+            std::vector<uint32_t> meta(npix);
+            CU_TRY(h, pull(pos.data(), h->d_cloud_pos.p, npix * sizeof(float4)));
+            CU_TRY(h, pull(meta.data(), h->d_cloud_meta.p, npix * 4));
+            tmp.resize(npix * 20);
+            for (size_t q = 0; q < npix; ++q) {
+                uint8_t* r = tmp.data() + q * 20;
+                memcpy(r, &pos[q], 16);
+                const uint16_t tr = (uint16_t)pt_track(meta[q]);
+                memcpy(r + 16, &tr, 2);
+                r[18] = (uint8_t)pt_label(meta[q]);
+                r[19] = (uint8_t)pt_valid(meta[q]);
+            }
+            break;
+        }
+        case DSPMAP_DUMP_PARTICLES: {
+            const size_t n = h->n_slots_local;
+            std::vector<float> x(n), y(n), z(n), w(n);
+            std::vector<uint64_t> m(n);
+            CU_TRY(h, pull(x.data(), h->sx.p, n * 4)); CU_TRY(h, pull(y.data(), h->sy.p, n * 4)); CU_TRY(h, pull(z.data(), h->sz.p, n * 4));
+            CU_TRY(h, pull(w.data(), h->sw.p, n * 4)); CU_TRY(h, pull(m.data(), h->smeta.p, n * 8));
+            tmp.resize(n * 24);
+            for (size_t i = 0; i < n; ++i) {
+                uint8_t* r = tmp.data() + i * 24;
+                memcpy(r, &x[i], 4); memcpy(r + 4, &y[i], 4); memcpy(r + 8, &z[i], 4); memcpy(r + 12, &w[i], 4); memcpy(r + 16, &m[i], 8);
+            }
+            break;
+        }
+        case DSPMAP_DUMP_PIXEL_OFFSETS:
+            tmp.resize((npix + 1) * 4);
+            CU_TRY(h, pull(tmp.data(), h->d_pix_offset.p, tmp.size()));
+            break;
+        case DSPMAP_DUMP_PIXEL_LISTS: {
+            const size_t n = std::min(h->last.n_pairs, f.vis_cap);
+            tmp.resize(n * 4);
+            if (n) CU_TRY(h, pull(tmp.data(), h->d_csr_idx.p, tmp.size()));
+            break;
+        }
+        case DSPMAP_DUMP_CK:
+            tmp.resize(npix * 4);
+            CU_TRY(h, pull(tmp.data(), h->d_ck.p, tmp.size()));
+            break;
+        case DSPMAP_DUMP_RING: {
+            tmp.resize(4 * (9 + f.NX + f.NY + f.NZ));
+            uint8_t* wp = tmp.data();
+            memcpy(wp, h->moved, 12); wp += 12; memcpy(wp, h->equiv, 12); wp += 12; memcpy(wp, h->map_center, 12); wp += 12;
+            for (int a = 0; a < 3; ++a) { memcpy(wp, h->stamps[a].data(), h->stamps[a].size() * 4); wp += h->stamps[a].size() * 4; }
+            break;
+        }
+        case DSPMAP_DUMP_VOXEL_STATE:
+            // the per-voxel state plane is only written once it has been asked for: the first call enables it
+            if (!h->want_state) { h->want_state = true; tmp.assign(h->v_local, (uint8_t)0x80); }
+            else { tmp.resize(h->v_local); if (h->d_voxel_state.p) CU_TRY(h, pull(tmp.data(), h->d_voxel_state.p, tmp.size())); }
+            break;
+        default:
+            return h->fail(DSPMAP_ERR_INVALID_ARG, "unknown dump %d", what);
+    }
+    if (n_bytes) *n_bytes = tmp.size();
+    if (dst && cap) memcpy(dst, tmp.data(), std::min(cap, tmp.size()));
+    return DSPMAP_OK;
+}
+
+}  // extern "C"

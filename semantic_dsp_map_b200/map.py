@@ -1,0 +1,262 @@
+"""Host-side mirror of the reference's ``SemanticDSPMap`` interface over the C ABI.
+
+The reference exposes one class, ``SemanticDSPMap`` (include/semantic_dsp_map.h:23-251), that the ROS node drives with
+five setters and ``update()`` (src/mapping.cpp:135-140, 273).  This module keeps the same method names, argument
+meaning and error behaviour for the hot path, and evaluates on the host only what the reference evaluates with string
+keys and tiny per-object loops (label look-ups, bbox from key points, the track-id wrap) before handing plain arrays
+to ``libdspmap_b200.so``.  The C++ adapter a ROS build would use is shown in INTEGRATION.md; this is its Python twin,
+used by the parity tests and the bench.  There is no CPU fallback: without the CUDA library or a GPU every entry point
+raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from .configs import MapConfig
+from .labels import LabelTables, ZED2_ROWS
+
+_DBL_MAX = sys.float_info.max
+_DBL_MIN = sys.float_info.min  # std::numeric_limits<double>::min(): smallest POSITIVE double (pointcloud_tools.h:178-180)
+
+
+@dataclass
+class MaskKpts:
+    """include/utils/tracking_result_handler.h:15-26."""
+    track_id: int
+    label: str
+    mask: np.ndarray                                   # uint8, input resolution
+    bbox: tuple = (0, 0, 0, 0)
+    kpts_current: np.ndarray = field(default_factory=lambda: np.zeros((0, 3)))
+    kpts_previous: np.ndarray = field(default_factory=lambda: np.zeros((0, 3)))
+
+
+@dataclass
+class OccupancyResult:
+    """What getOccupancyResult emits (semantic_dsp_map.h:1239-1383), before colouring."""
+    voxel_index: np.ndarray
+    xyz: np.ndarray
+    weight_sum: np.ndarray
+    track_id: np.ndarray
+    label_id: np.ndarray
+    state: np.ndarray
+    free_voxel_index: np.ndarray
+    free_xyz: np.ndarray
+
+
+def _as_array(ptr, count, dtype, shape=None):
+    if count == 0 or not ptr:
+        return np.zeros((0,) + tuple(shape[1:]) if shape else (0,), dtype)
+    n = count * (int(np.prod(shape[1:])) if shape else 1)
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    a = np.frombuffer(buf, dtype=dtype, count=n).copy()
+    return a.reshape((count,) + tuple(shape[1:])) if shape else a
+
+
+class Engine:
+    """Thin owner of one ``dspmap_t`` handle; used for both the CUDA library and (in tests) the oracle library."""
+
+    def __init__(self, lib, prefix: str, cfg: MapConfig, create_args=()):
+        self.lib, self.prefix, self.cfg = lib, prefix, cfg
+        self._h = C.c_void_p()
+        self._keep = []
+        self._create(cfg, *create_args)
+
+    def _fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def _create(self, cfg, *args):
+        cc = cfg.c_config(*args)
+        rc = self._fn("create")(C.byref(cc), C.byref(self._h))
+        if rc != _capi.DSPMAP_OK:
+            raise _capi.DspMapError(rc, "dspmap_create")
+
+    def check(self, rc, where):
+        if rc != _capi.DSPMAP_OK:
+            detail = self._fn("last_error")(self._h).decode() if hasattr(self.lib, self.prefix + "last_error") else ""
+            raise _capi.DspMapError(rc, where, detail)
+
+    def close(self):
+        if self._h:
+            self._fn("destroy")(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- setters -------------------------------------------------------------------------------------------
+    def set_params(self, p: _capi.Params):
+        self.check(self._fn("set_params")(self._h, C.byref(p)), "dspmap_set_params")
+
+    def set_label_luts(self, tables: LabelTables):
+        v2t = np.ascontiguousarray(tables.static_value_to_track(), np.uint16)
+        tracks, labels = tables.static_track_labels()
+        tracks = np.ascontiguousarray(tracks, np.uint16)
+        labels = np.ascontiguousarray(labels, np.uint8)
+        self.check(self._fn("set_label_luts")(self._h, v2t.ctypes.data, tracks.ctypes.data, labels.ctypes.data, len(tracks),
+                                              tables.max_movable_instance_id & 0xFFFF, tables.sky_track() & 0xFFFF),
+                   "dspmap_set_label_luts")
+
+    def set_random_table(self, table: np.ndarray):
+        t = np.ascontiguousarray(table, np.float32)
+        self.check(self._fn("set_random_table")(self._h, t.ctypes.data, t.size), "dspmap_set_random_table")
+
+    def clear(self):
+        self.check(self._fn("clear")(self._h), "dspmap_clear")
+
+    # ---- frame ---------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _pack_masks(masks):
+        arr = (_capi.Mask * max(len(masks), 1))()
+        for i, m in enumerate(masks):
+            arr[i].data = m["data"]
+            arr[i].row_stride = m["row_stride"]
+            arr[i].is_static = int(m["is_static"])
+            arr[i].track_id = int(m["track_id"])
+            arr[i].label_id = int(m["label_id"])
+            for a in range(3):
+                arr[i].bbox_min[a] = float(m["bbox_min"][a])
+                arr[i].bbox_max[a] = float(m["bbox_max"][a])
+        return arr
+
+    @staticmethod
+    def _pack_moves(moves):
+        arr = (_capi.ObjectMove * max(len(moves), 1))()
+        for i, (track, t) in enumerate(moves):
+            arr[i].track_id = int(track)
+            flat = np.asarray(t, np.float32).reshape(16)
+            for k in range(16):
+                arr[i].t[k] = float(flat[k])
+        return arr
+
+    def update_raw(self, fn_name, depth_ptr, rows, cols, stride, masks, position, orientation, moves=(), remove_tracks=(),
+                   want_freespace=False):
+        marr = self._pack_masks(masks)
+        mvarr = self._pack_moves(moves)
+        rm = (C.c_int32 * max(len(remove_tracks), 1))(*[int(t) for t in remove_tracks])
+        pos = (C.c_double * 3)(*[float(x) for x in position])
+        quat = (C.c_double * 4)(*[float(x) for x in orientation])
+        rc = self._fn(fn_name)(self._h, depth_ptr, rows, cols, stride, marr, len(masks), pos, quat, mvarr, len(moves), rm,
+                               len(remove_tracks), int(bool(want_freespace)))
+        self.check(rc, "dspmap_" + fn_name)
+
+    def result(self, device=False) -> _capi.Result:
+        r = _capi.Result()
+        self.check(self._fn("get_result_device" if device else "get_result")(self._h, C.byref(r)), "dspmap_get_result")
+        return r
+
+    def result_arrays(self) -> OccupancyResult:
+        r = self.result()
+        n, nf = r.count, r.free_count
+        return OccupancyResult(
+            _as_array(r.voxel_index, n, np.uint32), _as_array(r.xyz, n, np.float32, (n, 3)), _as_array(r.weight_sum, n, np.float32),
+            _as_array(r.track_id, n, np.uint16), _as_array(r.label_id, n, np.uint8), _as_array(r.state, n, np.int8),
+            _as_array(r.free_voxel_index, nf, np.uint32), _as_array(r.free_xyz, nf, np.float32, (nf, 3)))
+
+    def stats(self) -> dict:
+        s = _capi.FrameStats()
+        self.check(self._fn("get_stats")(self._h, C.byref(s)), "dspmap_get_stats")
+        return s.as_dict()
+
+    def dump(self, what: int, dtype=np.uint8) -> np.ndarray:
+        n = C.c_size_t()
+        self.check(self._fn("dump")(self._h, what, None, 0, C.byref(n)), "dspmap_dump")
+        buf = np.zeros(n.value, np.uint8)
+        if n.value:
+            self.check(self._fn("dump")(self._h, what, buf.ctypes.data, n.value, C.byref(n)), "dspmap_dump")
+        return buf.view(dtype)
+
+
+class SemanticDSPMap:
+    """The reference's public class, same method names (include/semantic_dsp_map.h:23-251)."""
+
+    def __init__(self, config: MapConfig, labels: Optional[LabelTables] = None, device: int = 0, _engine: Optional[Engine] = None):
+        self.config = config
+        self.labels = labels or LabelTables.from_rows(ZED2_ROWS)
+        self.engine = _engine or Engine(_capi.load(), "dspmap_", config, (0, 1, device, 0))
+        self._params = config.c_params()
+        self.engine.set_params(self._params)
+        self.engine.set_label_luts(self.labels)
+        self._movement = (0.0, 0.0, 0.0, 0.0)
+        self._keep = []
+        self._eval_format = False
+
+    # -- setters, semantic_dsp_map.h:101-166 ----------------------------------------------------------------------------
+    def setMapParameters(self, detection_probability, noise_number, nb_ptc_num_per_point, occupancy_threshold, max_obersevation_lost_time,
+                         forgetting_rate=1.0, max_forget_count=5, match_score_threshold=0.5, id_transition_probability=0.1):
+        p = self._params
+        p.detection_probability, p.noise_number = detection_probability, noise_number
+        p.nb_ptc_num_per_point, p.occupancy_threshold = nb_ptc_num_per_point, occupancy_threshold
+        p.forgetting_rate, p.max_forget_count = forgetting_rate, max_forget_count
+        p.id_transition_probability = id_transition_probability
+        self.max_obersevation_lost_time = max_obersevation_lost_time
+        self.match_score_threshold = match_score_threshold
+        self.engine.set_params(p)
+
+    def setMapOptions(self, if_consider_depth_noise, if_use_independent_filter):
+        self._params.consider_depth_noise = int(bool(if_consider_depth_noise))
+        self._params.use_independent_filter = int(bool(if_use_independent_filter))
+        self.engine.set_params(self._params)
+
+    def setVisualizeOptions(self, visualize_with_zero_center, if_out_evaluation_format=False):
+        self._params.zero_center = int(bool(visualize_with_zero_center))
+        self._eval_format = bool(if_out_evaluation_format)
+        self.engine.set_params(self._params)
+
+    def setBeyesianMovementParameters(self, a, b, c, d):
+        self._movement = (a, b, c, d)  # object layer (host, out of scope): kept for interface parity
+
+    def setDepthNoiseModelParameters(self, first_order, zero_order):
+        self._params.depth_noise_first_order, self._params.depth_noise_zero_order = first_order, zero_order
+        self.engine.set_params(self._params)
+
+    def setOccupancyThreshold(self, thr):
+        self._params.occupancy_threshold = thr
+        self.engine.set_params(self._params)
+
+    def clear(self):
+        self.engine.clear()
+
+    # -- host evaluation of the string-keyed parts of generateLabeledPointCloud ---------------------------------------------
+    def lower_masks(self, ins_seg_result: Sequence[MaskKpts]):
+        """MaskKpts -> C-ABI mask descriptors (pointcloud_tools.h:116-215; semantic_dsp_map.h:179-186)."""
+        out = []
+        max_movable = self.labels.max_movable_instance_id
+        for m in ins_seg_result:
+            if m.label != "static" and m.track_id > max_movable:        # semantic_dsp_map.h:179-186
+                m.track_id = m.track_id % max_movable
+            mask = np.ascontiguousarray(m.mask, np.uint8)
+            self._keep.append(mask)
+            mn, mx = [_DBL_MAX] * 3, [_DBL_MIN] * 3                      # pointcloud_tools.h:178-199
+            for k in np.asarray(m.kpts_current, np.float64).reshape(-1, 3):
+                for a in range(3):
+                    mn[a] = min(mn[a], float(k[a]))
+                    mx[a] = max(mx[a], float(k[a]))
+            out.append(dict(data=mask.ctypes.data, row_stride=mask.strides[0], is_static=(m.label == "static"),
+                            track_id=m.track_id, label_id=self.labels.label_id_of(m.label),
+                            bbox_min=[v - 1.0 for v in mn], bbox_max=[v + 1.0 for v in mx]))
+        return out
+
+    # -- semantic_dsp_map.h:170-251 -----------------------------------------------------------------------------------------
+    def update(self, depth_value_mat: np.ndarray, ins_seg_result: Sequence[MaskKpts], camera_position, camera_orientation,
+               if_get_freespace: bool = False, time_stamp_double: float = 0.0, moves=(), remove_tracks=()) -> OccupancyResult:
+        """One frame.  ``camera_orientation`` is (w, x, y, z).  ``moves`` = [(track_id, 4x4)], ``remove_tracks`` = [track_id]:
+        what the host-side object layer (objectLevelUpdate, out of scope) decided for this frame."""
+        depth = np.asarray(depth_value_mat)
+        if depth.dtype != np.float32 or depth.ndim != 2:
+            raise TypeError("depth must be a 2-D float32 array (CV_32FC1, metres)")
+        if depth.strides[1] != 4:
+            depth = np.ascontiguousarray(depth)
+        self._keep = [depth]
+        masks = self.lower_masks(ins_seg_result)
+        self.engine.update_raw("update", depth.ctypes.data, depth.shape[0], depth.shape[1], depth.strides[0] // 4, masks,
+                               camera_position, camera_orientation, moves, remove_tracks, if_get_freespace)
+        return self.engine.result_arrays()
