@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py — depth frames/sec of the particle-map update path (BASELINE.json metric) on config B
+(ZED2 mode, 256x64x256 voxels = "256x256x64 grid", 8 slots/voxel, 1280x720 depth + masks).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference] [--config B]
+
+A step = one SemanticDSPMap::update() over one synthetic frame (SURVEY.md §8d scene; seeded).
+  value : frames/s with the frame's depth + masks already resident in HBM (dspmap_update_device), timed with CUDA
+          events on the stream the kernels run on, max over ranks.
+  e2e   : frames/s through the reference-facing call with HOST buffers (dspmap_update + dspmap_get_result):
+          host->pinned->device copies of depth and masks and the device->host read of the occupied list are inside
+          the timed region.
+  roofline    : the dominant kernel (occupancy_labels) — algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json.
+  cpu_baseline: the CPU oracle (faithful single-thread restatement of the reference, reference iteration order) timed
+                on this box's host cores on a bounded sample of the same frames.
+N > 1: one process per GPU (torchrun); each rank updates its own map replica from its own frame stream (weak scaling,
+no data-path collective).  --impl reference times the CPU oracle instead (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "depth frames/sec on 256x256x64 grid, 8 particles/voxel"
+UNIT = "frames/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def _gen_frame(args):
+    name, t, overrides = args
+    from semantic_dsp_map_b200 import BASELINE, Scene
+    import dataclasses
+    cfg = dataclasses.replace(BASELINE[name], **overrides)
+    return Scene(cfg).frame(t)
+
+
+def generate_frames(name, n, overrides=None):
+    """Frames are a pure function of (config, t); fan the ray casting out over the host cores (before CUDA is touched)."""
+    from concurrent.futures import ProcessPoolExecutor
+    jobs = [(name, t, overrides or {}) for t in range(n)]
+    workers = max(1, min(os.cpu_count() or 1, 16, n))
+    if workers == 1:
+        return [_gen_frame(j) for j in jobs]
+    with ProcessPoolExecutor(workers) as ex:
+        return list(ex.map(_gen_frame, jobs, chunksize=max(1, n // (workers * 4))))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(s) > 2 + k and s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(self.samples)}
+
+
+def run_reference(args, cfg_name):
+    """The reference's own CPU implementation of the path: the oracle in the reference's iteration order (BFS sweep,
+    unordered_set object sets), single thread like the shipped code (semantic_dsp_map.h:749 calls the non-MT BFS)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from semantic_dsp_map_b200 import BASELINE, make_random_table
+    from oracle_lib import oracle_map
+    cfg = BASELINE[cfg_name]
+    # bounded: the CPU path runs at about 1 frame/s on this config
+    steps, warmup = min(args.steps, 20), min(args.warmup, 5)
+    frames = generate_frames(cfg_name, warmup + steps)
+    m = oracle_map(cfg, order=0)
+    m.engine.set_random_table(make_random_table(cfg.seed))
+    for fr in frames[:warmup]:
+        m.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves, remove_tracks=fr.remove_tracks)
+    t0 = time.perf_counter()
+    for fr in frames[warmup:]:
+        m.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves, remove_tracks=fr.remove_tracks)
+    dt = time.perf_counter() - t0
+    fps = steps / dt
+    sample = f"frames {warmup}..{warmup + steps - 1} of the seeded sequence after {warmup} untimed frames (requested steps={args.steps}, warmup={args.warmup}; bounded)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg.name, "grid": "256x64x256 voxels x 8 slots", "image": "1280x720 -> 640x360 internal"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=30)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--config", default="B")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args, args.config)
+    args.warmup = max(args.warmup, 3)
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    from semantic_dsp_map_b200 import BASELINE, SemanticDSPMap, _capi, make_random_table
+    cfg = BASELINE[args.config]
+    n_frames = args.warmup + args.steps
+    frames = generate_frames(args.config, n_frames)          # before CUDA / NCCL are touched (fork safety)
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    m = SemanticDSPMap(cfg, device=local)
+    eng = m.engine
+    eng.set_random_table(make_random_table(cfg.seed))
+    stream = torch.cuda.Stream(device=dev)
+    eng.check(eng.lib.dspmap_set_stream(eng._h, C.c_void_p(stream.cuda_stream)), "dspmap_set_stream")
+    eng.check(eng.lib.dspmap_set_profiling(eng._h, 1), "dspmap_set_profiling")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def launches():
+        n = C.c_uint64()
+        eng.lib.dspmap_get_launch_count(eng._h, C.byref(n))
+        return n.value
+
+    # ---------- device-resident arm ("value") -----------------------------------------------------------------
+    d_frames = []
+    for fr in frames:
+        lowered = m.lower_masks(fr.masks)
+        d_depth = torch.from_numpy(fr.depth).to(dev)
+        d_masks = [torch.from_numpy(np.ascontiguousarray(mk.mask)).to(dev) for mk in fr.masks]
+        for lm, dm in zip(lowered, d_masks):
+            lm["data"], lm["row_stride"] = dm.data_ptr(), dm.stride(0)
+        d_frames.append((d_depth, d_masks, lowered))
+    torch.cuda.synchronize(dev)
+
+    def step_device(k):
+        fr, (d_depth, _, lowered) = frames[k], d_frames[k]
+        eng.update_raw("update_device", d_depth.data_ptr(), fr.depth.shape[0], fr.depth.shape[1], d_depth.stride(0), lowered,
+                       fr.position, fr.orientation, fr.moves, fr.remove_tracks, False)
+
+    stage_ms = np.zeros(8)
+    acc = {"n_slots_known": 0, "n_occ": 0, "n_vis": 0, "n_swept": 0}
+    for k in range(args.warmup):
+        step_device(k)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(args.warmup, n_frames):
+        step_device(k)
+        st = eng.stats()
+        stage_ms += np.asarray(st["ms_stage"])
+        acc["n_occ"] += st["n_occupied"]; acc["n_vis"] += st["n_visible"]; acc["n_swept"] += st["n_swept_voxels"]
+    e1.record(stream)
+    barrier()
+    gpu_launches = launches() - l0
+    ms_device = e0.elapsed_time(e1)
+    clocks = sampler.summary()
+
+    # ---------- end-to-end arm: host buffers in, host result out -------------------------------------------------
+    eng.clear()
+    eng.check(eng.lib.dspmap_set_profiling(eng._h, 0), "dspmap_set_profiling")
+    h2d = d2h = 0
+    for k in range(args.warmup):
+        fr = frames[k]
+        m.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves, remove_tracks=fr.remove_tracks)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    t0 = time.perf_counter()
+    for k in range(args.warmup, n_frames):
+        fr = frames[k]
+        res = m.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves, remove_tracks=fr.remove_tracks)
+        h2d += fr.depth.nbytes + sum(mk.mask.nbytes for mk in fr.masks)
+        d2h += sum(a.nbytes for a in (res.voxel_index, res.xyz, res.weight_sum, res.track_id, res.label_id, res.state)) + 80
+    e3.record(stream)
+    barrier()
+    ms_e2e = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
+
+    t = torch.tensor([ms_device, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_device, ms_e2e = t.tolist()
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        # roofline of the dominant kernel: occupancy_labels streams the slot-0 time stamp of EVERY voxel and w + the packed
+        # 8-byte tail of every slot of every KNOWN voxel; algorithmic bytes per SURVEY.md §8(d): 11 B/slot over all N slots
+        # (+16 B per occupied voxel written) — the conservative, layout-independent figure — see DESIGN.md.
+        n_slots = cfg.n_slots
+        occ_bytes = 11.0 * n_slots + 24.0 * acc["n_occ"] / args.steps
+        occ_ms = stage_ms[6] / args.steps
+        achieved = occ_bytes / (occ_ms * 1e-3) / 1e9
+        out = {
+            "metric": METRIC, "value": world * args.steps / (ms_device * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_device / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg.name, "grid": "256x64x256 voxels x 8 slots (33.5M slots, 805 MB as 24 B records)",
+                       "image": "1280x720 depth + static mask + instance masks -> 640x360 internal", "l2": "inputs larger than L2 (805 MB particle store streamed every frame)",
+                       "parallelism": "replicas" if world > 1 else "single"},
+            "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
+            "gpu_launches": int(gpu_launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "k_occupancy", "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "algorithmic_bytes": occ_bytes, "ms": occ_ms},
+            "stage_ms": {n: float(v / args.steps) for n, v in zip(_capi.STAGE_NAMES, stage_ms)},
+        }
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args.config, frames)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(cfg_name, frames, warmup=3, steps=12):
+    """The oracle in the reference's own iteration order, one thread, on the first frames of the same sequence."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from semantic_dsp_map_b200 import BASELINE, make_random_table
+    from oracle_lib import oracle_map
+    cfg = BASELINE[cfg_name]
+    steps = min(steps, len(frames) - warmup)
+    m = oracle_map(cfg, order=0)
+    m.engine.set_random_table(make_random_table(cfg.seed))
+    for fr in frames[:warmup]:
+        m.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves, remove_tracks=fr.remove_tracks)
+    t0 = time.perf_counter()
+    for fr in frames[warmup:warmup + steps]:
+        m.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves, remove_tracks=fr.remove_tracks)
+    dt = time.perf_counter() - t0
+    return {"value": steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"frames {warmup}..{warmup + steps - 1} of the same seeded sequence (map still filling; the CPU path slows as it fills)",
+            "host_cores_available": os.cpu_count()}
+
+
+if __name__ == "__main__":
+    main()

@@ -207,6 +207,12 @@ int dspmap_get_stats(dspmap_t* h, dspmap_frame_stats* out);
  * semantic_dsp_map.h:912-953) */
 int dspmap_set_profiling(dspmap_t* h, int32_t on);
 
+/* run the handle's kernels and copies on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL = the
+ * handle's own stream).  Lets the caller bracket frames with its own events / overlap them with other work. */
+int dspmap_set_stream(dspmap_t* h, void* cuda_stream);
+/* kernels launched by this handle since creation (bench evidence: "gpu_launches") */
+int dspmap_get_launch_count(dspmap_t* h, uint64_t* count);
+
 /* number of live particles carrying `track_id` (device-side replacement of
  * ObjectParticleHashMap::indices_map[track].size(), object_layer.h:20-52) */
 int dspmap_object_particle_count(dspmap_t* h, int32_t track_id, uint32_t* count);

@@ -189,6 +189,7 @@ struct Oracle {
     dspmap_frame_stats stats{};
     uint64_t sweep_set_mismatch = 0;  // |BFS voxel set  xor  in-frustum-vertex voxel set|, reference order only
     uint64_t start_vertex_outside = 0;
+    bool diagnostics = false;  // the sweep-set check costs a full pass over the map: off when the oracle is being timed
     double stage_s[8]{};
     std::vector<uint32_t> csr_off, csr_idx;
 
@@ -733,6 +734,7 @@ struct Oracle {
                 q.push({nx, ny, nz});
             }
         }
+        if (!diagnostics) return;
         // diagnostic: how far is the BFS-reached voxel set from "touches any in-frustum vertex"?
         uint64_t mismatch = 0;
         for (int x = 0; x < (int)NX; ++x) for (int y = 0; y < (int)NY; ++y) for (int z = 0; z < (int)NZ; ++z) {
@@ -1062,6 +1064,7 @@ uint64_t orc_get_extra(void* h, int which) {
     auto* o = static_cast<Oracle*>(h);
     return which == 0 ? o->sweep_set_mismatch : o->start_vertex_outside;
 }
+void orc_set_diagnostics(void* h, int on) { static_cast<Oracle*>(h)->diagnostics = on != 0; }
 double orc_stage_seconds(void* h, int stage) { return static_cast<Oracle*>(h)->stage_s[stage & 7]; }
 
 int orc_dump(void* h, int32_t what, void* dst, size_t cap, size_t* n_bytes) {

@@ -105,6 +105,8 @@ SYMBOLS = {
     "dspmap_get_result_device": (C.c_int, [C.c_void_p, C.POINTER(Result)]),
     "dspmap_get_stats": (C.c_int, [C.c_void_p, C.POINTER(FrameStats)]),
     "dspmap_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
+    "dspmap_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dspmap_get_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "dspmap_object_particle_count": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_uint32)]),
     "dspmap_comm_unique_id": (C.c_int, [C.c_void_p]),
     "dspmap_comm_init": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -96,7 +96,8 @@ struct dspmap {
     std::string err = "";
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    uint64_t launches = 0;
 
     // host ring state (mc_ring/buffer.h:97-120)
     std::vector<uint32_t> stamps[3];
@@ -247,7 +248,8 @@ struct dspmap {
         p_depth.release(); p_masks.release(); p_cnt.release(); p_fp.release(); p_stamps.release(); p_maskdesc.release(); p_moves.release();
         hr_idx.release(); hr_free_idx.release(); hr_xyz.release(); hr_w.release(); hr_free_xyz.release(); hr_track.release(); hr_label.release(); hr_state.release();
         for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
-        if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+        if (own_stream) { cudaStreamDestroy(own_stream); own_stream = nullptr; }
+        stream = nullptr;
     }
 
     int init(const dspmap_config& c);
@@ -285,7 +287,8 @@ int dspmap::init(const dspmap_config& c) {
     cudaDeviceProp prop;
     CU_TRY(this, cudaGetDeviceProperties(&prop, device));
     sm_count = prop.multiProcessorCount;
-    CU_TRY(this, cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CU_TRY(this, cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+    stream = own_stream;
     for (auto& e : ev) CU_TRY(this, cudaEventCreate(&e));
 
     FrameParams& f = fp;
@@ -396,9 +399,9 @@ int dspmap::init(const dspmap_config& c) {
 // RingBufferOperations::clear (mc_ring/operations.h:684-723) + SemanticDSPMap::clear (semantic_dsp_map.h:74-81)
 int dspmap::clear_device() {
     reset_host_state();
-    k_clear_store<<<sm_count * 8, 256, 0, stream>>>(Store{sx.p, sy.p, sz.p, sw.p, smeta.p}, n_slots_local, fp.P - 1);
-    k_fill_u32<<<sm_count * 4, 256, 0, stream>>>(d_keys.p, d_keys.n, EMPTY_KEY);
-    k_fill_u32<<<sm_count * 4, 256, 0, stream>>>(d_ranks.p, d_ranks.n, NO_RANK);
+    ++launches; k_clear_store<<<sm_count * 8, 256, 0, stream>>>(Store{sx.p, sy.p, sz.p, sw.p, smeta.p}, n_slots_local, fp.P - 1);
+    ++launches; k_fill_u32<<<sm_count * 4, 256, 0, stream>>>(d_keys.p, d_keys.n, EMPTY_KEY);
+    ++launches; k_fill_u32<<<sm_count * 4, 256, 0, stream>>>(d_ranks.p, d_ranks.n, NO_RANK);
     CU_TRY(this, cudaMemsetAsync(d_pix_count.p, 0, d_pix_count.n * sizeof(uint32_t), stream));
     CU_TRY(this, cudaMemsetAsync(d_pix_offset.p, 0, d_pix_offset.n * sizeof(uint32_t), stream));
     CU_TRY(this, cudaMemsetAsync(d_cnt.p, 0, sizeof(Counters), stream));
@@ -432,13 +435,13 @@ int dspmap::run_moves(const dspmap_object_move* moves, int n_moves, const int32_
     for (int i = 0; i < n_remove; ++i) mt.remove_track[i] = remove_tracks[i];
     CU_TRY(this, cudaMemcpyAsync(d_moves.p, &mt, sizeof mt, cudaMemcpyHostToDevice, stream));
     CU_TRY(this, cudaMemsetAsync(d_lb_sel.p, 0, d_lb_sel.n * sizeof(uint64_t), stream));
-    k_select_tracks<<<(unsigned)d_lb_sel.n, SEL_BLOCK, 0, stream>>>(d_fp.p, st, d_moves.p, d_sel_idx.p, d_sel_move.p, d_lb_sel.p, d_cnt.p, sel_cap);
+    ++launches; k_select_tracks<<<(unsigned)d_lb_sel.n, SEL_BLOCK, 0, stream>>>(d_fp.p, st, d_moves.p, d_sel_idx.p, d_sel_move.p, d_lb_sel.p, d_cnt.p, sel_cap);
     if (n_moves > 0) {
-        k_move_sequence<<<1, 1024, 0, stream>>>(d_cnt.p, d_moves.p, d_sel_move.p, d_sel_seq.p, sel_cap);
-        k_move_apply<<<sm_count * 4, 256, 0, stream>>>(d_fp.p, d_cnt.p, st, d_moves.p, d_randoms.p, d_persist.p, d_sel_idx.p, d_sel_move.p,
+        ++launches; k_move_sequence<<<1, 1024, 0, stream>>>(d_cnt.p, d_moves.p, d_sel_move.p, d_sel_seq.p, sel_cap);
+        ++launches; k_move_apply<<<sm_count * 4, 256, 0, stream>>>(d_fp.p, d_cnt.p, st, d_moves.p, d_randoms.p, d_persist.p, d_sel_idx.p, d_sel_move.p,
                                                      d_sel_seq.p, d_mov_pos.p, d_mov_meta.p, d_keys.p, d_ranks.p, sel_cap);
-        k_advance_cursor<<<1, 1, 0, stream>>>(d_cnt.p, d_persist.p, rand_n, sel_cap);
-        k_move_replay<<<sm_count * 8, 128, 0, stream>>>(d_fp.p, st, d_stamps.p, d_stamps.p + fp.NX, d_stamps.p + fp.NX + fp.NY, d_mov_pos.p,
+        ++launches; k_advance_cursor<<<1, 1, 0, stream>>>(d_cnt.p, d_persist.p, rand_n, sel_cap);
+        ++launches; k_move_replay<<<sm_count * 8, 128, 0, stream>>>(d_fp.p, st, d_stamps.p, d_stamps.p + fp.NX, d_stamps.p + fp.NX + fp.NY, d_mov_pos.p,
                                                       d_mov_meta.p, d_keys.p, d_ranks.p, d_cnt.p);
     }
     CU_TRY(this, cudaGetLastError());
@@ -530,7 +533,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
 
     if (profiling) cudaEventRecord(ev[0], stream);
     // ---- K1 projection ---------------------------------------------------------------------------------------
-    k_project<<<(npix + 255) / 256, 256, 0, stream>>>(d_fp.p, d_depth, stride, d_masks.p, d_static_track.p, d_static_label.p,
+    ++launches; k_project<<<(npix + 255) / 256, 256, 0, stream>>>(d_fp.p, d_depth, stride, d_masks.p, d_static_track.p, d_static_label.p,
                                                      d_depth_int.p, d_cloud_pos.p, d_cloud_meta.p, d_cnt.p);
     if (profiling) { cudaEventRecord(ev[1], stream); cudaEventRecord(ev[2], stream); }
     // ---- P2/P3 object predict / prune ---------------------------------------------------------------------------
@@ -554,29 +557,29 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     if (profiling) cudaEventRecord(ev[3], stream);
     // ---- U2 visibility ---------------------------------------------------------------------------------------------
     if (f.start_in) {
-        k_vertex_mask<<<(n_vwords * 32 + 127) / 128, 128, 0, stream>>>(d_fp.p, d_vmask.p, words_per_row, n_vwords);
-        k_sweep<<<(v_local + 255) / 256, 256, 0, stream>>>(d_fp.p, st, stx, sty, stz, d_vmask.p, words_per_row, d_depth_int.p,
+        ++launches; k_vertex_mask<<<(n_vwords * 32 + 127) / 128, 128, 0, stream>>>(d_fp.p, d_vmask.p, words_per_row, n_vwords);
+        ++launches; k_sweep<<<(v_local + 255) / 256, 256, 0, stream>>>(d_fp.p, st, stx, sty, stz, d_vmask.p, words_per_row, d_depth_int.p,
                                                          d_pix_count.p, d_pairs.p, d_cnt.p);
     }
     const int nsb = (npix + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    k_scan_blocksum<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p);
-    k_scan_apply<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p, d_pix_offset.p);
-    k_fill<<<sm_count * 4, 256, 0, stream>>>(d_fp.p, d_cnt.p, d_pairs.p, d_pix_offset.p, d_pix_count.p, d_csr_idx.p, d_vis_pix.p);
-    k_sort_lists<<<(npix + 255) / 256, 256, 0, stream>>>(d_fp.p, d_pix_offset.p, d_csr_idx.p);
-    k_gather_visible<<<sm_count * 4, 256, 0, stream>>>(d_fp.p, d_cnt.p, st, d_csr_idx.p, d_vis_pos.p, d_vis_meta.p);
+    ++launches; k_scan_blocksum<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p);
+    ++launches; k_scan_apply<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p, d_pix_offset.p);
+    ++launches; k_fill<<<sm_count * 4, 256, 0, stream>>>(d_fp.p, d_cnt.p, d_pairs.p, d_pix_offset.p, d_pix_count.p, d_csr_idx.p, d_vis_pix.p);
+    ++launches; k_sort_lists<<<(npix + 255) / 256, 256, 0, stream>>>(d_fp.p, d_pix_offset.p, d_csr_idx.p);
+    ++launches; k_gather_visible<<<sm_count * 4, 256, 0, stream>>>(d_fp.p, d_cnt.p, st, d_csr_idx.p, d_vis_pos.p, d_vis_meta.p);
     if (profiling) cudaEventRecord(ev[4], stream);
     // ---- U3 weight update --------------------------------------------------------------------------------------------
-    k_ck<<<sm_count * 2, 512, lut_bytes, stream>>>(d_fp.p, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_pix_offset.p, d_vis_pos.p, d_vis_meta.p, d_ck.p);
-    k_weight_update<<<sm_count * 2, 512, lut_bytes, stream>>>(d_fp.p, d_cnt.p, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_ck.p, d_csr_idx.p,
+    ++launches; k_ck<<<sm_count * 2, 512, lut_bytes, stream>>>(d_fp.p, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_pix_offset.p, d_vis_pos.p, d_vis_meta.p, d_ck.p);
+    ++launches; k_weight_update<<<sm_count * 2, 512, lut_bytes, stream>>>(d_fp.p, d_cnt.p, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_ck.p, d_csr_idx.p,
                                                              d_vis_pix.p, d_vis_pos.p, d_vis_meta.p, st);
     if (profiling) cudaEventRecord(ev[5], stream);
     // ---- B1 birth + resample -----------------------------------------------------------------------------------------
-    k_birth_bin<<<(npix + 255) / 256, 256, 0, stream>>>(d_fp.p, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_cnt.p);
-    k_birth_replay<<<sm_count * 8, 128, 0, stream>>>(d_fp.p, st, stx, sty, stz, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_cnt.p);
+    ++launches; k_birth_bin<<<(npix + 255) / 256, 256, 0, stream>>>(d_fp.p, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_cnt.p);
+    ++launches; k_birth_replay<<<sm_count * 8, 128, 0, stream>>>(d_fp.p, st, stx, sty, stz, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_cnt.p);
     if (profiling) cudaEventRecord(ev[6], stream);
     // ---- O1 occupancy -------------------------------------------------------------------------------------------------
     ResultArrays out{r_idx.p, r_xyz.p, r_w.p, r_track.p, r_label.p, r_state.p, r_free_idx.p, r_free_xyz.p};
-    k_occupancy<<<(unsigned)d_lb_occ.n, OCC_BLOCK, 0, stream>>>(d_fp.p, st, stx, sty, stz, out, d_voxel_state.p, d_lb_occ.p, d_cnt.p);
+    ++launches; k_occupancy<<<(unsigned)d_lb_occ.n, OCC_BLOCK, 0, stream>>>(d_fp.p, st, stx, sty, stz, out, d_voxel_state.p, d_lb_occ.p, d_cnt.p);
     if (profiling) cudaEventRecord(ev[7], stream);
     CU_TRY(this, cudaMemcpyAsync(p_cnt.p, d_cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
     CU_TRY(this, cudaGetLastError());
@@ -776,11 +779,25 @@ int dspmap_set_profiling(dspmap_t* h, int32_t on) {
     return DSPMAP_OK;
 }
 
+int dspmap_set_stream(dspmap_t* h, void* cuda_stream) {
+    if (!h) return DSPMAP_ERR_INVALID_ARG;
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return DSPMAP_OK;
+}
+
+int dspmap_get_launch_count(dspmap_t* h, uint64_t* count) {
+    if (!h || !count) return DSPMAP_ERR_INVALID_ARG;
+    *count = h->launches;
+    return DSPMAP_OK;
+}
+
 int dspmap_object_particle_count(dspmap_t* h, int32_t track_id, uint32_t* count) {
     if (!h || !count) return DSPMAP_ERR_INVALID_ARG;
     CU_TRY(h, cudaSetDevice(h->device));
     CU_TRY(h, cudaMemsetAsync(&h->d_cnt.p->pad[0], 0, sizeof(uint32_t), h->stream));
-    k_count_track<<<h->sm_count * 8, 256, 0, h->stream>>>(Store{h->sx.p, h->sy.p, h->sz.p, h->sw.p, h->smeta.p}, h->n_slots_local, h->fp.P - 1, (uint32_t)track_id & 0xffffu, &h->d_cnt.p->pad[0]);
+    ++h->launches; k_count_track<<<h->sm_count * 8, 256, 0, h->stream>>>(Store{h->sx.p, h->sy.p, h->sz.p, h->sw.p, h->smeta.p}, h->n_slots_local, h->fp.P - 1, (uint32_t)track_id & 0xffffu, &h->d_cnt.p->pad[0]);
     CU_TRY(h, cudaMemcpyAsync(count, &h->d_cnt.p->pad[0], sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     return DSPMAP_OK;

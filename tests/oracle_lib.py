@@ -32,6 +32,8 @@ def load_oracle():
         lib.orc_destroy.argtypes = [C.c_void_p]
         lib.orc_get_extra.restype = C.c_uint64
         lib.orc_get_extra.argtypes = [C.c_void_p, C.c_int]
+        lib.orc_set_diagnostics.restype = None
+        lib.orc_set_diagnostics.argtypes = [C.c_void_p, C.c_int]
         lib.orc_stage_seconds.restype = C.c_double
         lib.orc_stage_seconds.argtypes = [C.c_void_p, C.c_int]
         _lib = lib
@@ -55,6 +57,9 @@ class OracleEngine(Engine):
     def check(self, rc, where):
         if rc != _capi.DSPMAP_OK:
             raise _capi.DspMapError(rc, where)
+
+    def set_diagnostics(self, on):
+        self.lib.orc_set_diagnostics(self._h, int(on))
 
     def extra(self, which):
         return int(self.lib.orc_get_extra(self._h, which))
