@@ -12,6 +12,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -62,6 +64,9 @@ void inverse4f(const float m[16], float o[16]) {
     for (int k = 0; k < 16; ++k) o[k] = adj[k] / det;
 }
 
+// constant-memory parameter slots (dspmap_device.cuh c_fp): one per live handle
+bool g_slot_used[MAX_HANDLES] = {};
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -95,6 +100,7 @@ struct dspmap {
     FrameParams fp{};
     std::string err = "";
     int device = 0;
+    int slot = -1;
     int sm_count = 148;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     uint64_t launches = 0;
@@ -117,6 +123,7 @@ struct dspmap {
     // device: store (allocated for this shard's slabs; pointers are biased so the global particle index applies)
     DevBuf<float> sx, sy, sz, sw;
     DevBuf<uint64_t> smeta;
+    DevBuf<uint32_t> shdr, d_entry_list;
     Store st{};
     size_t n_slots_local = 0, slot_lo = 0;
     uint32_t v_local = 0;
@@ -237,7 +244,7 @@ struct dspmap {
     }
 
     void release_all() {
-        sx.release(); sy.release(); sz.release(); sw.release(); smeta.release(); d_stamps.release(); d_lut.release(); d_randoms.release();
+        sx.release(); sy.release(); sz.release(); sw.release(); smeta.release(); shdr.release(); d_entry_list.release(); d_stamps.release(); d_lut.release(); d_randoms.release();
         d_static_track.release(); d_static_label.release(); d_fp.release(); d_cnt.release(); d_persist.release(); d_masks.release(); d_moves.release();
         d_depth_in.release(); d_depth_int.release(); d_ck.release(); d_mask_in.release(); d_cloud_pos.release(); d_cloud_meta.release();
         d_pix_count.release(); d_pix_offset.release(); d_scan_block.release(); d_vmask.release(); d_pairs.release(); d_csr_idx.release();
@@ -250,6 +257,7 @@ struct dspmap {
         for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (own_stream) { cudaStreamDestroy(own_stream); own_stream = nullptr; }
         stream = nullptr;
+        if (slot >= 0) { g_slot_used[slot] = false; slot = -1; }
     }
 
     int init(const dspmap_config& c);
@@ -258,7 +266,7 @@ struct dspmap {
     int run_moves(const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove);
     int frame(const float* d_depth, int rows, int cols, int stride, const dspmap_mask* masks, int n_masks, const double pos[3],
               const double quat[4], const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove,
-              int want_free);
+              int want_free, int pre_decimated);
     int fetch_result_to_host();
 };
 
@@ -283,6 +291,9 @@ int dspmap::init(const dspmap_config& c) {
     }
     if (c.device < 0 || c.device >= ndev) return fail(DSPMAP_ERR_INVALID_ARG, "device %d of %d", c.device, ndev);
     device = c.device;
+    for (int k = 0; k < MAX_HANDLES && slot < 0; ++k)
+        if (!g_slot_used[k]) { g_slot_used[k] = true; slot = k; }
+    if (slot < 0) return fail(DSPMAP_ERR_CONFIG, "at most %d maps may be alive in one process", MAX_HANDLES);
     CU_TRY(this, cudaSetDevice(device));
     cudaDeviceProp prop;
     CU_TRY(this, cudaGetDeviceProperties(&prop, device));
@@ -332,7 +343,11 @@ int dspmap::init(const dspmap_config& c) {
     slot_lo = ((size_t)f.z_lo << (f.Xb + f.Yb)) << f.Pb;
     CU_TRY(this, sx.alloc(n_slots_local)); CU_TRY(this, sy.alloc(n_slots_local)); CU_TRY(this, sz.alloc(n_slots_local));
     CU_TRY(this, sw.alloc(n_slots_local)); CU_TRY(this, smeta.alloc(n_slots_local));
+    const size_t v_pad = ((size_t)v_local + OCC_TILE - 1) / OCC_TILE * OCC_TILE;   // whole tiles for the per-voxel passes
+    CU_TRY(this, shdr.alloc(v_pad));
+    CU_TRY(this, cudaMemset(shdr.p, 0, v_pad * sizeof(uint32_t)));
     st.x = sx.p - slot_lo; st.y = sy.p - slot_lo; st.z = sz.p - slot_lo; st.w = sw.p - slot_lo; st.meta = smeta.p - slot_lo;
+    st.hdr = shdr.p - (slot_lo >> f.Pb);
 
     for (int a = 0; a < 3; ++a) stamps[a].assign(axis_n(a), 0u);
     CU_TRY(this, d_stamps.alloc(f.NX + f.NY + f.NZ));
@@ -360,7 +375,7 @@ int dspmap::init(const dspmap_config& c) {
     CU_TRY(this, d_pairs.alloc(f.vis_cap)); CU_TRY(this, d_csr_idx.alloc(f.vis_cap)); CU_TRY(this, d_vis_pix.alloc(f.vis_cap));
     CU_TRY(this, d_vis_meta.alloc(f.vis_cap)); CU_TRY(this, d_vis_pos.alloc(f.vis_cap));
 
-    sel_cap = (uint32_t)std::min<size_t>(usable, (size_t)4 << 20);
+    sel_cap = (uint32_t)std::min<size_t>(usable, (size_t)1 << 20);
     CU_TRY(this, d_sel_idx.alloc(sel_cap)); CU_TRY(this, d_sel_move.alloc(sel_cap)); CU_TRY(this, d_sel_seq.alloc(sel_cap));
     CU_TRY(this, d_mov_pos.alloc(sel_cap)); CU_TRY(this, d_mov_meta.alloc(sel_cap));
 
@@ -369,10 +384,10 @@ int dspmap::init(const dspmap_config& c) {
     uint32_t cap = 1024, bits = 10;
     while (cap < want) { cap <<= 1; ++bits; }
     f.hash_cap = cap; f.hash_shift = 32 - bits;
-    CU_TRY(this, d_keys.alloc(cap)); CU_TRY(this, d_ranks.alloc((size_t)cap * f.topk));
+    CU_TRY(this, d_keys.alloc(cap)); CU_TRY(this, d_ranks.alloc((size_t)cap * f.topk)); CU_TRY(this, d_entry_list.alloc(cap));
 
-    CU_TRY(this, d_lb_occ.alloc((v_local + OCC_BLOCK - 1) / OCC_BLOCK));
-    CU_TRY(this, d_lb_sel.alloc((n_slots_local + SEL_BLOCK - 1) / SEL_BLOCK));
+    CU_TRY(this, d_lb_occ.alloc((v_local + OCC_TILE - 1) / OCC_TILE));
+    CU_TRY(this, d_lb_sel.alloc((v_local + SEL_BLOCK - 1) / SEL_BLOCK));
     CU_TRY(this, r_idx.alloc(v_local)); CU_TRY(this, r_xyz.alloc(3 * (size_t)v_local)); CU_TRY(this, r_w.alloc(v_local));
     CU_TRY(this, r_track.alloc(v_local)); CU_TRY(this, r_label.alloc(v_local)); CU_TRY(this, r_state.alloc(v_local));
 
@@ -399,7 +414,7 @@ int dspmap::init(const dspmap_config& c) {
 // RingBufferOperations::clear (mc_ring/operations.h:684-723) + SemanticDSPMap::clear (semantic_dsp_map.h:74-81)
 int dspmap::clear_device() {
     reset_host_state();
-    ++launches; k_clear_store<<<sm_count * 8, 256, 0, stream>>>(Store{sx.p, sy.p, sz.p, sw.p, smeta.p}, n_slots_local, fp.P - 1);
+    ++launches; k_clear_store<<<sm_count * 8, 256, 0, stream>>>(Store{sx.p, sy.p, sz.p, sw.p, smeta.p, shdr.p}, n_slots_local, (uint32_t)fp.Pb);
     ++launches; k_fill_u32<<<sm_count * 4, 256, 0, stream>>>(d_keys.p, d_keys.n, EMPTY_KEY);
     ++launches; k_fill_u32<<<sm_count * 4, 256, 0, stream>>>(d_ranks.p, d_ranks.n, NO_RANK);
     CU_TRY(this, cudaMemsetAsync(d_pix_count.p, 0, d_pix_count.n * sizeof(uint32_t), stream));
@@ -435,14 +450,14 @@ int dspmap::run_moves(const dspmap_object_move* moves, int n_moves, const int32_
     for (int i = 0; i < n_remove; ++i) mt.remove_track[i] = remove_tracks[i];
     CU_TRY(this, cudaMemcpyAsync(d_moves.p, &mt, sizeof mt, cudaMemcpyHostToDevice, stream));
     CU_TRY(this, cudaMemsetAsync(d_lb_sel.p, 0, d_lb_sel.n * sizeof(uint64_t), stream));
-    ++launches; k_select_tracks<<<(unsigned)d_lb_sel.n, SEL_BLOCK, 0, stream>>>(d_fp.p, st, d_moves.p, d_sel_idx.p, d_sel_move.p, d_lb_sel.p, d_cnt.p, sel_cap);
+    ++launches; k_select_tracks<<<(unsigned)d_lb_sel.n, SEL_BLOCK, 0, stream>>>(slot, st, d_moves.p, d_sel_idx.p, d_sel_move.p, d_lb_sel.p, d_cnt.p, sel_cap);
     if (n_moves > 0) {
         ++launches; k_move_sequence<<<1, 1024, 0, stream>>>(d_cnt.p, d_moves.p, d_sel_move.p, d_sel_seq.p, sel_cap);
-        ++launches; k_move_apply<<<sm_count * 4, 256, 0, stream>>>(d_fp.p, d_cnt.p, st, d_moves.p, d_randoms.p, d_persist.p, d_sel_idx.p, d_sel_move.p,
-                                                     d_sel_seq.p, d_mov_pos.p, d_mov_meta.p, d_keys.p, d_ranks.p, sel_cap);
+        ++launches; k_move_apply<<<sm_count * 4, 256, 0, stream>>>(slot, d_cnt.p, st, d_moves.p, d_randoms.p, d_persist.p, d_sel_idx.p, d_sel_move.p,
+                                                     d_sel_seq.p, d_mov_pos.p, d_mov_meta.p, d_keys.p, d_ranks.p, d_entry_list.p, sel_cap);
         ++launches; k_advance_cursor<<<1, 1, 0, stream>>>(d_cnt.p, d_persist.p, rand_n, sel_cap);
-        ++launches; k_move_replay<<<sm_count * 8, 128, 0, stream>>>(d_fp.p, st, d_stamps.p, d_stamps.p + fp.NX, d_stamps.p + fp.NX + fp.NY, d_mov_pos.p,
-                                                      d_mov_meta.p, d_keys.p, d_ranks.p, d_cnt.p);
+        ++launches; k_move_replay<<<sm_count * 8, 128, 0, stream>>>(slot, st, d_stamps.p, d_stamps.p + fp.NX, d_stamps.p + fp.NX + fp.NY, d_mov_pos.p,
+                                                      d_mov_meta.p, d_keys.p, d_ranks.p, d_entry_list.p, d_cnt.p);
     }
     CU_TRY(this, cudaGetLastError());
     return DSPMAP_OK;
@@ -451,8 +466,9 @@ int dspmap::run_moves(const dspmap_object_move* moves, int n_moves, const int32_
 // SemanticDSPMap::update (semantic_dsp_map.h:170-251) -> subObjectLevelUpdate (:576-955)
 int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const dspmap_mask* masks, int n_masks, const double pos[3],
                   const double quat[4], const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove,
-                  int want_free) {
+                  int want_free, int pre_decimated) {
     FrameParams& f = fp;
+    f.pre_decimated = pre_decimated;
     if (prm.consider_depth_noise && prm.nb_ptc_num_per_point != 1)
         return fail(DSPMAP_ERR_UNSUPPORTED, "nb_ptc_num_per_point != 1 with the depth-noise model is not implemented");
     host_result_valid = false;
@@ -503,7 +519,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     f.rand_n = rand_n;
 
     if (want_free && !r_free_idx.p) { CU_TRY(this, r_free_idx.alloc(v_local)); CU_TRY(this, r_free_xyz.alloc(3 * (size_t)v_local)); }
-    if (want_state && !d_voxel_state.p) CU_TRY(this, d_voxel_state.alloc(v_local));
+    if (want_state && !d_voxel_state.p) CU_TRY(this, d_voxel_state.alloc(((size_t)v_local + OCC_TILE - 1) / OCC_TILE * OCC_TILE));
 
     // ---- uploads -------------------------------------------------------------------------------------------
     if ((size_t)n_masks > d_masks.n) { CU_TRY(this, d_masks.alloc(n_masks)); }
@@ -516,7 +532,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     }
     if (n_masks) CU_TRY(this, cudaMemcpyAsync(d_masks.p, p_maskdesc.p, n_masks * sizeof(MaskDesc), cudaMemcpyHostToDevice, stream));
     *p_fp.p = f;
-    CU_TRY(this, cudaMemcpyAsync(d_fp.p, p_fp.p, sizeof(FrameParams), cudaMemcpyHostToDevice, stream));
+    CU_TRY(this, cudaMemcpyToSymbolAsync(c_fp, p_fp.p, sizeof(FrameParams), (size_t)slot * sizeof(FrameParams), cudaMemcpyHostToDevice, stream));
     if (stamps_dirty) {
         uint32_t* s = p_stamps.p;
         for (int a = 0; a < 3; ++a) { memcpy(s, stamps[a].data(), stamps[a].size() * 4); s += stamps[a].size(); }
@@ -533,7 +549,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
 
     if (profiling) cudaEventRecord(ev[0], stream);
     // ---- K1 projection ---------------------------------------------------------------------------------------
-    ++launches; k_project<<<(npix + 255) / 256, 256, 0, stream>>>(d_fp.p, d_depth, stride, d_masks.p, d_static_track.p, d_static_label.p,
+    ++launches; k_project<<<(npix + 255) / 256, 256, 0, stream>>>(slot, d_depth, stride, d_masks.p, d_static_track.p, d_static_label.p,
                                                      d_depth_int.p, d_cloud_pos.p, d_cloud_meta.p, d_cnt.p);
     if (profiling) { cudaEventRecord(ev[1], stream); cudaEventRecord(ev[2], stream); }
     // ---- P2/P3 object predict / prune ---------------------------------------------------------------------------
@@ -557,29 +573,29 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     if (profiling) cudaEventRecord(ev[3], stream);
     // ---- U2 visibility ---------------------------------------------------------------------------------------------
     if (f.start_in) {
-        ++launches; k_vertex_mask<<<(n_vwords * 32 + 127) / 128, 128, 0, stream>>>(d_fp.p, d_vmask.p, words_per_row, n_vwords);
-        ++launches; k_sweep<<<(v_local + 255) / 256, 256, 0, stream>>>(d_fp.p, st, stx, sty, stz, d_vmask.p, words_per_row, d_depth_int.p,
+        ++launches; k_vertex_mask<<<(n_vwords * 32 + 255) / 256, 256, 0, stream>>>(slot, d_vmask.p, words_per_row, n_vwords);
+        ++launches; k_sweep<<<(v_local + 255) / 256, 256, 0, stream>>>(slot, st, stx, sty, stz, d_vmask.p, words_per_row, d_depth_int.p,
                                                          d_pix_count.p, d_pairs.p, d_cnt.p);
     }
     const int nsb = (npix + SCAN_BLOCK - 1) / SCAN_BLOCK;
     ++launches; k_scan_blocksum<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p);
     ++launches; k_scan_apply<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p, d_pix_offset.p);
-    ++launches; k_fill<<<sm_count * 4, 256, 0, stream>>>(d_fp.p, d_cnt.p, d_pairs.p, d_pix_offset.p, d_pix_count.p, d_csr_idx.p, d_vis_pix.p);
-    ++launches; k_sort_lists<<<(npix + 255) / 256, 256, 0, stream>>>(d_fp.p, d_pix_offset.p, d_csr_idx.p);
-    ++launches; k_gather_visible<<<sm_count * 4, 256, 0, stream>>>(d_fp.p, d_cnt.p, st, d_csr_idx.p, d_vis_pos.p, d_vis_meta.p);
+    ++launches; k_fill<<<sm_count * 4, 256, 0, stream>>>(slot, d_cnt.p, d_pairs.p, d_pix_offset.p, d_pix_count.p, d_csr_idx.p, d_vis_pix.p);
+    ++launches; k_sort_lists<<<(npix + 255) / 256, 256, 0, stream>>>(slot, d_pix_offset.p, d_csr_idx.p);
+    ++launches; k_gather_visible<<<sm_count * 4, 256, 0, stream>>>(slot, d_cnt.p, st, d_csr_idx.p, d_vis_pos.p, d_vis_meta.p);
     if (profiling) cudaEventRecord(ev[4], stream);
     // ---- U3 weight update --------------------------------------------------------------------------------------------
-    ++launches; k_ck<<<sm_count * 2, 512, lut_bytes, stream>>>(d_fp.p, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_pix_offset.p, d_vis_pos.p, d_vis_meta.p, d_ck.p);
-    ++launches; k_weight_update<<<sm_count * 2, 512, lut_bytes, stream>>>(d_fp.p, d_cnt.p, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_ck.p, d_csr_idx.p,
+    ++launches; k_ck<<<sm_count * 2, 512, lut_bytes, stream>>>(slot, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_pix_offset.p, d_vis_pos.p, d_vis_meta.p, d_ck.p);
+    ++launches; k_weight_update<<<sm_count * 2, 512, lut_bytes, stream>>>(slot, d_cnt.p, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_ck.p, d_csr_idx.p,
                                                              d_vis_pix.p, d_vis_pos.p, d_vis_meta.p, st);
     if (profiling) cudaEventRecord(ev[5], stream);
     // ---- B1 birth + resample -----------------------------------------------------------------------------------------
-    ++launches; k_birth_bin<<<(npix + 255) / 256, 256, 0, stream>>>(d_fp.p, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_cnt.p);
-    ++launches; k_birth_replay<<<sm_count * 8, 128, 0, stream>>>(d_fp.p, st, stx, sty, stz, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_cnt.p);
+    ++launches; k_birth_bin<<<(npix + 255) / 256, 256, 0, stream>>>(slot, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_entry_list.p, d_cnt.p);
+    ++launches; k_birth_replay<<<sm_count * 8, 128, 0, stream>>>(slot, st, stx, sty, stz, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_entry_list.p, d_cnt.p);
     if (profiling) cudaEventRecord(ev[6], stream);
     // ---- O1 occupancy -------------------------------------------------------------------------------------------------
     ResultArrays out{r_idx.p, r_xyz.p, r_w.p, r_track.p, r_label.p, r_state.p, r_free_idx.p, r_free_xyz.p};
-    ++launches; k_occupancy<<<(unsigned)d_lb_occ.n, OCC_BLOCK, 0, stream>>>(d_fp.p, st, stx, sty, stz, out, d_voxel_state.p, d_lb_occ.p, d_cnt.p);
+    ++launches; k_occupancy<<<(unsigned)d_lb_occ.n, OCC_BLOCK, 0, stream>>>(slot, st, stx, sty, stz, out, d_voxel_state.p, d_lb_occ.p, d_cnt.p);
     if (profiling) cudaEventRecord(ev[7], stream);
     CU_TRY(this, cudaMemcpyAsync(p_cnt.p, d_cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
     CU_TRY(this, cudaGetLastError());
@@ -715,35 +731,65 @@ int dspmap_update_device(dspmap_t* h, const float* d_depth, int32_t rows, int32_
     int rc = check_frame_args(h, d_depth, rows, cols, row_stride, masks, n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove);
     if (rc != DSPMAP_OK) return rc;
     CU_TRY(h, cudaSetDevice(h->device));
-    return h->frame(d_depth, rows, cols, row_stride, masks, n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove, want_freespace);
+    return h->frame(d_depth, rows, cols, row_stride, masks, n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove, want_freespace, 0);
+}
+
+static double host_now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
 int dspmap_update(dspmap_t* h, const float* depth, int32_t rows, int32_t cols, int32_t row_stride, const dspmap_mask* masks,
                   int32_t n_masks, const double position[3], const double orientation_wxyz[4], const dspmap_object_move* moves,
                   int32_t n_moves, const int32_t* remove_tracks, int32_t n_remove, int32_t want_freespace) {
+    static const bool trace = getenv("DSPMAP_TRACE") != nullptr;
+    const double t_a = trace ? host_now_ms() : 0.0;
     int rc = check_frame_args(h, depth, rows, cols, row_stride, masks, n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove);
     if (rc != DSPMAP_OK) return rc;
     CU_TRY(h, cudaSetDevice(h->device));
-    // stage the caller's (pageable) images through pinned memory, dense rows
-    const size_t npix = (size_t)rows * cols;
+    // Stage the caller's (pageable) images through pinned memory.  Under BOOST_MODE the nearest 1/2 resize of
+    // manualResize (pointcloud_tools.h:1104-1133: src = (int)(i * 2.0f), clamped) is applied while staging, so only the
+    // quarter of the pixels the map will read crosses PCIe; K1 then reads the staged image 1:1 (same source pixels).
+    const FrameParams& f = h->fp;
+    const int srows = f.boost ? f.H : rows, scols = f.boost ? f.W : cols;
+    const size_t npix = (size_t)srows * scols;
+    std::vector<int> src_col(scols);
+    for (int j = 0; j < scols; ++j) src_col[j] = f.boost ? std::min((int)((float)j * 2.0f), cols - 1) : j;
+    auto stage = [&](auto* dst, const auto* src, int src_stride) {
+        for (int i = 0; i < srows; ++i) {
+            const int si = f.boost ? std::min((int)((float)i * 2.0f), rows - 1) : i;
+            const auto* srow = src + (size_t)si * src_stride;
+            auto* drow = dst + (size_t)i * scols;
+            if (f.boost && 2 * scols <= cols) for (int j = 0; j < scols; ++j) drow[j] = srow[2 * j];   // src = 2j exactly: vectorisable
+            else if (f.boost) for (int j = 0; j < scols; ++j) drow[j] = srow[src_col[j]];
+            else memcpy(drow, srow, (size_t)scols * sizeof(*dst));
+        }
+    };
     CU_TRY(h, h->p_depth.reserve(npix));
-    for (int r = 0; r < rows; ++r) memcpy(h->p_depth.p + (size_t)r * cols, depth + (size_t)r * row_stride, (size_t)cols * sizeof(float));
+    stage(h->p_depth.p, depth, row_stride);
     CU_TRY(h, cudaMemcpyAsync(h->d_depth_in.p, h->p_depth.p, npix * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     std::vector<dspmap_mask> dm(masks, masks + n_masks);
     if (n_masks) {
         CU_TRY(h, h->p_masks.reserve(npix * n_masks));
         if (h->d_mask_in.n < npix * n_masks) CU_TRY(h, h->d_mask_in.alloc(npix * n_masks));
         for (int m = 0; m < n_masks; ++m) {
-            uint8_t* dst = h->p_masks.p + (size_t)m * npix;
-            for (int r = 0; r < rows; ++r) memcpy(dst + (size_t)r * cols, masks[m].data + (size_t)r * masks[m].row_stride, cols);
+            stage(h->p_masks.p + (size_t)m * npix, masks[m].data, masks[m].row_stride);
             dm[m].data = h->d_mask_in.p + (size_t)m * npix;
-            dm[m].row_stride = cols;
+            dm[m].row_stride = scols;
         }
         CU_TRY(h, cudaMemcpyAsync(h->d_mask_in.p, h->p_masks.p, npix * n_masks, cudaMemcpyHostToDevice, h->stream));
     }
-    rc = h->frame(h->d_depth_in.p, rows, cols, cols, dm.data(), n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove, want_freespace);
+    const double t_b = trace ? host_now_ms() : 0.0;
+    rc = h->frame(h->d_depth_in.p, rows, cols, scols, dm.data(), n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove,
+                  want_freespace, f.boost ? 1 : 0);
     if (rc != DSPMAP_OK) return rc;
-    return h->fetch_result_to_host();
+    const double t_c = trace ? host_now_ms() : 0.0;
+    rc = h->fetch_result_to_host();
+    if (trace && (h->T % 16) == 0)
+        fprintf(stderr, "[dspmap] frame %u: stage+h2d-enqueue %.3f ms, frame (launch+sync) %.3f ms, result d2h %.3f ms\n", h->T, t_b - t_a, t_c - t_b,
+                host_now_ms() - t_c);
+    return rc;
 }
 
 int dspmap_get_result(dspmap_t* h, dspmap_result* out) {
@@ -796,9 +842,9 @@ int dspmap_get_launch_count(dspmap_t* h, uint64_t* count) {
 int dspmap_object_particle_count(dspmap_t* h, int32_t track_id, uint32_t* count) {
     if (!h || !count) return DSPMAP_ERR_INVALID_ARG;
     CU_TRY(h, cudaSetDevice(h->device));
-    CU_TRY(h, cudaMemsetAsync(&h->d_cnt.p->pad[0], 0, sizeof(uint32_t), h->stream));
-    ++h->launches; k_count_track<<<h->sm_count * 8, 256, 0, h->stream>>>(Store{h->sx.p, h->sy.p, h->sz.p, h->sw.p, h->smeta.p}, h->n_slots_local, h->fp.P - 1, (uint32_t)track_id & 0xffffu, &h->d_cnt.p->pad[0]);
-    CU_TRY(h, cudaMemcpyAsync(count, &h->d_cnt.p->pad[0], sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemsetAsync(&h->d_cnt.p->scratch, 0, sizeof(uint32_t), h->stream));
+    ++h->launches; k_count_track<<<h->sm_count * 8, 256, 0, h->stream>>>(Store{h->sx.p, h->sy.p, h->sz.p, h->sw.p, h->smeta.p, h->shdr.p}, h->v_local, (uint32_t)h->fp.Pb, (uint32_t)track_id & 0xffffu, &h->d_cnt.p->scratch);
+    CU_TRY(h, cudaMemcpyAsync(count, &h->d_cnt.p->scratch, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     return DSPMAP_OK;
 }
@@ -845,6 +891,9 @@ int dspmap_dump(dspmap_t* h, int32_t what, void* dst, size_t cap, size_t* n_byte
             std::vector<uint64_t> m(n);
             CU_TRY(h, pull(x.data(), h->sx.p, n * 4)); CU_TRY(h, pull(y.data(), h->sy.p, n * 4)); CU_TRY(h, pull(z.data(), h->sz.p, n * 4));
             CU_TRY(h, pull(w.data(), h->sw.p, n * 4)); CU_TRY(h, pull(m.data(), h->smeta.p, n * 8));
+            std::vector<uint32_t> hd(h->v_local);
+            CU_TRY(h, pull(hd.data(), h->shdr.p, (size_t)h->v_local * 4));
+            for (size_t v = 0; v < h->v_local; ++v) m[v << f.Pb] = (m[v << f.Pb] & ~0xffffull) | hdr_ts(hd[v]);   // slot 0 = the time particle
             tmp.resize(n * 24);
             for (size_t i = 0; i < n; ++i) {
                 uint8_t* r = tmp.data() + i * 24;

@@ -17,7 +17,7 @@ struct Counters {
     uint32_t n_swept_voxels;
     uint32_t n_swept_nonempty;
     uint32_t n_born;
-    uint32_t n_birth_voxels;
+    uint32_t n_birth_voxels;   // also the length of the birth entry list
     uint32_t n_resampled;
     uint32_t n_occupied;
     uint32_t n_free;
@@ -25,11 +25,12 @@ struct Counters {
     uint32_t n_moved;
     uint32_t n_removed;
     uint32_t n_selected;       // particles selected by the object-move collection
-    uint32_t n_move_voxels;
+    uint32_t n_move_voxels;    // also the length of the move entry list
     uint32_t ticket_occ;       // dynamic block ids for the ordered compactions
     uint32_t ticket_sel;
-    uint32_t hash_overflow;    // birth/move hash table full (cannot happen with cap >= 2 * candidates)
-    uint32_t pad[3];
+    uint32_t hash_overflow;    // insertion hash table full (cannot happen with cap >= 2 * candidates)
+    uint32_t scratch;
+    uint32_t pad[2];
 };
 
 // survives across frames
@@ -41,6 +42,7 @@ struct Persist {
 struct Store {
     float* x; float* y; float* z; float* w;
     uint64_t* meta;
+    uint32_t* hdr;             // per voxel, see dspmap_device.cuh
 };
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
@@ -51,17 +53,17 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 // one thread per internal pixel; double-precision back-projection, float narrowing at the end.
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
-k_project(const FrameParams* __restrict__ fp, const float* __restrict__ depth, int depth_stride,
-          const MaskDesc* __restrict__ masks, const uint16_t* __restrict__ lut_static_track,
-          const uint8_t* __restrict__ lut_static_label, float* __restrict__ depth_int,
-          float4* __restrict__ cloud_pos, uint32_t* __restrict__ cloud_meta, Counters* __restrict__ cnt) {
-    const FrameParams& f = *fp;
+k_project(int slot, const float* __restrict__ depth, int depth_stride, const MaskDesc* __restrict__ masks,
+          const uint16_t* __restrict__ lut_static_track, const uint8_t* __restrict__ lut_static_label,
+          float* __restrict__ depth_int, float4* __restrict__ cloud_pos, uint32_t* __restrict__ cloud_meta,
+          Counters* __restrict__ cnt) {
+    const FrameParams& f = c_fp[slot];
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = false;
     if (q < f.W * f.H) {
         const int i = q / f.W, j = q - i * f.W;
         int si = i, sj = j;
-        if (f.boost) {  // :1104-1133, src = (int)(i * (1/0.5f)) clamped
+        if (f.boost && !f.pre_decimated) {  // :1104-1133, src = (int)(i * (1/0.5f)) clamped
             si = min((int)((float)i * 2.0f), f.in_H - 1);
             sj = min((int)((float)j * 2.0f), f.in_W - 1);
         }
@@ -126,9 +128,9 @@ k_project(const FrameParams* __restrict__ fp, const float* __restrict__ depth, i
 //                     (mc_ring/operations.h:1336-1338, isPointInFrustum :1240-1258), one bit per vertex.
 // one warp per 32 consecutive x vertices; rows are (z, y) in MAP coordinates.
 // =====================================================================================================
-__global__ void __launch_bounds__(128)
-k_vertex_mask(const FrameParams* __restrict__ fp, uint32_t* __restrict__ vmask, uint32_t words_per_row, uint32_t n_words) {
-    const FrameParams& f = *fp;
+__global__ void __launch_bounds__(256)
+k_vertex_mask(int slot, uint32_t* __restrict__ vmask, uint32_t words_per_row, uint32_t n_words) {
+    const FrameParams& f = c_fp[slot];
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= n_words) return;
     const uint32_t row = w / words_per_row, xw = w - row * words_per_row;
@@ -148,15 +150,16 @@ __device__ __forceinline__ bool vbit(const uint32_t* __restrict__ vmask, uint32_
 // =====================================================================================================
 // U2b  sweep          replaces getIdxOfVisibleParitlces minus its queue (mc_ring/operations.h:1344-1435)
 // one thread per storage voxel of this shard.  A voxel is swept when one of its 8 corner vertices is in the
-// frustum.  Swept particles are: invalidated when stale, reset to the newborn weight under a too-far depth pixel,
-// skipped when occluded, otherwise appended as a (pixel, particle) pair and counted per pixel.
+// frustum.  The header word says which slots are live, so an empty voxel costs 4 bytes.  Swept particles are:
+// invalidated when stale, reset to the newborn weight under a too-far depth pixel, skipped when occluded,
+// otherwise appended as a (pixel, particle) pair and counted per pixel.
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
-k_sweep(const FrameParams* __restrict__ fp, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
+k_sweep(int slot, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
         const uint32_t* __restrict__ stamp_z, const uint32_t* __restrict__ vmask, uint32_t words_per_row,
         const float* __restrict__ depth_int, uint32_t* __restrict__ pix_count, uint2* __restrict__ pairs,
         Counters* __restrict__ cnt) {
-    const FrameParams& f = *fp;
+    const FrameParams& f = c_fp[slot];
     const uint32_t v_lo = f.z_lo << (f.Xb + f.Yb), v_hi = f.z_hi << (f.Xb + f.Yb);
     const uint32_t v = v_lo + blockIdx.x * blockDim.x + threadIdx.x;
     bool swept = false;
@@ -175,32 +178,35 @@ k_sweep(const FrameParams* __restrict__ fp, Store st, const uint32_t* __restrict
     if (!__any_sync(0xffffffffu, swept)) return;
 
     const size_t base = (size_t)v << f.Pb;
-    const uint32_t stamp = swept ? slab_stamp(stamp_x, stamp_y, stamp_z, bx, by, bz) : 0u;
+    const uint32_t hdr = swept ? st.hdr[v] : 0u;
+    uint32_t todo = hdr_live(hdr), live = todo;
+    const uint32_t stamp = todo ? slab_stamp(stamp_x, stamp_y, stamp_z, bx, by, bz) : 0u;
     int nvalid = 0;
     bool observed = false;
-    for (uint32_t s = 1; s < f.P; ++s) {
+    while (__any_sync(0xffffffffu, todo != 0)) {
         bool emit = false;
-        uint32_t pix = 0;
-        if (swept) {
+        uint32_t pix = 0, s = 0;
+        if (todo) {
+            s = __ffs(todo) - 1;
+            todo &= todo - 1;
             const uint64_t m = st.meta[base + s];
-            if (meta_status(m) != ST_INVALID) {
-                if (meta_ts(m) < stamp) {
-                    st.meta[base + s] = meta_with_status(m, ST_INVALID);  // :1374-1378 outdated by the ring shift
-                } else {
-                    ++nvalid;
-                    int row, col;
-                    float cz;
-                    if (project_to_image(f, st.x[base + s], st.y[base + s], st.z[base + s], row, col, cz)) {
-                        const float d = __ldg(depth_int + row * f.W + col);
-                        if (d > f.depth_max) {             // :1389-1395 free space seen through this pixel
-                            st.w[base + s] = OCC_INIT_WEIGHT;
-                            observed = true;
-                        } else if (cz > d * ONE_SIGMA_COEFF) {  // :1397-1400 occluded
-                        } else {
-                            observed = true;
-                            emit = true;
-                            pix = (uint32_t)(row * f.W + col);
-                        }
+            if (meta_ts(m) < stamp) {
+                st.meta[base + s] = meta_with_status(m, ST_INVALID);  // :1374-1378 outdated by the ring shift
+                live &= ~(1u << s);
+            } else {
+                ++nvalid;
+                int row, col;
+                float cz;
+                if (project_to_image(f, st.x[base + s], st.y[base + s], st.z[base + s], row, col, cz)) {
+                    const float d = __ldg(depth_int + row * f.W + col);
+                    if (d > f.depth_max) {             // :1389-1395 free space seen through this pixel
+                        st.w[base + s] = OCC_INIT_WEIGHT;
+                        observed = true;
+                    } else if (cz > d * ONE_SIGMA_COEFF) {  // :1397-1400 occluded
+                    } else {
+                        observed = true;
+                        emit = true;
+                        pix = (uint32_t)(row * f.W + col);
                     }
                 }
             }
@@ -230,7 +236,8 @@ k_sweep(const FrameParams* __restrict__ fp, Store st, const uint32_t* __restrict
             float cz;
             if (project_to_image(f, gx, gy, gz, row, col, cz)) stamp0 = cz <= __ldg(depth_int + row * f.W + col);
         }
-        if (stamp0) st.meta[base] = (st.meta[base] & ~0xffffull) | (uint64_t)(f.T & 0xffffu);
+        const uint32_t nh = (stamp0 ? (f.T & 0xffffu) : hdr_ts(hdr)) | (hdr & HDR_MOVABLE) | (live << 16);
+        if (nh != hdr) st.hdr[v] = nh;
     }
     const uint32_t b_swept = __ballot_sync(0xffffffffu, swept), b_nonempty = __ballot_sync(0xffffffffu, swept && nvalid > 0);
     if (lane_id() == 0) {
@@ -245,8 +252,8 @@ k_sweep(const FrameParams* __restrict__ fp, Store st, const uint32_t* __restrict
 // =====================================================================================================
 constexpr int SCAN_BLOCK = 1024;
 
-__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t val, uint32_t* s_warp, uint32_t& total) {
-    // inclusive scan inside the warp
+// exclusive scan over the block (blockDim.x a multiple of 32, <= 1024); total = block sum
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t val, uint32_t* s_warp /*[33]*/, uint32_t& total) {
     uint32_t inc = val;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -279,7 +286,7 @@ k_scan_blocksum(const uint32_t* __restrict__ count, uint32_t n, uint32_t* __rest
     __shared__ uint32_t s_warp[33];
     const uint32_t i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
     uint32_t total;
-    block_exclusive_scan_1024(i < n ? count[i] : 0u, s_warp, total);
+    block_exclusive_scan(i < n ? count[i] : 0u, s_warp, total);
     if (threadIdx.x == 0) block_sum[blockIdx.x] = total;
 }
 
@@ -291,24 +298,23 @@ k_scan_apply(const uint32_t* __restrict__ count, uint32_t n, const uint32_t* __r
     uint32_t part = 0;
     for (uint32_t b = threadIdx.x; b < blockIdx.x; b += SCAN_BLOCK) part += block_sum[b];
     uint32_t tot;
-    block_exclusive_scan_1024(part, s_warp, tot);
+    block_exclusive_scan(part, s_warp, tot);
     if (threadIdx.x == 0) s_base = tot;
     __syncthreads();
     const uint32_t base = s_base;
     const uint32_t i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
     const uint32_t c = i < n ? count[i] : 0u;
     uint32_t total;
-    const uint32_t ex = block_exclusive_scan_1024(c, s_warp, total);
+    const uint32_t ex = block_exclusive_scan(c, s_warp, total);
     if (i < n) offset[i] = base + ex;
     if (i == n - 1) offset[n] = base + ex + c;
 }
 
 // scatter the pairs into their pixel segments (arrival order; sorted next)
 __global__ void __launch_bounds__(256)
-k_fill(const FrameParams* __restrict__ fp, const Counters* __restrict__ cnt, const uint2* __restrict__ pairs,
-       const uint32_t* __restrict__ offset, uint32_t* __restrict__ pix_count, uint32_t* __restrict__ csr_idx,
-       uint32_t* __restrict__ vis_pix) {
-    const uint32_t n = min(cnt->n_pairs, fp->vis_cap);
+k_fill(int slot, const Counters* __restrict__ cnt, const uint2* __restrict__ pairs, const uint32_t* __restrict__ offset,
+       uint32_t* __restrict__ pix_count, uint32_t* __restrict__ csr_idx, uint32_t* __restrict__ vis_pix) {
+    const uint32_t n = min(cnt->n_pairs, c_fp[slot].vis_cap);
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint2 pr = pairs[k];
         const uint32_t pos = offset[pr.x] + (atomicSub(pix_count + pr.x, 1u) - 1u);   // leaves the counts at zero
@@ -319,9 +325,9 @@ k_fill(const FrameParams* __restrict__ fp, const Counters* __restrict__ cnt, con
 
 // canonical order inside each pixel list: ascending particle index (insertion sort; lists are short)
 __global__ void __launch_bounds__(256)
-k_sort_lists(const FrameParams* __restrict__ fp, const uint32_t* __restrict__ offset, uint32_t* __restrict__ csr_idx) {
+k_sort_lists(int slot, const uint32_t* __restrict__ offset, uint32_t* __restrict__ csr_idx) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= fp->W * fp->H) return;
+    if (q >= c_fp[slot].W * c_fp[slot].H) return;
     const uint32_t b = offset[q], e = offset[q + 1];
     for (uint32_t i = b + 1; i < e; ++i) {
         const uint32_t key = csr_idx[i];
@@ -333,9 +339,9 @@ k_sort_lists(const FrameParams* __restrict__ fp, const uint32_t* __restrict__ of
 
 // gather the listed particles into compact, list-ordered arrays read by the two stencil passes
 __global__ void __launch_bounds__(256)
-k_gather_visible(const FrameParams* __restrict__ fp, const Counters* __restrict__ cnt, Store st,
-                 const uint32_t* __restrict__ csr_idx, float4* __restrict__ vis_pos, uint32_t* __restrict__ vis_meta) {
-    const uint32_t n = min(cnt->n_pairs, fp->vis_cap);
+k_gather_visible(int slot, const Counters* __restrict__ cnt, Store st, const uint32_t* __restrict__ csr_idx,
+                 float4* __restrict__ vis_pos, uint32_t* __restrict__ vis_meta) {
+    const uint32_t n = min(cnt->n_pairs, c_fp[slot].vis_cap);
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint32_t idx = csr_idx[k];
         const uint64_t m = st.meta[idx];
@@ -354,12 +360,12 @@ __device__ __forceinline__ void stage_lut(float* s_lut, const float* __restrict_
 }
 
 __global__ void __launch_bounds__(512)
-k_ck(const FrameParams* __restrict__ fp, const float* __restrict__ lut, const float4* __restrict__ cloud_pos,
-     const uint32_t* __restrict__ cloud_meta, const uint32_t* __restrict__ offset, const float4* __restrict__ vis_pos,
-     const uint32_t* __restrict__ vis_meta, float* __restrict__ ck) {
+k_ck(int slot, const float* __restrict__ lut, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta,
+     const uint32_t* __restrict__ offset, const float4* __restrict__ vis_pos, const uint32_t* __restrict__ vis_meta,
+     float* __restrict__ ck) {
     extern __shared__ float s_lut[];
     stage_lut(s_lut, lut);
-    const FrameParams& f = *fp;
+    const FrameParams& f = c_fp[slot];
     const int npix = f.W * f.H, r = f.win_r;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < npix; q += gridDim.x * blockDim.x) {
         const uint32_t om = cloud_meta[q];
@@ -393,13 +399,13 @@ k_ck(const FrameParams* __restrict__ fp, const float* __restrict__ lut, const fl
 // one thread per listed particle; sigma is the PARTICLE's pixel's sigma (:1047).
 // =====================================================================================================
 __global__ void __launch_bounds__(512)
-k_weight_update(const FrameParams* __restrict__ fp, const Counters* __restrict__ cnt, const float* __restrict__ lut,
-                const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta, const float* __restrict__ ck,
-                const uint32_t* __restrict__ csr_idx, const uint32_t* __restrict__ vis_pix, const float4* __restrict__ vis_pos,
-                const uint32_t* __restrict__ vis_meta, Store st) {
+k_weight_update(int slot, const Counters* __restrict__ cnt, const float* __restrict__ lut, const float4* __restrict__ cloud_pos,
+                const uint32_t* __restrict__ cloud_meta, const float* __restrict__ ck, const uint32_t* __restrict__ csr_idx,
+                const uint32_t* __restrict__ vis_pix, const float4* __restrict__ vis_pos, const uint32_t* __restrict__ vis_meta,
+                Store st) {
     extern __shared__ float s_lut[];
     stage_lut(s_lut, lut);
-    const FrameParams& f = *fp;
+    const FrameParams& f = c_fp[slot];
     const uint32_t n = min(cnt->n_pairs, f.vis_cap);
     const int r = f.win_r;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -447,17 +453,19 @@ k_weight_update(const FrameParams* __restrict__ fp, const Counters* __restrict__
 // (mc_ring/operations.h:782-803), so the outcome for a voxel depends only on the ORDER of the candidates that
 // fall into it.  A voxel can absorb at most topk = 2P-1 candidates before every later one is a no-op (P-1
 // slots, one resample that frees at most P-1 more), so: hash the voxel, keep the topk smallest ranks per
-// voxel with a cascade of atomicMin (order-independent result), then replay each voxel serially.
+// voxel with a cascade of atomicMin (order-independent result), then replay each touched voxel serially.
+// Touched hash entries are appended to a list so the replay never scans the table.
 // =====================================================================================================
 __device__ __forceinline__ uint32_t hash_slot(const FrameParams& f, uint32_t v) { return (v * 2654435761u) >> f.hash_shift; }
 
 __device__ __forceinline__ void topk_insert(const FrameParams& f, uint32_t v, uint32_t rank, uint32_t* __restrict__ keys,
-                                            uint32_t* __restrict__ ranks, uint32_t* n_new_voxels, uint32_t* overflow) {
+                                            uint32_t* __restrict__ ranks, uint32_t* __restrict__ entry_list, uint32_t* n_entries,
+                                            uint32_t* overflow) {
     uint32_t h = hash_slot(f, v);
     for (uint32_t probe = 0;; ++probe) {
         if (probe >= f.hash_cap) { atomicAdd(overflow, 1u); return; }
         const uint32_t old = atomicCAS(keys + h, EMPTY_KEY, v);
-        if (old == EMPTY_KEY) { atomicAdd(n_new_voxels, 1u); break; }
+        if (old == EMPTY_KEY) { entry_list[atomicAdd(n_entries, 1u)] = h; break; }
         if (old == v) break;
         h = (h + 1) & (f.hash_cap - 1);
     }
@@ -485,9 +493,9 @@ __device__ __forceinline__ int birth_rank_to_pixel(const FrameParams& f, uint32_
 }
 
 __global__ void __launch_bounds__(256)
-k_birth_bin(const FrameParams* __restrict__ fp, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta,
-            uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks, Counters* __restrict__ cnt) {
-    const FrameParams& f = *fp;
+k_birth_bin(int slot, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta, uint32_t* __restrict__ keys,
+            uint32_t* __restrict__ ranks, uint32_t* __restrict__ entry_list, Counters* __restrict__ cnt) {
+    const FrameParams& f = c_fp[slot];
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= f.W * f.H) return;
     if (!pt_valid(cloud_meta[q])) return;
@@ -497,40 +505,41 @@ k_birth_bin(const FrameParams* __restrict__ fp, const float4* __restrict__ cloud
     if (v == INVALID_INDEX) return;
     if (bz < f.z_lo || bz >= f.z_hi) return;   // another shard owns this voxel
     const int i = q / f.W, j = q - i * f.W;
-    topk_insert(f, v, birth_rank(f, i, j), keys, ranks, &cnt->n_birth_voxels, &cnt->hash_overflow);
+    topk_insert(f, v, birth_rank(f, i, j), keys, ranks, entry_list, &cnt->n_birth_voxels, &cnt->hash_overflow);
 }
 
-// first vacant slot 1..P-1 of a voxel (operations.h:790-796); 0 when full
-__device__ __forceinline__ uint32_t first_vacant(const Store& st, size_t base, uint32_t P, uint32_t stamp) {
-    for (uint32_t s = 1; s < P; ++s)
-        if (meta_vacant(st.meta[base + s], stamp)) return s;
+// first vacant slot 1..P-1 of a voxel (operations.h:790-796); 0 when full.  live = header mask (bit s)
+__device__ __forceinline__ uint32_t first_vacant(const Store& st, size_t base, uint32_t P, uint32_t live, uint32_t stamp) {
+    for (uint32_t s = 1; s < P; ++s) {
+        if (!((live >> s) & 1u)) return s;
+        if (meta_ts(st.meta[base + s]) < stamp) return s;
+    }
     return 0;
 }
 
 // SemanticDSPMap::resampleParticlesInVoxel (semantic_dsp_map.h:1448-1519); returns true when a resample ran
-__device__ __forceinline__ bool resample_voxel(const Store& st, size_t base, uint32_t P) {
+__device__ __forceinline__ bool resample_voxel(const Store& st, size_t base, uint32_t P, uint32_t& live) {
     float wsum = 0.f;
-    uint32_t n_upd = 0;
+    uint32_t n_upd = 0, upd = 0;
     for (uint32_t s = 1; s < P; ++s)
-        if (meta_status(st.meta[base + s]) == ST_UPDATED) { wsum += st.w[base + s]; ++n_upd; }
+        if (((live >> s) & 1u) && meta_status(st.meta[base + s]) == ST_UPDATED) { wsum += st.w[base + s]; ++n_upd; upd |= 1u << s; }
     const uint32_t trigger = P >> 1;
     if (n_upd <= trigger) return false;
     if (wsum < 0.01f) {
-        for (uint32_t s = 1; s < P; ++s) {
-            const uint64_t m = st.meta[base + s];
-            if (meta_status(m) == ST_UPDATED) st.meta[base + s] = meta_with_status(m, ST_INVALID);
-        }
+        for (uint32_t s = 1; s < P; ++s)
+            if ((upd >> s) & 1u) st.meta[base + s] = meta_with_status(st.meta[base + s], ST_INVALID);
+        live &= ~upd;
         return true;
     }
     float wpp = wsum / (float)trigger;
     if (wpp > 1.f) wpp = 1.f;
     float cum = 0.f, thr = wpp;
     for (uint32_t s = 1; s < P; ++s) {
-        const uint64_t m = st.meta[base + s];
-        if (meta_status(m) != ST_UPDATED) continue;
+        if (!((upd >> s) & 1u)) continue;
         cum += st.w[base + s];
         if (cum < thr) {
-            st.meta[base + s] = meta_with_status(m, ST_INVALID);
+            st.meta[base + s] = meta_with_status(st.meta[base + s], ST_INVALID);
+            live &= ~(1u << s);
         } else {
             st.w[base + s] = wpp;
             thr += wpp;
@@ -546,18 +555,22 @@ __device__ __forceinline__ bool resample_voxel(const Store& st, size_t base, uin
 //                     reference order.  Resets the hash entry it consumed.
 // =====================================================================================================
 __global__ void __launch_bounds__(128)
-k_birth_replay(const FrameParams* __restrict__ fp, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
+k_birth_replay(int slot, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
                const uint32_t* __restrict__ stamp_z, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta,
-               uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks, Counters* __restrict__ cnt) {
-    const FrameParams& f = *fp;
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < f.hash_cap; e += gridDim.x * blockDim.x) {
+               uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks, const uint32_t* __restrict__ entry_list,
+               Counters* __restrict__ cnt) {
+    const FrameParams& f = c_fp[slot];
+    const uint32_t n_entries = cnt->n_birth_voxels;
+    for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < n_entries; li += gridDim.x * blockDim.x) {
+        const uint32_t e = entry_list[li];
         const uint32_t v = keys[e];
-        if (v == EMPTY_KEY) continue;
         keys[e] = EMPTY_KEY;
         uint32_t bx, by, bz;
         voxel_to_buffer(f, v, bx, by, bz);
         const uint32_t stamp = slab_stamp(stamp_x, stamp_y, stamp_z, bx, by, bz);
         const size_t base = (size_t)v << f.Pb;
+        const uint32_t hdr = st.hdr[v];
+        uint32_t live = hdr_live(hdr), movable = hdr & HDR_MOVABLE;
         uint32_t* r = ranks + (size_t)e * f.topk;
         bool resampled = false, frozen = false;
         uint32_t born = 0, n_res = 0;
@@ -567,12 +580,12 @@ k_birth_replay(const FrameParams* __restrict__ fp, Store st, const uint32_t* __r
             r[t] = NO_RANK;
             if (frozen) continue;
             const int q = birth_rank_to_pixel(f, rank);
-            uint32_t s = first_vacant(st, base, f.P, stamp);
+            uint32_t s = first_vacant(st, base, f.P, live, stamp);
             bool try_resample;
             if (f.depth_noise) try_resample = (s == 0) && !resampled;      // :1205-1226 only when the voxel is full
             else try_resample = !resampled;                                 // :1165-1170 after every add
             if (f.depth_noise && try_resample) {
-                if (resample_voxel(st, base, f.P)) { resampled = true; ++n_res; s = first_vacant(st, base, f.P, stamp); }
+                if (resample_voxel(st, base, f.P, live)) { resampled = true; ++n_res; s = first_vacant(st, base, f.P, live, stamp); }
                 else frozen = true;            // full, and a resample can never trigger this frame
             }
             if (s) {
@@ -581,52 +594,65 @@ k_birth_replay(const FrameParams* __restrict__ fp, Store st, const uint32_t* __r
                 st.x[base + s] = p.x; st.y[base + s] = p.y; st.z[base + s] = p.z;
                 st.w[base + s] = OCC_INIT_WEIGHT;
                 st.meta[base + s] = meta_pack(f.T, pt_track(pm), pt_label(pm), ST_REGULAR_BORN, 0);   // operations.h:171-184
+                live |= 1u << s;
+                if (pt_track(pm) <= f.max_movable) movable = HDR_MOVABLE;
                 ++born;
             } else if (f.depth_noise) {
                 frozen = true;                 // full after the one allowed resample
             }
             if (!f.depth_noise && try_resample) {
-                if (resample_voxel(st, base, f.P)) { resampled = true; ++n_res; }
+                if (resample_voxel(st, base, f.P, live)) { resampled = true; ++n_res; }
                 else if (s == 0) frozen = true;  // full and births never create UPDATED particles
             } else if (!f.depth_noise && s == 0) {
                 frozen = true;
             }
         }
+        const uint32_t nh = hdr_ts(hdr) | movable | (live << 16);
+        if (nh != hdr) st.hdr[v] = nh;
         if (born) atomicAdd(&cnt->n_born, born);
         if (n_res) atomicAdd(&cnt->n_resampled, n_res);
     }
 }
 
 // =====================================================================================================
-// ordered stream compaction across blocks: decoupled look-back over (flag | count) words.
-// Blocks take a dynamic ticket so a block never waits on one that has not started.
+// ordered stream compaction across blocks: decoupled look-back over (flag | count) words, one warp looking
+// at 32 predecessors at a time.  Blocks take a dynamic ticket so a block never waits on one that has not started.
 // =====================================================================================================
 constexpr uint64_t LB_AGG = 1ull << 62, LB_INC = 2ull << 62, LB_MASK = (1ull << 62) - 1;
 
-// returns the exclusive prefix (packed two 31-bit counters) of this block; call from thread 0 only
-__device__ __forceinline__ uint64_t lookback_prefix(volatile uint64_t* status, uint32_t bid, uint64_t block_total) {
-    if (bid == 0) {
-        status[0] = LB_INC | block_total;
-        return 0;
-    }
-    status[bid] = LB_AGG | block_total;
+// call from every lane of warp 0; returns this block's exclusive prefix (two packed 31-bit counters) to all lanes
+__device__ __forceinline__ uint64_t lookback_prefix_warp(volatile uint64_t* status, uint32_t bid, uint64_t block_total) {
+    const uint32_t lane = lane_id();
+    if (lane == 0) status[bid] = (bid == 0 ? LB_INC : LB_AGG) | block_total;
+    if (bid == 0) return 0;
     uint64_t prefix = 0;
-    for (int j = (int)bid - 1;; --j) {
-        uint64_t s;
-        do { s = status[j]; } while ((s >> 62) == 0);
-        prefix += s & LB_MASK;
-        if ((s >> 62) == 2) break;
+    for (int j = (int)bid - 1;; j -= 32) {
+        const int k = j - (int)lane;
+        uint64_t s = LB_INC;   // before the first block: an inclusive zero
+        if (k >= 0) {
+            do { s = status[k]; } while ((s >> 62) == 0);
+        }
+        const uint32_t inc_mask = __ballot_sync(0xffffffffu, (s >> 62) == 2);
+        const uint32_t first_inc = inc_mask ? (uint32_t)(__ffs(inc_mask) - 1) : 32u;
+        uint64_t val = (lane <= first_inc) ? (s & LB_MASK) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
+        prefix += __shfl_sync(0xffffffffu, val, 0);
+        if (inc_mask) break;
     }
-    status[bid] = LB_INC | (prefix + block_total);
+    if (lane == 0) status[bid] = LB_INC | (prefix + block_total);
     return prefix;
 }
 
 // =====================================================================================================
 // O1  occupancy_labels  replaces getOccupancyResult + determineIfVoxelOccupied + calculateWeightAndSemanticsInVoxel
 //                       + getVoxelGlobalPosition (semantic_dsp_map.h:1239-1383; mc_ring/operations.h:390-448, 623-648)
-// one thread per storage voxel; sequential slot loop (the reference's summation order); ordered compaction.
+// one thread per OCC_VPT consecutive storage voxels; header word first, slot records only for live slots of known
+// voxels; sequential slot loop (the reference's summation order); ordered compaction of the emitted voxels.
 // =====================================================================================================
 constexpr int OCC_BLOCK = 256;
+constexpr int OCC_VPT = 4;                       // voxels per thread (one 16-byte header load)
+constexpr int OCC_TILE = OCC_BLOCK * OCC_VPT;
 constexpr int MAX_P = 16;
 
 struct ResultArrays {
@@ -635,113 +661,131 @@ struct ResultArrays {
 };
 
 __global__ void __launch_bounds__(OCC_BLOCK)
-k_occupancy(const FrameParams* __restrict__ fp, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
+k_occupancy(int slot, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
             const uint32_t* __restrict__ stamp_z, ResultArrays out, int8_t* __restrict__ voxel_state,
             uint64_t* __restrict__ lb_status, Counters* __restrict__ cnt) {
     __shared__ uint32_t s_bid;
-    __shared__ uint32_t s_warp_occ[OCC_BLOCK / 32], s_warp_free[OCC_BLOCK / 32];
+    __shared__ uint32_t s_warp[33];
     __shared__ uint64_t s_prefix;
-    const FrameParams& f = *fp;
+    const FrameParams& f = c_fp[slot];
     if (threadIdx.x == 0) s_bid = atomicAdd(&cnt->ticket_occ, 1u);
     __syncthreads();
     const uint32_t bid = s_bid;
-    const uint32_t v_lo = f.z_lo << (f.Xb + f.Yb), v_hi = f.z_hi << (f.Xb + f.Yb);
-    const uint32_t v = v_lo + bid * OCC_BLOCK + threadIdx.x;
+    const uint32_t v_lo = f.z_lo << (f.Xb + f.Yb);
+    const uint32_t v0 = v_lo + bid * OCC_TILE + threadIdx.x * OCC_VPT;   // the grid covers the shard exactly (V multiple of 1024)
 
-    int state = -1;
-    float wsum = -1.f;
-    uint32_t track = 0, label = 0;
-    bool nonempty = false;
-    uint32_t bx = 0, by = 0, bz = 0;
-    if (v < v_hi) {
-        voxel_to_buffer(f, v, bx, by, bz);
-        const size_t base = (size_t)v << f.Pb;
-        const uint32_t stamp = slab_stamp(stamp_x, stamp_y, stamp_z, bx, by, bz);
-        const uint32_t ts0 = meta_ts(st.meta[base]);
-        if (ts0 != 0 && !(ts0 < stamp)) {                   // isVoxelValid, operations.h:824-837
-            wsum = 0.f;
-            float gsum = 0.f;
-            // per-track weight histogram (std::map in the reference), at most P-1 distinct tracks
-            uint32_t h_track[MAX_P - 1], h_label[MAX_P - 1];
-            float h_w[MAX_P - 1];
-            int nh = 0;
-            for (uint32_t s = 1; s < f.P; ++s) {
-                const uint64_t m = st.meta[base + s];
-                if (meta_vacant(m, stamp)) continue;
-                nonempty = true;
-                float w = st.w[base + s];
-                wsum += w;                                  // the unclamped weight, operations.h:414
-                if (w > 1.f) { w = 1.f; st.w[base + s] = 1.f; }
-                const uint32_t status = meta_status(m);
-                if (status == ST_GUESSED_BORN) gsum += w;
-                else if (status == ST_UPDATED && w < OCC_INIT_WEIGHT) { st.meta[base + s] = meta_with_status(m, ST_INVALID); continue; }
-                const uint32_t tr = meta_track(m);
-                int k = 0;
-                while (k < nh && h_track[k] != tr) ++k;
-                if (k == nh) { h_track[k] = tr; h_w[k] = 0.f; ++nh; }
-                h_w[k] += w;
-                h_label[k] = meta_label(m) & 0xffu;
-            }
-            // first maximum in ascending track order, strict > from 0 (operations.h:439-446)
-            float mw = 0.f;
-            uint32_t best = 0xffffffffu;
-            for (int k = 0; k < nh; ++k) {
-                if (h_w[k] > 0.f && (h_w[k] > mw || (h_w[k] == mw && h_track[k] < best))) { mw = h_w[k]; best = h_track[k]; track = h_track[k]; label = h_label[k]; }
-            }
-            if (wsum > f.occ_thr) state = 1;
-            else if (gsum >= OCC_INIT_WEIGHT) state = 2;
-            else state = 0;
-        }
-        if (f.want_state) voxel_state[v] = (int8_t)state;
-    }
-    const bool is_occ = state > 0, is_free = f.want_free && state == 0;
-    const uint32_t b_occ = __ballot_sync(0xffffffffu, is_occ), b_free = __ballot_sync(0xffffffffu, is_free);
-    const uint32_t b_ne = __ballot_sync(0xffffffffu, nonempty);
-    const uint32_t wid = threadIdx.x >> 5;
-    if (lane_id() == 0) {
-        s_warp_occ[wid] = __popc(b_occ);
-        s_warp_free[wid] = __popc(b_free);
-        if (b_ne) atomicAdd(&cnt->n_nonempty_voxels, (uint32_t)__popc(b_ne));
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t to = 0, tf = 0;
+    const uint4 h4 = *reinterpret_cast<const uint4*>(st.hdr + v0);
+    const uint32_t hdrs[OCC_VPT] = {h4.x, h4.y, h4.z, h4.w};
+    uint32_t bx0, by, bz;
+    voxel_to_buffer(f, v0, bx0, by, bz);
+    const uint32_t stamp_yz = max(__ldg(stamp_y + by), __ldg(stamp_z + bz));
+
+    int state[OCC_VPT];
+    float wsum[OCC_VPT];
+    uint32_t tl[OCC_VPT];     // track | label << 16
+    uint32_t n_occ = 0, n_free = 0, n_nonempty = 0;
 #pragma unroll
-        for (int k = 0; k < OCC_BLOCK / 32; ++k) {
-            const uint32_t a = s_warp_occ[k], b = s_warp_free[k];
-            s_warp_occ[k] = to; s_warp_free[k] = tf;
-            to += a; tf += b;
+    for (int u = 0; u < OCC_VPT; ++u) {
+        const uint32_t hdr = hdrs[u], v = v0 + u;
+        const uint32_t stamp = max(stamp_yz, __ldg(stamp_x + bx0 + u));
+        const uint32_t ts0 = hdr_ts(hdr);
+        state[u] = -1; wsum[u] = -1.f; tl[u] = 0;
+        if (ts0 != 0 && !(ts0 < stamp)) {                   // isVoxelValid, operations.h:824-837
+            float ws = 0.f, gsum = 0.f;
+            uint32_t live = hdr_live(hdr), new_live = live;
+            uint32_t track = 0, label = 0;
+            if (live) {
+                const size_t base = (size_t)v << f.Pb;
+                // per-track weight histogram (std::map in the reference), at most P-1 distinct tracks
+                uint32_t h_track[MAX_P - 1], h_label[MAX_P - 1];
+                float h_w[MAX_P - 1];
+                int nh = 0;
+                bool any = false;
+                while (live) {
+                    const uint32_t s = __ffs(live) - 1;
+                    live &= live - 1;
+                    const uint64_t m = st.meta[base + s];
+                    if (meta_ts(m) < stamp) continue;           // vacant: outdated by the ring shift (operations.h:810-816)
+                    any = true;
+                    float w = st.w[base + s];
+                    ws += w;                                    // the unclamped weight, operations.h:414
+                    if (w > 1.f) { w = 1.f; st.w[base + s] = 1.f; }
+                    const uint32_t status = meta_status(m);
+                    if (status == ST_GUESSED_BORN) gsum += w;
+                    else if (status == ST_UPDATED && w < OCC_INIT_WEIGHT) {
+                        st.meta[base + s] = meta_with_status(m, ST_INVALID);
+                        new_live &= ~(1u << s);
+                        continue;
+                    }
+                    const uint32_t tr = meta_track(m);
+                    int k = 0;
+                    while (k < nh && h_track[k] != tr) ++k;
+                    if (k == nh) { h_track[k] = tr; h_w[k] = 0.f; ++nh; }
+                    h_w[k] += w;
+                    h_label[k] = meta_label(m) & 0xffu;
+                }
+                // first maximum in ascending track order, strict > from 0 (operations.h:439-446)
+                float mw = 0.f;
+                uint32_t best = 0xffffffffu;
+                for (int k = 0; k < nh; ++k)
+                    if (h_w[k] > 0.f && (h_w[k] > mw || (h_w[k] == mw && h_track[k] < best))) { mw = h_w[k]; best = h_track[k]; track = h_track[k]; label = h_label[k]; }
+                if (any) ++n_nonempty;
+                if (new_live != hdr_live(hdr)) st.hdr[v] = (hdr & 0x1ffffu) | (new_live << 16);
+            }
+            wsum[u] = ws; tl[u] = track | (label << 16);
+            if (ws > f.occ_thr) state[u] = 1;
+            else if (gsum >= OCC_INIT_WEIGHT) state[u] = 2;
+            else state[u] = 0;
         }
-        const uint64_t total = (uint64_t)to | ((uint64_t)tf << 31);
-        const uint64_t prefix = lookback_prefix(lb_status, bid, total);
-        s_prefix = prefix;
-        if (bid == gridDim.x - 1) {
-            const uint64_t inc = prefix + total;
-            cnt->n_occupied = (uint32_t)(inc & 0x7fffffffu);
-            cnt->n_free = (uint32_t)((inc >> 31) & 0x7fffffffu);
+        if (f.want_state) voxel_state[v] = (int8_t)state[u];
+        n_occ += state[u] > 0;
+        n_free += (f.want_free && state[u] == 0);
+    }
+    // block-wide exclusive scan of the two counters, packed
+    uint32_t total;
+    const uint32_t packed = n_occ | (n_free << 16);                 // <= 4 per thread, <= 1024 per block: 16 bits each suffice
+    const uint32_t ex = block_exclusive_scan(packed, s_warp, total);
+    if (threadIdx.x < 32) {
+        const uint64_t tot64 = (uint64_t)(total & 0xffffu) | ((uint64_t)(total >> 16) << 31);
+        const uint64_t prefix = lookback_prefix_warp(lb_status, bid, tot64);
+        if (threadIdx.x == 0) {
+            s_prefix = prefix;
+            if (bid == gridDim.x - 1) {
+                const uint64_t inc = prefix + tot64;
+                cnt->n_occupied = (uint32_t)(inc & 0x7fffffffu);
+                cnt->n_free = (uint32_t)((inc >> 31) & 0x7fffffffu);
+            }
         }
     }
+    n_nonempty = __reduce_add_sync(0xffffffffu, n_nonempty);
+    if (lane_id() == 0 && n_nonempty) atomicAdd(&cnt->n_nonempty_voxels, n_nonempty);
     __syncthreads();
-    if (is_occ || is_free) {
-        // voxelIdxToMapFramePos + map centre (operations.h:940-944, 970-983)
-        uint32_t mx, my, mz;
-        buffer_to_map(f, bx, by, bz, mx, my, mz);
-        float p0 = (float)mx * f.voxel + f.pmin[0], p1 = (float)my * f.voxel + f.pmin[1], p2 = (float)mz * f.voxel + f.pmin[2];
-        p0 += f.map_center[0]; p1 += f.map_center[1]; p2 += f.map_center[2];
-        if (f.zero_center) { p0 = p0 - f.cam[0]; p1 = p1 - f.cam[1]; p2 = p2 - f.cam[2]; }
-        const uint32_t lt = (1u << lane_id()) - 1u;
-        if (is_occ) {
-            const uint32_t pos = (uint32_t)(s_prefix & 0x7fffffffu) + s_warp_occ[wid] + __popc(b_occ & lt);
-            out.voxel_index[pos] = v;
-            out.xyz[3 * (size_t)pos + 0] = p0; out.xyz[3 * (size_t)pos + 1] = p1; out.xyz[3 * (size_t)pos + 2] = p2;
-            out.weight_sum[pos] = wsum;
-            out.track_id[pos] = (uint16_t)track;
-            out.label_id[pos] = (uint8_t)label;
-            out.state[pos] = (int8_t)state;
-        } else {
-            const uint32_t pos = (uint32_t)((s_prefix >> 31) & 0x7fffffffu) + s_warp_free[wid] + __popc(b_free & lt);
-            out.free_voxel_index[pos] = v;
-            out.free_xyz[3 * (size_t)pos + 0] = p0; out.free_xyz[3 * (size_t)pos + 1] = p1; out.free_xyz[3 * (size_t)pos + 2] = p2;
+    if (n_occ | n_free) {
+        uint32_t pos_occ = (uint32_t)(s_prefix & 0x7fffffffu) + (ex & 0xffffu);
+        uint32_t pos_free = (uint32_t)((s_prefix >> 31) & 0x7fffffffu) + (ex >> 16);
+#pragma unroll
+        for (int u = 0; u < OCC_VPT; ++u) {
+            const bool is_occ = state[u] > 0, is_free = f.want_free && state[u] == 0;
+            if (!is_occ && !is_free) continue;
+            // voxelIdxToMapFramePos + map centre (operations.h:940-944, 970-983)
+            uint32_t mx, my, mz;
+            buffer_to_map(f, bx0 + u, by, bz, mx, my, mz);
+            float p0 = (float)mx * f.voxel + f.pmin[0], p1 = (float)my * f.voxel + f.pmin[1], p2 = (float)mz * f.voxel + f.pmin[2];
+            p0 += f.map_center[0]; p1 += f.map_center[1]; p2 += f.map_center[2];
+            if (f.zero_center) { p0 = p0 - f.cam[0]; p1 = p1 - f.cam[1]; p2 = p2 - f.cam[2]; }
+            if (is_occ) {
+                const uint32_t pos = pos_occ++;
+                out.voxel_index[pos] = v0 + u;
+                out.xyz[3 * (size_t)pos + 0] = p0; out.xyz[3 * (size_t)pos + 1] = p1; out.xyz[3 * (size_t)pos + 2] = p2;
+                out.weight_sum[pos] = wsum[u];
+                out.track_id[pos] = (uint16_t)(tl[u] & 0xffffu);
+                out.label_id[pos] = (uint8_t)(tl[u] >> 16);
+                out.state[pos] = (int8_t)state[u];
+            } else {
+                const uint32_t pos = pos_free++;
+                out.free_voxel_index[pos] = v0 + u;
+                out.free_xyz[3 * (size_t)pos + 0] = p0; out.free_xyz[3 * (size_t)pos + 1] = p1; out.free_xyz[3 * (size_t)pos + 2] = p2;
+            }
         }
     }
 }
@@ -751,7 +795,7 @@ k_occupancy(const FrameParams* __restrict__ fp, Store st, const uint32_t* __rest
 //                      ObjectSet::removeObjectByTrackID (object_layer.h:414-425).
 // set(T) = { p : status(p) != INVALID and track(p) == T } in ascending particle index (canonical order).
 // =====================================================================================================
-constexpr int SEL_BLOCK = 256;
+constexpr int SEL_BLOCK = 1024;
 constexpr int MAX_MOVES = 64;
 
 struct MoveTable {
@@ -761,53 +805,68 @@ struct MoveTable {
     float t[MAX_MOVES][12];   // rows 0..2 of the 4x4
 };
 
+__device__ __forceinline__ int find_track(const int32_t* __restrict__ tab, int n, int tr) {
+    for (int k = 0; k < n; ++k)
+        if (tab[k] == tr) return k;
+    return -1;
+}
+
 // pass 1: ordered list of (particle index, move index) for every particle of a moved track; particles of a
-// removed track are invalidated on the spot.  One thread per slot, ordered compaction by decoupled look-back.
+// removed track are invalidated on the spot.  One thread per voxel; only voxels whose header carries the
+// "movable" flag are opened (the flag is cleared when no live movable-track particle is left).
 __global__ void __launch_bounds__(SEL_BLOCK)
-k_select_tracks(const FrameParams* __restrict__ fp, Store st, const MoveTable* __restrict__ mt, uint32_t* __restrict__ sel_idx,
-                uint32_t* __restrict__ sel_move, uint64_t* __restrict__ lb_status, Counters* __restrict__ cnt, uint32_t sel_cap) {
-    __shared__ uint32_t s_bid, s_warp[SEL_BLOCK / 32];
+k_select_tracks(int slot, Store st, const MoveTable* __restrict__ mt, uint32_t* __restrict__ sel_idx, uint32_t* __restrict__ sel_move,
+                uint64_t* __restrict__ lb_status, Counters* __restrict__ cnt, uint32_t sel_cap) {
+    __shared__ uint32_t s_bid, s_warp[33];
     __shared__ uint64_t s_prefix;
-    const FrameParams& f = *fp;
+    const FrameParams& f = c_fp[slot];
     if (threadIdx.x == 0) s_bid = atomicAdd(&cnt->ticket_sel, 1u);
     __syncthreads();
     const uint32_t bid = s_bid;
-    const size_t i_lo = (size_t)(f.z_lo << (f.Xb + f.Yb)) << f.Pb, i_hi = (size_t)(f.z_hi << (f.Xb + f.Yb)) << f.Pb;
-    const size_t i = i_lo + (size_t)bid * SEL_BLOCK + threadIdx.x;
-    int mv = -1;
-    bool removed = false;
-    if (i < i_hi && (i & (f.P - 1)) != 0) {
-        const uint64_t m = st.meta[i];
-        if (meta_status(m) != ST_INVALID) {
+    const uint32_t v = (f.z_lo << (f.Xb + f.Yb)) + bid * SEL_BLOCK + threadIdx.x;
+    const size_t base = (size_t)v << f.Pb;
+    const uint32_t hdr = st.hdr[v];
+    uint32_t sel = 0, n_removed = 0;
+    if (hdr & HDR_MOVABLE) {
+        uint32_t live = hdr_live(hdr), new_live = live;
+        bool any_movable = false;
+        while (live) {
+            const uint32_t s = __ffs(live) - 1;
+            live &= live - 1;
+            const uint64_t m = st.meta[base + s];
             const int tr = (int)meta_track(m);
-            for (int k = 0; k < mt->n_moves; ++k)
-                if (mt->move_track[k] == tr) { mv = k; break; }
-            if (mv < 0) {
-                for (int k = 0; k < mt->n_remove; ++k)
-                    if (mt->remove_track[k] == tr) { removed = true; break; }
-                if (removed) st.meta[i] = meta_with_status(m, ST_INVALID);
-            }
+            if ((uint32_t)tr > f.max_movable) continue;
+            if (find_track(mt->move_track, mt->n_moves, tr) >= 0) { sel |= 1u << s; any_movable = true; }
+            else if (find_track(mt->remove_track, mt->n_remove, tr) >= 0) {
+                st.meta[base + s] = meta_with_status(m, ST_INVALID);
+                new_live &= ~(1u << s);
+                ++n_removed;
+            } else any_movable = true;
+        }
+        const uint32_t nh = hdr_ts(hdr) | (any_movable ? HDR_MOVABLE : 0u) | (new_live << 16);
+        if (nh != hdr) st.hdr[v] = nh;
+    }
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan((uint32_t)__popc(sel), s_warp, total);
+    if (threadIdx.x < 32) {
+        const uint64_t prefix = lookback_prefix_warp(lb_status, bid, total);
+        if (threadIdx.x == 0) {
+            s_prefix = prefix;
+            if (bid == gridDim.x - 1) cnt->n_selected = (uint32_t)(prefix + total);
         }
     }
-    const uint32_t b_sel = __ballot_sync(0xffffffffu, mv >= 0), b_rm = __ballot_sync(0xffffffffu, removed);
-    const uint32_t wid = threadIdx.x >> 5;
-    if (lane_id() == 0) {
-        s_warp[wid] = __popc(b_sel);
-        if (b_rm) atomicAdd(&cnt->n_removed, (uint32_t)__popc(b_rm));
-    }
+    n_removed = __reduce_add_sync(0xffffffffu, n_removed);
+    if (lane_id() == 0 && n_removed) atomicAdd(&cnt->n_removed, n_removed);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0;
-#pragma unroll
-        for (int k = 0; k < SEL_BLOCK / 32; ++k) { const uint32_t a = s_warp[k]; s_warp[k] = tot; tot += a; }
-        const uint64_t prefix = lookback_prefix(lb_status, bid, tot);
-        s_prefix = prefix;
-        if (bid == gridDim.x - 1) cnt->n_selected = (uint32_t)(prefix + tot);
-    }
-    __syncthreads();
-    if (mv >= 0) {
-        const uint32_t pos = (uint32_t)s_prefix + s_warp[wid] + __popc(b_sel & ((1u << lane_id()) - 1u));
-        if (pos < sel_cap) { sel_idx[pos] = (uint32_t)i; sel_move[pos] = (uint32_t)mv; }
+    uint32_t pos = (uint32_t)s_prefix + ex;
+    while (sel) {
+        const uint32_t s = __ffs(sel) - 1;
+        sel &= sel - 1;
+        if (pos < sel_cap) {
+            sel_idx[pos] = (uint32_t)(base + s);
+            sel_move[pos] = (uint32_t)find_track(mt->move_track, mt->n_moves, (int)meta_track(st.meta[base + s]));
+        }
+        ++pos;
     }
 }
 
@@ -833,8 +892,9 @@ k_move_sequence(const Counters* __restrict__ cnt, const MoveTable* __restrict__ 
         const uint32_t k = c + threadIdx.x;
         const int my = k < n ? (int)sel_move[k] : -1;
         for (int m = 0; m < mt->n_moves; ++m) {
+            if (s_count[m] == 0) continue;
             uint32_t total;
-            const uint32_t ex = block_exclusive_scan_1024(my == m ? 1u : 0u, s_warp, total);
+            const uint32_t ex = block_exclusive_scan(my == m ? 1u : 0u, s_warp, total);
             if (my == m) sel_seq[k] = s_offset[m] + s_running[m] + ex;
             __syncthreads();
             if (threadIdx.x == 0) s_running[m] += total;
@@ -845,11 +905,11 @@ k_move_sequence(const Counters* __restrict__ cnt, const MoveTable* __restrict__ 
 
 // pass 3: transform + table noise into a staging record, delete the original, bin by destination voxel
 __global__ void __launch_bounds__(256)
-k_move_apply(const FrameParams* __restrict__ fp, Counters* __restrict__ cnt, Store st, const MoveTable* __restrict__ mt,
-             const float* __restrict__ randoms, const Persist* __restrict__ persist, const uint32_t* __restrict__ sel_idx,
-             const uint32_t* __restrict__ sel_move, const uint32_t* __restrict__ sel_seq, float4* __restrict__ mov_pos,
-             uint64_t* __restrict__ mov_meta, uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks, uint32_t sel_cap) {
-    const FrameParams& f = *fp;
+k_move_apply(int slot, Counters* __restrict__ cnt, Store st, const MoveTable* __restrict__ mt, const float* __restrict__ randoms,
+             const Persist* __restrict__ persist, const uint32_t* __restrict__ sel_idx, const uint32_t* __restrict__ sel_move,
+             const uint32_t* __restrict__ sel_seq, float4* __restrict__ mov_pos, uint64_t* __restrict__ mov_meta,
+             uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks, uint32_t* __restrict__ entry_list, uint32_t sel_cap) {
+    const FrameParams& f = c_fp[slot];
     const uint32_t n = min(cnt->n_selected, sel_cap);
     const uint32_t cur = persist->cursor_ring;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -868,9 +928,10 @@ k_move_apply(const FrameParams* __restrict__ fp, Counters* __restrict__ cnt, Sto
         mov_pos[seq] = make_float4(px, py, pz, st.w[idx]);
         mov_meta[seq] = m;
         st.meta[idx] = meta_with_status(m, ST_INVALID);                        // operations.h:346
+        atomicAnd(st.hdr + (idx >> f.Pb), ~(1u << (16 + (idx & (f.P - 1)))));
         uint32_t bx, by, bz;
         const uint32_t v = global_pos_to_voxel(f, px, py, pz, bx, by, bz);
-        if (v != INVALID_INDEX) topk_insert(f, v, seq, keys, ranks, &cnt->n_move_voxels, &cnt->hash_overflow);
+        if (v != INVALID_INDEX) topk_insert(f, v, seq, keys, ranks, entry_list, &cnt->n_move_voxels, &cnt->hash_overflow);
     }
 }
 
@@ -881,18 +942,22 @@ __global__ void k_advance_cursor(const Counters* __restrict__ cnt, Persist* __re
 
 // pass 4: re-insert in sequence order (operations.h:351-360); one thread per destination voxel
 __global__ void __launch_bounds__(128)
-k_move_replay(const FrameParams* __restrict__ fp, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
+k_move_replay(int slot, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
               const uint32_t* __restrict__ stamp_z, const float4* __restrict__ mov_pos, const uint64_t* __restrict__ mov_meta,
-              uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks, Counters* __restrict__ cnt) {
-    const FrameParams& f = *fp;
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < f.hash_cap; e += gridDim.x * blockDim.x) {
+              uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks, const uint32_t* __restrict__ entry_list,
+              Counters* __restrict__ cnt) {
+    const FrameParams& f = c_fp[slot];
+    const uint32_t n_entries = cnt->n_move_voxels;
+    for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < n_entries; li += gridDim.x * blockDim.x) {
+        const uint32_t e = entry_list[li];
         const uint32_t v = keys[e];
-        if (v == EMPTY_KEY) continue;
         keys[e] = EMPTY_KEY;
         uint32_t bx, by, bz;
         voxel_to_buffer(f, v, bx, by, bz);
         const uint32_t stamp = slab_stamp(stamp_x, stamp_y, stamp_z, bx, by, bz);
         const size_t base = (size_t)v << f.Pb;
+        const uint32_t hdr = st.hdr[v];
+        uint32_t live = hdr_live(hdr);
         uint32_t* r = ranks + (size_t)e * f.topk;
         uint32_t moved = 0;
         bool full = false;
@@ -901,14 +966,18 @@ k_move_replay(const FrameParams* __restrict__ fp, Store st, const uint32_t* __re
             if (seq == NO_RANK) break;
             r[t] = NO_RANK;
             if (full) continue;
-            const uint32_t s = first_vacant(st, base, f.P, stamp);
+            const uint32_t s = first_vacant(st, base, f.P, live, stamp);
             if (!s) { full = true; continue; }
             const float4 p = mov_pos[seq];
             st.x[base + s] = p.x; st.y[base + s] = p.y; st.z[base + s] = p.z; st.w[base + s] = p.w;
             st.meta[base + s] = mov_meta[seq];
+            live |= 1u << s;
             ++moved;
         }
-        if (moved) atomicAdd(&cnt->n_moved, moved);
+        if (moved) {
+            st.hdr[v] = hdr_ts(hdr) | HDR_MOVABLE | (live << 16);   // moved particles belong to a movable track by construction
+            atomicAdd(&cnt->n_moved, moved);
+        }
     }
 }
 
@@ -916,10 +985,12 @@ k_move_replay(const FrameParams* __restrict__ fp, Store st, const uint32_t* __re
 // store initialisation (mc_ring/operations.h:684-723): everything zero, slot 0 of each voxel = TIMEPTC
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
-k_clear_store(Store st, size_t n_slots, uint32_t slot_mask) {
+k_clear_store(Store st, size_t n_slots, uint32_t slot_bits) {
+    const uint32_t slot_mask = (1u << slot_bits) - 1u;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (size_t)gridDim.x * blockDim.x) {
         st.x[i] = 0.f; st.y[i] = 0.f; st.z[i] = 0.f; st.w[i] = 0.f;
-        st.meta[i] = (i & slot_mask) == 0 ? meta_pack(0, 0, 0, ST_TIMEPTC, 0) : 0ull;
+        if ((i & slot_mask) == 0) { st.meta[i] = meta_pack(0, 0, 0, ST_TIMEPTC, 0); st.hdr[i >> slot_bits] = 0u; }
+        else st.meta[i] = 0ull;
     }
 }
 
@@ -929,12 +1000,15 @@ __global__ void k_fill_u32(uint32_t* p, size_t n, uint32_t value) {
 
 // live particles of one track (device-side ObjectParticleHashMap::indices_map[track].size(), object_layer.h:20-52)
 __global__ void __launch_bounds__(256)
-k_count_track(Store st, size_t n_slots, uint32_t slot_mask, uint32_t track, uint32_t* __restrict__ out) {
+k_count_track(Store st, uint32_t n_voxels, uint32_t slot_bits, uint32_t track, uint32_t* __restrict__ out) {
     uint32_t c = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (size_t)gridDim.x * blockDim.x) {
-        if ((i & slot_mask) == 0) continue;
-        const uint64_t m = st.meta[i];
-        if (meta_status(m) != ST_INVALID && meta_track(m) == track) ++c;
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n_voxels; v += gridDim.x * blockDim.x) {
+        uint32_t live = hdr_live(st.hdr[v]);
+        while (live) {
+            const uint32_t s = __ffs(live) - 1;
+            live &= live - 1;
+            if (meta_track(st.meta[((size_t)v << slot_bits) + s]) == track) ++c;
+        }
     }
     c = __reduce_add_sync(0xffffffffu, c);
     if (lane_id() == 0 && c) atomicAdd(out, c);
