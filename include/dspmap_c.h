@@ -236,6 +236,10 @@ enum {
                                  then stamps x,y,z as u32                                  */
     DSPMAP_DUMP_VOXEL_STATE = 7 /* V i8: -1 unknown, 0 free, 1 occupied, 2 guessed          */
 };
+/* test hook: evaluates the engine's hoisted-reciprocal division (csrc/dspmap_device.cuh InvDiv) against the compiler's
+ * IEEE division on n pseudo-random operand pairs (divisor in [b_lo, b_hi], |dividend| <= a_max) and counts results that
+ * differ in any bit */
+int dspmap_selftest_division(dspmap_t* h, uint64_t n, uint64_t seed, float b_lo, float b_hi, float a_max, uint64_t* mismatches);
 /* copies at most cap bytes to dst (host); *n_bytes = full size of the dump */
 int dspmap_dump(dspmap_t* h, int32_t what, void* dst, size_t cap, size_t* n_bytes);
 

@@ -110,6 +110,7 @@ SYMBOLS = {
     "dspmap_object_particle_count": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_uint32)]),
     "dspmap_comm_unique_id": (C.c_int, [C.c_void_p]),
     "dspmap_comm_init": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dspmap_selftest_division": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_uint64)]),
     "dspmap_dump": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
 }
 

@@ -64,9 +64,6 @@ void inverse4f(const float m[16], float o[16]) {
     for (int k = 0; k < 16; ++k) o[k] = adj[k] / det;
 }
 
-// constant-memory parameter slots (dspmap_device.cuh c_fp): one per live handle
-bool g_slot_used[MAX_HANDLES] = {};
-
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -100,7 +97,6 @@ struct dspmap {
     FrameParams fp{};
     std::string err = "";
     int device = 0;
-    int slot = -1;
     int sm_count = 148;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     uint64_t launches = 0;
@@ -123,7 +119,7 @@ struct dspmap {
     // device: store (allocated for this shard's slabs; pointers are biased so the global particle index applies)
     DevBuf<float> sx, sy, sz, sw;
     DevBuf<uint64_t> smeta;
-    DevBuf<uint32_t> shdr, d_entry_list;
+    DevBuf<uint32_t> shdr, d_entry_list, d_entry_voxel;
     Store st{};
     size_t n_slots_local = 0, slot_lo = 0;
     uint32_t v_local = 0;
@@ -150,18 +146,24 @@ struct dspmap {
     // ordered insertion
     DevBuf<uint32_t> d_keys, d_ranks;
     // object moves
-    DevBuf<uint32_t> d_sel_idx, d_sel_move, d_sel_seq;
+    DevBuf<uint32_t> d_movl_idx, d_movl_seq;
+    DevBuf<uint16_t> d_movl_track, d_mov_mask;
+    DevBuf<uint8_t> d_vstate;
+    DevBuf<float> d_res_w;
+    DevBuf<uint32_t> d_res_tl;
+    DevBuf<uint4> d_blk_cnt, d_blk_off;
+    DevBuf<uint32_t> d_work;
+    uint32_t n_occ_blocks = 0;
+    uint32_t ck_seg_stride = 1;
     DevBuf<float4> d_mov_pos;
     DevBuf<uint64_t> d_mov_meta;
     uint32_t sel_cap = 0;
     // occupancy
-    DevBuf<uint64_t> d_lb_occ, d_lb_sel;
     DevBuf<uint32_t> r_idx, r_free_idx;
     DevBuf<float> r_xyz, r_w, r_free_xyz;
     DevBuf<uint16_t> r_track;
     DevBuf<uint8_t> r_label;
-    DevBuf<int8_t> r_state, d_voxel_state;
-    bool want_state = false;
+    DevBuf<int8_t> r_state;
 
     // pinned staging
     PinBuf<float> p_depth;
@@ -179,6 +181,7 @@ struct dspmap {
     bool host_result_valid = false;
 
     Counters last{};
+    uint32_t n_visible_last = 0;
     dspmap_frame_stats stats{};
     bool profiling = false;
     cudaEvent_t ev[9]{};
@@ -244,31 +247,38 @@ struct dspmap {
     }
 
     void release_all() {
-        sx.release(); sy.release(); sz.release(); sw.release(); smeta.release(); shdr.release(); d_entry_list.release(); d_stamps.release(); d_lut.release(); d_randoms.release();
+        sx.release(); sy.release(); sz.release(); sw.release(); smeta.release(); shdr.release(); d_entry_list.release(); d_entry_voxel.release(); d_stamps.release(); d_lut.release(); d_randoms.release();
         d_static_track.release(); d_static_label.release(); d_fp.release(); d_cnt.release(); d_persist.release(); d_masks.release(); d_moves.release();
         d_depth_in.release(); d_depth_int.release(); d_ck.release(); d_mask_in.release(); d_cloud_pos.release(); d_cloud_meta.release();
         d_pix_count.release(); d_pix_offset.release(); d_scan_block.release(); d_vmask.release(); d_pairs.release(); d_csr_idx.release();
-        d_vis_pix.release(); d_vis_meta.release(); d_vis_pos.release(); d_keys.release(); d_ranks.release(); d_sel_idx.release();
-        d_sel_move.release(); d_sel_seq.release(); d_mov_pos.release(); d_mov_meta.release(); d_lb_occ.release(); d_lb_sel.release();
+        d_vis_pix.release(); d_vis_meta.release(); d_vis_pos.release(); d_keys.release(); d_ranks.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_work.release(); d_mov_pos.release(); d_mov_meta.release();
         r_idx.release(); r_free_idx.release(); r_xyz.release(); r_w.release(); r_free_xyz.release(); r_track.release(); r_label.release();
-        r_state.release(); d_voxel_state.release();
+        r_state.release();
         p_depth.release(); p_masks.release(); p_cnt.release(); p_fp.release(); p_stamps.release(); p_maskdesc.release(); p_moves.release();
         hr_idx.release(); hr_free_idx.release(); hr_xyz.release(); hr_w.release(); hr_free_xyz.release(); hr_track.release(); hr_label.release(); hr_state.release();
         for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (own_stream) { cudaStreamDestroy(own_stream); own_stream = nullptr; }
         stream = nullptr;
-        if (slot >= 0) { g_slot_used[slot] = false; slot = -1; }
     }
 
     int init(const dspmap_config& c);
     int clear_device();
     int apply_params();
-    int run_moves(const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove);
+    int run_moves(const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove, bool scan_remove);
     int frame(const float* d_depth, int rows, int cols, int stride, const dspmap_mask* masks, int n_masks, const double pos[3],
               const double quat[4], const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove,
               int want_free, int pre_decimated);
     int fetch_result_to_host();
 };
+
+// kernels templated on the slot-count bits
+#define DISPATCH_PB(pb, CALL)                                   \
+    switch (pb) {                                               \
+        case 1: { constexpr int PB = 1; CALL; break; }          \
+        case 2: { constexpr int PB = 2; CALL; break; }          \
+        case 3: { constexpr int PB = 3; CALL; break; }          \
+        default: { constexpr int PB = 4; CALL; break; }         \
+    }
 
 // ------------------------------------------------------------------------------------------------------------
 int dspmap::init(const dspmap_config& c) {
@@ -291,9 +301,6 @@ int dspmap::init(const dspmap_config& c) {
     }
     if (c.device < 0 || c.device >= ndev) return fail(DSPMAP_ERR_INVALID_ARG, "device %d of %d", c.device, ndev);
     device = c.device;
-    for (int k = 0; k < MAX_HANDLES && slot < 0; ++k)
-        if (!g_slot_used[k]) { g_slot_used[k] = true; slot = k; }
-    if (slot < 0) return fail(DSPMAP_ERR_CONFIG, "at most %d maps may be alive in one process", MAX_HANDLES);
     CU_TRY(this, cudaSetDevice(device));
     cudaDeviceProp prop;
     CU_TRY(this, cudaGetDeviceProperties(&prop, device));
@@ -343,7 +350,8 @@ int dspmap::init(const dspmap_config& c) {
     slot_lo = ((size_t)f.z_lo << (f.Xb + f.Yb)) << f.Pb;
     CU_TRY(this, sx.alloc(n_slots_local)); CU_TRY(this, sy.alloc(n_slots_local)); CU_TRY(this, sz.alloc(n_slots_local));
     CU_TRY(this, sw.alloc(n_slots_local)); CU_TRY(this, smeta.alloc(n_slots_local));
-    const size_t v_pad = ((size_t)v_local + OCC_TILE - 1) / OCC_TILE * OCC_TILE;   // whole tiles for the per-voxel passes
+    constexpr size_t PAD = OCC_TILE;
+    const size_t v_pad = ((size_t)v_local + PAD - 1) / PAD * PAD;   // whole tiles for the per-voxel passes
     CU_TRY(this, shdr.alloc(v_pad));
     CU_TRY(this, cudaMemset(shdr.p, 0, v_pad * sizeof(uint32_t)));
     st.x = sx.p - slot_lo; st.y = sy.p - slot_lo; st.z = sz.p - slot_lo; st.w = sw.p - slot_lo; st.meta = smeta.p - slot_lo;
@@ -376,7 +384,7 @@ int dspmap::init(const dspmap_config& c) {
     CU_TRY(this, d_vis_meta.alloc(f.vis_cap)); CU_TRY(this, d_vis_pos.alloc(f.vis_cap));
 
     sel_cap = (uint32_t)std::min<size_t>(usable, (size_t)1 << 20);
-    CU_TRY(this, d_sel_idx.alloc(sel_cap)); CU_TRY(this, d_sel_move.alloc(sel_cap)); CU_TRY(this, d_sel_seq.alloc(sel_cap));
+    CU_TRY(this, d_movl_idx.alloc(sel_cap)); CU_TRY(this, d_movl_seq.alloc(sel_cap)); CU_TRY(this, d_movl_track.alloc(sel_cap));
     CU_TRY(this, d_mov_pos.alloc(sel_cap)); CU_TRY(this, d_mov_meta.alloc(sel_cap));
 
     // hash table for ordered insertion: >= 2x the larger candidate population (pixels, moved particles)
@@ -384,14 +392,27 @@ int dspmap::init(const dspmap_config& c) {
     uint32_t cap = 1024, bits = 10;
     while (cap < want) { cap <<= 1; ++bits; }
     f.hash_cap = cap; f.hash_shift = 32 - bits;
-    CU_TRY(this, d_keys.alloc(cap)); CU_TRY(this, d_ranks.alloc((size_t)cap * f.topk)); CU_TRY(this, d_entry_list.alloc(cap));
+    {
+        uint32_t bcap = 1024, bbits = 10;
+        while (bcap < 2 * npix) { bcap <<= 1; ++bbits; }
+        f.birth_hash_cap = bcap; f.birth_hash_shift = 32 - bbits;
+    }
+    CU_TRY(this, d_keys.alloc(cap)); CU_TRY(this, d_ranks.alloc((size_t)cap * f.topk)); CU_TRY(this, d_entry_list.alloc(cap)); CU_TRY(this, d_entry_voxel.alloc(cap));
 
-    CU_TRY(this, d_lb_occ.alloc((v_local + OCC_TILE - 1) / OCC_TILE));
-    CU_TRY(this, d_lb_sel.alloc((v_local + SEL_BLOCK - 1) / SEL_BLOCK));
+    n_occ_blocks = (uint32_t)(v_pad / OCC_TILE);
+    {   // a stride coprime with the number of 32-pixel segments, near the golden ratio of it (k_ck's segment shuffle)
+        const uint32_t n_seg = (uint32_t)(npix + 31) / 32;
+        auto gcd = [](uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; };
+        ck_seg_stride = std::max<uint32_t>(1, (uint32_t)(n_seg * 0.6180339887));
+        while (gcd(ck_seg_stride, n_seg) != 1) ++ck_seg_stride;
+    }
+    CU_TRY(this, d_vstate.alloc(v_pad)); CU_TRY(this, d_res_w.alloc(v_pad)); CU_TRY(this, d_res_tl.alloc(v_pad)); CU_TRY(this, d_mov_mask.alloc(v_pad));
+    CU_TRY(this, d_blk_cnt.alloc(n_occ_blocks)); CU_TRY(this, d_blk_off.alloc(n_occ_blocks)); CU_TRY(this, d_work.alloc(v_pad));
+    CU_TRY(this, cudaMemset(d_vstate.p, 0, v_pad));
     CU_TRY(this, r_idx.alloc(v_local)); CU_TRY(this, r_xyz.alloc(3 * (size_t)v_local)); CU_TRY(this, r_w.alloc(v_local));
     CU_TRY(this, r_track.alloc(v_local)); CU_TRY(this, r_label.alloc(v_local)); CU_TRY(this, r_state.alloc(v_local));
 
-    CU_TRY(this, p_cnt.reserve(1)); CU_TRY(this, p_fp.reserve(1)); CU_TRY(this, p_stamps.reserve(f.NX + f.NY + f.NZ));
+    CU_TRY(this, p_cnt.reserve(1)); CU_TRY(this, p_fp.reserve(1)); CU_TRY(this, p_stamps.reserve(f.NX + f.NY + f.NZ + 1));
     CU_TRY(this, p_maskdesc.reserve(64)); CU_TRY(this, p_moves.reserve(1));
 
     // Gaussian PDF LUT (utils/basic_algorithms.h:403-407, 455-459): (1/sqrt(2*M_PI_2f32)) * exp(-v^2/2), v=(i-10000)*0.001
@@ -420,6 +441,8 @@ int dspmap::clear_device() {
     CU_TRY(this, cudaMemsetAsync(d_pix_count.p, 0, d_pix_count.n * sizeof(uint32_t), stream));
     CU_TRY(this, cudaMemsetAsync(d_pix_offset.p, 0, d_pix_offset.n * sizeof(uint32_t), stream));
     CU_TRY(this, cudaMemsetAsync(d_cnt.p, 0, sizeof(Counters), stream));
+    CU_TRY(this, cudaMemsetAsync(d_persist.p, 0, sizeof(Persist), stream));
+    CU_TRY(this, cudaMemsetAsync(d_vstate.p, 0, d_vstate.n, stream));
     CU_TRY(this, cudaGetLastError());
     CU_TRY(this, cudaStreamSynchronize(stream));
     memset(&last, 0, sizeof last);
@@ -441,7 +464,8 @@ int dspmap::apply_params() {
 }
 
 // moveParticlesInSetsByTransformations + removeObjectByTrackID (mc_ring/operations.h:321-362; object_layer.h:414-425)
-int dspmap::run_moves(const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove) {
+// scan_remove: the movable list no longer describes the store (second phase of a move-then-remove frame)
+int dspmap::run_moves(const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove, bool scan_remove) {
     if (n_moves > MAX_MOVES || n_remove > MAX_MOVES) return fail(DSPMAP_ERR_CAPACITY, "at most %d moves and %d removals per frame", MAX_MOVES, MAX_MOVES);
     MoveTable& mt = *p_moves.p;
     memset(&mt, 0, sizeof mt);
@@ -449,15 +473,20 @@ int dspmap::run_moves(const dspmap_object_move* moves, int n_moves, const int32_
     for (int i = 0; i < n_moves; ++i) { mt.move_track[i] = moves[i].track_id; memcpy(mt.t[i], moves[i].t, 12 * sizeof(float)); }
     for (int i = 0; i < n_remove; ++i) mt.remove_track[i] = remove_tracks[i];
     CU_TRY(this, cudaMemcpyAsync(d_moves.p, &mt, sizeof mt, cudaMemcpyHostToDevice, stream));
-    CU_TRY(this, cudaMemsetAsync(d_lb_sel.p, 0, d_lb_sel.n * sizeof(uint64_t), stream));
-    ++launches; k_select_tracks<<<(unsigned)d_lb_sel.n, SEL_BLOCK, 0, stream>>>(slot, st, d_moves.p, d_sel_idx.p, d_sel_move.p, d_lb_sel.p, d_cnt.p, sel_cap);
-    if (n_moves > 0) {
-        ++launches; k_move_sequence<<<1, 1024, 0, stream>>>(d_cnt.p, d_moves.p, d_sel_move.p, d_sel_seq.p, sel_cap);
-        ++launches; k_move_apply<<<sm_count * 4, 256, 0, stream>>>(slot, d_cnt.p, st, d_moves.p, d_randoms.p, d_persist.p, d_sel_idx.p, d_sel_move.p,
-                                                     d_sel_seq.p, d_mov_pos.p, d_mov_meta.p, d_keys.p, d_ranks.p, d_entry_list.p, sel_cap);
-        ++launches; k_advance_cursor<<<1, 1, 0, stream>>>(d_cnt.p, d_persist.p, rand_n, sel_cap);
-        ++launches; k_move_replay<<<sm_count * 8, 128, 0, stream>>>(slot, st, d_stamps.p, d_stamps.p + fp.NX, d_stamps.p + fp.NX + fp.NY, d_mov_pos.p,
-                                                      d_mov_meta.p, d_keys.p, d_ranks.p, d_entry_list.p, d_cnt.p);
+    const uint32_t* stx = d_stamps.p;
+    const uint32_t* sty = d_stamps.p + fp.NX;
+    const uint32_t* stz = d_stamps.p + fp.NX + fp.NY;
+    if (scan_remove) {
+        ++launches; k_remove_tracks_scan<<<sm_count * 8, 256, 0, stream>>>(fp, st, d_moves.p, d_cnt.p);
+    } else {
+        ++launches; k_move_prepare<<<1, 1024, 0, stream>>>(d_moves.p, d_movl_track.p, d_movl_seq.p, sel_cap, rand_n, d_cnt.p, d_persist.p);
+        ++launches; k_move_apply<<<sm_count * 2, 256, 0, stream>>>(fp, d_cnt.p, st, d_moves.p, d_randoms.p, d_persist.p, d_movl_idx.p, d_movl_track.p,
+                                                             d_movl_seq.p, sel_cap, d_mov_pos.p, d_mov_meta.p, d_keys.p, d_ranks.p, d_entry_list.p);
+        if (n_moves > 0) {
+            DISPATCH_PB(fp.Pb, (k_move_replay<PB><<<sm_count * 2, 128, 0, stream>>>(fp, st, stx, sty, stz, d_keys.p, d_ranks.p, d_entry_list.p, d_entry_voxel.p, d_cnt.p)));
+            ++launches;
+            ++launches; k_move_write<<<sm_count * 2, 256, 0, stream>>>(fp, st, d_mov_pos.p, d_mov_meta.p, d_ranks.p, d_entry_list.p, d_entry_voxel.p, d_cnt.p);
+        }
     }
     CU_TRY(this, cudaGetLastError());
     return DSPMAP_OK;
@@ -513,13 +542,29 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
         const float c2 = ((f.ext[8] * vx + f.ext[9] * vy) + f.ext[10] * vz) + f.ext[11] * 1.0f;
         f.start_in = !(c2 < f.depth_min || c2 > f.depth_max) && !(std::abs(c0) > c2 * f.tan_hx) && !(std::abs(c1) > c2 * f.tan_hy);
     }
+    // conservative bounding box of the frustum in lattice-vertex indices: its 8 corners in the map frame, +-2 vertices
+    {
+        float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+        for (int k = 0; k < 8; ++k) {
+            const float z = (k & 1) ? f.depth_max : f.depth_min;
+            const float x = ((k & 2) ? 1.f : -1.f) * z * f.tan_hx, y = ((k & 4) ? 1.f : -1.f) * z * f.tan_hy;
+            for (int a = 0; a < 3; ++a) {
+                const float g = inv_ext[a * 4 + 0] * x + inv_ext[a * 4 + 1] * y + inv_ext[a * 4 + 2] * z + inv_ext[a * 4 + 3];
+                const float vi = (g - f.vox_off[a]) * f.voxel_recip;
+                lo[a] = std::min(lo[a], vi); hi[a] = std::max(hi[a], vi);
+            }
+        }
+        for (int a = 0; a < 3; ++a) {
+            f.vb_lo[a] = std::max(0, (int)std::floor(lo[a]) - 2);
+            f.vb_hi[a] = std::min((int)axis_n(a), (int)std::ceil(hi[a]) + 2);
+        }
+    }
     f.n_masks = n_masks;
     f.max_movable = max_movable; f.sky_track = sky_track;
-    f.want_free = want_free ? 1 : 0; f.want_state = want_state ? 1 : 0;
+    f.want_free = want_free ? 1 : 0; f.want_state = 0;
     f.rand_n = rand_n;
 
     if (want_free && !r_free_idx.p) { CU_TRY(this, r_free_idx.alloc(v_local)); CU_TRY(this, r_free_xyz.alloc(3 * (size_t)v_local)); }
-    if (want_state && !d_voxel_state.p) CU_TRY(this, d_voxel_state.alloc(((size_t)v_local + OCC_TILE - 1) / OCC_TILE * OCC_TILE));
 
     // ---- uploads -------------------------------------------------------------------------------------------
     if ((size_t)n_masks > d_masks.n) { CU_TRY(this, d_masks.alloc(n_masks)); }
@@ -531,8 +576,6 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
         for (int a = 0; a < 3; ++a) { md.bbox_min[a] = masks[m].bbox_min[a]; md.bbox_max[a] = masks[m].bbox_max[a]; }
     }
     if (n_masks) CU_TRY(this, cudaMemcpyAsync(d_masks.p, p_maskdesc.p, n_masks * sizeof(MaskDesc), cudaMemcpyHostToDevice, stream));
-    *p_fp.p = f;
-    CU_TRY(this, cudaMemcpyToSymbolAsync(c_fp, p_fp.p, sizeof(FrameParams), (size_t)slot * sizeof(FrameParams), cudaMemcpyHostToDevice, stream));
     if (stamps_dirty) {
         uint32_t* s = p_stamps.p;
         for (int a = 0; a < 3; ++a) { memcpy(s, stamps[a].data(), stamps[a].size() * 4); s += stamps[a].size(); }
@@ -540,7 +583,6 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
         stamps_dirty = false;
     }
     CU_TRY(this, cudaMemsetAsync(d_cnt.p, 0, sizeof(Counters), stream));
-    CU_TRY(this, cudaMemsetAsync(d_lb_occ.p, 0, d_lb_occ.n * sizeof(uint64_t), stream));
     const uint32_t* stx = d_stamps.p;
     const uint32_t* sty = d_stamps.p + f.NX;
     const uint32_t* stz = d_stamps.p + f.NX + f.NY;
@@ -549,7 +591,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
 
     if (profiling) cudaEventRecord(ev[0], stream);
     // ---- K1 projection ---------------------------------------------------------------------------------------
-    ++launches; k_project<<<(npix + 255) / 256, 256, 0, stream>>>(slot, d_depth, stride, d_masks.p, d_static_track.p, d_static_label.p,
+    ++launches; k_project<<<(npix + 255) / 256, 256, 0, stream>>>(fp, d_depth, stride, d_masks.p, d_static_track.p, d_static_label.p,
                                                      d_depth_int.p, d_cloud_pos.p, d_cloud_meta.p, d_cnt.p);
     if (profiling) { cudaEventRecord(ev[1], stream); cudaEventRecord(ev[2], stream); }
     // ---- P2/P3 object predict / prune ---------------------------------------------------------------------------
@@ -561,50 +603,66 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
             for (int k = 0; k < n_moves; ++k) also_moved |= moves[k].track_id == remove_tracks[i];
             (also_moved ? rm_after : rm_now).push_back(remove_tracks[i]);
         }
-        int rc = run_moves(moves, n_moves, rm_now.data(), (int)rm_now.size());
+        int rc = run_moves(moves, n_moves, rm_now.data(), (int)rm_now.size(), false);
         if (rc != DSPMAP_OK) return rc;
         if (!rm_after.empty()) {
             CU_TRY(this, cudaStreamSynchronize(stream));   // the move table staging buffer is reused
-            CU_TRY(this, cudaMemsetAsync(&d_cnt.p->ticket_sel, 0, sizeof(uint32_t), stream));
-            rc = run_moves(nullptr, 0, rm_after.data(), (int)rm_after.size());
+            rc = run_moves(nullptr, 0, rm_after.data(), (int)rm_after.size(), true);
             if (rc != DSPMAP_OK) return rc;
         }
     }
     if (profiling) cudaEventRecord(ev[3], stream);
     // ---- U2 visibility ---------------------------------------------------------------------------------------------
     if (f.start_in) {
-        ++launches; k_vertex_mask<<<(n_vwords * 32 + 255) / 256, 256, 0, stream>>>(slot, d_vmask.p, words_per_row, n_vwords);
-        ++launches; k_sweep<<<(v_local + 255) / 256, 256, 0, stream>>>(slot, st, stx, sty, stz, d_vmask.p, words_per_row, d_depth_int.p,
-                                                         d_pix_count.p, d_pairs.p, d_cnt.p);
+        const int y0 = std::max(f.vb_lo[1] - 1, 0), y1 = std::min(f.vb_hi[1] + 1, (int)f.NY);
+        const int z0 = std::max(f.vb_lo[2] - 1, 0), z1 = std::min(f.vb_hi[2] + 1, (int)f.NZ);
+        ++launches; k_vertex_mask<<<dim3((words_per_row * 32 + 255) / 256, (y1 - y0 + 1) * (z1 - z0 + 1)), 256, 0, stream>>>(fp, d_vmask.p, words_per_row, y0, y1 - y0 + 1, z0);
+        ++launches; k_sweep_select<<<(v_local + 255) / 256, 256, 0, stream>>>(fp, st, d_vmask.p, words_per_row, d_depth_int.p, d_work.p, d_cnt.p);
+        DISPATCH_PB(f.Pb, (k_sweep_slots<PB><<<sm_count * 8, 256, 0, stream>>>(fp, st, stx, sty, stz, d_work.p, d_depth_int.p, d_pix_count.p, d_pairs.p, d_cnt.p)));
+        ++launches;
     }
     const int nsb = (npix + SCAN_BLOCK - 1) / SCAN_BLOCK;
     ++launches; k_scan_blocksum<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p);
     ++launches; k_scan_apply<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p, d_pix_offset.p);
-    ++launches; k_fill<<<sm_count * 4, 256, 0, stream>>>(slot, d_cnt.p, d_pairs.p, d_pix_offset.p, d_pix_count.p, d_csr_idx.p, d_vis_pix.p);
-    ++launches; k_sort_lists<<<(npix + 255) / 256, 256, 0, stream>>>(slot, d_pix_offset.p, d_csr_idx.p);
-    ++launches; k_gather_visible<<<sm_count * 4, 256, 0, stream>>>(slot, d_cnt.p, st, d_csr_idx.p, d_vis_pos.p, d_vis_meta.p);
+    ++launches; k_fill<<<sm_count * 4, 256, 0, stream>>>(fp, d_cnt.p, d_pairs.p, d_pix_offset.p, d_pix_count.p, d_csr_idx.p, d_vis_pix.p);
+    ++launches; k_sort_lists<<<(npix + 255) / 256, 256, 0, stream>>>(fp, d_pix_offset.p, d_csr_idx.p);
+    ++launches; k_gather_visible<<<sm_count * 4, 256, 0, stream>>>(fp, d_pix_offset.p + npix, st, d_csr_idx.p, d_vis_pos.p, d_vis_meta.p);
     if (profiling) cudaEventRecord(ev[4], stream);
     // ---- U3 weight update --------------------------------------------------------------------------------------------
-    ++launches; k_ck<<<sm_count * 2, 512, lut_bytes, stream>>>(slot, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_pix_offset.p, d_vis_pos.p, d_vis_meta.p, d_ck.p);
-    ++launches; k_weight_update<<<sm_count * 2, 512, lut_bytes, stream>>>(slot, d_cnt.p, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_ck.p, d_csr_idx.p,
+    ++launches; k_ck<<<sm_count * 2, 1024, lut_bytes, stream>>>(fp, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_pix_offset.p, d_vis_pos.p, d_vis_meta.p, d_ck.p, ck_seg_stride);
+    ++launches; k_weight_update<<<sm_count * 2, 1024, lut_bytes, stream>>>(fp, d_pix_offset.p + npix, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_ck.p, d_csr_idx.p,
                                                              d_vis_pix.p, d_vis_pos.p, d_vis_meta.p, st);
     if (profiling) cudaEventRecord(ev[5], stream);
     // ---- B1 birth + resample -----------------------------------------------------------------------------------------
-    ++launches; k_birth_bin<<<(npix + 255) / 256, 256, 0, stream>>>(slot, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_entry_list.p, d_cnt.p);
-    ++launches; k_birth_replay<<<sm_count * 8, 128, 0, stream>>>(slot, st, stx, sty, stz, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_entry_list.p, d_cnt.p);
+    {
+        const int n_ranks = 9 * ((f.H + 2) / 3) * ((f.W + 2) / 3);
+        ++launches; k_birth_bin<<<(n_ranks + 255) / 256, 256, 0, stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_entry_list.p, d_cnt.p);
+        DISPATCH_PB(f.Pb, (k_birth_replay<PB><<<sm_count * 4, 128, 0, stream>>>(fp, st, stx, sty, stz, d_keys.p, d_ranks.p, d_entry_list.p, d_entry_voxel.p, d_cnt.p)));
+        ++launches;
+        ++launches; k_birth_write<<<sm_count * 8, 256, 0, stream>>>(fp, st, d_cloud_pos.p, d_cloud_meta.p, d_ranks.p, d_entry_list.p, d_entry_voxel.p, d_cnt.p);
+    }
     if (profiling) cudaEventRecord(ev[6], stream);
     // ---- O1 occupancy -------------------------------------------------------------------------------------------------
     ResultArrays out{r_idx.p, r_xyz.p, r_w.p, r_track.p, r_label.p, r_state.p, r_free_idx.p, r_free_xyz.p};
-    ++launches; k_occupancy<<<(unsigned)d_lb_occ.n, OCC_BLOCK, 0, stream>>>(slot, st, stx, sty, stz, out, d_voxel_state.p, d_lb_occ.p, d_cnt.p);
+    OccScratch osc{d_vstate.p, d_res_w.p - (slot_lo >> f.Pb), d_res_tl.p - (slot_lo >> f.Pb), d_mov_mask.p - (slot_lo >> f.Pb), d_blk_cnt.p, d_blk_off.p};
+    DISPATCH_PB(f.Pb, (k_occ_headers<PB><<<n_occ_blocks, OCC_BLOCK, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, d_cnt.p)));
+    ++launches;
+    DISPATCH_PB(f.Pb, (k_occ_slots<PB><<<sm_count * 8, 256, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, d_cnt.p)));
+    ++launches;
+    ++launches; k_occ_scan<<<1, 1024, 0, stream>>>(osc, n_occ_blocks, d_cnt.p, d_persist.p);
+    DISPATCH_PB(f.Pb, (k_occ_emit<PB><<<n_occ_blocks, OCC_BLOCK, 0, stream>>>(fp, st, osc, out, d_movl_idx.p, d_movl_track.p, sel_cap)));
+    ++launches;
     if (profiling) cudaEventRecord(ev[7], stream);
     CU_TRY(this, cudaMemcpyAsync(p_cnt.p, d_cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+    CU_TRY(this, cudaMemcpyAsync(p_stamps.p + (f.NX + f.NY + f.NZ), d_pix_offset.p + npix, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     CU_TRY(this, cudaGetLastError());
     CU_TRY(this, cudaStreamSynchronize(stream));
     last = *p_cnt.p;
 
     stats.time_stamp = T;
     stats.n_swept_voxels = last.n_swept_voxels; stats.n_swept_nonempty = last.n_swept_nonempty;
-    stats.n_visible = std::min(last.n_pairs, f.vis_cap); stats.n_valid_points = last.n_valid_points;
+    n_visible_last = p_stamps.p[f.NX + f.NY + f.NZ];
+    stats.n_visible = n_visible_last; stats.n_valid_points = last.n_valid_points;
     stats.n_born = last.n_born; stats.n_birth_voxels = last.n_birth_voxels; stats.n_resampled = last.n_resampled;
     stats.n_occupied = last.n_occupied; stats.n_nonempty_voxels = last.n_nonempty_voxels;
     stats.n_moved = last.n_moved; stats.n_removed = last.n_removed;
@@ -613,7 +671,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
         cudaEventElapsedTime(&stats.ms_stage[7], ev[0], ev[7]);
     }
     if (last.n_pairs > f.vis_cap) return fail(DSPMAP_ERR_CAPACITY, "visible-particle list overflow: %u > max_visible %u", last.n_pairs, f.vis_cap);
-    if (last.n_selected > sel_cap) return fail(DSPMAP_ERR_CAPACITY, "moved-particle list overflow: %u > %u", last.n_selected, sel_cap);
+    if (last.n_movable > sel_cap) return fail(DSPMAP_ERR_CAPACITY, "movable-particle list overflow: %u > %u", last.n_movable, sel_cap);
     if (last.hash_overflow) return fail(DSPMAP_ERR_CAPACITY, "insertion hash table overflow");
     return DSPMAP_OK;
 }
@@ -860,6 +918,21 @@ int dspmap_comm_init(dspmap_t* h, const uint8_t id[DSPMAP_COMM_ID_BYTES]) {
     return h->fail(DSPMAP_ERR_UNSUPPORTED, "sharded maps are not implemented yet");
 }
 
+int dspmap_selftest_division(dspmap_t* h, uint64_t n, uint64_t seed, float b_lo, float b_hi, float a_max, uint64_t* mismatches) {
+    if (!h || !mismatches) return DSPMAP_ERR_INVALID_ARG;
+    CU_TRY(h, cudaSetDevice(h->device));
+    unsigned long long* d = nullptr;
+    CU_TRY(h, cudaMalloc(&d, sizeof(unsigned long long)));
+    CU_TRY(h, cudaMemsetAsync(d, 0, sizeof(unsigned long long), h->stream));
+    k_selftest_invdiv<<<h->sm_count * 8, 256, 0, h->stream>>>(n, seed, b_lo, b_hi, a_max, d);
+    unsigned long long out = 0;
+    CU_TRY(h, cudaMemcpyAsync(&out, d, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d);
+    *mismatches = out;
+    return DSPMAP_OK;
+}
+
 int dspmap_dump(dspmap_t* h, int32_t what, void* dst, size_t cap, size_t* n_bytes) {
     if (!h) return DSPMAP_ERR_INVALID_ARG;
     CU_TRY(h, cudaSetDevice(h->device));
@@ -906,7 +979,7 @@ int dspmap_dump(dspmap_t* h, int32_t what, void* dst, size_t cap, size_t* n_byte
             CU_TRY(h, pull(tmp.data(), h->d_pix_offset.p, tmp.size()));
             break;
         case DSPMAP_DUMP_PIXEL_LISTS: {
-            const size_t n = std::min(h->last.n_pairs, f.vis_cap);
+            const size_t n = h->n_visible_last;
             tmp.resize(n * 4);
             if (n) CU_TRY(h, pull(tmp.data(), h->d_csr_idx.p, tmp.size()));
             break;
@@ -922,11 +995,12 @@ int dspmap_dump(dspmap_t* h, int32_t what, void* dst, size_t cap, size_t* n_byte
             for (int a = 0; a < 3; ++a) { memcpy(wp, h->stamps[a].data(), h->stamps[a].size() * 4); wp += h->stamps[a].size() * 4; }
             break;
         }
-        case DSPMAP_DUMP_VOXEL_STATE:
-            // the per-voxel state plane is only written once it has been asked for: the first call enables it
-            if (!h->want_state) { h->want_state = true; tmp.assign(h->v_local, (uint8_t)0x80); }
-            else { tmp.resize(h->v_local); if (h->d_voxel_state.p) CU_TRY(h, pull(tmp.data(), h->d_voxel_state.p, tmp.size())); }
+        case DSPMAP_DUMP_VOXEL_STATE: {
+            tmp.resize(h->v_local);
+            CU_TRY(h, pull(tmp.data(), h->d_vstate.p, tmp.size()));
+            for (auto& b8 : tmp) b8 = (uint8_t)(int8_t)((int)(b8 & 3u) - 1);   // state byte -> -1 unknown, 0 free, 1 occupied, 2 guessed
             break;
+        }
         default:
             return h->fail(DSPMAP_ERR_INVALID_ARG, "unknown dump %d", what);
     }

@@ -26,17 +26,20 @@ struct Counters {
     uint32_t n_removed;
     uint32_t n_selected;       // particles selected by the object-move collection
     uint32_t n_move_voxels;    // also the length of the move entry list
-    uint32_t ticket_occ;       // dynamic block ids for the ordered compactions
-    uint32_t ticket_sel;
+    uint32_t n_movable;        // live particles of movable tracks listed by the occupancy pass
+    uint32_t move_cursor0;     // random-table cursor the object moves of this frame start from
     uint32_t hash_overflow;    // insertion hash table full (cannot happen with cap >= 2 * candidates)
     uint32_t scratch;
-    uint32_t pad[2];
+    uint32_t n_sweep_work;     // swept voxels with live slots (work list of the slot pass)
+    uint32_t n_occ_work;       // voxels whose occupancy needs the slot records
+    uint32_t ck_ticket;        // dynamic segment scheduler of the ck pass
 };
 
 // survives across frames
 struct Persist {
     uint32_t cursor_ring;      // RingBufferOperations::gaussian_random_calculator_ cursor (operations.h:1460)
     uint32_t cursor_map;       // SemanticDSPMap::gaussian_random_ cursor (semantic_dsp_map.h:265)
+    uint32_t n_movable;        // length of the movable-particle list left by the last occupancy pass
 };
 
 struct Store {
@@ -53,11 +56,10 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 // one thread per internal pixel; double-precision back-projection, float narrowing at the end.
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
-k_project(int slot, const float* __restrict__ depth, int depth_stride, const MaskDesc* __restrict__ masks,
+k_project(const __grid_constant__ FrameParams f, const float* __restrict__ depth, int depth_stride, const MaskDesc* __restrict__ masks,
           const uint16_t* __restrict__ lut_static_track, const uint8_t* __restrict__ lut_static_label,
           float* __restrict__ depth_int, float4* __restrict__ cloud_pos, uint32_t* __restrict__ cloud_meta,
           Counters* __restrict__ cnt) {
-    const FrameParams& f = c_fp[slot];
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = false;
     if (q < f.W * f.H) {
@@ -126,124 +128,201 @@ k_project(int slot, const float* __restrict__ depth, int depth_stride, const Mas
 // =====================================================================================================
 // U2a  vertex_mask    the "is this lattice vertex inside the frustum" predicate of the BFS
 //                     (mc_ring/operations.h:1336-1338, isPointInFrustum :1240-1258), one bit per vertex.
-// one warp per 32 consecutive x vertices; rows are (z, y) in MAP coordinates.
+// one warp per 32 consecutive x vertices; blockIdx.y = row (z, y) in MAP coordinates.  Vertices outside the
+// host-computed bounding box of the frustum (conservative, in vertex indices) are written as 0 without the test.
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
-k_vertex_mask(int slot, uint32_t* __restrict__ vmask, uint32_t words_per_row, uint32_t n_words) {
-    const FrameParams& f = c_fp[slot];
-    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= n_words) return;
-    const uint32_t row = w / words_per_row, xw = w - row * words_per_row;
-    const uint32_t z = row / (f.NY + 1), y = row - z * (f.NY + 1);
+k_vertex_mask(const __grid_constant__ FrameParams f, uint32_t* __restrict__ vmask, uint32_t words_per_row, int y0, int ny, int z0) {
+    // blockIdx.y enumerates the (y, z) rows of the bounding box grown by one vertex (what k_sweep_select may read)
+    const uint32_t xw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (xw >= words_per_row) return;
+    const uint32_t z = (uint32_t)z0 + blockIdx.y / (uint32_t)ny, y = (uint32_t)y0 + blockIdx.y % (uint32_t)ny;
+    const uint32_t row = z * (f.NY + 1) + y;
     const uint32_t x = xw * 32 + lane_id();
     bool in = false;
-    if (x <= f.NX)
+    if (x <= f.NX && (int)x >= f.vb_lo[0] && (int)x <= f.vb_hi[0] && (int)y >= f.vb_lo[1] && (int)y <= f.vb_hi[1] && (int)z >= f.vb_lo[2] && (int)z <= f.vb_hi[2])
         in = point_in_frustum(f, (float)(int)x * f.voxel + f.vox_off[0], (float)(int)y * f.voxel + f.vox_off[1], (float)(int)z * f.voxel + f.vox_off[2]);
     const uint32_t bits = __ballot_sync(0xffffffffu, in);
-    if (lane_id() == 0) vmask[w] = bits;
+    if (lane_id() == 0) vmask[(size_t)row * words_per_row + xw] = bits;
 }
 
 __device__ __forceinline__ bool vbit(const uint32_t* __restrict__ vmask, uint32_t wpr, uint32_t NYp1, uint32_t x, uint32_t y, uint32_t z) {
     return (__ldg(vmask + (size_t)(z * NYp1 + y) * wpr + (x >> 5)) >> (x & 31u)) & 1u;
 }
 
+// ---- warp work queue: P-lane groups take the voxels that need slot-level work ---------------------------------
+// `need` marks the lanes whose voxel needs it.  Each step hands the next G = 32/P such voxels to the G groups of the
+// warp: lane = g*P + s works on slot s of the voxel owned by lane `src` (0xffffffff: group idle this step).
+template <int P>
+struct GroupQueue {
+    static constexpr int G = 32 / P;
+    uint32_t pending;
+    __device__ __forceinline__ explicit GroupQueue(bool need) : pending(__ballot_sync(0xffffffffu, need)) {}
+    __device__ __forceinline__ bool next(uint32_t& src) {
+        if (!pending) return false;
+        src = __fns(pending, 0, (int)(lane_id() / P) + 1);
+#pragma unroll
+        for (int i = 0; i < G; ++i) pending &= pending - 1;
+        return true;
+    }
+};
+template <int P> __device__ __forceinline__ uint32_t group_mask() { return (P == 32 ? 0xffffffffu : ((1u << P) - 1u)) << ((lane_id() / P) * P); }
+
 // =====================================================================================================
 // U2b  sweep          replaces getIdxOfVisibleParitlces minus its queue (mc_ring/operations.h:1344-1435)
-// one thread per storage voxel of this shard.  A voxel is swept when one of its 8 corner vertices is in the
-// frustum.  The header word says which slots are live, so an empty voxel costs 4 bytes.  Swept particles are:
-// invalidated when stale, reset to the newborn weight under a too-far depth pixel, skipped when occluded,
-// otherwise appended as a (pixel, particle) pair and counted per pixel.
+// Two launches.
+//   select : one thread per storage voxel of this shard decides "swept" (one of the 8 corner vertices in the frustum)
+//            and reads the 4-byte header.  Empty swept voxels are finished on the spot (corner visibility test,
+//            :1418-1431); swept voxels with live slots are appended to a work list (order is irrelevant: the pixel
+//            lists are sorted afterwards).
+//   slots  : one P-lane group per listed voxel, lane s = slot s (coalesced 8 B tail + 3 x 4 B position per lane):
+//            invalidate when stale, reset to the newborn weight under a too-far depth pixel, skip when occluded,
+//            otherwise append a (pixel, particle) pair (one atomic per warp) and count it per pixel.
 // =====================================================================================================
+__device__ __forceinline__ bool corner_visible(const FrameParams& f, const float* __restrict__ depth_int, uint32_t cmx, uint32_t cmy, uint32_t cmz) {
+    const float gx = (float)(int)cmx * f.voxel + f.pmin[0] + f.map_center[0];   // mapXYZIdxToGlobalPose, operations.h:986-991
+    const float gy = (float)(int)cmy * f.voxel + f.pmin[1] + f.map_center[1];
+    const float gz = (float)(int)cmz * f.voxel + f.pmin[2] + f.map_center[2];
+    int row, col;
+    float cz;
+    if (project_to_image(f, gx, gy, gz, row, col, cz)) return cz <= __ldg(depth_int + row * f.W + col);
+    return false;
+}
+
 __global__ void __launch_bounds__(256)
-k_sweep(int slot, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
-        const uint32_t* __restrict__ stamp_z, const uint32_t* __restrict__ vmask, uint32_t words_per_row,
-        const float* __restrict__ depth_int, uint32_t* __restrict__ pix_count, uint2* __restrict__ pairs,
-        Counters* __restrict__ cnt) {
-    const FrameParams& f = c_fp[slot];
+k_sweep_select(const __grid_constant__ FrameParams f, Store st, const uint32_t* __restrict__ vmask, uint32_t words_per_row,
+               const float* __restrict__ depth_int, uint32_t* __restrict__ work, Counters* __restrict__ cnt) {
     const uint32_t v_lo = f.z_lo << (f.Xb + f.Yb), v_hi = f.z_hi << (f.Xb + f.Yb);
     const uint32_t v = v_lo + blockIdx.x * blockDim.x + threadIdx.x;
     bool swept = false;
-    uint32_t bx = 0, by = 0, bz = 0, mx = 0, my = 0, mz = 0;
+    uint32_t mx = 0, my = 0, mz = 0;
     if (v < v_hi) {
+        uint32_t bx, by, bz;
         voxel_to_buffer(f, v, bx, by, bz);
         buffer_to_map(f, bx, by, bz, mx, my, mz);
-        const uint32_t nyp = f.NY + 1;
+        // a voxel's vertices are m..m+1 per axis: outside the frustum's vertex bounding box nothing can be set
+        if ((int)mx + 1 >= f.vb_lo[0] && (int)mx <= f.vb_hi[0] && (int)my + 1 >= f.vb_lo[1] && (int)my <= f.vb_hi[1] &&
+            (int)mz + 1 >= f.vb_lo[2] && (int)mz <= f.vb_hi[2]) {
+            const uint32_t nyp = f.NY + 1;
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
-            for (int b = 0; b < 2; ++b)
+                for (int b = 0; b < 2; ++b)
 #pragma unroll
-                for (int a = 0; a < 2; ++a) swept |= vbit(vmask, words_per_row, nyp, mx + a, my + b, mz + c);
+                    for (int a = 0; a < 2; ++a) swept |= vbit(vmask, words_per_row, nyp, mx + a, my + b, mz + c);
+        }
     }
-    if (!__any_sync(0xffffffffu, swept)) return;
-
-    const size_t base = (size_t)v << f.Pb;
+    __shared__ uint32_t s_swept, s_heavy, s_base;
+    if (threadIdx.x == 0) { s_swept = 0; s_heavy = 0; }
     const uint32_t hdr = swept ? st.hdr[v] : 0u;
-    uint32_t todo = hdr_live(hdr), live = todo;
-    const uint32_t stamp = todo ? slab_stamp(stamp_x, stamp_y, stamp_z, bx, by, bz) : 0u;
-    int nvalid = 0;
-    bool observed = false;
-    while (__any_sync(0xffffffffu, todo != 0)) {
-        bool emit = false;
-        uint32_t pix = 0, s = 0;
-        if (todo) {
-            s = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint64_t m = st.meta[base + s];
-            if (meta_ts(m) < stamp) {
-                st.meta[base + s] = meta_with_status(m, ST_INVALID);  // :1374-1378 outdated by the ring shift
-                live &= ~(1u << s);
+    const bool heavy = swept && hdr_live(hdr) != 0;
+    if (swept && !heavy) {
+        if (corner_visible(f, depth_int, mx, my, mz)) st.hdr[v] = (f.T & 0xffffu) | (hdr & HDR_MOVABLE);
+    }
+    __syncthreads();
+    // one pair of global atomics per block: position of this block's heavy voxels in the work list
+    const uint32_t b_swept = __ballot_sync(0xffffffffu, swept), b_heavy = __ballot_sync(0xffffffffu, heavy);
+    uint32_t woff = 0;
+    if (lane_id() == 0) {
+        if (b_swept) atomicAdd(&s_swept, (uint32_t)__popc(b_swept));
+        if (b_heavy) woff = atomicAdd(&s_heavy, (uint32_t)__popc(b_heavy));
+    }
+    woff = __shfl_sync(0xffffffffu, woff, 0);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_swept) atomicAdd(&cnt->n_swept_voxels, s_swept);
+        s_base = s_heavy ? atomicAdd(&cnt->n_sweep_work, s_heavy) : 0u;
+    }
+    __syncthreads();
+    if (heavy) work[s_base + woff + __popc(b_heavy & ((1u << lane_id()) - 1u))] = v;
+}
+
+template <int PB>
+__global__ void __launch_bounds__(256)
+k_sweep_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
+              const uint32_t* __restrict__ stamp_z, const uint32_t* __restrict__ work, const float* __restrict__ depth_int,
+              uint32_t* __restrict__ pix_count, uint2* __restrict__ pairs, Counters* __restrict__ cnt) {
+    constexpr int P = 1 << PB, G = 32 / P;
+    const uint32_t n_work = cnt->n_sweep_work;
+    const uint32_t s = lane_id() & (P - 1), g = lane_id() / P, gbase = lane_id() & ~(uint32_t)(P - 1);
+    const uint32_t gmask = group_mask<P>();
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t n_nonempty = 0;
+    // the pair list is reserved PAIR_CHUNK entries at a time per warp; unused tails are filled with a sentinel pixel
+    constexpr uint32_t PAIR_CHUNK = 128;
+    uint32_t chunk_base = 0, chunk_used = PAIR_CHUNK;
+    for (uint32_t w0 = warp * G; w0 < n_work; w0 += n_warps * G) {     // warp-uniform trip count
+        const uint32_t wi = w0 + g;
+        const bool active = wi < n_work;
+        const uint32_t g_v = active ? work[wi] : 0u;
+        const uint32_t g_hdr = active ? st.hdr[g_v] : 0u;
+        const size_t base = (size_t)g_v << PB;
+        const bool has = active && s != 0 && ((g_hdr >> (16 + s)) & 1u);
+        uint64_t m = 0;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (has) { m = st.meta[base + s]; x = st.x[base + s]; y = st.y[base + s]; z = st.z[base + s]; }
+        uint32_t bx, by, bz;
+        voxel_to_buffer(f, g_v, bx, by, bz);
+        const uint32_t stamp = slab_stamp(stamp_x, stamp_y, stamp_z, bx, by, bz);
+        const bool stale = has && meta_ts(m) < stamp;
+        const bool counted = has && !stale;
+        bool observed = false, emit = false;
+        uint32_t pix = 0;
+        if (stale) st.meta[base + s] = meta_with_status(m, ST_INVALID);  // :1374-1378 outdated by the ring shift
+        int row, col;
+        float cz;
+        if (counted && project_to_image(f, x, y, z, row, col, cz)) {
+            const float d = __ldg(depth_int + row * f.W + col);
+            if (d > f.depth_max) {                 // :1389-1395 free space seen through this pixel
+                st.w[base + s] = OCC_INIT_WEIGHT;
+                observed = true;
+            } else if (cz > d * ONE_SIGMA_COEFF) {  // :1397-1400 occluded
             } else {
-                ++nvalid;
-                int row, col;
-                float cz;
-                if (project_to_image(f, st.x[base + s], st.y[base + s], st.z[base + s], row, col, cz)) {
-                    const float d = __ldg(depth_int + row * f.W + col);
-                    if (d > f.depth_max) {             // :1389-1395 free space seen through this pixel
-                        st.w[base + s] = OCC_INIT_WEIGHT;
-                        observed = true;
-                    } else if (cz > d * ONE_SIGMA_COEFF) {  // :1397-1400 occluded
-                    } else {
-                        observed = true;
-                        emit = true;
-                        pix = (uint32_t)(row * f.W + col);
-                    }
-                }
+                observed = true;
+                emit = true;
+                pix = (uint32_t)(row * f.W + col);
             }
         }
-        const uint32_t bal = __ballot_sync(0xffffffffu, emit);
-        if (bal) {
-            uint32_t off = 0;
-            const uint32_t leader = __ffs(bal) - 1;
-            if (lane_id() == leader) off = atomicAdd(&cnt->n_pairs, (uint32_t)__popc(bal));
-            off = __shfl_sync(0xffffffffu, off, leader);
+        const uint32_t b_stale = __ballot_sync(0xffffffffu, stale), b_cnt = __ballot_sync(0xffffffffu, counted);
+        const uint32_t b_obs = __ballot_sync(0xffffffffu, observed), b_emit = __ballot_sync(0xffffffffu, emit);
+        if (b_emit) {
+            const uint32_t ne = __popc(b_emit);
+            if (chunk_used + ne > PAIR_CHUNK) {                      // warp-uniform: retire the chunk, reserve a new one
+                for (uint32_t k = chunk_used + lane_id(); k < PAIR_CHUNK; k += 32)
+                    if (chunk_base + k < f.vis_cap) pairs[chunk_base + k] = make_uint2(0xffffffffu, 0u);
+                uint32_t nb = 0;
+                if (lane_id() == 0) nb = atomicAdd(&cnt->n_pairs, PAIR_CHUNK);
+                chunk_base = __shfl_sync(0xffffffffu, nb, 0);
+                chunk_used = 0;
+            }
             if (emit) {
-                const uint32_t pos = off + __popc(bal & ((1u << lane_id()) - 1u));
+                const uint32_t pos = chunk_base + chunk_used + __popc(b_emit & ((1u << lane_id()) - 1u));
                 if (pos < f.vis_cap) {
                     pairs[pos] = make_uint2(pix, (uint32_t)(base + s));
                     atomicAdd(pix_count + pix, 1u);
                 }
             }
+            chunk_used += ne;
+        }
+        if (active && s == 0) {                                     // group leader: the voxel's header
+            const bool g_observed = (b_obs & gmask) != 0;
+            const uint32_t g_nvalid = __popc(b_cnt & gmask);
+            const uint32_t new_live = hdr_live(g_hdr) & ~((b_stale & gmask) >> gbase);
+            bool stamp0 = g_observed;                                // :1415-1417
+            if (!g_observed && g_nvalid == 0) {                      // every live slot was stale: the empty-voxel rule applies
+                uint32_t gmx, gmy, gmz;
+                buffer_to_map(f, bx, by, bz, gmx, gmy, gmz);
+                stamp0 = corner_visible(f, depth_int, gmx, gmy, gmz);
+            }
+            const uint32_t nh = (stamp0 ? (f.T & 0xffffu) : hdr_ts(g_hdr)) | (g_hdr & HDR_MOVABLE) | (new_live << 16);
+            if (nh != g_hdr) st.hdr[g_v] = nh;
+            n_nonempty += g_nvalid > 0;
         }
     }
-    if (swept) {
-        bool stamp0 = observed;                                    // :1415-1417
-        if (!observed && nvalid == 0) {                            // :1418-1431 imaginary particle at the voxel's min corner
-            const float gx = (float)(int)mx * f.voxel + f.pmin[0] + f.map_center[0];
-            const float gy = (float)(int)my * f.voxel + f.pmin[1] + f.map_center[1];
-            const float gz = (float)(int)mz * f.voxel + f.pmin[2] + f.map_center[2];
-            int row, col;
-            float cz;
-            if (project_to_image(f, gx, gy, gz, row, col, cz)) stamp0 = cz <= __ldg(depth_int + row * f.W + col);
-        }
-        const uint32_t nh = (stamp0 ? (f.T & 0xffffu) : hdr_ts(hdr)) | (hdr & HDR_MOVABLE) | (live << 16);
-        if (nh != hdr) st.hdr[v] = nh;
-    }
-    const uint32_t b_swept = __ballot_sync(0xffffffffu, swept), b_nonempty = __ballot_sync(0xffffffffu, swept && nvalid > 0);
-    if (lane_id() == 0) {
-        atomicAdd(&cnt->n_swept_voxels, (uint32_t)__popc(b_swept));
-        if (b_nonempty) atomicAdd(&cnt->n_swept_nonempty, (uint32_t)__popc(b_nonempty));
-    }
+    for (uint32_t k = chunk_used + lane_id(); k < PAIR_CHUNK; k += 32)          // retire the last chunk
+        if (chunk_base + k < f.vis_cap) pairs[chunk_base + k] = make_uint2(0xffffffffu, 0u);
+    n_nonempty = __reduce_add_sync(0xffffffffu, n_nonempty);
+    if (lane_id() == 0 && n_nonempty) atomicAdd(&cnt->n_swept_nonempty, n_nonempty);
 }
 
 // =====================================================================================================
@@ -312,11 +391,12 @@ k_scan_apply(const uint32_t* __restrict__ count, uint32_t n, const uint32_t* __r
 
 // scatter the pairs into their pixel segments (arrival order; sorted next)
 __global__ void __launch_bounds__(256)
-k_fill(int slot, const Counters* __restrict__ cnt, const uint2* __restrict__ pairs, const uint32_t* __restrict__ offset,
+k_fill(const __grid_constant__ FrameParams f, const Counters* __restrict__ cnt, const uint2* __restrict__ pairs, const uint32_t* __restrict__ offset,
        uint32_t* __restrict__ pix_count, uint32_t* __restrict__ csr_idx, uint32_t* __restrict__ vis_pix) {
-    const uint32_t n = min(cnt->n_pairs, c_fp[slot].vis_cap);
+    const uint32_t n = min(cnt->n_pairs, f.vis_cap);
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint2 pr = pairs[k];
+        if (pr.x == 0xffffffffu) continue;     // unused tail of a reserved chunk
         const uint32_t pos = offset[pr.x] + (atomicSub(pix_count + pr.x, 1u) - 1u);   // leaves the counts at zero
         csr_idx[pos] = pr.y;
         vis_pix[pos] = pr.x;
@@ -325,9 +405,9 @@ k_fill(int slot, const Counters* __restrict__ cnt, const uint2* __restrict__ pai
 
 // canonical order inside each pixel list: ascending particle index (insertion sort; lists are short)
 __global__ void __launch_bounds__(256)
-k_sort_lists(int slot, const uint32_t* __restrict__ offset, uint32_t* __restrict__ csr_idx) {
+k_sort_lists(const __grid_constant__ FrameParams f, const uint32_t* __restrict__ offset, uint32_t* __restrict__ csr_idx) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= c_fp[slot].W * c_fp[slot].H) return;
+    if (q >= f.W * f.H) return;
     const uint32_t b = offset[q], e = offset[q + 1];
     for (uint32_t i = b + 1; i < e; ++i) {
         const uint32_t key = csr_idx[i];
@@ -339,9 +419,9 @@ k_sort_lists(int slot, const uint32_t* __restrict__ offset, uint32_t* __restrict
 
 // gather the listed particles into compact, list-ordered arrays read by the two stencil passes
 __global__ void __launch_bounds__(256)
-k_gather_visible(int slot, const Counters* __restrict__ cnt, Store st, const uint32_t* __restrict__ csr_idx,
+k_gather_visible(const __grid_constant__ FrameParams f, const uint32_t* __restrict__ n_visible, Store st, const uint32_t* __restrict__ csr_idx,
                  float4* __restrict__ vis_pos, uint32_t* __restrict__ vis_meta) {
-    const uint32_t n = min(cnt->n_pairs, c_fp[slot].vis_cap);
+    const uint32_t n = *n_visible;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint32_t idx = csr_idx[k];
         const uint64_t m = st.meta[idx];
@@ -354,42 +434,57 @@ k_gather_visible(int slot, const Counters* __restrict__ cnt, Store st, const uin
 // U3a  ck_accumulate  replaces SemanticDSPMap::updateParticles pass 1 (semantic_dsp_map.h:973-1037)
 // one thread per observation pixel; window rows are contiguous CSR ranges; Gaussian LUT in shared memory.
 // =====================================================================================================
-__device__ __forceinline__ void stage_lut(float* s_lut, const float* __restrict__ lut) {
+__device__ __forceinline__ void stage_lut(const float* __restrict__ lut) {
     for (int i = threadIdx.x; i < PDF_NUM / 4; i += blockDim.x) reinterpret_cast<float4*>(s_lut)[i] = reinterpret_cast<const float4*>(lut)[i];
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(512)
-k_ck(int slot, const float* __restrict__ lut, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta,
+template <bool FAST>
+__device__ __forceinline__ float ck_pixel(const FrameParams& f, const float4 o, const uint32_t otrack, int i, int j,
+                                          const uint32_t* __restrict__ offset, const float4* __restrict__ vis_pos,
+                                          const uint32_t* __restrict__ vis_meta) {
+    const InvDiv sigma(o.w);
+    const int r = f.win_r;
+    const int j0 = max(j - r, 0), j1 = min(j + r, f.W - 1);
+    float acc = 0.f;
+    for (int ni = max(i - r, 0); ni <= min(i + r, f.H - 1); ++ni) {
+        const uint32_t kb = offset[ni * f.W + j0], ke = offset[ni * f.W + j1 + 1];
+        for (uint32_t k = kb; k < ke; ++k) {
+            const uint32_t pm = vis_meta[k];
+            const bool same = (pm & 0xffffu) == otrack;
+            if (f.indep && !same) continue;
+            const float4 p = vis_pos[k];
+            float gk = query_pdf<FAST>(p.x, o.x, sigma) * query_pdf<FAST>(p.y, o.y, sigma) * query_pdf<FAST>(p.z, o.z, sigma);
+            if (!f.indep) {
+                gk *= forgetting_factor(f, pm >> 16);
+                if (!same) gk *= f.tau;
+            }
+            acc += p.w * gk;
+        }
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(1024, 2)
+k_ck(const __grid_constant__ FrameParams f, const float* __restrict__ lut, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta,
      const uint32_t* __restrict__ offset, const float4* __restrict__ vis_pos, const uint32_t* __restrict__ vis_meta,
-     float* __restrict__ ck) {
-    extern __shared__ float s_lut[];
-    stage_lut(s_lut, lut);
-    const FrameParams& f = c_fp[slot];
-    const int npix = f.W * f.H, r = f.win_r;
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < npix; q += gridDim.x * blockDim.x) {
+     float* __restrict__ ck, uint32_t seg_stride) {
+    stage_lut(lut);
+    const int npix = f.W * f.H;
+    const uint32_t n_seg = (uint32_t)(npix + 31) / 32;
+    // a warp takes 32-pixel segments w, w + n_warps, ...; the index maps to an image segment through a stride coprime
+    // with the segment count, so the (very uneven) per-pixel work of neighbouring image rows spreads over all SMs
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t t = warp; t < n_seg; t += n_warps) {
+        const int q = (int)((uint32_t)(((uint64_t)t * seg_stride) % n_seg) * 32u + lane_id());
+        if (q >= npix) continue;
         const uint32_t om = cloud_meta[q];
         if (!pt_valid(om)) { ck[q] = 0.f; continue; }
         const float4 o = cloud_pos[q];
-        const uint32_t otrack = pt_track(om);
         const int i = q / f.W, j = q - i * f.W;
-        const int j0 = max(j - r, 0), j1 = min(j + r, f.W - 1);
-        float acc = 0.f;
-        for (int ni = max(i - r, 0); ni <= min(i + r, f.H - 1); ++ni) {
-            const uint32_t kb = offset[ni * f.W + j0], ke = offset[ni * f.W + j1 + 1];
-            for (uint32_t k = kb; k < ke; ++k) {
-                const uint32_t pm = vis_meta[k];
-                const bool same = (pm & 0xffffu) == otrack;
-                if (f.indep && !same) continue;
-                const float4 p = vis_pos[k];
-                float gk = query_pdf(s_lut, p.x, o.x, o.w) * query_pdf(s_lut, p.y, o.y, o.w) * query_pdf(s_lut, p.z, o.z, o.w);
-                if (!f.indep) {
-                    gk *= forgetting_factor(f, pm >> 16);
-                    if (!same) gk *= f.tau;
-                }
-                acc += p.w * gk;
-            }
-        }
+        const float ao = fabsf(o.w);
+        const float acc = (ao > 1e-6f && ao < 1e6f) ? ck_pixel<true>(f, o, pt_track(om), i, j, offset, vis_pos, vis_meta)
+                                                    : ck_pixel<false>(f, o, pt_track(om), i, j, offset, vis_pos, vis_meta);
         ck[q] = acc * f.Pd + f.kappa;
     }
 }
@@ -398,43 +493,52 @@ k_ck(int slot, const float* __restrict__ lut, const float4* __restrict__ cloud_p
 // U3b  weight_update  replaces SemanticDSPMap::updateParticles pass 2 (semantic_dsp_map.h:1041-1119)
 // one thread per listed particle; sigma is the PARTICLE's pixel's sigma (:1047).
 // =====================================================================================================
-__global__ void __launch_bounds__(512)
-k_weight_update(int slot, const Counters* __restrict__ cnt, const float* __restrict__ lut, const float4* __restrict__ cloud_pos,
+template <bool FAST>
+__device__ __forceinline__ float wu_particle(const FrameParams& f, const float4 p, const uint32_t ptrack, const float phi, const float sig,
+                                             int i, int j, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta,
+                                             const float* __restrict__ ck, bool& right_id) {
+    const InvDiv sigma(sig);
+    const int r = f.win_r;
+    float acc = 0.f;
+    for (int ni = max(i - r, 0); ni <= min(i + r, f.H - 1); ++ni) {
+        for (int nj = max(j - r, 0); nj <= min(j + r, f.W - 1); ++nj) {
+            const int oq = ni * f.W + nj;
+            const uint32_t om = cloud_meta[oq];
+            if (!pt_valid(om)) continue;
+            const bool same = pt_track(om) == ptrack;
+            if (f.indep && !same) continue;
+            const float4 o = cloud_pos[oq];
+            float gk = query_pdf<FAST>(p.x, o.x, sigma) * query_pdf<FAST>(p.y, o.y, sigma) * query_pdf<FAST>(p.z, o.z, sigma);
+            if (!f.indep) {
+                if (!same) gk *= f.tau;
+                else if (gk > MIN_RIGHTLY_UPDATED_PDF) right_id = true;
+                gk *= phi;
+            }
+            acc += gk / ck[oq];
+        }
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(1024, 2)
+k_weight_update(const __grid_constant__ FrameParams f, const uint32_t* __restrict__ n_visible, const float* __restrict__ lut, const float4* __restrict__ cloud_pos,
                 const uint32_t* __restrict__ cloud_meta, const float* __restrict__ ck, const uint32_t* __restrict__ csr_idx,
                 const uint32_t* __restrict__ vis_pix, const float4* __restrict__ vis_pos, const uint32_t* __restrict__ vis_meta,
                 Store st) {
-    extern __shared__ float s_lut[];
-    stage_lut(s_lut, lut);
-    const FrameParams& f = c_fp[slot];
-    const uint32_t n = min(cnt->n_pairs, f.vis_cap);
-    const int r = f.win_r;
+    stage_lut(lut);
+    const uint32_t n = *n_visible;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const int q = (int)vis_pix[k];
         const int i = q / f.W, j = q - i * f.W;
-        const float sigma = cloud_pos[q].w;
+        const float sig = cloud_pos[q].w;
         const float4 p = vis_pos[k];
         const uint32_t pm = vis_meta[k];
         const uint32_t ptrack = pm & 0xffffu, pforget = pm >> 16;
         const float phi = f.indep ? 1.f : forgetting_factor(f, pforget);
-        float acc = 0.f;
         bool right_id = false;
-        for (int ni = max(i - r, 0); ni <= min(i + r, f.H - 1); ++ni) {
-            for (int nj = max(j - r, 0); nj <= min(j + r, f.W - 1); ++nj) {
-                const int oq = ni * f.W + nj;
-                const uint32_t om = cloud_meta[oq];
-                if (!pt_valid(om)) continue;
-                const bool same = pt_track(om) == ptrack;
-                if (f.indep && !same) continue;
-                const float4 o = cloud_pos[oq];
-                float gk = query_pdf(s_lut, p.x, o.x, sigma) * query_pdf(s_lut, p.y, o.y, sigma) * query_pdf(s_lut, p.z, o.z, sigma);
-                if (!f.indep) {
-                    if (!same) gk *= f.tau;
-                    else if (gk > MIN_RIGHTLY_UPDATED_PDF) right_id = true;
-                    gk *= phi;
-                }
-                acc += gk / ck[oq];
-            }
-        }
+        const float as = fabsf(sig);
+        const float acc = (as > 1e-6f && as < 1e6f) ? wu_particle<true>(f, p, ptrack, phi, sig, i, j, cloud_pos, cloud_meta, ck, right_id)
+                                                    : wu_particle<false>(f, p, ptrack, phi, sig, i, j, cloud_pos, cloud_meta, ck, right_id);
         const uint32_t idx = csr_idx[k];
         const uint64_t m = st.meta[idx];
         uint32_t forget = meta_forget(m);
@@ -456,18 +560,19 @@ k_weight_update(int slot, const Counters* __restrict__ cnt, const float* __restr
 // voxel with a cascade of atomicMin (order-independent result), then replay each touched voxel serially.
 // Touched hash entries are appended to a list so the replay never scans the table.
 // =====================================================================================================
-__device__ __forceinline__ uint32_t hash_slot(const FrameParams& f, uint32_t v) { return (v * 2654435761u) >> f.hash_shift; }
+__device__ __forceinline__ uint32_t hash_slot(uint32_t v, uint32_t shift) { return (v * 2654435761u) >> shift; }
 
-__device__ __forceinline__ void topk_insert(const FrameParams& f, uint32_t v, uint32_t rank, uint32_t* __restrict__ keys,
-                                            uint32_t* __restrict__ ranks, uint32_t* __restrict__ entry_list, uint32_t* n_entries,
-                                            uint32_t* overflow) {
-    uint32_t h = hash_slot(f, v);
+// cap/shift: the power-of-two prefix of the table in use (births: 2x the pixel count; moves: the whole table)
+__device__ __forceinline__ void topk_insert(const FrameParams& f, uint32_t cap, uint32_t shift, uint32_t v, uint32_t rank,
+                                            uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks, uint32_t* __restrict__ entry_list,
+                                            uint32_t* n_entries, uint32_t* overflow) {
+    uint32_t h = hash_slot(v, shift);
     for (uint32_t probe = 0;; ++probe) {
-        if (probe >= f.hash_cap) { atomicAdd(overflow, 1u); return; }
+        if (probe >= cap) { atomicAdd(overflow, 1u); return; }
         const uint32_t old = atomicCAS(keys + h, EMPTY_KEY, v);
         if (old == EMPTY_KEY) { entry_list[atomicAdd(n_entries, 1u)] = h; break; }
         if (old == v) break;
-        h = (h + 1) & (f.hash_cap - 1);
+        h = (h + 1) & (cap - 1);
     }
     uint32_t* r = ranks + (size_t)h * f.topk;
     // early out: the last entry only ever decreases
@@ -492,281 +597,414 @@ __device__ __forceinline__ int birth_rank_to_pixel(const FrameParams& f, uint32_
     return ((ph / 3) + 3 * a) * f.W + (ph % 3) + 3 * b;
 }
 
+// One thread per birth RANK (not per pixel): the lowest ranks are binned by the first blocks, so by the time the
+// later 3x3 phases arrive most per-voxel lists are full and their cascades end at the first comparison.
 __global__ void __launch_bounds__(256)
-k_birth_bin(int slot, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta, uint32_t* __restrict__ keys,
+k_birth_bin(const __grid_constant__ FrameParams f, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta, uint32_t* __restrict__ keys,
             uint32_t* __restrict__ ranks, uint32_t* __restrict__ entry_list, Counters* __restrict__ cnt) {
-    const FrameParams& f = c_fp[slot];
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= f.W * f.H) return;
+    const uint32_t rank = blockIdx.x * blockDim.x + threadIdx.x;
+    const int hc = (f.H + 2) / 3, wc = (f.W + 2) / 3;
+    if (rank >= (uint32_t)(9 * hc * wc)) return;
+    const int b = (int)(rank % (uint32_t)wc), a = (int)((rank / (uint32_t)wc) % (uint32_t)hc), ph = (int)(rank / (uint32_t)(wc * hc));
+    const int i = ph / 3 + 3 * a, j = ph % 3 + 3 * b;
+    if (i >= f.H || j >= f.W) return;
+    const int q = i * f.W + j;
     if (!pt_valid(cloud_meta[q])) return;
     const float4 p = cloud_pos[q];
     uint32_t bx, by, bz;
     const uint32_t v = global_pos_to_voxel(f, p.x, p.y, p.z, bx, by, bz);
     if (v == INVALID_INDEX) return;
     if (bz < f.z_lo || bz >= f.z_hi) return;   // another shard owns this voxel
-    const int i = q / f.W, j = q - i * f.W;
-    topk_insert(f, v, birth_rank(f, i, j), keys, ranks, entry_list, &cnt->n_birth_voxels, &cnt->hash_overflow);
+    topk_insert(f, f.birth_hash_cap, f.birth_hash_shift, v, rank, keys, ranks, entry_list, &cnt->n_birth_voxels, &cnt->hash_overflow);
 }
 
-// first vacant slot 1..P-1 of a voxel (operations.h:790-796); 0 when full.  live = header mask (bit s)
-__device__ __forceinline__ uint32_t first_vacant(const Store& st, size_t base, uint32_t P, uint32_t live, uint32_t stamp) {
-    for (uint32_t s = 1; s < P; ++s) {
-        if (!((live >> s) & 1u)) return s;
-        if (meta_ts(st.meta[base + s]) < stamp) return s;
-    }
-    return 0;
-}
+// ---- per-voxel slot state held in registers while candidates are replayed ------------------------------------------
+template <int P>
+struct VoxelSlots {
+    uint64_t m[P];
+    float w[P];
+    uint32_t live, vac, upd;   // bit s: status != INVALID / vacant (operations.h:810-816) / status == UPDATED
 
-// SemanticDSPMap::resampleParticlesInVoxel (semantic_dsp_map.h:1448-1519); returns true when a resample ran
-__device__ __forceinline__ bool resample_voxel(const Store& st, size_t base, uint32_t P, uint32_t& live) {
-    float wsum = 0.f;
-    uint32_t n_upd = 0, upd = 0;
-    for (uint32_t s = 1; s < P; ++s)
-        if (((live >> s) & 1u) && meta_status(st.meta[base + s]) == ST_UPDATED) { wsum += st.w[base + s]; ++n_upd; upd |= 1u << s; }
-    const uint32_t trigger = P >> 1;
-    if (n_upd <= trigger) return false;
-    if (wsum < 0.01f) {
-        for (uint32_t s = 1; s < P; ++s)
-            if ((upd >> s) & 1u) st.meta[base + s] = meta_with_status(st.meta[base + s], ST_INVALID);
-        live &= ~upd;
-        return true;
-    }
-    float wpp = wsum / (float)trigger;
-    if (wpp > 1.f) wpp = 1.f;
-    float cum = 0.f, thr = wpp;
-    for (uint32_t s = 1; s < P; ++s) {
-        if (!((upd >> s) & 1u)) continue;
-        cum += st.w[base + s];
-        if (cum < thr) {
-            st.meta[base + s] = meta_with_status(st.meta[base + s], ST_INVALID);
-            live &= ~(1u << s);
+    __device__ __forceinline__ void load(const Store& st, size_t base, uint32_t hdr, uint32_t stamp) {
+        live = hdr_live(hdr);
+        vac = 0; upd = 0;
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < P / 2; ++i) {
+                const uint4 q = reinterpret_cast<const uint4*>(st.meta + base)[i];
+                m[2 * i] = (uint64_t)q.x | ((uint64_t)q.y << 32);
+                m[2 * i + 1] = (uint64_t)q.z | ((uint64_t)q.w << 32);
+            }
+#pragma unroll
+            for (int i = 0; i < P / 2; ++i) {
+                const float2 q = reinterpret_cast<const float2*>(st.w + base)[i];
+                w[2 * i] = q.x; w[2 * i + 1] = q.y;
+            }
         } else {
-            st.w[base + s] = wpp;
-            thr += wpp;
-            while (cum > thr) thr += wpp;
+#pragma unroll
+            for (int i = 0; i < P; ++i) { m[i] = 0; w[i] = 0.f; }
+        }
+#pragma unroll
+        for (int s = 1; s < P; ++s) {
+            const bool lv = (live >> s) & 1u;
+            if (!lv || meta_ts(m[s]) < stamp) vac |= 1u << s;
+            if (lv && meta_status(m[s]) == ST_UPDATED) upd |= 1u << s;
         }
     }
-    return true;
-}
+    // first vacant slot 1..P-1 (operations.h:790-796); 0 when full
+    __device__ __forceinline__ uint32_t first_vacant() const { return vac ? (uint32_t)(__ffs(vac) - 1) : 0u; }
+    __device__ __forceinline__ void occupy(uint32_t s) { vac &= ~(1u << s); upd &= ~(1u << s); live |= 1u << s; }
+
+    // SemanticDSPMap::resampleParticlesInVoxel (semantic_dsp_map.h:1448-1519); returns true when a resample ran
+    __device__ __forceinline__ bool resample(const Store& st, size_t base) {
+        const uint32_t trigger = P >> 1;
+        if ((uint32_t)__popc(upd) <= trigger) return false;
+        float wsum = 0.f;
+#pragma unroll
+        for (int s = 1; s < P; ++s)
+            if ((upd >> s) & 1u) wsum += w[s];
+        uint32_t kill = 0;
+        if (wsum < 0.01f) {
+            kill = upd;
+        } else {
+            float wpp = wsum / (float)trigger;
+            if (wpp > 1.f) wpp = 1.f;
+            float cum = 0.f, thr = wpp;
+#pragma unroll
+            for (int s = 1; s < P; ++s) {
+                if (!((upd >> s) & 1u)) continue;
+                cum += w[s];
+                if (cum < thr) {
+                    kill |= 1u << s;
+                } else {
+                    w[s] = wpp;
+                    st.w[base + s] = wpp;
+                    thr += wpp;
+                    while (cum > thr) thr += wpp;
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 1; s < P; ++s)
+            if ((kill >> s) & 1u) st.meta[base + s] = meta_with_status(m[s], ST_INVALID);
+        live &= ~kill; upd &= ~kill; vac |= kill;
+        return true;
+    }
+};
 
 // =====================================================================================================
 // B1  birth_replay    replaces the birth loop + addNewbornParticle[WithNoise]AndResample
-//                     (semantic_dsp_map.h:768-800, 1148-1230) — one thread per touched voxel, candidates in
-//                     reference order.  Resets the hash entry it consumed.
+//                     (semantic_dsp_map.h:768-800, 1148-1230) — one thread per touched voxel replays its candidates in
+//                     reference order on a register copy of the slot state.  Accepted candidates are left in the
+//                     voxel's rank list as (rank | slot << 24) for k_birth_write; the hash entry is released.
 // =====================================================================================================
+template <int PB>
 __global__ void __launch_bounds__(128)
-k_birth_replay(int slot, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
-               const uint32_t* __restrict__ stamp_z, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta,
-               uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks, const uint32_t* __restrict__ entry_list,
-               Counters* __restrict__ cnt) {
-    const FrameParams& f = c_fp[slot];
+k_birth_replay(const __grid_constant__ FrameParams f, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
+               const uint32_t* __restrict__ stamp_z, uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks,
+               const uint32_t* __restrict__ entry_list, uint32_t* __restrict__ entry_voxel, Counters* __restrict__ cnt) {
+    constexpr int P = 1 << PB, K = 2 * P - 1;
     const uint32_t n_entries = cnt->n_birth_voxels;
     for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < n_entries; li += gridDim.x * blockDim.x) {
         const uint32_t e = entry_list[li];
         const uint32_t v = keys[e];
         keys[e] = EMPTY_KEY;
+        entry_voxel[li] = v;
+        uint32_t* r = ranks + (size_t)e * K;
+        uint32_t rk[K];
+#pragma unroll
+        for (int t = 0; t < K; ++t) rk[t] = r[t];
         uint32_t bx, by, bz;
         voxel_to_buffer(f, v, bx, by, bz);
         const uint32_t stamp = slab_stamp(stamp_x, stamp_y, stamp_z, bx, by, bz);
-        const size_t base = (size_t)v << f.Pb;
+        const size_t base = (size_t)v << PB;
         const uint32_t hdr = st.hdr[v];
-        uint32_t live = hdr_live(hdr), movable = hdr & HDR_MOVABLE;
-        uint32_t* r = ranks + (size_t)e * f.topk;
+        VoxelSlots<P> vs;
+        vs.load(st, base, hdr, stamp);
         bool resampled = false, frozen = false;
         uint32_t born = 0, n_res = 0;
-        for (uint32_t t = 0; t < f.topk; ++t) {
-            const uint32_t rank = r[t];
-            if (rank == NO_RANK) break;
-            r[t] = NO_RANK;
-            if (frozen) continue;
-            const int q = birth_rank_to_pixel(f, rank);
-            uint32_t s = first_vacant(st, base, f.P, live, stamp);
-            bool try_resample;
-            if (f.depth_noise) try_resample = (s == 0) && !resampled;      // :1205-1226 only when the voxel is full
-            else try_resample = !resampled;                                 // :1165-1170 after every add
+#pragma unroll
+        for (int t = 0; t < K; ++t) {
+            const uint32_t rank = rk[t];
+            if (rank == NO_RANK) continue;
+            if (frozen) { r[t] = NO_RANK; continue; }
+            uint32_t s = vs.first_vacant();
+            const bool try_resample = f.depth_noise ? ((s == 0) && !resampled)     // :1205-1226 only when the voxel is full
+                                                    : !resampled;                  // :1165-1170 after every add
             if (f.depth_noise && try_resample) {
-                if (resample_voxel(st, base, f.P, live)) { resampled = true; ++n_res; s = first_vacant(st, base, f.P, live, stamp); }
+                if (vs.resample(st, base)) { resampled = true; ++n_res; s = vs.first_vacant(); }
                 else frozen = true;            // full, and a resample can never trigger this frame
             }
             if (s) {
-                const float4 p = cloud_pos[q];
-                const uint32_t pm = cloud_meta[q];
-                st.x[base + s] = p.x; st.y[base + s] = p.y; st.z[base + s] = p.z;
-                st.w[base + s] = OCC_INIT_WEIGHT;
-                st.meta[base + s] = meta_pack(f.T, pt_track(pm), pt_label(pm), ST_REGULAR_BORN, 0);   // operations.h:171-184
-                live |= 1u << s;
-                if (pt_track(pm) <= f.max_movable) movable = HDR_MOVABLE;
+                vs.occupy(s);
                 ++born;
             } else if (f.depth_noise) {
                 frozen = true;                 // full after the one allowed resample
             }
             if (!f.depth_noise && try_resample) {
-                if (resample_voxel(st, base, f.P, live)) { resampled = true; ++n_res; }
+                if (vs.resample(st, base)) { resampled = true; ++n_res; }
                 else if (s == 0) frozen = true;  // full and births never create UPDATED particles
             } else if (!f.depth_noise && s == 0) {
                 frozen = true;
             }
+            r[t] = s ? (rank | (s << 24)) : NO_RANK;
         }
-        const uint32_t nh = hdr_ts(hdr) | movable | (live << 16);
+        const uint32_t nh = (hdr & 0x1ffffu) | (vs.live << 16);
         if (nh != hdr) st.hdr[v] = nh;
         if (born) atomicAdd(&cnt->n_born, born);
         if (n_res) atomicAdd(&cnt->n_resampled, n_res);
     }
 }
 
-// =====================================================================================================
-// ordered stream compaction across blocks: decoupled look-back over (flag | count) words, one warp looking
-// at 32 predecessors at a time.  Blocks take a dynamic ticket so a block never waits on one that has not started.
-// =====================================================================================================
-constexpr uint64_t LB_AGG = 1ull << 62, LB_INC = 2ull << 62, LB_MASK = (1ull << 62) - 1;
-
-// call from every lane of warp 0; returns this block's exclusive prefix (two packed 31-bit counters) to all lanes
-__device__ __forceinline__ uint64_t lookback_prefix_warp(volatile uint64_t* status, uint32_t bid, uint64_t block_total) {
-    const uint32_t lane = lane_id();
-    if (lane == 0) status[bid] = (bid == 0 ? LB_INC : LB_AGG) | block_total;
-    if (bid == 0) return 0;
-    uint64_t prefix = 0;
-    for (int j = (int)bid - 1;; j -= 32) {
-        const int k = j - (int)lane;
-        uint64_t s = LB_INC;   // before the first block: an inclusive zero
-        if (k >= 0) {
-            do { s = status[k]; } while ((s >> 62) == 0);
-        }
-        const uint32_t inc_mask = __ballot_sync(0xffffffffu, (s >> 62) == 2);
-        const uint32_t first_inc = inc_mask ? (uint32_t)(__ffs(inc_mask) - 1) : 32u;
-        uint64_t val = (lane <= first_inc) ? (s & LB_MASK) : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
-        prefix += __shfl_sync(0xffffffffu, val, 0);
-        if (inc_mask) break;
+// one thread per (touched voxel, candidate): write the accepted newborn particles (operations.h:171-184)
+__global__ void __launch_bounds__(256)
+k_birth_write(const __grid_constant__ FrameParams f, Store st, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta,
+              uint32_t* __restrict__ ranks, const uint32_t* __restrict__ entry_list, const uint32_t* __restrict__ entry_voxel,
+              const Counters* __restrict__ cnt) {
+    const uint32_t K = f.topk, n = cnt->n_birth_voxels * K;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const uint32_t li = t / K, i = t - li * K;
+        uint32_t* r = ranks + (size_t)entry_list[li] * K + i;
+        const uint32_t a = *r;
+        if (a == NO_RANK) continue;
+        *r = NO_RANK;
+        const uint32_t s = a >> 24, v = entry_voxel[li];
+        const int q = birth_rank_to_pixel(f, a & 0xffffffu);
+        const float4 p = cloud_pos[q];
+        const uint32_t pm = cloud_meta[q];
+        const size_t idx = ((size_t)v << f.Pb) + s;
+        st.x[idx] = p.x; st.y[idx] = p.y; st.z[idx] = p.z;
+        st.w[idx] = OCC_INIT_WEIGHT;
+        st.meta[idx] = meta_pack(f.T, pt_track(pm), pt_label(pm), ST_REGULAR_BORN, 0);
+        if (pt_track(pm) <= f.max_movable && !(st.hdr[v] & HDR_MOVABLE)) atomicOr(st.hdr + v, HDR_MOVABLE);
     }
-    if (lane == 0) status[bid] = LB_INC | (prefix + block_total);
-    return prefix;
 }
 
 // =====================================================================================================
 // O1  occupancy_labels  replaces getOccupancyResult + determineIfVoxelOccupied + calculateWeightAndSemanticsInVoxel
 //                       + getVoxelGlobalPosition (semantic_dsp_map.h:1239-1383; mc_ring/operations.h:390-448, 623-648)
-// one thread per OCC_VPT consecutive storage voxels; header word first, slot records only for live slots of known
-// voxels; sequential slot loop (the reference's summation order); ordered compaction of the emitted voxels.
+// Four launches, no inter-block dependency inside any of them:
+//   headers  : each thread streams OCC_VPT consecutive header words (one 16-byte load).  Unknown voxels and known-but-
+//              empty voxels are decided from the header alone; voxels with live slots are appended to a work list.
+//   slots    : one P-lane group per listed voxel: lane s holds slot s (coalesced 8 B tail + 4 B weight) and every lane
+//              replays the reference's slot-order sums through shuffles (weight sum, guessed weight, summed weight of
+//              its own track), so all floats are added in the reference order; the arg-max track is a butterfly over
+//              (weight desc, track asc).  Output: one state byte per voxel, sparse per-voxel results for emitted
+//              voxels, per-tile counts.
+//   scan     : exclusive scan of the per-block counts.
+//   emit     : ordered compaction (ascending storage index) of occupied / free voxels and of the live particles of
+//              movable tracks — the next frame's object-move step works from that list instead of a map pass.
 // =====================================================================================================
 constexpr int OCC_BLOCK = 256;
 constexpr int OCC_VPT = 4;                       // voxels per thread (one 16-byte header load)
 constexpr int OCC_TILE = OCC_BLOCK * OCC_VPT;
 constexpr int MAX_P = 16;
+// state byte: bits 0..1 = state + 1 (0 unknown, 1 free, 2 occupied, 3 guessed occupied), bit 2 = holds movable particles
+constexpr uint32_t VS_MOVABLE = 4u;
 
 struct ResultArrays {
     uint32_t* voxel_index; float* xyz; float* weight_sum; uint16_t* track_id; uint8_t* label_id; int8_t* state;
     uint32_t* free_voxel_index; float* free_xyz;
 };
 
-__global__ void __launch_bounds__(OCC_BLOCK)
-k_occupancy(int slot, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
-            const uint32_t* __restrict__ stamp_z, ResultArrays out, int8_t* __restrict__ voxel_state,
-            uint64_t* __restrict__ lb_status, Counters* __restrict__ cnt) {
-    __shared__ uint32_t s_bid;
-    __shared__ uint32_t s_warp[33];
-    __shared__ uint64_t s_prefix;
-    const FrameParams& f = c_fp[slot];
-    if (threadIdx.x == 0) s_bid = atomicAdd(&cnt->ticket_occ, 1u);
-    __syncthreads();
-    const uint32_t bid = s_bid;
-    const uint32_t v_lo = f.z_lo << (f.Xb + f.Yb);
-    const uint32_t v0 = v_lo + bid * OCC_TILE + threadIdx.x * OCC_VPT;   // the grid covers the shard exactly (V multiple of 1024)
+struct OccScratch {
+    uint8_t* vstate;        // V bytes
+    float* res_w;           // V, written for emitted voxels only
+    uint32_t* res_tl;       // V, track | label << 16
+    uint16_t* mov_mask;     // V, slots holding live particles of movable tracks (written where VS_MOVABLE)
+    uint4* blk_cnt;         // per block: occupied, free, movable particles
+    uint4* blk_off;         // exclusive prefix of blk_cnt
+};
 
+template <int PB>
+__global__ void __launch_bounds__(OCC_BLOCK)
+k_occ_headers(const __grid_constant__ FrameParams f, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
+              const uint32_t* __restrict__ stamp_z, OccScratch sc, uint32_t* __restrict__ work, Counters* __restrict__ cnt) {
+    __shared__ uint32_t s_free;
+    if (threadIdx.x == 0) s_free = 0;
+    __syncthreads();
+    const uint32_t v_lo = f.z_lo << (f.Xb + f.Yb);
+    const uint32_t v0 = v_lo + blockIdx.x * OCC_TILE + threadIdx.x * OCC_VPT;   // header plane is padded to whole tiles
     const uint4 h4 = *reinterpret_cast<const uint4*>(st.hdr + v0);
     const uint32_t hdrs[OCC_VPT] = {h4.x, h4.y, h4.z, h4.w};
     uint32_t bx0, by, bz;
     voxel_to_buffer(f, v0, bx0, by, bz);
     const uint32_t stamp_yz = max(__ldg(stamp_y + by), __ldg(stamp_z + bz));
-
-    int state[OCC_VPT];
-    float wsum[OCC_VPT];
-    uint32_t tl[OCC_VPT];     // track | label << 16
-    uint32_t n_occ = 0, n_free = 0, n_nonempty = 0;
+    uint32_t sb4 = 0, heavy = 0, n_free = 0;
 #pragma unroll
     for (int u = 0; u < OCC_VPT; ++u) {
-        const uint32_t hdr = hdrs[u], v = v0 + u;
+        const uint32_t hdr = hdrs[u];
         const uint32_t stamp = max(stamp_yz, __ldg(stamp_x + bx0 + u));
         const uint32_t ts0 = hdr_ts(hdr);
-        state[u] = -1; wsum[u] = -1.f; tl[u] = 0;
-        if (ts0 != 0 && !(ts0 < stamp)) {                   // isVoxelValid, operations.h:824-837
-            float ws = 0.f, gsum = 0.f;
-            uint32_t live = hdr_live(hdr), new_live = live;
-            uint32_t track = 0, label = 0;
-            if (live) {
-                const size_t base = (size_t)v << f.Pb;
-                // per-track weight histogram (std::map in the reference), at most P-1 distinct tracks
-                uint32_t h_track[MAX_P - 1], h_label[MAX_P - 1];
-                float h_w[MAX_P - 1];
-                int nh = 0;
-                bool any = false;
-                while (live) {
-                    const uint32_t s = __ffs(live) - 1;
-                    live &= live - 1;
-                    const uint64_t m = st.meta[base + s];
-                    if (meta_ts(m) < stamp) continue;           // vacant: outdated by the ring shift (operations.h:810-816)
-                    any = true;
-                    float w = st.w[base + s];
-                    ws += w;                                    // the unclamped weight, operations.h:414
-                    if (w > 1.f) { w = 1.f; st.w[base + s] = 1.f; }
-                    const uint32_t status = meta_status(m);
-                    if (status == ST_GUESSED_BORN) gsum += w;
-                    else if (status == ST_UPDATED && w < OCC_INIT_WEIGHT) {
-                        st.meta[base + s] = meta_with_status(m, ST_INVALID);
-                        new_live &= ~(1u << s);
-                        continue;
-                    }
-                    const uint32_t tr = meta_track(m);
-                    int k = 0;
-                    while (k < nh && h_track[k] != tr) ++k;
-                    if (k == nh) { h_track[k] = tr; h_w[k] = 0.f; ++nh; }
-                    h_w[k] += w;
-                    h_label[k] = meta_label(m) & 0xffu;
-                }
-                // first maximum in ascending track order, strict > from 0 (operations.h:439-446)
-                float mw = 0.f;
-                uint32_t best = 0xffffffffu;
-                for (int k = 0; k < nh; ++k)
-                    if (h_w[k] > 0.f && (h_w[k] > mw || (h_w[k] == mw && h_track[k] < best))) { mw = h_w[k]; best = h_track[k]; track = h_track[k]; label = h_label[k]; }
-                if (any) ++n_nonempty;
-                if (new_live != hdr_live(hdr)) st.hdr[v] = (hdr & 0x1ffffu) | (new_live << 16);
-            }
-            wsum[u] = ws; tl[u] = track | (label << 16);
-            if (ws > f.occ_thr) state[u] = 1;
-            else if (gsum >= OCC_INIT_WEIGHT) state[u] = 2;
-            else state[u] = 0;
-        }
-        if (f.want_state) voxel_state[v] = (int8_t)state[u];
-        n_occ += state[u] > 0;
-        n_free += (f.want_free && state[u] == 0);
+        const bool known = ts0 != 0 && !(ts0 < stamp);                  // isVoxelValid, operations.h:824-837
+        const bool hv = hdr_live(hdr) != 0 && (known || (hdr & HDR_MOVABLE));
+        // decided by the header alone: unknown (-1), or known and empty (0: weight sum 0, no guessed weight)
+        sb4 |= (known ? 1u : 0u) << (8 * u);
+        heavy |= (hv ? 1u : 0u) << u;
+        n_free += known && !hv;
     }
-    // block-wide exclusive scan of the two counters, packed
-    uint32_t total;
-    const uint32_t packed = n_occ | (n_free << 16);                 // <= 4 per thread, <= 1024 per block: 16 bits each suffice
-    const uint32_t ex = block_exclusive_scan(packed, s_warp, total);
-    if (threadIdx.x < 32) {
-        const uint64_t tot64 = (uint64_t)(total & 0xffffu) | ((uint64_t)(total >> 16) << 31);
-        const uint64_t prefix = lookback_prefix_warp(lb_status, bid, tot64);
-        if (threadIdx.x == 0) {
-            s_prefix = prefix;
-            if (bid == gridDim.x - 1) {
-                const uint64_t inc = prefix + tot64;
-                cnt->n_occupied = (uint32_t)(inc & 0x7fffffffu);
-                cnt->n_free = (uint32_t)((inc >> 31) & 0x7fffffffu);
+    *reinterpret_cast<uint32_t*>(sc.vstate + (v0 - v_lo)) = sb4;
+    // append this warp's heavy voxels to the work list (one atomic per warp)
+    const uint32_t nh = __popc(heavy);
+    uint32_t inc = nh;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane_id() >= (uint32_t)o) inc += n;
+    }
+    const uint32_t warp_total = __shfl_sync(0xffffffffu, inc, 31);
+    n_free = __reduce_add_sync(0xffffffffu, n_free);
+    uint32_t base = 0;
+    if (lane_id() == 31) {
+        if (warp_total) base = atomicAdd(&cnt->n_occ_work, warp_total);
+        if (n_free) atomicAdd(&s_free, n_free);
+    }
+    if (warp_total) {
+        base = __shfl_sync(0xffffffffu, base, 31);
+        uint32_t pos = base + inc - nh;
+#pragma unroll
+        for (int u = 0; u < OCC_VPT; ++u)
+            if ((heavy >> u) & 1u) work[pos++] = v0 + u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sc.blk_cnt[blockIdx.x] = make_uint4(0u, f.want_free ? s_free : 0u, 0u, 0u);
+}
+
+template <int PB>
+__global__ void __launch_bounds__(256)
+k_occ_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
+            const uint32_t* __restrict__ stamp_z, OccScratch sc, const uint32_t* __restrict__ work, Counters* __restrict__ cnt) {
+    constexpr int P = 1 << PB, G = 32 / P;
+    const uint32_t n_work = cnt->n_occ_work;
+    const uint32_t v_lo = f.z_lo << (f.Xb + f.Yb);
+    const uint32_t sl = lane_id() & (P - 1), g = lane_id() / P, gbase = lane_id() & ~(uint32_t)(P - 1);
+    const uint32_t gmask = group_mask<P>();
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t n_nonempty = 0;
+    for (uint32_t w0 = warp * G; w0 < n_work; w0 += n_warps * G) {     // warp-uniform trip count
+        const uint32_t wi = w0 + g;
+        const bool active = wi < n_work;
+        const uint32_t g_v = active ? work[wi] : v_lo;
+        const uint32_t g_hdr = active ? st.hdr[g_v] : 0u;
+        const size_t base = (size_t)g_v << PB;
+        const bool has = active && sl != 0 && ((g_hdr >> (16 + sl)) & 1u);
+        uint64_t m = 0;
+        float w = 0.f;
+        if (has) { m = st.meta[base + sl]; w = st.w[base + sl]; }
+        uint32_t bx, by, bz;
+        voxel_to_buffer(f, g_v, bx, by, bz);
+        const uint32_t g_stamp = slab_stamp(stamp_x, stamp_y, stamp_z, bx, by, bz);
+        const uint32_t ts0 = hdr_ts(g_hdr);
+        const bool g_known = ts0 != 0 && !(ts0 < g_stamp);
+        const bool nonvac = has && g_known && !(meta_ts(m) < g_stamp);   // isParticleVacant, operations.h:810-816
+        float wc = w;
+        if (nonvac && w > 1.f) { wc = 1.f; st.w[base + sl] = 1.f; }     // :416-419 clamp the stored weight
+        const uint32_t status = meta_status(m);
+        const bool guessed = nonvac && status == ST_GUESSED_BORN;
+        const bool pruned = nonvac && status == ST_UPDATED && wc < OCC_INIT_WEIGHT;   // :423-427
+        if (pruned) st.meta[base + sl] = meta_with_status(m, ST_INVALID);
+        const bool included = nonvac && !pruned;
+        const uint32_t my_track = meta_track(m);
+        const bool movable = has && !pruned && my_track <= f.max_movable;   // still live after this pass
+        const uint32_t packed = my_track | ((meta_label(m) & 0xffu) << 16) | ((uint32_t)nonvac << 24) | ((uint32_t)guessed << 25) | ((uint32_t)included << 26);
+        // replay the slot loop: every lane accumulates the voxel sums and the sum of its own track, in slot order
+        float ws = 0.f, gs = 0.f, tot = 0.f;
+        uint32_t last_label = 0;
+#pragma unroll
+        for (int s2 = 1; s2 < P; ++s2) {
+            const float w2 = __shfl_sync(0xffffffffu, w, gbase + s2), wc2 = __shfl_sync(0xffffffffu, wc, gbase + s2);
+            const uint32_t p2 = __shfl_sync(0xffffffffu, packed, gbase + s2);
+            if ((p2 >> 24) & 1u) ws += w2;                          // the unclamped weight, :414
+            if ((p2 >> 25) & 1u) gs += wc2;
+            if (((p2 >> 26) & 1u) && (p2 & 0xffffu) == my_track) { tot += wc2; last_label = (p2 >> 16) & 0xffu; }
+        }
+        // arg-max over the included slots: largest summed weight, lowest track on ties, strictly positive
+        // (std::map ascending iteration with '>' from 0, :439-446)
+        float best_w = included ? tot : -1.f;
+        uint32_t best_tl = my_track | (last_label << 16);
+#pragma unroll
+        for (int o = 1; o < P; o <<= 1) {
+            const float ow = __shfl_xor_sync(0xffffffffu, best_w, o);
+            const uint32_t otl = __shfl_xor_sync(0xffffffffu, best_tl, o);
+            if (ow > best_w || (ow == best_w && (otl & 0xffffu) < (best_tl & 0xffffu))) { best_w = ow; best_tl = otl; }
+        }
+        const uint32_t b_pruned = __ballot_sync(0xffffffffu, pruned), b_nonvac = __ballot_sync(0xffffffffu, nonvac);
+        const uint32_t b_mov = __ballot_sync(0xffffffffu, movable);
+        if (active && sl == 0) {
+            uint32_t sb = 0;
+            uint32_t* tile_cnt = reinterpret_cast<uint32_t*>(sc.blk_cnt + (g_v - v_lo) / OCC_TILE);
+            if (g_known) {
+                int state;
+                if (ws > f.occ_thr) state = 1;
+                else if (gs >= OCC_INIT_WEIGHT) state = 2;
+                else state = 0;
+                sb = (uint32_t)(state + 1);
+                if (state > 0) { sc.res_w[g_v] = ws; sc.res_tl[g_v] = best_w > 0.f ? best_tl : 0u; atomicAdd(tile_cnt + 0, 1u); }
+                else if (f.want_free) atomicAdd(tile_cnt + 1, 1u);
+                n_nonempty += (b_nonvac & gmask) != 0;
             }
+            const uint32_t mv = (b_mov & gmask) >> gbase;
+            if (mv) { sc.mov_mask[g_v] = (uint16_t)mv; sb |= VS_MOVABLE; atomicAdd(tile_cnt + 2, (uint32_t)__popc(mv)); }
+            sc.vstate[g_v - v_lo] = (uint8_t)sb;
+            const uint32_t nh = hdr_ts(g_hdr) | (mv ? HDR_MOVABLE : 0u) | ((hdr_live(g_hdr) & ~((b_pruned & gmask) >> gbase)) << 16);
+            if (nh != g_hdr) st.hdr[g_v] = nh;
         }
     }
     n_nonempty = __reduce_add_sync(0xffffffffu, n_nonempty);
     if (lane_id() == 0 && n_nonempty) atomicAdd(&cnt->n_nonempty_voxels, n_nonempty);
-    __syncthreads();
-    if (n_occ | n_free) {
-        uint32_t pos_occ = (uint32_t)(s_prefix & 0x7fffffffu) + (ex & 0xffffu);
-        uint32_t pos_free = (uint32_t)((s_prefix >> 31) & 0x7fffffffu) + (ex >> 16);
+}
+
+// exclusive scan of the per-block (occupied, free, movable) counts; single block, any number of tiles
+__global__ void __launch_bounds__(1024)
+k_occ_scan(OccScratch sc, uint32_t n_blocks, Counters* __restrict__ cnt, Persist* __restrict__ persist) {
+    __shared__ uint32_t s_warp[33];
+    uint32_t run0 = 0, run1 = 0, run2 = 0;
+    for (uint32_t c = 0; c < n_blocks; c += blockDim.x) {
+        const uint32_t b = c + threadIdx.x;
+        const uint4 v = b < n_blocks ? sc.blk_cnt[b] : make_uint4(0, 0, 0, 0);
+        uint32_t t0, t1, t2;
+        const uint32_t e0 = block_exclusive_scan(v.x, s_warp, t0);
+        const uint32_t e1 = block_exclusive_scan(v.y, s_warp, t1);
+        const uint32_t e2 = block_exclusive_scan(v.z, s_warp, t2);
+        if (b < n_blocks) sc.blk_off[b] = make_uint4(run0 + e0, run1 + e1, run2 + e2, 0u);
+        run0 += t0; run1 += t1; run2 += t2;
+    }
+    if (threadIdx.x == 0) { cnt->n_occupied = run0; cnt->n_free = run1; cnt->n_movable = run2; persist->n_movable = run2; }
+}
+
+template <int PB>
+__global__ void __launch_bounds__(OCC_BLOCK)
+k_occ_emit(const __grid_constant__ FrameParams f, Store st, OccScratch sc, ResultArrays out, uint32_t* __restrict__ movl_idx,
+           uint16_t* __restrict__ movl_track, uint32_t movl_cap) {
+    __shared__ uint32_t s_warp[33];
+    const uint4 cntb = sc.blk_cnt[blockIdx.x];
+    if ((cntb.x | cntb.y | cntb.z) == 0) return;          // nothing to emit from this tile
+    const uint32_t v_lo = f.z_lo << (f.Xb + f.Yb);
+    const uint32_t v0 = v_lo + blockIdx.x * OCC_TILE + threadIdx.x * OCC_VPT;
+    const uint32_t sb4 = *reinterpret_cast<const uint32_t*>(sc.vstate + (v0 - v_lo));
+    uint32_t n_occ = 0, n_free = 0, n_mov = 0;
+    uint32_t mmask[OCC_VPT];
 #pragma unroll
-        for (int u = 0; u < OCC_VPT; ++u) {
-            const bool is_occ = state[u] > 0, is_free = f.want_free && state[u] == 0;
-            if (!is_occ && !is_free) continue;
+    for (int u = 0; u < OCC_VPT; ++u) {
+        const uint32_t sb = (sb4 >> (8 * u)) & 0xffu, stt = sb & 3u;
+        n_occ += stt >= 2;
+        n_free += (f.want_free && stt == 1);
+        mmask[u] = (sb & VS_MOVABLE) ? (uint32_t)sc.mov_mask[v0 + u] : 0u;
+        n_mov += __popc(mmask[u]);
+    }
+    uint32_t tot_a, tot_b;
+    const uint32_t ex_a = block_exclusive_scan(n_occ | (n_free << 16), s_warp, tot_a);   // <= 1024 each
+    const uint32_t ex_b = block_exclusive_scan(n_mov, s_warp, tot_b);
+    if ((n_occ | n_free | n_mov) == 0) return;
+    const uint4 off = sc.blk_off[blockIdx.x];
+    uint32_t pos_occ = off.x + (ex_a & 0xffffu), pos_free = off.y + (ex_a >> 16), pos_mov = off.z + ex_b;
+    uint32_t bx0, by, bz;
+    voxel_to_buffer(f, v0, bx0, by, bz);
+#pragma unroll
+    for (int u = 0; u < OCC_VPT; ++u) {
+        const uint32_t stt = (sb4 >> (8 * u)) & 3u, v = v0 + u;
+        const bool is_occ = stt >= 2, is_free = f.want_free && stt == 1;
+        if (is_occ || is_free) {
             // voxelIdxToMapFramePos + map centre (operations.h:940-944, 970-983)
             uint32_t mx, my, mz;
             buffer_to_map(f, bx0 + u, by, bz, mx, my, mz);
@@ -775,17 +1013,26 @@ k_occupancy(int slot, Store st, const uint32_t* __restrict__ stamp_x, const uint
             if (f.zero_center) { p0 = p0 - f.cam[0]; p1 = p1 - f.cam[1]; p2 = p2 - f.cam[2]; }
             if (is_occ) {
                 const uint32_t pos = pos_occ++;
-                out.voxel_index[pos] = v0 + u;
+                const uint32_t tl = sc.res_tl[v];
+                out.voxel_index[pos] = v;
                 out.xyz[3 * (size_t)pos + 0] = p0; out.xyz[3 * (size_t)pos + 1] = p1; out.xyz[3 * (size_t)pos + 2] = p2;
-                out.weight_sum[pos] = wsum[u];
-                out.track_id[pos] = (uint16_t)(tl[u] & 0xffffu);
-                out.label_id[pos] = (uint8_t)(tl[u] >> 16);
-                out.state[pos] = (int8_t)state[u];
+                out.weight_sum[pos] = sc.res_w[v];
+                out.track_id[pos] = (uint16_t)(tl & 0xffffu);
+                out.label_id[pos] = (uint8_t)((tl >> 16) & 0xffu);
+                out.state[pos] = (int8_t)((int)stt - 1);
             } else {
                 const uint32_t pos = pos_free++;
-                out.free_voxel_index[pos] = v0 + u;
+                out.free_voxel_index[pos] = v;
                 out.free_xyz[3 * (size_t)pos + 0] = p0; out.free_xyz[3 * (size_t)pos + 1] = p1; out.free_xyz[3 * (size_t)pos + 2] = p2;
             }
+        }
+        uint32_t mm = mmask[u];
+        while (mm) {
+            const uint32_t s = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const size_t idx = ((size_t)v << PB) + s;
+            if (pos_mov < movl_cap) { movl_idx[pos_mov] = (uint32_t)idx; movl_track[pos_mov] = (uint16_t)meta_track(st.meta[idx]); }
+            ++pos_mov;
         }
     }
 }
@@ -793,10 +1040,11 @@ k_occupancy(int slot, Store st, const uint32_t* __restrict__ stamp_x, const uint
 // =====================================================================================================
 // P2/P3  object moves  replaces moveParticlesInSetsByTransformations (mc_ring/operations.h:321-362) and
 //                      ObjectSet::removeObjectByTrackID (object_layer.h:414-425).
-// set(T) = { p : status(p) != INVALID and track(p) == T } in ascending particle index (canonical order).
+// set(T) = { p : status(p) != INVALID and track(p) == T } in ascending particle index (canonical order), read from
+// the movable-particle list the previous frame's occupancy pass left behind (nothing touches the store in between).
 // =====================================================================================================
-constexpr int SEL_BLOCK = 1024;
 constexpr int MAX_MOVES = 64;
+constexpr uint32_t SEQ_REMOVE = 0xfffffffeu;
 
 struct MoveTable {
     int32_t n_moves, n_remove;
@@ -811,110 +1059,77 @@ __device__ __forceinline__ int find_track(const int32_t* __restrict__ tab, int n
     return -1;
 }
 
-// pass 1: ordered list of (particle index, move index) for every particle of a moved track; particles of a
-// removed track are invalidated on the spot.  One thread per voxel; only voxels whose header carries the
-// "movable" flag are opened (the flag is cleared when no live movable-track particle is left).
-__global__ void __launch_bounds__(SEL_BLOCK)
-k_select_tracks(int slot, Store st, const MoveTable* __restrict__ mt, uint32_t* __restrict__ sel_idx, uint32_t* __restrict__ sel_move,
-                uint64_t* __restrict__ lb_status, Counters* __restrict__ cnt, uint32_t sel_cap) {
-    __shared__ uint32_t s_bid, s_warp[33];
-    __shared__ uint64_t s_prefix;
-    const FrameParams& f = c_fp[slot];
-    if (threadIdx.x == 0) s_bid = atomicAdd(&cnt->ticket_sel, 1u);
-    __syncthreads();
-    const uint32_t bid = s_bid;
-    const uint32_t v = (f.z_lo << (f.Xb + f.Yb)) + bid * SEL_BLOCK + threadIdx.x;
-    const size_t base = (size_t)v << f.Pb;
-    const uint32_t hdr = st.hdr[v];
-    uint32_t sel = 0, n_removed = 0;
-    if (hdr & HDR_MOVABLE) {
-        uint32_t live = hdr_live(hdr), new_live = live;
-        bool any_movable = false;
-        while (live) {
-            const uint32_t s = __ffs(live) - 1;
-            live &= live - 1;
-            const uint64_t m = st.meta[base + s];
-            const int tr = (int)meta_track(m);
-            if ((uint32_t)tr > f.max_movable) continue;
-            if (find_track(mt->move_track, mt->n_moves, tr) >= 0) { sel |= 1u << s; any_movable = true; }
-            else if (find_track(mt->remove_track, mt->n_remove, tr) >= 0) {
-                st.meta[base + s] = meta_with_status(m, ST_INVALID);
-                new_live &= ~(1u << s);
-                ++n_removed;
-            } else any_movable = true;
-        }
-        const uint32_t nh = hdr_ts(hdr) | (any_movable ? HDR_MOVABLE : 0u) | (new_live << 16);
-        if (nh != hdr) st.hdr[v] = nh;
-    }
-    uint32_t total;
-    const uint32_t ex = block_exclusive_scan((uint32_t)__popc(sel), s_warp, total);
-    if (threadIdx.x < 32) {
-        const uint64_t prefix = lookback_prefix_warp(lb_status, bid, total);
-        if (threadIdx.x == 0) {
-            s_prefix = prefix;
-            if (bid == gridDim.x - 1) cnt->n_selected = (uint32_t)(prefix + total);
-        }
-    }
-    n_removed = __reduce_add_sync(0xffffffffu, n_removed);
-    if (lane_id() == 0 && n_removed) atomicAdd(&cnt->n_removed, n_removed);
-    __syncthreads();
-    uint32_t pos = (uint32_t)s_prefix + ex;
-    while (sel) {
-        const uint32_t s = __ffs(sel) - 1;
-        sel &= sel - 1;
-        if (pos < sel_cap) {
-            sel_idx[pos] = (uint32_t)(base + s);
-            sel_move[pos] = (uint32_t)find_track(mt->move_track, mt->n_moves, (int)meta_track(st.meta[base + s]));
-        }
-        ++pos;
-    }
-}
-
-// pass 2: sequence number of every selected particle in the reference's processing order (object by object,
-// ascending index inside an object) = offset[move] + rank among the same move's entries.  Single block.
+// pass 1 (single block): sequence number of every listed particle of a moved track in the reference's processing
+// order — object by object, ascending index inside an object — = offset[move] + stable rank among the move's entries.
+// Entries of a removed track are tagged SEQ_REMOVE, everything else NO_RANK.  Also advances the random cursor.
 __global__ void __launch_bounds__(1024)
-k_move_sequence(const Counters* __restrict__ cnt, const MoveTable* __restrict__ mt, const uint32_t* __restrict__ sel_move,
-                uint32_t* __restrict__ sel_seq, uint32_t sel_cap) {
+k_move_prepare(const MoveTable* __restrict__ mt, const uint16_t* __restrict__ movl_track, uint32_t* __restrict__ movl_seq,
+               uint32_t movl_cap, uint32_t rand_n, Counters* __restrict__ cnt, Persist* __restrict__ persist) {
     __shared__ uint32_t s_count[MAX_MOVES], s_offset[MAX_MOVES], s_running[MAX_MOVES];
-    __shared__ uint32_t s_warp[33];
-    const uint32_t n = min(cnt->n_selected, sel_cap);
+    __shared__ uint32_t s_wcount[32][MAX_MOVES];
+    const uint32_t n = min(persist->n_movable, movl_cap);
+    const int n_moves = mt->n_moves;
     if (threadIdx.x < MAX_MOVES) { s_count[threadIdx.x] = 0; s_running[threadIdx.x] = 0; }
     __syncthreads();
-    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) atomicAdd(&s_count[sel_move[k]], 1u);
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+        const int mv = find_track(mt->move_track, n_moves, (int)movl_track[k]);
+        if (mv >= 0) atomicAdd(&s_count[mv], 1u);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t acc = 0;
-        for (int m = 0; m < mt->n_moves; ++m) { s_offset[m] = acc; acc += s_count[m]; }
+        for (int m = 0; m < n_moves; ++m) { s_offset[m] = acc; acc += s_count[m]; }
+        cnt->n_selected = acc;
+        cnt->move_cursor0 = persist->cursor_ring;
+        persist->cursor_ring = (uint32_t)(((uint64_t)persist->cursor_ring + 3ull * acc) % rand_n);   // basic_algorithms.h:426-433
     }
-    __syncthreads();
-    // stable rank inside each move: chunks of blockDim entries, one move at a time
+    const uint32_t wid = threadIdx.x >> 5;
     for (uint32_t c = 0; c < n; c += blockDim.x) {
+        for (int i = threadIdx.x; i < 32 * MAX_MOVES; i += blockDim.x) (&s_wcount[0][0])[i] = 0;
+        __syncthreads();
         const uint32_t k = c + threadIdx.x;
-        const int my = k < n ? (int)sel_move[k] : -1;
-        for (int m = 0; m < mt->n_moves; ++m) {
-            if (s_count[m] == 0) continue;
-            uint32_t total;
-            const uint32_t ex = block_exclusive_scan(my == m ? 1u : 0u, s_warp, total);
-            if (my == m) sel_seq[k] = s_offset[m] + s_running[m] + ex;
-            __syncthreads();
-            if (threadIdx.x == 0) s_running[m] += total;
-            __syncthreads();
+        int mv = -1;
+        bool rm = false;
+        if (k < n) {
+            const int tr = (int)movl_track[k];
+            mv = find_track(mt->move_track, n_moves, tr);
+            if (mv < 0) rm = find_track(mt->remove_track, mt->n_remove, tr) >= 0;
         }
+        const uint32_t peers = __match_any_sync(0xffffffffu, mv);
+        const uint32_t rank_in_warp = __popc(peers & ((1u << lane_id()) - 1u));
+        if (mv >= 0 && rank_in_warp == 0) s_wcount[wid][mv] = __popc(peers);
+        __syncthreads();
+        if ((int)threadIdx.x < n_moves) {          // exclusive prefix over the warps of this chunk, per move
+            uint32_t acc = s_running[threadIdx.x];
+            for (int w = 0; w < 32; ++w) { const uint32_t t = s_wcount[w][threadIdx.x]; s_wcount[w][threadIdx.x] = acc; acc += t; }
+            s_running[threadIdx.x] = acc;
+        }
+        __syncthreads();
+        if (k < n) movl_seq[k] = mv >= 0 ? s_offset[mv] + s_wcount[wid][mv] + rank_in_warp : (rm ? SEQ_REMOVE : NO_RANK);
+        __syncthreads();
     }
 }
 
-// pass 3: transform + table noise into a staging record, delete the original, bin by destination voxel
+// pass 2: transform + table noise into a staging record, delete the original, bin by destination voxel; removed
+// tracks' particles are invalidated here too
 __global__ void __launch_bounds__(256)
-k_move_apply(int slot, Counters* __restrict__ cnt, Store st, const MoveTable* __restrict__ mt, const float* __restrict__ randoms,
-             const Persist* __restrict__ persist, const uint32_t* __restrict__ sel_idx, const uint32_t* __restrict__ sel_move,
-             const uint32_t* __restrict__ sel_seq, float4* __restrict__ mov_pos, uint64_t* __restrict__ mov_meta,
-             uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks, uint32_t* __restrict__ entry_list, uint32_t sel_cap) {
-    const FrameParams& f = c_fp[slot];
-    const uint32_t n = min(cnt->n_selected, sel_cap);
-    const uint32_t cur = persist->cursor_ring;
+k_move_apply(const __grid_constant__ FrameParams f, Counters* __restrict__ cnt, Store st, const MoveTable* __restrict__ mt,
+             const float* __restrict__ randoms, const Persist* __restrict__ persist, const uint32_t* __restrict__ movl_idx,
+             const uint16_t* __restrict__ movl_track, const uint32_t* __restrict__ movl_seq, uint32_t movl_cap,
+             float4* __restrict__ mov_pos, uint64_t* __restrict__ mov_meta, uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks,
+             uint32_t* __restrict__ entry_list) {
+    const uint32_t n = min(persist->n_movable, movl_cap);
+    const uint32_t cur = cnt->move_cursor0;
+    uint32_t n_removed = 0;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const uint32_t idx = sel_idx[k], seq = sel_seq[k];
-        const float* t = mt->t[sel_move[k]];
+        const uint32_t seq = movl_seq[k];
+        if (seq == NO_RANK) continue;
+        const uint32_t idx = movl_idx[k];
+        const uint64_t m = st.meta[idx];
+        st.meta[idx] = meta_with_status(m, ST_INVALID);                        // operations.h:346 / object_layer.h:418-421
+        atomicAnd(st.hdr + (idx >> f.Pb), ~(1u << (16 + (idx & (f.P - 1)))));
+        if (seq == SEQ_REMOVE) { ++n_removed; continue; }
+        const float* t = mt->t[find_track(mt->move_track, mt->n_moves, (int)movl_track[k])];
         const float ox = st.x[idx], oy = st.y[idx], oz = st.z[idx];
         const float nx = ((t[0] * ox + t[1] * oy) + t[2] * oz) + t[3];       // operations.h:340
         const float ny = ((t[4] * ox + t[5] * oy) + t[6] * oz) + t[7];
@@ -924,60 +1139,95 @@ k_move_apply(int slot, Counters* __restrict__ cnt, Store st, const MoveTable* __
         const float px = nx + randoms[(d0 + 1) % f.rand_n];
         const float py = ny + randoms[(d0 + 2) % f.rand_n];
         const float pz = nz + randoms[(d0 + 3) % f.rand_n];
-        const uint64_t m = st.meta[idx];
         mov_pos[seq] = make_float4(px, py, pz, st.w[idx]);
         mov_meta[seq] = m;
-        st.meta[idx] = meta_with_status(m, ST_INVALID);                        // operations.h:346
-        atomicAnd(st.hdr + (idx >> f.Pb), ~(1u << (16 + (idx & (f.P - 1)))));
         uint32_t bx, by, bz;
         const uint32_t v = global_pos_to_voxel(f, px, py, pz, bx, by, bz);
-        if (v != INVALID_INDEX) topk_insert(f, v, seq, keys, ranks, entry_list, &cnt->n_move_voxels, &cnt->hash_overflow);
+        if (v != INVALID_INDEX) topk_insert(f, f.hash_cap, f.hash_shift, v, seq, keys, ranks, entry_list, &cnt->n_move_voxels, &cnt->hash_overflow);
     }
+    if (n_removed) atomicAdd(&cnt->n_removed, n_removed);
 }
 
-__global__ void k_advance_cursor(const Counters* __restrict__ cnt, Persist* __restrict__ persist, uint32_t rand_n, uint32_t sel_cap) {
-    const uint32_t n = min(cnt->n_selected, sel_cap);
-    persist->cursor_ring = (uint32_t)(((uint64_t)persist->cursor_ring + 3ull * n) % rand_n);
+// fallback removal by a pass over the header plane (used when the movable list does not describe the store any more:
+// a track that is moved AND removed in the same frame, which the reference removes after the move)
+__global__ void __launch_bounds__(256)
+k_remove_tracks_scan(const __grid_constant__ FrameParams f, Store st, const MoveTable* __restrict__ mt, Counters* __restrict__ cnt) {
+    const uint32_t v_lo = f.z_lo << (f.Xb + f.Yb), v_hi = f.z_hi << (f.Xb + f.Yb);
+    uint32_t n_removed = 0;
+    for (uint32_t v = v_lo + blockIdx.x * blockDim.x + threadIdx.x; v < v_hi; v += gridDim.x * blockDim.x) {
+        const uint32_t hdr = st.hdr[v];
+        if (!(hdr & HDR_MOVABLE)) continue;
+        const size_t base = (size_t)v << f.Pb;
+        uint32_t live = hdr_live(hdr), new_live = live;
+        while (live) {
+            const uint32_t s = __ffs(live) - 1;
+            live &= live - 1;
+            const uint64_t m = st.meta[base + s];
+            if (find_track(mt->remove_track, mt->n_remove, (int)meta_track(m)) >= 0) {
+                st.meta[base + s] = meta_with_status(m, ST_INVALID);
+                new_live &= ~(1u << s);
+                ++n_removed;
+            }
+        }
+        if (new_live != hdr_live(hdr)) st.hdr[v] = (hdr & 0x1ffffu) | (new_live << 16);
+    }
+    if (n_removed) atomicAdd(&cnt->n_removed, n_removed);
 }
 
-// pass 4: re-insert in sequence order (operations.h:351-360); one thread per destination voxel
+// pass 4: re-insert in sequence order (operations.h:351-360); one thread per destination voxel decides the slots
+template <int PB>
 __global__ void __launch_bounds__(128)
-k_move_replay(int slot, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
-              const uint32_t* __restrict__ stamp_z, const float4* __restrict__ mov_pos, const uint64_t* __restrict__ mov_meta,
-              uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks, const uint32_t* __restrict__ entry_list,
-              Counters* __restrict__ cnt) {
-    const FrameParams& f = c_fp[slot];
+k_move_replay(const __grid_constant__ FrameParams f, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
+              const uint32_t* __restrict__ stamp_z, uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks,
+              const uint32_t* __restrict__ entry_list, uint32_t* __restrict__ entry_voxel, Counters* __restrict__ cnt) {
+    constexpr int P = 1 << PB, K = 2 * P - 1;
     const uint32_t n_entries = cnt->n_move_voxels;
     for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < n_entries; li += gridDim.x * blockDim.x) {
         const uint32_t e = entry_list[li];
         const uint32_t v = keys[e];
         keys[e] = EMPTY_KEY;
+        entry_voxel[li] = v;
+        uint32_t* r = ranks + (size_t)e * K;
+        uint32_t rk[K];
+#pragma unroll
+        for (int t = 0; t < K; ++t) rk[t] = r[t];
         uint32_t bx, by, bz;
         voxel_to_buffer(f, v, bx, by, bz);
         const uint32_t stamp = slab_stamp(stamp_x, stamp_y, stamp_z, bx, by, bz);
-        const size_t base = (size_t)v << f.Pb;
         const uint32_t hdr = st.hdr[v];
-        uint32_t live = hdr_live(hdr);
-        uint32_t* r = ranks + (size_t)e * f.topk;
+        VoxelSlots<P> vs;
+        vs.load(st, (size_t)v << PB, hdr, stamp);
         uint32_t moved = 0;
-        bool full = false;
-        for (uint32_t t = 0; t < f.topk; ++t) {
-            const uint32_t seq = r[t];
-            if (seq == NO_RANK) break;
-            r[t] = NO_RANK;
-            if (full) continue;
-            const uint32_t s = first_vacant(st, base, f.P, live, stamp);
-            if (!s) { full = true; continue; }
-            const float4 p = mov_pos[seq];
-            st.x[base + s] = p.x; st.y[base + s] = p.y; st.z[base + s] = p.z; st.w[base + s] = p.w;
-            st.meta[base + s] = mov_meta[seq];
-            live |= 1u << s;
-            ++moved;
+#pragma unroll
+        for (int t = 0; t < K; ++t) {
+            const uint32_t seq = rk[t];
+            if (seq == NO_RANK) continue;
+            const uint32_t s = vs.first_vacant();
+            if (s) { vs.occupy(s); ++moved; }
+            r[t] = s ? (seq | (s << 24)) : NO_RANK;
         }
         if (moved) {
-            st.hdr[v] = hdr_ts(hdr) | HDR_MOVABLE | (live << 16);   // moved particles belong to a movable track by construction
+            st.hdr[v] = hdr_ts(hdr) | HDR_MOVABLE | (vs.live << 16);   // moved particles belong to a movable track by construction
             atomicAdd(&cnt->n_moved, moved);
         }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_move_write(const __grid_constant__ FrameParams f, Store st, const float4* __restrict__ mov_pos, const uint64_t* __restrict__ mov_meta, uint32_t* __restrict__ ranks,
+             const uint32_t* __restrict__ entry_list, const uint32_t* __restrict__ entry_voxel, const Counters* __restrict__ cnt) {
+    const uint32_t K = f.topk, n = cnt->n_move_voxels * K;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const uint32_t li = t / K, i = t - li * K;
+        uint32_t* r = ranks + (size_t)entry_list[li] * K + i;
+        const uint32_t a = *r;
+        if (a == NO_RANK) continue;
+        *r = NO_RANK;
+        const uint32_t s = a >> 24, seq = a & 0xffffffu;
+        const size_t idx = ((size_t)entry_voxel[li] << f.Pb) + s;
+        const float4 p = mov_pos[seq];
+        st.x[idx] = p.x; st.y[idx] = p.y; st.z[idx] = p.z; st.w[idx] = p.w;
+        st.meta[idx] = mov_meta[seq];
     }
 }
 
@@ -1012,6 +1262,27 @@ k_count_track(Store st, uint32_t n_voxels, uint32_t slot_bits, uint32_t track, u
     }
     c = __reduce_add_sync(0xffffffffu, c);
     if (lane_id() == 0 && c) atomicAdd(out, c);
+}
+
+// brute-force check of InvDiv against the compiler's IEEE division (test hook)
+__global__ void k_selftest_invdiv(uint64_t n, uint64_t seed, float b_lo, float b_hi, float a_max, unsigned long long* __restrict__ mismatches) {
+    uint64_t local = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t z = seed + i * 0x9E3779B97F4A7C15ull;            // splitmix64
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+        const float ub = (float)(uint32_t)(z & 0xffffffu) * (1.0f / 16777216.0f);
+        const float b = b_lo + ub * (b_hi - b_lo);
+        // dividend: random sign, random mantissa, magnitude spread over many binades up to a_max
+        const uint32_t bits = (uint32_t)(z >> 24);
+        const float mant = 1.0f + (float)(bits & 0x7fffffu) * (1.0f / 8388608.0f);
+        const int ex = (int)((bits >> 23) & 31u) - 24;            // 2^-24 .. 2^7
+        float a = ldexpf(mant, ex) * ((bits >> 28) & 1u ? -1.f : 1.f);
+        if (fabsf(a) > a_max) a = a_max * 0.73f;
+        const InvDiv d(b);
+        const float q1 = d.ok ? d.div<true>(a) : d.div<false>(a), q2 = a / b;
+        if (__float_as_uint(q1) != __float_as_uint(q2)) ++local;
+    }
+    if (local) atomicAdd(mismatches, (unsigned long long)local);
 }
 
 }  // namespace dspk

@@ -43,3 +43,14 @@ def test_fast_motion_ring_wrap():
     cfg = dataclasses.replace(tiny(BASELINE["B"]), speed=2.0)
     eng, orc = _pair(cfg)
     run_pair(eng, orc, Scene(cfg), 12, make_random_table(cfg.seed, 50_000))
+
+
+def test_hoisted_reciprocal_division_is_ieee_exact():
+    # the stencil kernels divide by a per-thread sigma with a hoisted reciprocal (InvDiv); it must equal `/` bit for bit
+    import ctypes as C
+    cfg = tiny(BASELINE["B"])
+    eng = SemanticDSPMap(cfg).engine
+    for seed, (b_lo, b_hi, a_max) in enumerate([(0.05, 1.5, 64.0), (0.3, 0.6, 16.0), (0.1, 0.1000001, 4.0), (1e-3, 50.0, 1e4)]):
+        bad = C.c_uint64(123)
+        eng.check(eng.lib.dspmap_selftest_division(eng._h, 1 << 30, 1234 + seed, b_lo, b_hi, a_max, C.byref(bad)), "selftest")
+        assert bad.value == 0, (b_lo, b_hi, a_max, bad.value)
