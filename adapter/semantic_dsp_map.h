@@ -1,0 +1,177 @@
+// semantic_dsp_map.h — drop-in replacement for the reference header of the same name
+// (reference include/semantic_dsp_map.h:23-251): class SemanticDSPMap with the same public methods, implemented over
+// the C ABI of the B200 engine (include/dspmap_c.h, libdspmap_b200.so).  src/mapping.cpp includes this header instead
+// of the reference one and compiles unchanged: same constructor, the five setters it calls (mapping.cpp:135-140) and
+// update() (mapping.cpp:273).  Host work kept here = what the reference does with string keys and tiny per-object
+// loops: label look-ups, bbox from key points, the track-id wrap.  Nothing here touches particles, pixels or voxels.
+//
+// Needs the same third-party headers as the reference (Eigen, OpenCV, PCL).  The object layer
+// (objectLevelUpdate, reference :306-566) is out of scope for the engine: an integrator keeps the reference's
+// object_layer.h and passes what it decides through setObjectMoves() before update().
+#pragma once
+#include <Eigen/Dense>
+#include <opencv2/opencv.hpp>
+#include <pcl/point_cloud.h>
+#include <pcl/point_types.h>
+
+#include <cfloat>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "dspmap_c.h"
+
+// reference include/utils/tracking_result_handler.h:15-26
+struct BBox2D { int x = 0, y = 0, width = 0, height = 0; };
+struct MaskKpts {
+    int track_id = 0;
+    std::string label;
+    std::vector<Eigen::Vector3d> kpts_current;
+    std::vector<Eigen::Vector3d> kpts_previous;
+    cv::Mat mask;
+    BBox2D bbox;
+};
+
+// label tables: what ObjectInfoHandler::readObjectInfo leaves in the reference's globals
+// (include/utils/data_base.h:108-212; include/utils/object_info_handler.h:28-91)
+struct DspLabelTables {
+    std::unordered_map<std::string, int> label_id;            // g_label_id_map_default
+    std::unordered_map<int, std::string> label_id_reversed;   // g_label_id_map_reversed
+    std::unordered_map<std::string, int> label_id_static;     // g_label_id_map_static
+    std::unordered_map<std::string, int> label_to_instance;   // g_label_to_instance_id_map_default
+    std::map<int, std::string> instance_to_label;             // g_instance_id_to_label_map_default
+    int max_movable_instance_id = 65523;                      // g_max_movable_object_instance_id
+
+    void addRow(int id, const std::string& name, int instance_id) {   // object_info_handler.h:51-86
+        label_id[name] = id;
+        label_id_reversed[id] = name;
+        if (instance_id > 0) {
+            label_id_static[name] = id;
+            label_to_instance[name] = instance_id;
+            instance_to_label[instance_id] = name;
+            if (instance_id - 1 < max_movable_instance_id) max_movable_instance_id = instance_id - 1;
+        }
+    }
+    template <class M, class K> static int getOr0(const M& m, const K& k) { auto it = m.find(k); return it == m.end() ? 0 : it->second; }
+};
+
+class SemanticDSPMap {
+public:
+    // compile-time constants of the reference (include/settings/settings.h) become this runtime config
+    explicit SemanticDSPMap(const dspmap_config& cfg, const DspLabelTables& labels = DspLabelTables()) : cfg_(cfg), labels_(labels) {
+        if (dspmap_create(&cfg_, &h_) != DSPMAP_OK) { std::fprintf(stderr, "dspmap_create failed\n"); std::exit(-1); }   // reference: exit(-1), operations.h:57
+        prm_ = dspmap_params{0.95f, 0.1f, 3, 0.2f, 1.0f, 5, 0.1f, 0.0f, 0.1f, 0, 0, 0};   // ctor defaults, reference :25-43
+        pushLabels();
+    }
+    ~SemanticDSPMap() { dspmap_destroy(h_); }
+    SemanticDSPMap(const SemanticDSPMap&) = delete;
+    SemanticDSPMap& operator=(const SemanticDSPMap&) = delete;
+
+    void clear() { dspmap_clear(h_); }                                                          // reference :74-81
+    void setTemplatePath(std::string) {}                                                         // template matching: out of scope
+    void setMapParameters(float detection_probability, float noise_number, int nb_ptc_num_per_point, float occupancy_threshold,
+                          int max_obersevation_lost_time, float forgetting_rate = 1.f, int max_forget_count = 5,
+                          float match_score_threshold = 0.5f, float id_transition_probability = 0.1f) {   // reference :101-119
+        prm_.detection_probability = detection_probability; prm_.noise_number = noise_number;
+        prm_.nb_ptc_num_per_point = nb_ptc_num_per_point; prm_.occupancy_threshold = occupancy_threshold;
+        prm_.forgetting_rate = forgetting_rate; prm_.max_forget_count = max_forget_count;
+        prm_.id_transition_probability = id_transition_probability;
+        max_obersevation_lost_time_ = max_obersevation_lost_time; match_score_threshold_ = match_score_threshold;
+        dspmap_set_params(h_, &prm_);
+    }
+    void setMapOptions(bool if_consider_depth_noise, bool if_use_independent_filter) {          // reference :121-126
+        prm_.consider_depth_noise = if_consider_depth_noise; prm_.use_independent_filter = if_use_independent_filter;
+        dspmap_set_params(h_, &prm_);
+    }
+    void setVisualizeOptions(bool visualize_with_zero_center, bool if_out_evaluation_format = false) {   // reference :130-134
+        prm_.zero_center = visualize_with_zero_center; if_out_evaluation_format_ = if_out_evaluation_format;
+        dspmap_set_params(h_, &prm_);
+    }
+    void setBeyesianMovementParameters(double, double, double, double) {}                        // object layer (host), reference :142-150
+    void setOccupancyThreshold(float t) { prm_.occupancy_threshold = t; dspmap_set_params(h_, &prm_); }   // reference :153-156
+    void setDepthNoiseModelParameters(float first_order, float zero_order) {                     // reference :161-166
+        prm_.depth_noise_first_order = first_order; prm_.depth_noise_zero_order = zero_order;
+        dspmap_set_params(h_, &prm_);
+    }
+    // what the integrator's object layer decided for the coming frame (rigid motion per moving track, tracks to drop)
+    void setObjectMoves(const std::vector<dspmap_object_move>& moves, const std::vector<int32_t>& remove_tracks) {
+        moves_ = moves; remove_ = remove_tracks;
+    }
+
+    // reference :170-251.  Unlike the reference the caller's depth/mask Mats are NOT resized in place.
+    void update(cv::Mat& depth_value_mat, std::vector<MaskKpts>& ins_seg_result, Eigen::Vector3d& camera_position,
+                Eigen::Quaterniond& camera_orientation, pcl::PointCloud<pcl::PointXYZRGB>::Ptr& occupied_point_cloud,
+                pcl::PointCloud<pcl::PointXYZRGB>::Ptr& freespace_point_cloud, bool if_get_freespace = false, double = 0.0) {
+        std::vector<dspmap_mask> masks(ins_seg_result.size());
+        for (size_t i = 0; i < ins_seg_result.size(); ++i) {
+            MaskKpts& m = ins_seg_result[i];
+            if (m.label != "static" && m.track_id > labels_.max_movable_instance_id) {           // reference :179-186
+                std::printf("Reach the maximum movable object instance id. ID reallocated.\n");
+                m.track_id = m.track_id % labels_.max_movable_instance_id;
+            }
+            dspmap_mask& d = masks[i];
+            d.data = m.mask.data; d.row_stride = (int32_t)m.mask.step; d.is_static = m.label == "static";
+            d.track_id = m.track_id; d.label_id = DspLabelTables::getOr0(labels_.label_id, m.label);
+            double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {DBL_MIN, DBL_MIN, DBL_MIN};     // pointcloud_tools.h:178-199
+            for (const auto& k : m.kpts_current)
+                for (int a = 0; a < 3; ++a) { if (k[a] < mn[a]) mn[a] = k[a]; if (k[a] > mx[a]) mx[a] = k[a]; }
+            for (int a = 0; a < 3; ++a) { d.bbox_min[a] = mn[a] - 1.0; d.bbox_max[a] = mx[a] + 1.0; }
+        }
+        const double pos[3] = {camera_position.x(), camera_position.y(), camera_position.z()};
+        const double quat[4] = {camera_orientation.w(), camera_orientation.x(), camera_orientation.y(), camera_orientation.z()};
+        const int rc = dspmap_update(h_, reinterpret_cast<const float*>(depth_value_mat.data), depth_value_mat.rows, depth_value_mat.cols,
+                                     (int32_t)(depth_value_mat.step / sizeof(float)), masks.data(), (int32_t)masks.size(), pos, quat,
+                                     moves_.data(), (int32_t)moves_.size(), remove_.data(), (int32_t)remove_.size(), if_get_freespace);
+        moves_.clear(); remove_.clear();
+        if (rc != DSPMAP_OK) { std::fprintf(stderr, "dspmap_update: %s\n", dspmap_last_error(h_)); return; }   // reference: no error channel
+        dspmap_result r;
+        if (dspmap_get_result(h_, &r) != DSPMAP_OK) return;
+        for (uint32_t i = 0; i < r.count; ++i) {                                                  // reference :1274-1351
+            pcl::PointXYZRGB pt;
+            pt.x = r.xyz[3 * i]; pt.y = r.xyz[3 * i + 1]; pt.z = r.xyz[3 * i + 2];
+            if (r.state[i] == 2) { pt.r = pt.g = pt.b = 255; }                                   // guessed occupied: white (:1326-1330)
+            else if (if_out_evaluation_format_) { pt.r = r.label_id[i]; pt.g = r.track_id[i] >> 8; pt.b = r.track_id[i] & 0xFF; }   // :1311-1315
+            else { pt.r = 160; pt.g = (uint8_t)(r.track_id[i] * 37u); pt.b = (uint8_t)(r.label_id[i] * 29u); }   // colour maps: next (§8 f1)
+            occupied_point_cloud->push_back(pt);
+        }
+        for (uint32_t i = 0; i < r.free_count; ++i) {                                             // reference :1354-1376
+            pcl::PointXYZRGB pt;
+            pt.x = r.free_xyz[3 * i]; pt.y = r.free_xyz[3 * i + 1]; pt.z = r.free_xyz[3 * i + 2];
+            pt.r = 0; pt.g = 255; pt.b = 0;
+            freespace_point_cloud->push_back(pt);
+        }
+    }
+
+    dspmap_t* handle() { return h_; }
+
+private:
+    void pushLabels() {
+        uint16_t v2t[256];
+        for (int v = 0; v < 256; ++v) {   // pointcloud_tools.h:137-138 with operator[] default-insert semantics
+            auto it = labels_.label_id_reversed.find(v + 1);
+            v2t[v] = (uint16_t)(it == labels_.label_id_reversed.end() ? 0 : DspLabelTables::getOr0(labels_.label_to_instance, it->second));
+        }
+        std::vector<uint16_t> tracks;
+        std::vector<uint8_t> labs;
+        for (const auto& kv : labels_.instance_to_label) {   // pointcloud_tools.h:277-279
+            tracks.push_back((uint16_t)kv.first);
+            labs.push_back((uint8_t)DspLabelTables::getOr0(labels_.label_id_static, kv.second));
+        }
+        dspmap_set_label_luts(h_, v2t, tracks.data(), labs.data(), (int32_t)tracks.size(), (uint16_t)labels_.max_movable_instance_id,
+                              (uint16_t)DspLabelTables::getOr0(labels_.label_to_instance, std::string("Sky")));   // pointcloud_tools.h:236
+    }
+
+    dspmap_config cfg_;
+    DspLabelTables labels_;
+    dspmap_params prm_{};
+    dspmap_t* h_ = nullptr;
+    int max_obersevation_lost_time_ = 0;
+    float match_score_threshold_ = 0.5f;
+    bool if_out_evaluation_format_ = false;
+    std::vector<dspmap_object_move> moves_;
+    std::vector<int32_t> remove_;
+};

@@ -54,3 +54,64 @@ def test_hoisted_reciprocal_division_is_ieee_exact():
         bad = C.c_uint64(123)
         eng.check(eng.lib.dspmap_selftest_division(eng._h, 1 << 30, 1234 + seed, b_lo, b_hi, a_max, C.byref(bad)), "selftest")
         assert bad.value == 0, (b_lo, b_hi, a_max, bad.value)
+
+
+@pytest.mark.parametrize("name", ["A_static", "B_zed2", "C_vkitti2", "B_fast_ring_wrap", "B_no_depth_noise"])
+def test_engine_reproduces_committed_golden_vectors(name):
+    # no oracle in the loop: the CUDA engine against tests/golden/*.npz (results + SHA-256 of the full particle store)
+    from test_oracle_golden_cpu import check_against_golden
+    check_against_golden(name, lambda cfg: SemanticDSPMap(cfg))
+
+
+def test_error_codes_through_the_c_abi():
+    from semantic_dsp_map_b200 import _capi
+    cfg = tiny(BASELINE["B"])
+    m = SemanticDSPMap(cfg)
+    with pytest.raises(_capi.DspMapError) as e:
+        m.update(np.ones((cfg.image_height, cfg.image_width + 2), np.float32), [], np.zeros(3), np.array([1.0, 0, 0, 0]))
+    assert e.value.rc == -3    # DSPMAP_ERR_IMAGE_SIZE instead of the reference's silent out-of-bounds read
+    with pytest.raises(TypeError):
+        m.update(np.ones((cfg.image_height, cfg.image_width), np.float64), [], np.zeros(3), np.array([1.0, 0, 0, 0]))
+    # an empty frame list is fine: a frame with no masks at all
+    r = m.update(np.full((cfg.image_height, cfg.image_width), 2.0, np.float32), [], np.zeros(3), np.array([1.0, 0, 0, 0]))
+    assert r.voxel_index.size >= 0
+
+
+def test_clear_then_continue_matches_oracle():
+    # SemanticDSPMap::clear (semantic_dsp_map.h:74-81): the store, the slab stamps and the time stamp reset; the ring
+    # offsets stay where the last pose left them
+    cfg = tiny(BASELINE["B"])
+    eng, orc = _pair(cfg)
+    table = make_random_table(cfg.seed, 50_000)
+    scene = Scene(cfg)
+    run_pair(eng, orc, scene, 4, table, check_frames=(3,))
+    eng.clear(); orc.clear()
+    from parity import compare_frame
+    for t in range(4, 8):
+        fr = scene.frame(t)
+        re = eng.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves)
+        fr = scene.frame(t)
+        ro = orc.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves)
+        compare_frame(eng, orc, re, ro, t)
+
+
+def test_track_removed_and_moved_in_one_frame():
+    # the reference removes a track AFTER moving it (semantic_dsp_map.h:588-737); plus a plain removal of another track
+    cfg = tiny(BASELINE["B"])
+    eng, orc = _pair(cfg)
+    table = make_random_table(cfg.seed, 50_000)
+    scene = Scene(cfg)
+    from parity import compare_frame
+    for m in (eng, orc):
+        m.engine.set_random_table(table)
+    for t in range(7):
+        outs = []
+        for m in (eng, orc):
+            fr = scene.frame(t)
+            rm = []
+            if t == 4:
+                rm = [1]                      # track 1 is moving in this scene: moved and removed in the same frame
+            if t == 5:
+                rm = [2]                      # plain removal
+            outs.append(m.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves, remove_tracks=rm))
+        compare_frame(eng, orc, outs[0], outs[1], t)
