@@ -369,6 +369,7 @@ int dspmap::init(const dspmap_config& c) {
     CU_TRY(this, cudaMemcpy(d_static_track.p, h_static_track, sizeof h_static_track, cudaMemcpyHostToDevice));
     CU_TRY(this, cudaMemset(d_static_label.p, 0, 65536));
     CU_TRY(this, d_fp.alloc(1)); CU_TRY(this, d_cnt.alloc(1)); CU_TRY(this, d_persist.alloc(1)); CU_TRY(this, d_moves.alloc(1));
+    CU_TRY(this, cudaMemset(d_persist.p, 0, sizeof(Persist)));
     CU_TRY(this, d_masks.alloc(64));
     CU_TRY(this, d_depth_in.alloc(npix_in)); CU_TRY(this, d_depth_int.alloc(npix)); CU_TRY(this, d_ck.alloc(npix));
     CU_TRY(this, d_cloud_pos.alloc(npix)); CU_TRY(this, d_cloud_meta.alloc(npix));
@@ -441,7 +442,8 @@ int dspmap::clear_device() {
     CU_TRY(this, cudaMemsetAsync(d_pix_count.p, 0, d_pix_count.n * sizeof(uint32_t), stream));
     CU_TRY(this, cudaMemsetAsync(d_pix_offset.p, 0, d_pix_offset.n * sizeof(uint32_t), stream));
     CU_TRY(this, cudaMemsetAsync(d_cnt.p, 0, sizeof(Counters), stream));
-    CU_TRY(this, cudaMemsetAsync(d_persist.p, 0, sizeof(Persist), stream));
+    // the movable-particle list is empty again; the random-table cursors survive a clear, as in the reference
+    CU_TRY(this, cudaMemsetAsync(&d_persist.p->n_movable, 0, sizeof(uint32_t), stream));
     CU_TRY(this, cudaMemsetAsync(d_vstate.p, 0, d_vstate.n, stream));
     CU_TRY(this, cudaGetLastError());
     CU_TRY(this, cudaStreamSynchronize(stream));
