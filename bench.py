@@ -10,7 +10,8 @@ A step = one SemanticDSPMap::update() over one synthetic frame (SURVEY.md §8d s
   e2e   : frames/s through the reference-facing call with HOST buffers (dspmap_update + dspmap_get_result):
           host->pinned->device copies of depth and masks and the device->host read of the occupied list are inside
           the timed region.
-  roofline    : the dominant kernel (occupancy_labels) — algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json.
+  roofline    : the HBM-streaming kernel (k_occ_headers, the per-voxel header pass of occupancy_labels) — algorithmic
+                bytes / CUDA-event duration of that launch vs MEASURED_PEAKS.json; stage_ms lists every stage.
   cpu_baseline: the CPU oracle (faithful single-thread restatement of the reference, reference iteration order) timed
                 on this box's host cores on a bounded sample of the same frames.
 N > 1: one process per GPU (torchrun); each rank updates its own map replica from its own frame stream (weak scaling,
@@ -184,7 +185,7 @@ def main():
                        fr.position, fr.orientation, fr.moves, fr.remove_tracks, False)
 
     stage_ms = np.zeros(8)
-    acc = {"n_slots_known": 0, "n_occ": 0, "n_vis": 0, "n_swept": 0}
+    acc = {"n_listed": 0, "n_occ": 0, "n_vis": 0, "n_swept": 0}
     for k in range(args.warmup):
         step_device(k)
     barrier()
@@ -198,6 +199,7 @@ def main():
         st = eng.stats()
         stage_ms += np.asarray(st["ms_stage"])
         acc["n_occ"] += st["n_occupied"]; acc["n_vis"] += st["n_visible"]; acc["n_swept"] += st["n_swept_voxels"]
+        acc["n_listed"] += st["n_nonempty_voxels"]
     e1.record(stream)
     barrier()
     gpu_launches = launches() - l0
@@ -217,7 +219,8 @@ def main():
     t0 = time.perf_counter()
     for k in range(args.warmup, n_frames):
         fr = frames[k]
-        res = m.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves, remove_tracks=fr.remove_tracks)
+        # results are read where dspmap_get_result leaves them: the handle's pinned host buffers (valid until the next update)
+        res = m.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves, remove_tracks=fr.remove_tracks, copy_result=False)
         h2d += fr.depth.nbytes + sum(mk.mask.nbytes for mk in fr.masks)
         d2h += sum(a.nbytes for a in (res.voxel_index, res.xyz, res.weight_sum, res.track_id, res.label_id, res.state)) + 80
     e3.record(stream)
@@ -231,12 +234,12 @@ def main():
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        # roofline of the dominant kernel: occupancy_labels streams the slot-0 time stamp of EVERY voxel and w + the packed
-        # 8-byte tail of every slot of every KNOWN voxel; algorithmic bytes per SURVEY.md §8(d): 11 B/slot over all N slots
-        # (+16 B per occupied voxel written) — the conservative, layout-independent figure — see DESIGN.md.
-        n_slots = cfg.n_slots
-        occ_bytes = 11.0 * n_slots + 24.0 * acc["n_occ"] / args.steps
-        occ_ms = stage_ms[6] / args.steps
+        # roofline of the HBM-streaming kernel, k_occ_headers: it reads the 4-byte header of EVERY voxel, writes one state
+        # byte per voxel and appends the voxels that need their slot records to a work list:
+        #   algorithmic bytes = 4*V + 1*V + 4*n_listed,  duration = CUDA events around that launch alone (engine stream)
+        n_vox = cfg.n_voxels
+        occ_bytes = 5.0 * n_vox + 4.0 * acc["n_listed"] / args.steps
+        occ_ms = stage_ms[1] / args.steps
         achieved = occ_bytes / (occ_ms * 1e-3) / 1e9
         out = {
             "metric": METRIC, "value": world * args.steps / (ms_device * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -248,7 +251,7 @@ def main():
             "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
-            "roofline": {"kernel": "k_occupancy", "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+            "roofline": {"kernel": "k_occ_headers", "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "algorithmic_bytes": occ_bytes, "ms": occ_ms},
             "stage_ms": {n: float(v / args.steps) for n, v in zip(_capi.STAGE_NAMES, stage_ms)},
         }

@@ -136,8 +136,9 @@ typedef struct dspmap_frame_stats {
     uint32_t n_nonempty_voxels; /* voxels with >=1 non-vacant particle at extraction    */
     uint32_t n_moved;           /* particles moved by object transforms                */
     uint32_t n_removed;         /* particles deleted by track removal                  */
-    float    ms_stage[8];       /* device time per stage when profiling is on: project, shift,
-                                   predict, visibility, update, birth, occupancy, total */
+    float    ms_stage[8];       /* device time per stage when profiling is on: project, occ_headers kernel alone
+                                   (the HBM-streaming kernel of the roofline), predict, visibility, update, birth,
+                                   occupancy, total */
 } dspmap_frame_stats;
 
 /* ---- lifecycle ---------------------------------------------------------- */

@@ -83,7 +83,7 @@ class FrameStats(C.Structure):
         return d
 
 
-STAGE_NAMES = ("project", "shift", "predict", "visibility", "update", "birth", "occupancy", "total")
+STAGE_NAMES = ("project", "occ_headers_kernel", "predict", "visibility", "update", "birth", "occupancy", "total")
 
 # name -> (restype, argtypes); every symbol include/dspmap_c.h declares
 SYMBOLS = {

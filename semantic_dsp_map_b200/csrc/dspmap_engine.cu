@@ -14,7 +14,13 @@
 #include <cstring>
 #include <cstdlib>
 #include <ctime>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace dspk;
@@ -63,6 +69,63 @@ void inverse4f(const float m[16], float o[16]) {
     const float det = ((M(0, 0) * adj[0] + M(1, 0) * adj[1]) + M(2, 0) * adj[2]) + M(3, 0) * adj[3];
     for (int k = 0; k < 16; ++k) o[k] = adj[k] / det;
 }
+
+// A few persistent host threads for the pageable -> pinned staging copies of dspmap_update (row blocks of the depth
+// image and of every mask are independent).  Workers sleep on a condition variable between frames.
+class StagePool {
+public:
+    explicit StagePool(int n_workers) {
+        for (int i = 0; i < n_workers; ++i) workers_.emplace_back([this] { loop(); });
+    }
+    ~StagePool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    // runs fn(i) for i in [0, n) on the workers and the calling thread; returns when all are done
+    void run(int n, const std::function<void(int)>& fn) {
+        if (n <= 0) return;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn; n_ = n; next_.store(0); pending_.store(n); ++epoch_;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [this] { return pending_.load() == 0; });
+        fn_ = nullptr;
+    }
+
+private:
+    void work() {
+        for (;;) {
+            const int i = next_.fetch_add(1);
+            if (i >= n_) break;
+            (*fn_)(i);
+            if (pending_.fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk(mu_); done_cv_.notify_all(); }
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || epoch_ != seen; });
+                if (stop_) return;
+                seen = epoch_;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int n_ = 0;
+    std::atomic<int> next_{0}, pending_{0};
+    uint64_t epoch_ = 0;
+    bool stop_ = false;
+};
 
 template <typename T>
 struct DevBuf {
@@ -179,12 +242,13 @@ struct dspmap {
     PinBuf<uint8_t> hr_label;
     PinBuf<int8_t> hr_state;
     bool host_result_valid = false;
+    std::unique_ptr<StagePool> stage_pool;
 
     Counters last{};
     uint32_t n_visible_last = 0;
     dspmap_frame_stats stats{};
     bool profiling = false;
-    cudaEvent_t ev[9]{};
+    cudaEvent_t ev[10]{};
 
     int fail(int rc, const char* fmt, ...) {
         char buf[512];
@@ -267,7 +331,7 @@ struct dspmap {
     int run_moves(const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove, bool scan_remove);
     int frame(const float* d_depth, int rows, int cols, int stride, const dspmap_mask* masks, int n_masks, const double pos[3],
               const double quat[4], const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove,
-              int want_free, int pre_decimated);
+              int want_free, int pre_decimated, const std::function<int(dspmap_mask*)>* late_masks = nullptr);
     int fetch_result_to_host();
 };
 
@@ -497,7 +561,9 @@ int dspmap::run_moves(const dspmap_object_move* moves, int n_moves, const int32_
 // SemanticDSPMap::update (semantic_dsp_map.h:170-251) -> subObjectLevelUpdate (:576-955)
 int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const dspmap_mask* masks, int n_masks, const double pos[3],
                   const double quat[4], const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove,
-                  int want_free, int pre_decimated) {
+                  int want_free, int pre_decimated, const std::function<int(dspmap_mask*)>* late_masks) {
+    // late_masks: the mask images are not on the device yet; the callback (host staging + H2D enqueue) runs after the
+    // mask-independent kernels have been launched, so the copy engine and the CPU work under them
     FrameParams& f = fp;
     f.pre_decimated = pre_decimated;
     if (prm.consider_depth_noise && prm.nb_ptc_num_per_point != 1)
@@ -569,15 +635,6 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     if (want_free && !r_free_idx.p) { CU_TRY(this, r_free_idx.alloc(v_local)); CU_TRY(this, r_free_xyz.alloc(3 * (size_t)v_local)); }
 
     // ---- uploads -------------------------------------------------------------------------------------------
-    if ((size_t)n_masks > d_masks.n) { CU_TRY(this, d_masks.alloc(n_masks)); }
-    CU_TRY(this, p_maskdesc.reserve(std::max(n_masks, 1)));
-    for (int m = 0; m < n_masks; ++m) {
-        MaskDesc& md = p_maskdesc.p[m];
-        md.data = masks[m].data; md.row_stride = masks[m].row_stride; md.is_static = masks[m].is_static;
-        md.track_id = masks[m].track_id; md.label_id = masks[m].label_id;
-        for (int a = 0; a < 3; ++a) { md.bbox_min[a] = masks[m].bbox_min[a]; md.bbox_max[a] = masks[m].bbox_max[a]; }
-    }
-    if (n_masks) CU_TRY(this, cudaMemcpyAsync(d_masks.p, p_maskdesc.p, n_masks * sizeof(MaskDesc), cudaMemcpyHostToDevice, stream));
     if (stamps_dirty) {
         uint32_t* s = p_stamps.p;
         for (int a = 0; a < 3; ++a) { memcpy(s, stamps[a].data(), stamps[a].size() * 4); s += stamps[a].size(); }
@@ -592,10 +649,9 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     const size_t lut_bytes = PDF_NUM * sizeof(float);
 
     if (profiling) cudaEventRecord(ev[0], stream);
-    // ---- K1 projection ---------------------------------------------------------------------------------------
-    ++launches; k_project<<<(npix + 255) / 256, 256, 0, stream>>>(fp, d_depth, stride, d_masks.p, d_static_track.p, d_static_label.p,
-                                                     d_depth_int.p, d_cloud_pos.p, d_cloud_meta.p, d_cnt.p);
-    if (profiling) { cudaEventRecord(ev[1], stream); cudaEventRecord(ev[2], stream); }
+    // ---- K1a internal depth image ----------------------------------------------------------------------------------
+    ++launches; k_depth_int<<<(npix + 255) / 256, 256, 0, stream>>>(fp, d_depth, stride, d_depth_int.p);
+    if (profiling) cudaEventRecord(ev[1], stream);
     // ---- P2/P3 object predict / prune ---------------------------------------------------------------------------
     if (n_moves > 0 || n_remove > 0) {
         // a track that is both moved and removed is removed AFTER its move (the reference order)
@@ -613,7 +669,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
             if (rc != DSPMAP_OK) return rc;
         }
     }
-    if (profiling) cudaEventRecord(ev[3], stream);
+    if (profiling) cudaEventRecord(ev[2], stream);
     // ---- U2 visibility ---------------------------------------------------------------------------------------------
     if (f.start_in) {
         const int y0 = std::max(f.vb_lo[1] - 1, 0), y1 = std::min(f.vb_hi[1] + 1, (int)f.NY);
@@ -629,6 +685,21 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     ++launches; k_fill<<<sm_count * 4, 256, 0, stream>>>(fp, d_cnt.p, d_pairs.p, d_pix_offset.p, d_pix_count.p, d_csr_idx.p, d_vis_pix.p);
     ++launches; k_sort_lists<<<(npix + 255) / 256, 256, 0, stream>>>(fp, d_pix_offset.p, d_csr_idx.p);
     ++launches; k_gather_visible<<<sm_count * 4, 256, 0, stream>>>(fp, d_pix_offset.p + npix, st, d_csr_idx.p, d_vis_pos.p, d_vis_meta.p);
+    if (profiling) cudaEventRecord(ev[3], stream);
+    // ---- K1 projection + labels (needs the masks) -----------------------------------------------------------------------
+    std::vector<dspmap_mask> mask_copy(masks, masks + n_masks);
+    if (late_masks) { const int rc = (*late_masks)(mask_copy.data()); if (rc != DSPMAP_OK) return rc; }
+    if ((size_t)n_masks > d_masks.n) { CU_TRY(this, d_masks.alloc(n_masks)); }
+    CU_TRY(this, p_maskdesc.reserve(std::max(n_masks, 1)));
+    for (int m = 0; m < n_masks; ++m) {
+        MaskDesc& md = p_maskdesc.p[m];
+        md.data = mask_copy[m].data; md.row_stride = mask_copy[m].row_stride; md.is_static = mask_copy[m].is_static;
+        md.track_id = mask_copy[m].track_id; md.label_id = mask_copy[m].label_id;
+        for (int a = 0; a < 3; ++a) { md.bbox_min[a] = mask_copy[m].bbox_min[a]; md.bbox_max[a] = mask_copy[m].bbox_max[a]; }
+    }
+    if (n_masks) CU_TRY(this, cudaMemcpyAsync(d_masks.p, p_maskdesc.p, n_masks * sizeof(MaskDesc), cudaMemcpyHostToDevice, stream));
+    ++launches; k_project<<<(npix + 255) / 256, 256, 0, stream>>>(fp, d_masks.p, d_static_track.p, d_static_label.p,
+                                                     d_depth_int.p, d_cloud_pos.p, d_cloud_meta.p, d_cnt.p);
     if (profiling) cudaEventRecord(ev[4], stream);
     // ---- U3 weight update --------------------------------------------------------------------------------------------
     ++launches; k_ck<<<sm_count * 2, 1024, lut_bytes, stream>>>(fp, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_pix_offset.p, d_vis_pos.p, d_vis_meta.p, d_ck.p, ck_seg_stride);
@@ -647,8 +718,10 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     // ---- O1 occupancy -------------------------------------------------------------------------------------------------
     ResultArrays out{r_idx.p, r_xyz.p, r_w.p, r_track.p, r_label.p, r_state.p, r_free_idx.p, r_free_xyz.p};
     OccScratch osc{d_vstate.p, d_res_w.p - (slot_lo >> f.Pb), d_res_tl.p - (slot_lo >> f.Pb), d_mov_mask.p - (slot_lo >> f.Pb), d_blk_cnt.p, d_blk_off.p};
+    if (profiling) cudaEventRecord(ev[8], stream);
     DISPATCH_PB(f.Pb, (k_occ_headers<PB><<<n_occ_blocks, OCC_BLOCK, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, d_cnt.p)));
     ++launches;
+    if (profiling) cudaEventRecord(ev[9], stream);
     DISPATCH_PB(f.Pb, (k_occ_slots<PB><<<sm_count * 8, 256, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, d_cnt.p)));
     ++launches;
     ++launches; k_occ_scan<<<1, 1024, 0, stream>>>(osc, n_occ_blocks, d_cnt.p, d_persist.p);
@@ -669,7 +742,14 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     stats.n_occupied = last.n_occupied; stats.n_nonempty_voxels = last.n_nonempty_voxels;
     stats.n_moved = last.n_moved; stats.n_removed = last.n_removed;
     if (profiling) {
-        for (int k = 0; k < 7; ++k) cudaEventElapsedTime(&stats.ms_stage[k], ev[k], ev[k + 1]);
+        // events: 0 start | 1 depth | 2 moves | 3 visibility | 4 project | 5 update | 6 birth | 7 occupancy
+        float d01, d12, d23, d34, d45, d56, d67;
+        cudaEventElapsedTime(&d01, ev[0], ev[1]); cudaEventElapsedTime(&d12, ev[1], ev[2]); cudaEventElapsedTime(&d23, ev[2], ev[3]);
+        cudaEventElapsedTime(&d34, ev[3], ev[4]); cudaEventElapsedTime(&d45, ev[4], ev[5]); cudaEventElapsedTime(&d56, ev[5], ev[6]);
+        cudaEventElapsedTime(&d67, ev[6], ev[7]);
+        stats.ms_stage[0] = d01 + d34; cudaEventElapsedTime(&stats.ms_stage[1], ev[8], ev[9]);   // [1]: the header-streaming kernel alone
+        stats.ms_stage[2] = d12; stats.ms_stage[3] = d23;
+        stats.ms_stage[4] = d45; stats.ms_stage[5] = d56; stats.ms_stage[6] = d67;
         cudaEventElapsedTime(&stats.ms_stage[7], ev[0], ev[7]);
     }
     if (last.n_pairs > f.vis_cap) return fail(DSPMAP_ERR_CAPACITY, "visible-particle list overflow: %u > max_visible %u", last.n_pairs, f.vis_cap);
@@ -816,8 +896,19 @@ int dspmap_update(dspmap_t* h, const float* depth, int32_t rows, int32_t cols, i
     const size_t npix = (size_t)srows * scols;
     std::vector<int> src_col(scols);
     for (int j = 0; j < scols; ++j) src_col[j] = f.boost ? std::min((int)((float)j * 2.0f), cols - 1) : j;
-    auto stage = [&](auto* dst, const auto* src, int src_stride) {
-        for (int i = 0; i < srows; ++i) {
+    CU_TRY(h, h->p_depth.reserve(npix));
+    std::vector<dspmap_mask> dm(masks, masks + n_masks);
+    if (n_masks) {
+        CU_TRY(h, h->p_masks.reserve(npix * n_masks));
+        if (h->d_mask_in.n < npix * n_masks) CU_TRY(h, h->d_mask_in.alloc(npix * n_masks));
+    }
+    if (!h->stage_pool) {
+        const char* env = getenv("DSPMAP_STAGE_THREADS");
+        const int want = env ? atoi(env) : 0;   // helper threads for the staging copies; 0 = stage on the calling thread
+        h->stage_pool.reset(new StagePool(std::max(0, std::min(want, (int)std::thread::hardware_concurrency() - 1))));
+    }
+    auto stage_rows = [&](auto* dst, const auto* src, int src_stride, int r0, int r1) {
+        for (int i = r0; i < r1; ++i) {
             const int si = f.boost ? std::min((int)((float)i * 2.0f), rows - 1) : i;
             const auto* srow = src + (size_t)si * src_stride;
             auto* drow = dst + (size_t)i * scols;
@@ -826,23 +917,20 @@ int dspmap_update(dspmap_t* h, const float* depth, int32_t rows, int32_t cols, i
             else memcpy(drow, srow, (size_t)scols * sizeof(*dst));
         }
     };
-    CU_TRY(h, h->p_depth.reserve(npix));
-    stage(h->p_depth.p, depth, row_stride);
+    // depth first: the sweep and the pixel lists need nothing else, so the GPU starts while the masks are still being staged
+    const int depth_parts = 4;
+    h->stage_pool->run(depth_parts, [&](int t) { stage_rows(h->p_depth.p, depth, row_stride, srows * t / depth_parts, srows * (t + 1) / depth_parts); });
     CU_TRY(h, cudaMemcpyAsync(h->d_depth_in.p, h->p_depth.p, npix * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    std::vector<dspmap_mask> dm(masks, masks + n_masks);
-    if (n_masks) {
-        CU_TRY(h, h->p_masks.reserve(npix * n_masks));
-        if (h->d_mask_in.n < npix * n_masks) CU_TRY(h, h->d_mask_in.alloc(npix * n_masks));
-        for (int m = 0; m < n_masks; ++m) {
-            stage(h->p_masks.p + (size_t)m * npix, masks[m].data, masks[m].row_stride);
-            dm[m].data = h->d_mask_in.p + (size_t)m * npix;
-            dm[m].row_stride = scols;
-        }
+    const std::function<int(dspmap_mask*)> late_masks = [&](dspmap_mask* dmv) -> int {
+        if (!n_masks) return DSPMAP_OK;
+        h->stage_pool->run(n_masks, [&](int m) { stage_rows(h->p_masks.p + (size_t)m * npix, masks[m].data, masks[m].row_stride, 0, srows); });
+        for (int m = 0; m < n_masks; ++m) { dmv[m].data = h->d_mask_in.p + (size_t)m * npix; dmv[m].row_stride = scols; }
         CU_TRY(h, cudaMemcpyAsync(h->d_mask_in.p, h->p_masks.p, npix * n_masks, cudaMemcpyHostToDevice, h->stream));
-    }
+        return DSPMAP_OK;
+    };
     const double t_b = trace ? host_now_ms() : 0.0;
     rc = h->frame(h->d_depth_in.p, rows, cols, scols, dm.data(), n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove,
-                  want_freespace, f.boost ? 1 : 0);
+                  want_freespace, f.boost ? 1 : 0, &late_masks);
     if (rc != DSPMAP_OK) return rc;
     const double t_c = trace ? host_now_ms() : 0.0;
     rc = h->fetch_result_to_host();

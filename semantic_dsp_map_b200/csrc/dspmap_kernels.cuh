@@ -51,14 +51,31 @@ struct Store {
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 // =====================================================================================================
+// K1a depth_int       the internal-resolution depth image (manualResize of the depth Mat, pointcloud_tools.h:1104-1133):
+//                     everything up to the pixel lists needs only this, so it runs before the masks have arrived.
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+k_depth_int(const __grid_constant__ FrameParams f, const float* __restrict__ depth, int depth_stride, float* __restrict__ depth_int) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= f.W * f.H) return;
+    const int i = q / f.W, j = q - i * f.W;
+    int si = i, sj = j;
+    if (f.boost && !f.pre_decimated) {
+        si = min((int)((float)i * 2.0f), f.in_H - 1);
+        sj = min((int)((float)j * 2.0f), f.in_W - 1);
+    }
+    depth_int[q] = depth[(size_t)si * depth_stride + sj];
+}
+
+// =====================================================================================================
 // K1  project_label   replaces PointCloudTools::manualResize + generateLabeledPointCloud
 //                     (utils/pointcloud_tools.h:1104-1133, 88-310)
 // one thread per internal pixel; double-precision back-projection, float narrowing at the end.
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
-k_project(const __grid_constant__ FrameParams f, const float* __restrict__ depth, int depth_stride, const MaskDesc* __restrict__ masks,
+k_project(const __grid_constant__ FrameParams f, const MaskDesc* __restrict__ masks,
           const uint16_t* __restrict__ lut_static_track, const uint8_t* __restrict__ lut_static_label,
-          float* __restrict__ depth_int, float4* __restrict__ cloud_pos, uint32_t* __restrict__ cloud_meta,
+          const float* __restrict__ depth_int, float4* __restrict__ cloud_pos, uint32_t* __restrict__ cloud_meta,
           Counters* __restrict__ cnt) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = false;
@@ -69,8 +86,7 @@ k_project(const __grid_constant__ FrameParams f, const float* __restrict__ depth
             si = min((int)((float)i * 2.0f), f.in_H - 1);
             sj = min((int)((float)j * 2.0f), f.in_W - 1);
         }
-        const float d = depth[(size_t)si * depth_stride + sj];
-        depth_int[q] = d;
+        const float d = depth_int[q];
 
         // track id image, :116-155 (first static mask only), :162-215 (instance masks overwrite in list order)
         uint32_t inst = 65535u;

@@ -49,12 +49,19 @@ class OccupancyResult:
     free_xyz: np.ndarray
 
 
-def _as_array(ptr, count, dtype, shape=None):
+_memview = C.pythonapi.PyMemoryView_FromMemory
+_memview.restype = C.py_object
+_memview.argtypes = [C.c_void_p, C.c_ssize_t, C.c_int]
+
+
+def _as_array(ptr, count, dtype, shape=None, copy=True):
     if count == 0 or not ptr:
         return np.zeros((0,) + tuple(shape[1:]) if shape else (0,), dtype)
     n = count * (int(np.prod(shape[1:])) if shape else 1)
-    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
-    a = np.frombuffer(buf, dtype=dtype, count=n).copy()
+    buf = _memview(ptr, n * np.dtype(dtype).itemsize, 0x100)   # PyBUF_READ
+    a = np.frombuffer(buf, dtype=dtype, count=n)
+    if copy:
+        a = a.copy()
     return a.reshape((count,) + tuple(shape[1:])) if shape else a
 
 
@@ -153,13 +160,15 @@ class Engine:
         self.check(self._fn("get_result_device" if device else "get_result")(self._h, C.byref(r)), "dspmap_get_result")
         return r
 
-    def result_arrays(self) -> OccupancyResult:
+    def result_arrays(self, copy=True) -> OccupancyResult:
+        """copy=False returns views of the handle's pinned host buffers, valid until the next update (dspmap_c.h)."""
         r = self.result()
         n, nf = r.count, r.free_count
         return OccupancyResult(
-            _as_array(r.voxel_index, n, np.uint32), _as_array(r.xyz, n, np.float32, (n, 3)), _as_array(r.weight_sum, n, np.float32),
-            _as_array(r.track_id, n, np.uint16), _as_array(r.label_id, n, np.uint8), _as_array(r.state, n, np.int8),
-            _as_array(r.free_voxel_index, nf, np.uint32), _as_array(r.free_xyz, nf, np.float32, (nf, 3)))
+            _as_array(r.voxel_index, n, np.uint32, None, copy), _as_array(r.xyz, n, np.float32, (n, 3), copy),
+            _as_array(r.weight_sum, n, np.float32, None, copy), _as_array(r.track_id, n, np.uint16, None, copy),
+            _as_array(r.label_id, n, np.uint8, None, copy), _as_array(r.state, n, np.int8, None, copy),
+            _as_array(r.free_voxel_index, nf, np.uint32, None, copy), _as_array(r.free_xyz, nf, np.float32, (nf, 3), copy))
 
     def stats(self) -> dict:
         s = _capi.FrameStats()
@@ -247,7 +256,8 @@ class SemanticDSPMap:
 
     # -- semantic_dsp_map.h:170-251 -----------------------------------------------------------------------------------------
     def update(self, depth_value_mat: np.ndarray, ins_seg_result: Sequence[MaskKpts], camera_position, camera_orientation,
-               if_get_freespace: bool = False, time_stamp_double: float = 0.0, moves=(), remove_tracks=()) -> OccupancyResult:
+               if_get_freespace: bool = False, time_stamp_double: float = 0.0, moves=(), remove_tracks=(),
+               copy_result: bool = True) -> OccupancyResult:
         """One frame.  ``camera_orientation`` is (w, x, y, z).  ``moves`` = [(track_id, 4x4)], ``remove_tracks`` = [track_id]:
         what the host-side object layer (objectLevelUpdate, out of scope) decided for this frame."""
         depth = np.asarray(depth_value_mat)
@@ -259,4 +269,4 @@ class SemanticDSPMap:
         masks = self.lower_masks(ins_seg_result)
         self.engine.update_raw("update", depth.ctypes.data, depth.shape[0], depth.shape[1], depth.strides[0] // 4, masks,
                                camera_position, camera_orientation, moves, remove_tracks, if_get_freespace)
-        return self.engine.result_arrays()
+        return self.engine.result_arrays(copy_result)
