@@ -36,7 +36,7 @@ enum {
     DSPMAP_ERR_CAPACITY = -5,    /* a device work list overflowed its configured capacity      */
     DSPMAP_ERR_NO_DEVICE = -6,   /* no CUDA device: there is NO CPU fallback                   */
     DSPMAP_ERR_UNSUPPORTED = -7, /* option the engine does not implement (stated in DESIGN.md) */
-    DSPMAP_ERR_COMM = -8         /* NCCL failure in a sharded map                              */
+    DSPMAP_ERR_COMM = -8         /* sharded map: peers not connected, or a peer missed a barrier */
 };
 
 /* ---- configuration (compile-time constants of the reference made runtime) ---- */
@@ -218,12 +218,19 @@ int dspmap_get_launch_count(dspmap_t* h, uint64_t* count);
  * ObjectParticleHashMap::indices_map[track].size(), object_layer.h:20-52) */
 int dspmap_object_particle_count(dspmap_t* h, int32_t track_id, uint32_t* count);
 
-/* ---- sharded maps (one process per GPU) ------------------------------------ */
-/* unique id bytes come from dspmap_comm_unique_id on rank 0 and are broadcast by the
- * caller's own plumbing (torch.distributed in bench.py) */
-#define DSPMAP_COMM_ID_BYTES 128
-int dspmap_comm_unique_id(uint8_t id[DSPMAP_COMM_ID_BYTES]);
-int dspmap_comm_init(dspmap_t* h, const uint8_t id[DSPMAP_COMM_ID_BYTES]);
+/* ---- sharded maps (one process per GPU, all GPUs on one NVLink/NVSwitch node) ---------------------- */
+/* A map created with shard_count = G > 1 holds the storage-z slabs [rank*NZ/G, (rank+1)*NZ/G) of the particle store.
+ * Ranks exchange what the frame couples — visible-particle records, the ck image, moved particles, result offsets —
+ * by writing straight into each other's "exchange arena" over NVLink (CUDA IPC peer mappings) and meeting at
+ * device-side barriers; there is no host synchronisation and no collective library in the data path.
+ *   1. every rank: dspmap_create(cfg with shard_rank/shard_count), dspmap_comm_export(h, handle)
+ *   2. the caller's own plumbing all-gathers the G handles (bench.py: torch.distributed)
+ *   3. every rank: dspmap_comm_connect(h, handles)   with handles = G * DSPMAP_COMM_HANDLE_BYTES bytes in rank order
+ * Every rank then calls dspmap_update* with the SAME frame; rank 0's dspmap_get_result returns the whole map's result
+ * (identical, bit for bit, to an unsharded map's), the other ranks return an empty list. */
+#define DSPMAP_COMM_HANDLE_BYTES 128
+int dspmap_comm_export(dspmap_t* h, uint8_t handle[DSPMAP_COMM_HANDLE_BYTES]);
+int dspmap_comm_connect(dspmap_t* h, const uint8_t* handles);
 
 /* ---- parity / debug dumps (tests only) ------------------------------------- */
 enum {

@@ -17,7 +17,7 @@ ERRORS = {
     0: "OK", -1: "INVALID_ARG", -2: "CONFIG", -3: "IMAGE_SIZE", -4: "CUDA", -5: "CAPACITY",
     -6: "NO_DEVICE", -7: "UNSUPPORTED", -8: "COMM",
 }
-COMM_ID_BYTES = 128
+COMM_HANDLE_BYTES = 128
 
 DUMP_POINTS, DUMP_PARTICLES, DUMP_PIXEL_OFFSETS, DUMP_PIXEL_LISTS, DUMP_CK, DUMP_RING, DUMP_VOXEL_STATE = 1, 2, 3, 4, 5, 6, 7
 
@@ -108,8 +108,8 @@ SYMBOLS = {
     "dspmap_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dspmap_get_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "dspmap_object_particle_count": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_uint32)]),
-    "dspmap_comm_unique_id": (C.c_int, [C.c_void_p]),
-    "dspmap_comm_init": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dspmap_comm_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dspmap_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dspmap_selftest_division": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_uint64)]),
     "dspmap_dump": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
 }

@@ -196,15 +196,15 @@ struct dspmap {
     DevBuf<MaskDesc> d_masks;
     DevBuf<MoveTable> d_moves;
     // images
-    DevBuf<float> d_depth_in, d_depth_int, d_ck;
+    DevBuf<float> d_depth_in, d_depth_int;
     DevBuf<uint8_t> d_mask_in;
     DevBuf<float4> d_cloud_pos;
     DevBuf<uint32_t> d_cloud_meta, d_pix_count, d_pix_offset, d_scan_block;
     // visibility
     DevBuf<uint32_t> d_vmask;
     uint32_t words_per_row = 0, n_vwords = 0;
-    DevBuf<uint2> d_pairs;
-    DevBuf<uint32_t> d_csr_idx, d_vis_pix, d_vis_meta;
+    DevBuf<uint64_t> d_csr_key;
+    DevBuf<uint32_t> d_csr_idx, d_vis_pix, d_vis_meta, d_seq_ref, d_mov_out;
     DevBuf<float4> d_vis_pos;
     // ordered insertion
     DevBuf<uint32_t> d_keys, d_ranks;
@@ -218,15 +218,22 @@ struct dspmap {
     DevBuf<uint32_t> d_work;
     uint32_t n_occ_blocks = 0;
     uint32_t ck_seg_stride = 1;
-    DevBuf<float4> d_mov_pos;
-    DevBuf<uint64_t> d_mov_meta;
     uint32_t sel_cap = 0;
     // occupancy
-    DevBuf<uint32_t> r_idx, r_free_idx;
-    DevBuf<float> r_xyz, r_w, r_free_xyz;
-    DevBuf<uint16_t> r_track;
-    DevBuf<uint8_t> r_label;
-    DevBuf<int8_t> r_state;
+    // exchange arena (one allocation, exported over CUDA IPC in sharded maps): barrier flags, counts, visible records,
+    // incoming moved particles, the ck image and the (global) result arrays
+    DevBuf<uint8_t> arena;
+    struct ArenaLayout { size_t flags, counts, move_counts, recs, movs, ck, r_idx, r_xyz, r_w, r_track, r_label, r_state, r_free_idx, r_free_xyz, total; } lay{};
+    CommView cv{};
+    uint32_t comm_epoch = 0;
+    void* peer_base[MAX_RANKS]{};
+    bool comm_connected = false;
+    uint32_t *r_idx = nullptr, *r_free_idx = nullptr;
+    float *r_xyz = nullptr, *r_w = nullptr, *r_free_xyz = nullptr, *d_ck = nullptr;
+    uint16_t* r_track = nullptr;
+    uint8_t* r_label = nullptr;
+    int8_t* r_state = nullptr;
+    uint32_t* d_counts = nullptr;      // this rank's counts[source rank][COMM_COUNTS]
 
     // pinned staging
     PinBuf<float> p_depth;
@@ -245,7 +252,7 @@ struct dspmap {
     std::unique_ptr<StagePool> stage_pool;
 
     Counters last{};
-    uint32_t n_visible_last = 0;
+    uint32_t n_visible_last = 0, result_n = 0, result_nf = 0, n_occ_global = 0;
     dspmap_frame_stats stats{};
     bool profiling = false;
     cudaEvent_t ev[10]{};
@@ -313,11 +320,11 @@ struct dspmap {
     void release_all() {
         sx.release(); sy.release(); sz.release(); sw.release(); smeta.release(); shdr.release(); d_entry_list.release(); d_entry_voxel.release(); d_stamps.release(); d_lut.release(); d_randoms.release();
         d_static_track.release(); d_static_label.release(); d_fp.release(); d_cnt.release(); d_persist.release(); d_masks.release(); d_moves.release();
-        d_depth_in.release(); d_depth_int.release(); d_ck.release(); d_mask_in.release(); d_cloud_pos.release(); d_cloud_meta.release();
-        d_pix_count.release(); d_pix_offset.release(); d_scan_block.release(); d_vmask.release(); d_pairs.release(); d_csr_idx.release();
-        d_vis_pix.release(); d_vis_meta.release(); d_vis_pos.release(); d_keys.release(); d_ranks.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_work.release(); d_mov_pos.release(); d_mov_meta.release();
-        r_idx.release(); r_free_idx.release(); r_xyz.release(); r_w.release(); r_free_xyz.release(); r_track.release(); r_label.release();
-        r_state.release();
+        d_depth_in.release(); d_depth_int.release(); d_mask_in.release(); d_cloud_pos.release(); d_cloud_meta.release();
+        d_pix_count.release(); d_pix_offset.release(); d_scan_block.release(); d_vmask.release(); d_csr_key.release(); d_seq_ref.release(); d_mov_out.release(); d_csr_idx.release();
+        d_vis_pix.release(); d_vis_meta.release(); d_vis_pos.release(); d_keys.release(); d_ranks.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_work.release();
+        for (int p = 0; p < MAX_RANKS; ++p) if (peer_base[p] && p != cfg.shard_rank) { cudaIpcCloseMemHandle(peer_base[p]); peer_base[p] = nullptr; }
+        arena.release();
         p_depth.release(); p_masks.release(); p_cnt.release(); p_fp.release(); p_stamps.release(); p_maskdesc.release(); p_moves.release();
         hr_idx.release(); hr_free_idx.release(); hr_xyz.release(); hr_w.release(); hr_free_xyz.release(); hr_track.release(); hr_label.release(); hr_state.release();
         for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -325,6 +332,26 @@ struct dspmap {
         stream = nullptr;
     }
 
+    // (re)builds the comm view from the mapped arenas; result arrays always point at rank 0's arena once connected
+    void bind_arena(int have_rank0) {
+        const int G = cfg.shard_count, me = cfg.shard_rank;
+        cv.rank = me; cv.size = G; cv.rec_cap = fp.vis_cap; cv.mov_cap = sel_cap;
+        for (int p = 0; p < G; ++p) {
+            uint8_t* b = (uint8_t*)(peer_base[p] ? peer_base[p] : arena.p);
+            cv.flags[p] = (uint32_t*)(b + lay.flags); cv.counts[p] = (uint32_t*)(b + lay.counts); cv.move_counts[p] = (uint32_t*)(b + lay.move_counts);
+            cv.recs[p] = (VisRec*)(b + lay.recs); cv.movs[p] = (MovRec*)(b + lay.movs); cv.ck[p] = (float*)(b + lay.ck);
+        }
+        uint8_t* mine = arena.p;
+        d_ck = (float*)(mine + lay.ck); d_counts = (uint32_t*)(mine + lay.counts);
+        uint8_t* r0 = (uint8_t*)(peer_base[0] && have_rank0 >= 0 ? peer_base[0] : arena.p);
+        r_idx = (uint32_t*)(r0 + lay.r_idx); r_xyz = (float*)(r0 + lay.r_xyz); r_w = (float*)(r0 + lay.r_w); r_track = (uint16_t*)(r0 + lay.r_track);
+        r_label = (uint8_t*)(r0 + lay.r_label); r_state = (int8_t*)(r0 + lay.r_state); r_free_idx = (uint32_t*)(r0 + lay.r_free_idx); r_free_xyz = (float*)(r0 + lay.r_free_xyz);
+    }
+    int barrier() {
+        if (cfg.shard_count == 1) return DSPMAP_OK;
+        ++launches; k_comm_barrier<<<1, 32, 0, stream>>>(cv, ++comm_epoch, &d_cnt.p->comm_errors);
+        return DSPMAP_OK;
+    }
     int init(const dspmap_config& c);
     int clear_device();
     int apply_params();
@@ -356,7 +383,7 @@ int dspmap::init(const dspmap_config& c) {
         return fail(DSPMAP_ERR_CONFIG, "bad voxel size / image size / intrinsics / depth range");
     if (c.shard_count < 1 || c.shard_rank < 0 || c.shard_rank >= c.shard_count || ((1 << c.voxel_bits_z) % c.shard_count) != 0)
         return fail(DSPMAP_ERR_CONFIG, "shard_count must divide the storage-z extent and shard_rank must be in range");
-    if (c.shard_count > 1) return fail(DSPMAP_ERR_UNSUPPORTED, "sharded maps are not implemented yet");
+    if (c.shard_count > MAX_RANKS) return fail(DSPMAP_ERR_CONFIG, "at most %d shards", MAX_RANKS);
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -435,7 +462,7 @@ int dspmap::init(const dspmap_config& c) {
     CU_TRY(this, d_fp.alloc(1)); CU_TRY(this, d_cnt.alloc(1)); CU_TRY(this, d_persist.alloc(1)); CU_TRY(this, d_moves.alloc(1));
     CU_TRY(this, cudaMemset(d_persist.p, 0, sizeof(Persist)));
     CU_TRY(this, d_masks.alloc(64));
-    CU_TRY(this, d_depth_in.alloc(npix_in)); CU_TRY(this, d_depth_int.alloc(npix)); CU_TRY(this, d_ck.alloc(npix));
+    CU_TRY(this, d_depth_in.alloc(npix_in)); CU_TRY(this, d_depth_int.alloc(npix));
     CU_TRY(this, d_cloud_pos.alloc(npix)); CU_TRY(this, d_cloud_meta.alloc(npix));
     CU_TRY(this, d_pix_count.alloc(npix)); CU_TRY(this, d_pix_offset.alloc(npix + 1));
     CU_TRY(this, d_scan_block.alloc((npix + SCAN_BLOCK - 1) / SCAN_BLOCK));
@@ -444,13 +471,16 @@ int dspmap::init(const dspmap_config& c) {
     CU_TRY(this, d_vmask.alloc(n_vwords));
 
     const size_t usable = n_slots_local - v_local;
-    f.vis_cap = (uint32_t)std::min<size_t>(usable, c.max_visible ? (size_t)c.max_visible : (size_t)16 << 20);
-    CU_TRY(this, d_pairs.alloc(f.vis_cap)); CU_TRY(this, d_csr_idx.alloc(f.vis_cap)); CU_TRY(this, d_vis_pix.alloc(f.vis_cap));
-    CU_TRY(this, d_vis_meta.alloc(f.vis_cap)); CU_TRY(this, d_vis_pos.alloc(f.vis_cap));
+    // capacity of ONE rank's visible-record segment; the pixel lists hold the records of all ranks
+    f.vis_cap = (uint32_t)std::min<size_t>(usable, c.max_visible ? (size_t)c.max_visible : (size_t)4 << 20);
+    const size_t list_cap = (size_t)f.vis_cap * c.shard_count;
+    CU_TRY(this, d_csr_key.alloc(list_cap)); CU_TRY(this, d_csr_idx.alloc(list_cap)); CU_TRY(this, d_vis_pix.alloc(list_cap));
+    CU_TRY(this, d_vis_meta.alloc(list_cap)); CU_TRY(this, d_vis_pos.alloc(list_cap));
 
     sel_cap = (uint32_t)std::min<size_t>(usable, (size_t)1 << 20);
     CU_TRY(this, d_movl_idx.alloc(sel_cap)); CU_TRY(this, d_movl_seq.alloc(sel_cap)); CU_TRY(this, d_movl_track.alloc(sel_cap));
-    CU_TRY(this, d_mov_pos.alloc(sel_cap)); CU_TRY(this, d_mov_meta.alloc(sel_cap));
+    CU_TRY(this, d_seq_ref.alloc(sel_cap)); CU_TRY(this, d_mov_out.alloc(MAX_RANKS));
+    CU_TRY(this, cudaMemset(d_mov_out.p, 0, MAX_RANKS * sizeof(uint32_t)));
 
     // hash table for ordered insertion: >= 2x the larger candidate population (pixels, moved particles)
     size_t want = 2 * std::max<size_t>(npix, sel_cap);
@@ -474,10 +504,25 @@ int dspmap::init(const dspmap_config& c) {
     CU_TRY(this, d_vstate.alloc(v_pad)); CU_TRY(this, d_res_w.alloc(v_pad)); CU_TRY(this, d_res_tl.alloc(v_pad)); CU_TRY(this, d_mov_mask.alloc(v_pad));
     CU_TRY(this, d_blk_cnt.alloc(n_occ_blocks)); CU_TRY(this, d_blk_off.alloc(n_occ_blocks)); CU_TRY(this, d_work.alloc(v_pad));
     CU_TRY(this, cudaMemset(d_vstate.p, 0, v_pad));
-    CU_TRY(this, r_idx.alloc(v_local)); CU_TRY(this, r_xyz.alloc(3 * (size_t)v_local)); CU_TRY(this, r_w.alloc(v_local));
-    CU_TRY(this, r_track.alloc(v_local)); CU_TRY(this, r_label.alloc(v_local)); CU_TRY(this, r_state.alloc(v_local));
+    {   // exchange arena
+        const int G = c.shard_count;
+        size_t off = 0;
+        auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+        lay.flags = take(64 * 4); lay.counts = take((size_t)MAX_RANKS * COMM_COUNTS * 4); lay.move_counts = take((size_t)MAX_RANKS * MAX_MOVES * 4);
+        lay.recs = take((size_t)G * f.vis_cap * sizeof(VisRec)); lay.movs = take((size_t)G * sel_cap * sizeof(MovRec));
+        lay.ck = take(npix * 4);
+        const size_t Vg = f.V;   // rank 0 receives the global result
+        lay.r_idx = take(Vg * 4); lay.r_xyz = take(Vg * 12); lay.r_w = take(Vg * 4); lay.r_track = take(Vg * 2); lay.r_label = take(Vg); lay.r_state = take(Vg);
+        lay.r_free_idx = take(Vg * 4); lay.r_free_xyz = take(Vg * 12);
+        lay.total = off;
+        CU_TRY(this, arena.alloc(lay.total));
+        CU_TRY(this, cudaMemset(arena.p, 0, lay.flags + 64 * 4 + (size_t)MAX_RANKS * COMM_COUNTS * 4 + (size_t)MAX_RANKS * MAX_MOVES * 4 + 1024));
+        peer_base[c.shard_rank] = arena.p;
+        bind_arena(c.shard_rank == 0 ? 0 : -1);
+        comm_connected = G == 1;
+    }
 
-    CU_TRY(this, p_cnt.reserve(1)); CU_TRY(this, p_fp.reserve(1)); CU_TRY(this, p_stamps.reserve(f.NX + f.NY + f.NZ + 1));
+    CU_TRY(this, p_cnt.reserve(1)); CU_TRY(this, p_fp.reserve(1)); CU_TRY(this, p_stamps.reserve(f.NX + f.NY + f.NZ + 1 + MAX_RANKS * COMM_COUNTS));
     CU_TRY(this, p_maskdesc.reserve(64)); CU_TRY(this, p_moves.reserve(1));
 
     // Gaussian PDF LUT (utils/basic_algorithms.h:403-407, 455-459): (1/sqrt(2*M_PI_2f32)) * exp(-v^2/2), v=(i-10000)*0.001
@@ -545,13 +590,20 @@ int dspmap::run_moves(const dspmap_object_move* moves, int n_moves, const int32_
     if (scan_remove) {
         ++launches; k_remove_tracks_scan<<<sm_count * 8, 256, 0, stream>>>(fp, st, d_moves.p, d_cnt.p);
     } else {
-        ++launches; k_move_prepare<<<1, 1024, 0, stream>>>(d_moves.p, d_movl_track.p, d_movl_seq.p, sel_cap, rand_n, d_cnt.p, d_persist.p);
+        ++launches; k_move_count<<<1, 1024, 0, stream>>>(d_moves.p, d_movl_track.p, sel_cap, d_persist.p, cv);
+        barrier();   // every rank knows how many particles of each moved track the lower ranks hold
+        ++launches; k_move_prepare<<<1, 1024, 0, stream>>>(d_moves.p, d_movl_track.p, d_movl_seq.p, sel_cap, rand_n, d_cnt.p, d_persist.p, cv,
+                                                         cv.move_counts[cv.rank]);
         ++launches; k_move_apply<<<sm_count * 2, 256, 0, stream>>>(fp, d_cnt.p, st, d_moves.p, d_randoms.p, d_persist.p, d_movl_idx.p, d_movl_track.p,
-                                                             d_movl_seq.p, sel_cap, d_mov_pos.p, d_mov_meta.p, d_keys.p, d_ranks.p, d_entry_list.p);
+                                                             d_movl_seq.p, sel_cap, cv, d_mov_out.p);
         if (n_moves > 0) {
+            ++launches; k_move_publish<<<1, 32, 0, stream>>>(cv, d_mov_out.p);
+            barrier();   // the moved particles bound for this rank have arrived
+            ++launches; k_move_bin<<<sm_count * 2, 256, 0, stream>>>(fp, cv, cv.movs[cv.rank], d_counts, d_seq_ref.p, sel_cap, d_keys.p, d_ranks.p,
+                                                               d_entry_list.p, d_cnt.p);
             DISPATCH_PB(fp.Pb, (k_move_replay<PB><<<sm_count * 2, 128, 0, stream>>>(fp, st, stx, sty, stz, d_keys.p, d_ranks.p, d_entry_list.p, d_entry_voxel.p, d_cnt.p)));
             ++launches;
-            ++launches; k_move_write<<<sm_count * 2, 256, 0, stream>>>(fp, st, d_mov_pos.p, d_mov_meta.p, d_ranks.p, d_entry_list.p, d_entry_voxel.p, d_cnt.p);
+            ++launches; k_move_write<<<sm_count * 2, 256, 0, stream>>>(fp, st, cv.movs[cv.rank], d_seq_ref.p, d_ranks.p, d_entry_list.p, d_entry_voxel.p, d_cnt.p);
         }
     }
     CU_TRY(this, cudaGetLastError());
@@ -632,7 +684,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     f.want_free = want_free ? 1 : 0; f.want_state = 0;
     f.rand_n = rand_n;
 
-    if (want_free && !r_free_idx.p) { CU_TRY(this, r_free_idx.alloc(v_local)); CU_TRY(this, r_free_xyz.alloc(3 * (size_t)v_local)); }
+    if (!comm_connected) return fail(DSPMAP_ERR_COMM, "sharded map: call dspmap_comm_connect on every rank before the first update");
 
     // ---- uploads -------------------------------------------------------------------------------------------
     if (stamps_dirty) {
@@ -676,15 +728,21 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
         const int z0 = std::max(f.vb_lo[2] - 1, 0), z1 = std::min(f.vb_hi[2] + 1, (int)f.NZ);
         ++launches; k_vertex_mask<<<dim3((words_per_row * 32 + 255) / 256, (y1 - y0 + 1) * (z1 - z0 + 1)), 256, 0, stream>>>(fp, d_vmask.p, words_per_row, y0, y1 - y0 + 1, z0);
         ++launches; k_sweep_select<<<(v_local + 255) / 256, 256, 0, stream>>>(fp, st, d_vmask.p, words_per_row, d_depth_int.p, d_work.p, d_cnt.p);
-        DISPATCH_PB(f.Pb, (k_sweep_slots<PB><<<sm_count * 8, 256, 0, stream>>>(fp, st, stx, sty, stz, d_work.p, d_depth_int.p, d_pix_count.p, d_pairs.p, d_cnt.p)));
+        DISPATCH_PB(f.Pb, (k_sweep_slots<PB><<<sm_count * 8, 256, 0, stream>>>(fp, st, stx, sty, stz, d_work.p, d_depth_int.p, d_pix_count.p, cv, d_cnt.p)));
         ++launches;
+    }
+    // every rank tells every rank how many visible records it wrote into their arenas
+    ++launches; k_publish_pairs<<<1, 32, 0, stream>>>(cv, d_cnt.p);
+    if (cv.size > 1) {
+        barrier();
+        ++launches; k_count_remote<<<sm_count * 2, 256, 0, stream>>>(cv, cv.recs[cv.rank], d_counts, d_pix_count.p);
     }
     const int nsb = (npix + SCAN_BLOCK - 1) / SCAN_BLOCK;
     ++launches; k_scan_blocksum<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p);
     ++launches; k_scan_apply<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p, d_pix_offset.p);
-    ++launches; k_fill<<<sm_count * 4, 256, 0, stream>>>(fp, d_cnt.p, d_pairs.p, d_pix_offset.p, d_pix_count.p, d_csr_idx.p, d_vis_pix.p);
-    ++launches; k_sort_lists<<<(npix + 255) / 256, 256, 0, stream>>>(fp, d_pix_offset.p, d_csr_idx.p);
-    ++launches; k_gather_visible<<<sm_count * 4, 256, 0, stream>>>(fp, d_pix_offset.p + npix, st, d_csr_idx.p, d_vis_pos.p, d_vis_meta.p);
+    ++launches; k_fill<<<sm_count * 4, 256, 0, stream>>>(cv, cv.recs[cv.rank], d_counts, d_pix_offset.p, d_pix_count.p, d_csr_key.p);
+    ++launches; k_sort_lists<<<(npix + 255) / 256, 256, 0, stream>>>(fp, d_pix_offset.p, d_csr_key.p);
+    ++launches; k_gather_visible<<<sm_count * 4, 256, 0, stream>>>(d_pix_offset.p + npix, cv.recs[cv.rank], d_csr_key.p, d_csr_idx.p, d_vis_pix.p, d_vis_pos.p, d_vis_meta.p);
     if (profiling) cudaEventRecord(ev[3], stream);
     // ---- K1 projection + labels (needs the masks) -----------------------------------------------------------------------
     std::vector<dspmap_mask> mask_copy(masks, masks + n_masks);
@@ -702,8 +760,9 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
                                                      d_depth_int.p, d_cloud_pos.p, d_cloud_meta.p, d_cnt.p);
     if (profiling) cudaEventRecord(ev[4], stream);
     // ---- U3 weight update --------------------------------------------------------------------------------------------
-    ++launches; k_ck<<<sm_count * 2, 1024, lut_bytes, stream>>>(fp, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_pix_offset.p, d_vis_pos.p, d_vis_meta.p, d_ck.p, ck_seg_stride);
-    ++launches; k_weight_update<<<sm_count * 2, 1024, lut_bytes, stream>>>(fp, d_pix_offset.p + npix, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_ck.p, d_csr_idx.p,
+    ++launches; k_ck<<<sm_count * 2, 1024, lut_bytes, stream>>>(fp, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_pix_offset.p, d_vis_pos.p, d_vis_meta.p, cv, ck_seg_stride);
+    barrier();   // sharded map: every rank's ck image is complete
+    ++launches; k_weight_update<<<sm_count * 2, 1024, lut_bytes, stream>>>(fp, d_pix_offset.p + npix, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_ck, d_csr_idx.p,
                                                              d_vis_pix.p, d_vis_pos.p, d_vis_meta.p, st);
     if (profiling) cudaEventRecord(ev[5], stream);
     // ---- B1 birth + resample -----------------------------------------------------------------------------------------
@@ -716,7 +775,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     }
     if (profiling) cudaEventRecord(ev[6], stream);
     // ---- O1 occupancy -------------------------------------------------------------------------------------------------
-    ResultArrays out{r_idx.p, r_xyz.p, r_w.p, r_track.p, r_label.p, r_state.p, r_free_idx.p, r_free_xyz.p};
+    ResultArrays out{r_idx, r_xyz, r_w, r_track, r_label, r_state, r_free_idx, r_free_xyz};
     OccScratch osc{d_vstate.p, d_res_w.p - (slot_lo >> f.Pb), d_res_tl.p - (slot_lo >> f.Pb), d_mov_mask.p - (slot_lo >> f.Pb), d_blk_cnt.p, d_blk_off.p};
     if (profiling) cudaEventRecord(ev[8], stream);
     DISPATCH_PB(f.Pb, (k_occ_headers<PB><<<n_occ_blocks, OCC_BLOCK, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, d_cnt.p)));
@@ -724,12 +783,15 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     if (profiling) cudaEventRecord(ev[9], stream);
     DISPATCH_PB(f.Pb, (k_occ_slots<PB><<<sm_count * 8, 256, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, d_cnt.p)));
     ++launches;
-    ++launches; k_occ_scan<<<1, 1024, 0, stream>>>(osc, n_occ_blocks, d_cnt.p, d_persist.p);
-    DISPATCH_PB(f.Pb, (k_occ_emit<PB><<<n_occ_blocks, OCC_BLOCK, 0, stream>>>(fp, st, osc, out, d_movl_idx.p, d_movl_track.p, sel_cap)));
+    ++launches; k_occ_scan<<<1, 1024, 0, stream>>>(osc, n_occ_blocks, d_cnt.p, d_persist.p, cv);
+    barrier();   // the lower ranks' totals are this rank's base offsets
+    DISPATCH_PB(f.Pb, (k_occ_emit<PB><<<n_occ_blocks, OCC_BLOCK, 0, stream>>>(fp, st, osc, out, d_movl_idx.p, d_movl_track.p, sel_cap, cv, d_counts)));
     ++launches;
+    barrier();   // rank 0 holds the whole result
     if (profiling) cudaEventRecord(ev[7], stream);
     CU_TRY(this, cudaMemcpyAsync(p_cnt.p, d_cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
     CU_TRY(this, cudaMemcpyAsync(p_stamps.p + (f.NX + f.NY + f.NZ), d_pix_offset.p + npix, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CU_TRY(this, cudaMemcpyAsync(p_stamps.p + (f.NX + f.NY + f.NZ) + 1, d_counts, (size_t)MAX_RANKS * COMM_COUNTS * 4, cudaMemcpyDeviceToHost, stream));
     CU_TRY(this, cudaGetLastError());
     CU_TRY(this, cudaStreamSynchronize(stream));
     last = *p_cnt.p;
@@ -737,9 +799,17 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     stats.time_stamp = T;
     stats.n_swept_voxels = last.n_swept_voxels; stats.n_swept_nonempty = last.n_swept_nonempty;
     n_visible_last = p_stamps.p[f.NX + f.NY + f.NZ];
+    {   // global result size (rank 0 reads the whole list; the other ranks report their own share only)
+        const uint32_t* cc = p_stamps.p + (f.NX + f.NY + f.NZ) + 1;
+        uint32_t occ = 0, fre = 0;
+        for (int g = 0; g < cv.size; ++g) { occ += cc[g * COMM_COUNTS + CC_OCC]; fre += cc[g * COMM_COUNTS + CC_FREE]; }
+        result_n = cv.rank == 0 ? occ : 0; result_nf = cv.rank == 0 ? fre : 0;
+        n_occ_global = occ;
+    }
+    if (last.comm_errors) return fail(DSPMAP_ERR_COMM, "a peer did not reach a barrier within the timeout");
     stats.n_visible = n_visible_last; stats.n_valid_points = last.n_valid_points;
     stats.n_born = last.n_born; stats.n_birth_voxels = last.n_birth_voxels; stats.n_resampled = last.n_resampled;
-    stats.n_occupied = last.n_occupied; stats.n_nonempty_voxels = last.n_nonempty_voxels;
+    stats.n_occupied = n_occ_global; stats.n_nonempty_voxels = last.n_nonempty_voxels;
     stats.n_moved = last.n_moved; stats.n_removed = last.n_removed;
     if (profiling) {
         // events: 0 start | 1 depth | 2 moves | 3 visibility | 4 project | 5 update | 6 birth | 7 occupancy
@@ -760,22 +830,22 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
 
 int dspmap::fetch_result_to_host() {
     if (host_result_valid) return DSPMAP_OK;
-    const size_t n = last.n_occupied, nf = fp.want_free ? last.n_free : 0;
+    const size_t n = result_n, nf = fp.want_free ? result_nf : 0;
     CU_TRY(this, hr_idx.reserve(std::max<size_t>(n, 1))); CU_TRY(this, hr_xyz.reserve(std::max<size_t>(3 * n, 1)));
     CU_TRY(this, hr_w.reserve(std::max<size_t>(n, 1))); CU_TRY(this, hr_track.reserve(std::max<size_t>(n, 1)));
     CU_TRY(this, hr_label.reserve(std::max<size_t>(n, 1))); CU_TRY(this, hr_state.reserve(std::max<size_t>(n, 1)));
     if (n) {
-        CU_TRY(this, cudaMemcpyAsync(hr_idx.p, r_idx.p, n * 4, cudaMemcpyDeviceToHost, stream));
-        CU_TRY(this, cudaMemcpyAsync(hr_xyz.p, r_xyz.p, n * 12, cudaMemcpyDeviceToHost, stream));
-        CU_TRY(this, cudaMemcpyAsync(hr_w.p, r_w.p, n * 4, cudaMemcpyDeviceToHost, stream));
-        CU_TRY(this, cudaMemcpyAsync(hr_track.p, r_track.p, n * 2, cudaMemcpyDeviceToHost, stream));
-        CU_TRY(this, cudaMemcpyAsync(hr_label.p, r_label.p, n, cudaMemcpyDeviceToHost, stream));
-        CU_TRY(this, cudaMemcpyAsync(hr_state.p, r_state.p, n, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(this, cudaMemcpyAsync(hr_idx.p, r_idx, n * 4, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(this, cudaMemcpyAsync(hr_xyz.p, r_xyz, n * 12, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(this, cudaMemcpyAsync(hr_w.p, r_w, n * 4, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(this, cudaMemcpyAsync(hr_track.p, r_track, n * 2, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(this, cudaMemcpyAsync(hr_label.p, r_label, n, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(this, cudaMemcpyAsync(hr_state.p, r_state, n, cudaMemcpyDeviceToHost, stream));
     }
     if (nf) {
         CU_TRY(this, hr_free_idx.reserve(nf)); CU_TRY(this, hr_free_xyz.reserve(3 * nf));
-        CU_TRY(this, cudaMemcpyAsync(hr_free_idx.p, r_free_idx.p, nf * 4, cudaMemcpyDeviceToHost, stream));
-        CU_TRY(this, cudaMemcpyAsync(hr_free_xyz.p, r_free_xyz.p, nf * 12, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(this, cudaMemcpyAsync(hr_free_idx.p, r_free_idx, nf * 4, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(this, cudaMemcpyAsync(hr_free_xyz.p, r_free_xyz, nf * 12, cudaMemcpyDeviceToHost, stream));
     }
     CU_TRY(this, cudaStreamSynchronize(stream));
     host_result_valid = true;
@@ -945,8 +1015,8 @@ int dspmap_get_result(dspmap_t* h, dspmap_result* out) {
     CU_TRY(h, cudaSetDevice(h->device));
     const int rc = h->fetch_result_to_host();
     if (rc != DSPMAP_OK) return rc;
-    out->count = h->last.n_occupied;
-    out->free_count = h->fp.want_free ? h->last.n_free : 0;
+    out->count = h->result_n;
+    out->free_count = h->fp.want_free ? h->result_nf : 0;
     out->voxel_index = h->hr_idx.p; out->xyz = h->hr_xyz.p; out->weight_sum = h->hr_w.p; out->track_id = h->hr_track.p;
     out->label_id = h->hr_label.p; out->state = h->hr_state.p; out->free_voxel_index = h->hr_free_idx.p; out->free_xyz = h->hr_free_xyz.p;
     return DSPMAP_OK;
@@ -954,10 +1024,10 @@ int dspmap_get_result(dspmap_t* h, dspmap_result* out) {
 
 int dspmap_get_result_device(dspmap_t* h, dspmap_result* out) {
     if (!h || !out) return DSPMAP_ERR_INVALID_ARG;
-    out->count = h->last.n_occupied;
-    out->free_count = h->fp.want_free ? h->last.n_free : 0;
-    out->voxel_index = h->r_idx.p; out->xyz = h->r_xyz.p; out->weight_sum = h->r_w.p; out->track_id = h->r_track.p;
-    out->label_id = h->r_label.p; out->state = h->r_state.p; out->free_voxel_index = h->r_free_idx.p; out->free_xyz = h->r_free_xyz.p;
+    out->count = h->result_n;
+    out->free_count = h->fp.want_free ? h->result_nf : 0;
+    out->voxel_index = h->r_idx; out->xyz = h->r_xyz; out->weight_sum = h->r_w; out->track_id = h->r_track;
+    out->label_id = h->r_label; out->state = h->r_state; out->free_voxel_index = h->r_free_idx; out->free_xyz = h->r_free_xyz;
     return DSPMAP_OK;
 }
 
@@ -997,15 +1067,33 @@ int dspmap_object_particle_count(dspmap_t* h, int32_t track_id, uint32_t* count)
     return DSPMAP_OK;
 }
 
-int dspmap_comm_unique_id(uint8_t id[DSPMAP_COMM_ID_BYTES]) {
-    if (!id) return DSPMAP_ERR_INVALID_ARG;
-    memset(id, 0, DSPMAP_COMM_ID_BYTES);
-    return DSPMAP_ERR_UNSUPPORTED;
+int dspmap_comm_export(dspmap_t* h, uint8_t handle[DSPMAP_COMM_HANDLE_BYTES]) {
+    if (!h || !handle) return DSPMAP_ERR_INVALID_ARG;
+    CU_TRY(h, cudaSetDevice(h->device));
+    memset(handle, 0, DSPMAP_COMM_HANDLE_BYTES);
+    static_assert(sizeof(cudaIpcMemHandle_t) <= DSPMAP_COMM_HANDLE_BYTES, "handle buffer too small");
+    cudaIpcMemHandle_t ipc;
+    CU_TRY(h, cudaIpcGetMemHandle(&ipc, h->arena.p));
+    memcpy(handle, &ipc, sizeof ipc);
+    return DSPMAP_OK;
 }
 
-int dspmap_comm_init(dspmap_t* h, const uint8_t id[DSPMAP_COMM_ID_BYTES]) {
-    if (!h || !id) return DSPMAP_ERR_INVALID_ARG;
-    return h->fail(DSPMAP_ERR_UNSUPPORTED, "sharded maps are not implemented yet");
+int dspmap_comm_connect(dspmap_t* h, const uint8_t* handles) {
+    if (!h || !handles) return DSPMAP_ERR_INVALID_ARG;
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int G = h->cfg.shard_count, me = h->cfg.shard_rank;
+    for (int p = 0; p < G; ++p) {
+        if (p == me) { h->peer_base[p] = h->arena.p; continue; }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, handles + (size_t)p * DSPMAP_COMM_HANDLE_BYTES, sizeof ipc);
+        void* base = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&base, ipc, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return h->fail(DSPMAP_ERR_COMM, "cudaIpcOpenMemHandle(rank %d): %s", p, cudaGetErrorString(e));
+        h->peer_base[p] = base;
+    }
+    h->bind_arena(0);
+    h->comm_connected = true;
+    return DSPMAP_OK;
 }
 
 int dspmap_selftest_division(dspmap_t* h, uint64_t n, uint64_t seed, float b_lo, float b_hi, float a_max, uint64_t* mismatches) {
@@ -1076,7 +1164,7 @@ int dspmap_dump(dspmap_t* h, int32_t what, void* dst, size_t cap, size_t* n_byte
         }
         case DSPMAP_DUMP_CK:
             tmp.resize(npix * 4);
-            CU_TRY(h, pull(tmp.data(), h->d_ck.p, tmp.size()));
+            CU_TRY(h, pull(tmp.data(), h->d_ck, tmp.size()));
             break;
         case DSPMAP_DUMP_RING: {
             tmp.resize(4 * (9 + f.NX + f.NY + f.NZ));

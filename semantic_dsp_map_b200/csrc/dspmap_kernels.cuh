@@ -32,7 +32,7 @@ struct Counters {
     uint32_t scratch;
     uint32_t n_sweep_work;     // swept voxels with live slots (work list of the slot pass)
     uint32_t n_occ_work;       // voxels whose occupancy needs the slot records
-    uint32_t ck_ticket;        // dynamic segment scheduler of the ck pass
+    uint32_t comm_errors;      // barriers that timed out (sharded maps)
 };
 
 // survives across frames
@@ -49,6 +49,56 @@ struct Store {
 };
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// ---- sharded maps: peer memory over NVLink ------------------------------------------------------------------------
+// Each rank owns a contiguous range of storage-z slabs and an "exchange arena" (one cudaMalloc, exported with CUDA IPC
+// and mapped by every peer).  Kernels write what other ranks need straight into the peers' arenas; ranks meet at
+// device-side barriers (monotonic flags in peer memory, system-scope fences, a timeout instead of a hang).
+constexpr int MAX_RANKS = 8;
+constexpr int COMM_COUNTS = 16;              // u32 per (destination rank, source rank)
+enum { CC_PAIRS = 0, CC_OCC = 1, CC_FREE = 2, CC_MOVREC = 3, CC_MOVE0 = 4 /* .. CC_MOVE0 + unused */ };
+
+// one listed (visible) particle: everything the pixel lists and the two stencil passes need, 32 bytes
+struct __align__(16) VisRec {
+    uint32_t pix, idx;
+    float x, y;
+    float z, w;
+    uint32_t tf;      // track | forget << 16
+    uint32_t pad;
+};
+
+// one moved particle on its way to the rank that owns its destination voxel, 32 bytes
+struct __align__(16) MovRec {
+    float x, y, z, w;
+    uint64_t meta;
+    uint32_t seq, voxel;
+};
+
+struct CommView {
+    int32_t rank, size;
+    uint32_t rec_cap;                  // records per (rank) segment of the visible list
+    uint32_t mov_cap;                  // records per (source rank) segment of the incoming moved-particle list
+    uint32_t* flags[MAX_RANKS];        // peer p's barrier flags, indexed by source rank
+    uint32_t* counts[MAX_RANKS];       // peer p's counts[source rank][COMM_COUNTS]
+    VisRec* recs[MAX_RANKS];           // peer p's visible-record arena: [source rank][rec_cap]
+    MovRec* movs[MAX_RANKS];           // peer p's incoming moved particles: [source rank][mov_cap]
+    float* ck[MAX_RANKS];              // peer p's ck image
+    uint32_t* move_counts[MAX_RANKS];  // peer p's per-move particle counts: [source rank][MAX_MOVES]
+};
+
+// all ranks arrive, then all leave.  One block of 32 threads; thread p handles peer p.
+__global__ void k_comm_barrier(CommView c, uint32_t epoch, uint32_t* __restrict__ err) {
+    const int p = threadIdx.x;
+    __threadfence_system();
+    if (p < c.size) {
+        *(volatile uint32_t*)(c.flags[p] + c.rank) = epoch;
+        const long long t0 = clock64();
+        while (*(volatile uint32_t*)(c.flags[c.rank] + p) < epoch) {
+            if (clock64() - t0 > 4000000000ll) { atomicAdd(err, 1u); break; }   // ~2 s: report instead of hanging the GPU
+        }
+    }
+    __threadfence_system();
+}
 
 // =====================================================================================================
 // K1a depth_int       the internal-resolution depth image (manualResize of the depth Mat, pointcloud_tools.h:1104-1133):
@@ -257,7 +307,7 @@ template <int PB>
 __global__ void __launch_bounds__(256)
 k_sweep_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
               const uint32_t* __restrict__ stamp_z, const uint32_t* __restrict__ work, const float* __restrict__ depth_int,
-              uint32_t* __restrict__ pix_count, uint2* __restrict__ pairs, Counters* __restrict__ cnt) {
+              uint32_t* __restrict__ pix_count, CommView cv, Counters* __restrict__ cnt) {
     constexpr int P = 1 << PB, G = 32 / P;
     const uint32_t n_work = cnt->n_sweep_work;
     const uint32_t s = lane_id() & (P - 1), g = lane_id() / P, gbase = lane_id() & ~(uint32_t)(P - 1);
@@ -267,6 +317,9 @@ k_sweep_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* _
     // the pair list is reserved PAIR_CHUNK entries at a time per warp; unused tails are filled with a sentinel pixel
     constexpr uint32_t PAIR_CHUNK = 128;
     uint32_t chunk_base = 0, chunk_used = PAIR_CHUNK;
+    auto put_sentinel = [&](uint32_t pos) {
+        for (int pr = 0; pr < cv.size; ++pr) (cv.recs[pr] + (size_t)cv.rank * cv.rec_cap + pos)->pix = 0xffffffffu;
+    };
     for (uint32_t w0 = warp * G; w0 < n_work; w0 += n_warps * G) {     // warp-uniform trip count
         const uint32_t wi = w0 + g;
         const bool active = wi < n_work;
@@ -305,7 +358,7 @@ k_sweep_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* _
             const uint32_t ne = __popc(b_emit);
             if (chunk_used + ne > PAIR_CHUNK) {                      // warp-uniform: retire the chunk, reserve a new one
                 for (uint32_t k = chunk_used + lane_id(); k < PAIR_CHUNK; k += 32)
-                    if (chunk_base + k < f.vis_cap) pairs[chunk_base + k] = make_uint2(0xffffffffu, 0u);
+                    if (chunk_base + k < f.vis_cap) put_sentinel(chunk_base + k);
                 uint32_t nb = 0;
                 if (lane_id() == 0) nb = atomicAdd(&cnt->n_pairs, PAIR_CHUNK);
                 chunk_base = __shfl_sync(0xffffffffu, nb, 0);
@@ -314,7 +367,12 @@ k_sweep_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* _
             if (emit) {
                 const uint32_t pos = chunk_base + chunk_used + __popc(b_emit & ((1u << lane_id()) - 1u));
                 if (pos < f.vis_cap) {
-                    pairs[pos] = make_uint2(pix, (uint32_t)(base + s));
+                    const uint4 lo = make_uint4(pix, (uint32_t)(base + s), __float_as_uint(x), __float_as_uint(y));
+                    const uint4 hi = make_uint4(__float_as_uint(z), __float_as_uint(st.w[base + s]), meta_track(m) | (meta_forget(m) << 16), 0u);
+                    for (int pr = 0; pr < cv.size; ++pr) {          // every rank builds the full pixel lists
+                        uint4* dst = reinterpret_cast<uint4*>(cv.recs[pr] + (size_t)cv.rank * cv.rec_cap + pos);
+                        dst[0] = lo; dst[1] = hi;
+                    }
                     atomicAdd(pix_count + pix, 1u);
                 }
             }
@@ -336,7 +394,8 @@ k_sweep_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* _
         }
     }
     for (uint32_t k = chunk_used + lane_id(); k < PAIR_CHUNK; k += 32)          // retire the last chunk
-        if (chunk_base + k < f.vis_cap) pairs[chunk_base + k] = make_uint2(0xffffffffu, 0u);
+        if (chunk_base + k < f.vis_cap) put_sentinel(chunk_base + k);
+    __threadfence_system();
     n_nonempty = __reduce_add_sync(0xffffffffu, n_nonempty);
     if (lane_id() == 0 && n_nonempty) atomicAdd(&cnt->n_swept_nonempty, n_nonempty);
 }
@@ -405,44 +464,70 @@ k_scan_apply(const uint32_t* __restrict__ count, uint32_t n, const uint32_t* __r
     if (i == n - 1) offset[n] = base + ex + c;
 }
 
-// scatter the pairs into their pixel segments (arrival order; sorted next)
+// this rank's record count goes into every rank's counts table
+__global__ void k_publish_pairs(CommView cv, const Counters* __restrict__ cnt) {
+    const int p = threadIdx.x;
+    if (p < cv.size) cv.counts[p][cv.rank * COMM_COUNTS + CC_PAIRS] = cnt->n_pairs;
+    __threadfence_system();
+}
+
+// per-pixel counts of the records that arrived from the OTHER ranks (own records were counted by the sweep)
 __global__ void __launch_bounds__(256)
-k_fill(const __grid_constant__ FrameParams f, const Counters* __restrict__ cnt, const uint2* __restrict__ pairs, const uint32_t* __restrict__ offset,
-       uint32_t* __restrict__ pix_count, uint32_t* __restrict__ csr_idx, uint32_t* __restrict__ vis_pix) {
-    const uint32_t n = min(cnt->n_pairs, f.vis_cap);
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const uint2 pr = pairs[k];
-        if (pr.x == 0xffffffffu) continue;     // unused tail of a reserved chunk
-        const uint32_t pos = offset[pr.x] + (atomicSub(pix_count + pr.x, 1u) - 1u);   // leaves the counts at zero
-        csr_idx[pos] = pr.y;
-        vis_pix[pos] = pr.x;
+k_count_remote(CommView cv, const VisRec* __restrict__ recs, const uint32_t* __restrict__ counts, uint32_t* __restrict__ pix_count) {
+    for (int g = 0; g < cv.size; ++g) {
+        if (g == cv.rank) continue;
+        const uint32_t n = min(counts[g * COMM_COUNTS + CC_PAIRS], cv.rec_cap);
+        const VisRec* seg = recs + (size_t)g * cv.rec_cap;
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+            const uint32_t pix = seg[k].pix;
+            if (pix != 0xffffffffu) atomicAdd(pix_count + pix, 1u);
+        }
+    }
+}
+
+// scatter (particle index, record reference) keys into their pixel segments (arrival order; sorted next)
+__global__ void __launch_bounds__(256)
+k_fill(CommView cv, const VisRec* __restrict__ recs, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offset,
+       uint32_t* __restrict__ pix_count, uint64_t* __restrict__ csr_key) {
+    for (int g = 0; g < cv.size; ++g) {
+        const uint32_t n = min(counts[g * COMM_COUNTS + CC_PAIRS], cv.rec_cap);
+        const VisRec* seg = recs + (size_t)g * cv.rec_cap;
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+            const uint32_t pix = seg[k].pix;
+            if (pix == 0xffffffffu) continue;     // unused tail of a reserved chunk
+            const uint32_t pos = offset[pix] + (atomicSub(pix_count + pix, 1u) - 1u);   // leaves the counts at zero
+            csr_key[pos] = ((uint64_t)seg[k].idx << 32) | (uint64_t)((uint32_t)g * cv.rec_cap + k);
+        }
     }
 }
 
 // canonical order inside each pixel list: ascending particle index (insertion sort; lists are short)
 __global__ void __launch_bounds__(256)
-k_sort_lists(const __grid_constant__ FrameParams f, const uint32_t* __restrict__ offset, uint32_t* __restrict__ csr_idx) {
+k_sort_lists(const __grid_constant__ FrameParams f, const uint32_t* __restrict__ offset, uint64_t* __restrict__ csr_key) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= f.W * f.H) return;
     const uint32_t b = offset[q], e = offset[q + 1];
     for (uint32_t i = b + 1; i < e; ++i) {
-        const uint32_t key = csr_idx[i];
+        const uint64_t key = csr_key[i];
         uint32_t j = i;
-        while (j > b && csr_idx[j - 1] > key) { csr_idx[j] = csr_idx[j - 1]; --j; }
-        csr_idx[j] = key;
+        while (j > b && csr_key[j - 1] > key) { csr_key[j] = csr_key[j - 1]; --j; }
+        csr_key[j] = key;
     }
 }
 
-// gather the listed particles into compact, list-ordered arrays read by the two stencil passes
+// lay the listed particles out in list order for the two stencil passes (from the records, not from the store)
 __global__ void __launch_bounds__(256)
-k_gather_visible(const __grid_constant__ FrameParams f, const uint32_t* __restrict__ n_visible, Store st, const uint32_t* __restrict__ csr_idx,
-                 float4* __restrict__ vis_pos, uint32_t* __restrict__ vis_meta) {
+k_gather_visible(const uint32_t* __restrict__ n_visible, const VisRec* __restrict__ recs, const uint64_t* __restrict__ csr_key,
+                 uint32_t* __restrict__ csr_idx, uint32_t* __restrict__ vis_pix, float4* __restrict__ vis_pos, uint32_t* __restrict__ vis_meta) {
     const uint32_t n = *n_visible;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const uint32_t idx = csr_idx[k];
-        const uint64_t m = st.meta[idx];
-        vis_pos[k] = make_float4(st.x[idx], st.y[idx], st.z[idx], st.w[idx]);
-        vis_meta[k] = meta_track(m) | (meta_forget(m) << 16);
+        const uint64_t key = csr_key[k];
+        const uint4* r = reinterpret_cast<const uint4*>(recs + (uint32_t)key);
+        const uint4 lo = r[0], hi = r[1];
+        csr_idx[k] = (uint32_t)(key >> 32);
+        vis_pix[k] = lo.x;
+        vis_pos[k] = make_float4(__uint_as_float(lo.z), __uint_as_float(lo.w), __uint_as_float(hi.x), __uint_as_float(hi.y));
+        vis_meta[k] = hi.z;
     }
 }
 
@@ -484,25 +569,28 @@ __device__ __forceinline__ float ck_pixel(const FrameParams& f, const float4 o, 
 __global__ void __launch_bounds__(1024, 2)
 k_ck(const __grid_constant__ FrameParams f, const float* __restrict__ lut, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta,
      const uint32_t* __restrict__ offset, const float4* __restrict__ vis_pos, const uint32_t* __restrict__ vis_meta,
-     float* __restrict__ ck, uint32_t seg_stride) {
+     CommView cv, uint32_t seg_stride) {
     stage_lut(lut);
     const int npix = f.W * f.H;
     const uint32_t n_seg = (uint32_t)(npix + 31) / 32;
     // a warp takes 32-pixel segments w, w + n_warps, ...; the index maps to an image segment through a stride coprime
     // with the segment count, so the (very uneven) per-pixel work of neighbouring image rows spreads over all SMs
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t t = warp; t < n_seg; t += n_warps) {
+    // sharded map: rank r evaluates every size-th segment and writes its values into every rank's ck image
+    for (uint32_t t = warp * (uint32_t)cv.size + (uint32_t)cv.rank; t < n_seg; t += n_warps * (uint32_t)cv.size) {
         const int q = (int)((uint32_t)(((uint64_t)t * seg_stride) % n_seg) * 32u + lane_id());
         if (q >= npix) continue;
         const uint32_t om = cloud_meta[q];
-        if (!pt_valid(om)) { ck[q] = 0.f; continue; }
+        if (!pt_valid(om)) { for (int pr = 0; pr < cv.size; ++pr) cv.ck[pr][q] = 0.f; continue; }
         const float4 o = cloud_pos[q];
         const int i = q / f.W, j = q - i * f.W;
         const float ao = fabsf(o.w);
         const float acc = (ao > 1e-6f && ao < 1e6f) ? ck_pixel<true>(f, o, pt_track(om), i, j, offset, vis_pos, vis_meta)
                                                     : ck_pixel<false>(f, o, pt_track(om), i, j, offset, vis_pos, vis_meta);
-        ck[q] = acc * f.Pd + f.kappa;
+        const float val = acc * f.Pd + f.kappa;
+        for (int pr = 0; pr < cv.size; ++pr) cv.ck[pr][q] = val;
     }
+    __threadfence_system();
 }
 
 // =====================================================================================================
@@ -544,6 +632,9 @@ k_weight_update(const __grid_constant__ FrameParams f, const uint32_t* __restric
     stage_lut(lut);
     const uint32_t n = *n_visible;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t pidx = csr_idx[k];
+        const uint32_t pz = (pidx >> f.Pb) >> (f.Xb + f.Yb);
+        if (pz < f.z_lo || pz >= f.z_hi) continue;          // another shard updates this particle
         const int q = (int)vis_pix[k];
         const int i = q / f.W, j = q - i * f.W;
         const float sig = cloud_pos[q].w;
@@ -555,7 +646,7 @@ k_weight_update(const __grid_constant__ FrameParams f, const uint32_t* __restric
         const float as = fabsf(sig);
         const float acc = (as > 1e-6f && as < 1e6f) ? wu_particle<true>(f, p, ptrack, phi, sig, i, j, cloud_pos, cloud_meta, ck, right_id)
                                                     : wu_particle<false>(f, p, ptrack, phi, sig, i, j, cloud_pos, cloud_meta, ck, right_id);
-        const uint32_t idx = csr_idx[k];
+        const uint32_t idx = pidx;
         const uint64_t m = st.meta[idx];
         uint32_t forget = meta_forget(m);
         if (!f.indep) {
@@ -972,7 +1063,7 @@ k_occ_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* __r
 
 // exclusive scan of the per-block (occupied, free, movable) counts; single block, any number of tiles
 __global__ void __launch_bounds__(1024)
-k_occ_scan(OccScratch sc, uint32_t n_blocks, Counters* __restrict__ cnt, Persist* __restrict__ persist) {
+k_occ_scan(OccScratch sc, uint32_t n_blocks, Counters* __restrict__ cnt, Persist* __restrict__ persist, CommView cv) {
     __shared__ uint32_t s_warp[33];
     uint32_t run0 = 0, run1 = 0, run2 = 0;
     for (uint32_t c = 0; c < n_blocks; c += blockDim.x) {
@@ -986,13 +1077,21 @@ k_occ_scan(OccScratch sc, uint32_t n_blocks, Counters* __restrict__ cnt, Persist
         run0 += t0; run1 += t1; run2 += t2;
     }
     if (threadIdx.x == 0) { cnt->n_occupied = run0; cnt->n_free = run1; cnt->n_movable = run2; persist->n_movable = run2; }
+    if ((int)threadIdx.x < cv.size) {      // every rank learns every rank's totals (the emit pass needs the lower ranks')
+        uint32_t* row = cv.counts[threadIdx.x] + cv.rank * COMM_COUNTS;
+        row[CC_OCC] = run0; row[CC_FREE] = run1;
+    }
+    __threadfence_system();
 }
 
 template <int PB>
 __global__ void __launch_bounds__(OCC_BLOCK)
 k_occ_emit(const __grid_constant__ FrameParams f, Store st, OccScratch sc, ResultArrays out, uint32_t* __restrict__ movl_idx,
-           uint16_t* __restrict__ movl_track, uint32_t movl_cap) {
+           uint16_t* __restrict__ movl_track, uint32_t movl_cap, CommView cv, const uint32_t* __restrict__ counts) {
     __shared__ uint32_t s_warp[33];
+    // sharded map: `out` is rank 0's result arrays; this rank's entries start after the lower ranks' (ascending storage index)
+    uint32_t base_occ = 0, base_free = 0;
+    for (int g = 0; g < cv.rank; ++g) { base_occ += counts[g * COMM_COUNTS + CC_OCC]; base_free += counts[g * COMM_COUNTS + CC_FREE]; }
     const uint4 cntb = sc.blk_cnt[blockIdx.x];
     if ((cntb.x | cntb.y | cntb.z) == 0) return;          // nothing to emit from this tile
     const uint32_t v_lo = f.z_lo << (f.Xb + f.Yb);
@@ -1013,7 +1112,7 @@ k_occ_emit(const __grid_constant__ FrameParams f, Store st, OccScratch sc, Resul
     const uint32_t ex_b = block_exclusive_scan(n_mov, s_warp, tot_b);
     if ((n_occ | n_free | n_mov) == 0) return;
     const uint4 off = sc.blk_off[blockIdx.x];
-    uint32_t pos_occ = off.x + (ex_a & 0xffffu), pos_free = off.y + (ex_a >> 16), pos_mov = off.z + ex_b;
+    uint32_t pos_occ = base_occ + off.x + (ex_a & 0xffffu), pos_free = base_free + off.y + (ex_a >> 16), pos_mov = off.z + ex_b;
     uint32_t bx0, by, bz;
     voxel_to_buffer(f, v0, bx0, by, bz);
 #pragma unroll
@@ -1051,6 +1150,7 @@ k_occ_emit(const __grid_constant__ FrameParams f, Store st, OccScratch sc, Resul
             ++pos_mov;
         }
     }
+    __threadfence_system();
 }
 
 // =====================================================================================================
@@ -1075,30 +1175,51 @@ __device__ __forceinline__ int find_track(const int32_t* __restrict__ tab, int n
     return -1;
 }
 
-// pass 1 (single block): sequence number of every listed particle of a moved track in the reference's processing
-// order — object by object, ascending index inside an object — = offset[move] + stable rank among the move's entries.
-// Entries of a removed track are tagged SEQ_REMOVE, everything else NO_RANK.  Also advances the random cursor.
+// pass 1a: this rank's number of listed particles per moved track, published to every rank
 __global__ void __launch_bounds__(1024)
-k_move_prepare(const MoveTable* __restrict__ mt, const uint16_t* __restrict__ movl_track, uint32_t* __restrict__ movl_seq,
-               uint32_t movl_cap, uint32_t rand_n, Counters* __restrict__ cnt, Persist* __restrict__ persist) {
-    __shared__ uint32_t s_count[MAX_MOVES], s_offset[MAX_MOVES], s_running[MAX_MOVES];
-    __shared__ uint32_t s_wcount[32][MAX_MOVES];
+k_move_count(const MoveTable* __restrict__ mt, const uint16_t* __restrict__ movl_track, uint32_t movl_cap, const Persist* __restrict__ persist,
+             CommView cv) {
+    __shared__ uint32_t s_count[MAX_MOVES];
     const uint32_t n = min(persist->n_movable, movl_cap);
     const int n_moves = mt->n_moves;
-    if (threadIdx.x < MAX_MOVES) { s_count[threadIdx.x] = 0; s_running[threadIdx.x] = 0; }
+    if (threadIdx.x < MAX_MOVES) s_count[threadIdx.x] = 0;
     __syncthreads();
     for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
         const int mv = find_track(mt->move_track, n_moves, (int)movl_track[k]);
         if (mv >= 0) atomicAdd(&s_count[mv], 1u);
     }
     __syncthreads();
+    if (threadIdx.x < MAX_MOVES)
+        for (int pr = 0; pr < cv.size; ++pr) cv.move_counts[pr][cv.rank * MAX_MOVES + threadIdx.x] = s_count[threadIdx.x];
+    __threadfence_system();
+}
+
+// pass 1b (single block): sequence number of every listed particle of a moved track in the reference's processing
+// order — object by object, ascending particle index inside an object (= ascending rank, then ascending local index) —
+// = offset[move] + particles of that move on lower ranks + stable local rank.  Entries of a removed track are tagged
+// SEQ_REMOVE, everything else NO_RANK.  Also advances the random cursor by the GLOBAL draw count (replicated state).
+__global__ void __launch_bounds__(1024)
+k_move_prepare(const MoveTable* __restrict__ mt, const uint16_t* __restrict__ movl_track, uint32_t* __restrict__ movl_seq,
+               uint32_t movl_cap, uint32_t rand_n, Counters* __restrict__ cnt, Persist* __restrict__ persist, CommView cv,
+               const uint32_t* __restrict__ move_counts) {
+    __shared__ uint32_t s_offset[MAX_MOVES], s_running[MAX_MOVES];
+    __shared__ uint32_t s_wcount[32][MAX_MOVES];
+    const uint32_t n = min(persist->n_movable, movl_cap);
+    const int n_moves = mt->n_moves;
     if (threadIdx.x == 0) {
         uint32_t acc = 0;
-        for (int m = 0; m < n_moves; ++m) { s_offset[m] = acc; acc += s_count[m]; }
+        for (int m = 0; m < n_moves; ++m) {
+            uint32_t below = 0, all = 0;
+            for (int g = 0; g < cv.size; ++g) { const uint32_t c = move_counts[g * MAX_MOVES + m]; if (g < cv.rank) below += c; all += c; }
+            s_offset[m] = acc + below;
+            s_running[m] = 0;
+            acc += all;
+        }
         cnt->n_selected = acc;
         cnt->move_cursor0 = persist->cursor_ring;
         persist->cursor_ring = (uint32_t)(((uint64_t)persist->cursor_ring + 3ull * acc) % rand_n);   // basic_algorithms.h:426-433
     }
+    __syncthreads();
     const uint32_t wid = threadIdx.x >> 5;
     for (uint32_t c = 0; c < n; c += blockDim.x) {
         for (int i = threadIdx.x; i < 32 * MAX_MOVES; i += blockDim.x) (&s_wcount[0][0])[i] = 0;
@@ -1126,16 +1247,16 @@ k_move_prepare(const MoveTable* __restrict__ mt, const uint16_t* __restrict__ mo
     }
 }
 
-// pass 2: transform + table noise into a staging record, delete the original, bin by destination voxel; removed
-// tracks' particles are invalidated here too
+// pass 2: transform + table noise, delete the original, hand the moved particle to the rank that owns its destination
+// voxel (a record in that rank's arena); removed tracks' particles are invalidated here too
 __global__ void __launch_bounds__(256)
 k_move_apply(const __grid_constant__ FrameParams f, Counters* __restrict__ cnt, Store st, const MoveTable* __restrict__ mt,
              const float* __restrict__ randoms, const Persist* __restrict__ persist, const uint32_t* __restrict__ movl_idx,
-             const uint16_t* __restrict__ movl_track, const uint32_t* __restrict__ movl_seq, uint32_t movl_cap,
-             float4* __restrict__ mov_pos, uint64_t* __restrict__ mov_meta, uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks,
-             uint32_t* __restrict__ entry_list) {
+             const uint16_t* __restrict__ movl_track, const uint32_t* __restrict__ movl_seq, uint32_t movl_cap, CommView cv,
+             uint32_t* __restrict__ out_count /*[MAX_RANKS]*/) {
     const uint32_t n = min(persist->n_movable, movl_cap);
     const uint32_t cur = cnt->move_cursor0;
+    const uint32_t slabs = f.z_hi - f.z_lo;
     uint32_t n_removed = 0;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint32_t seq = movl_seq[k];
@@ -1155,13 +1276,43 @@ k_move_apply(const __grid_constant__ FrameParams f, Counters* __restrict__ cnt, 
         const float px = nx + randoms[(d0 + 1) % f.rand_n];
         const float py = ny + randoms[(d0 + 2) % f.rand_n];
         const float pz = nz + randoms[(d0 + 3) % f.rand_n];
-        mov_pos[seq] = make_float4(px, py, pz, st.w[idx]);
-        mov_meta[seq] = m;
         uint32_t bx, by, bz;
         const uint32_t v = global_pos_to_voxel(f, px, py, pz, bx, by, bz);
-        if (v != INVALID_INDEX) topk_insert(f, f.hash_cap, f.hash_shift, v, seq, keys, ranks, entry_list, &cnt->n_move_voxels, &cnt->hash_overflow);
+        if (v == INVALID_INDEX) continue;                                      // left the map
+        const uint32_t owner = bz / slabs;
+        const uint32_t pos = atomicAdd(out_count + owner, 1u);
+        if (pos < cv.mov_cap) {
+            uint4* dst = reinterpret_cast<uint4*>(cv.movs[owner] + (size_t)cv.rank * cv.mov_cap + pos);
+            dst[0] = make_uint4(__float_as_uint(px), __float_as_uint(py), __float_as_uint(pz), __float_as_uint(st.w[idx]));
+            dst[1] = make_uint4((uint32_t)m, (uint32_t)(m >> 32), seq, v);
+        }
     }
     if (n_removed) atomicAdd(&cnt->n_removed, n_removed);
+    __threadfence_system();
+}
+
+// tell every destination rank how many moved particles this rank sent it
+__global__ void k_move_publish(CommView cv, uint32_t* __restrict__ out_count) {
+    const int p = threadIdx.x;
+    if (p < cv.size) { cv.counts[p][cv.rank * COMM_COUNTS + CC_MOVREC] = out_count[p]; out_count[p] = 0; }
+    __threadfence_system();
+}
+
+// pass 3: bin the moved particles that arrived here by destination voxel, ranked by sequence number
+__global__ void __launch_bounds__(256)
+k_move_bin(const __grid_constant__ FrameParams f, CommView cv, const MovRec* __restrict__ movs, const uint32_t* __restrict__ counts,
+           uint32_t* __restrict__ seq_ref, uint32_t seq_cap, uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks,
+           uint32_t* __restrict__ entry_list, Counters* __restrict__ cnt) {
+    for (int g = 0; g < cv.size; ++g) {
+        const uint32_t n = counts[g * COMM_COUNTS + CC_MOVREC];
+        if (n > cv.mov_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->hash_overflow, 1u); }
+        const MovRec* seg = movs + (size_t)g * cv.mov_cap;
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < min(n, cv.mov_cap); k += gridDim.x * blockDim.x) {
+            const uint32_t seq = seg[k].seq, v = seg[k].voxel;
+            if (seq < seq_cap) seq_ref[seq] = (uint32_t)g * cv.mov_cap + k;
+            topk_insert(f, f.hash_cap, f.hash_shift, v, seq, keys, ranks, entry_list, &cnt->n_move_voxels, &cnt->hash_overflow);
+        }
+    }
 }
 
 // fallback removal by a pass over the header plane (used when the movable list does not describe the store any more:
@@ -1230,8 +1381,9 @@ k_move_replay(const __grid_constant__ FrameParams f, Store st, const uint32_t* _
 }
 
 __global__ void __launch_bounds__(256)
-k_move_write(const __grid_constant__ FrameParams f, Store st, const float4* __restrict__ mov_pos, const uint64_t* __restrict__ mov_meta, uint32_t* __restrict__ ranks,
-             const uint32_t* __restrict__ entry_list, const uint32_t* __restrict__ entry_voxel, const Counters* __restrict__ cnt) {
+k_move_write(const __grid_constant__ FrameParams f, Store st, const MovRec* __restrict__ movs, const uint32_t* __restrict__ seq_ref,
+             uint32_t* __restrict__ ranks, const uint32_t* __restrict__ entry_list, const uint32_t* __restrict__ entry_voxel,
+             const Counters* __restrict__ cnt) {
     const uint32_t K = f.topk, n = cnt->n_move_voxels * K;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
         const uint32_t li = t / K, i = t - li * K;
@@ -1241,9 +1393,10 @@ k_move_write(const __grid_constant__ FrameParams f, Store st, const float4* __re
         *r = NO_RANK;
         const uint32_t s = a >> 24, seq = a & 0xffffffu;
         const size_t idx = ((size_t)entry_voxel[li] << f.Pb) + s;
-        const float4 p = mov_pos[seq];
-        st.x[idx] = p.x; st.y[idx] = p.y; st.z[idx] = p.z; st.w[idx] = p.w;
-        st.meta[idx] = mov_meta[seq];
+        const uint4* rec = reinterpret_cast<const uint4*>(movs + seq_ref[seq]);
+        const uint4 lo = rec[0], hi = rec[1];
+        st.x[idx] = __uint_as_float(lo.x); st.y[idx] = __uint_as_float(lo.y); st.z[idx] = __uint_as_float(lo.z); st.w[idx] = __uint_as_float(lo.w);
+        st.meta[idx] = (uint64_t)hi.x | ((uint64_t)hi.y << 32);
     }
 }
 

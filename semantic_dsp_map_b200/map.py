@@ -119,6 +119,18 @@ class Engine:
     def clear(self):
         self.check(self._fn("clear")(self._h), "dspmap_clear")
 
+    # ---- sharded maps ------------------------------------------------------------------------------------------
+    def comm_export(self) -> bytes:
+        buf = (C.c_uint8 * _capi.COMM_HANDLE_BYTES)()
+        self.check(self._fn("comm_export")(self._h, buf), "dspmap_comm_export")
+        return bytes(buf)
+
+    def comm_connect(self, handles: Sequence[bytes]):
+        blob = b"".join(handles)
+        assert len(blob) == _capi.COMM_HANDLE_BYTES * len(handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self.check(self._fn("comm_connect")(self._h, buf), "dspmap_comm_connect")
+
     # ---- frame ---------------------------------------------------------------------------------------------------
     @staticmethod
     def _pack_masks(masks):
@@ -184,13 +196,28 @@ class Engine:
         return buf.view(dtype)
 
 
+def connect_shards(dsp_map: "SemanticDSPMap", all_gather_object):
+    """Exchange the exchange-arena handles of a sharded map.  ``all_gather_object(obj) -> list`` is the caller's plumbing
+    (e.g. a wrapper of torch.distributed.all_gather_object over NCCL or gloo): it must return every rank's object in rank
+    order."""
+    handles = all_gather_object(dsp_map.engine.comm_export())
+    if len(handles) != dsp_map.shard_count:
+        raise ValueError(f"expected {dsp_map.shard_count} handles, got {len(handles)}")
+    dsp_map.engine.comm_connect(handles)
+    return handles
+
+
 class SemanticDSPMap:
     """The reference's public class, same method names (include/semantic_dsp_map.h:23-251)."""
 
-    def __init__(self, config: MapConfig, labels: Optional[LabelTables] = None, device: int = 0, _engine: Optional[Engine] = None):
+    def __init__(self, config: MapConfig, labels: Optional[LabelTables] = None, device: int = 0, _engine: Optional[Engine] = None,
+                 shard_rank: int = 0, shard_count: int = 1):
+        """shard_count > 1: this process holds storage-z slabs [rank*NZ/G, (rank+1)*NZ/G) of one map on `device`; call
+        connect_shards() on every rank before the first update (include/dspmap_c.h, "sharded maps")."""
         self.config = config
         self.labels = labels or LabelTables.from_rows(ZED2_ROWS)
-        self.engine = _engine or Engine(_capi.load(), "dspmap_", config, (0, 1, device, 0))
+        self.engine = _engine or Engine(_capi.load(), "dspmap_", config, (shard_rank, shard_count, device, 0))
+        self.shard_rank, self.shard_count = shard_rank, shard_count
         self._params = config.c_params()
         self.engine.set_params(self._params)
         self.engine.set_label_luts(self.labels)
