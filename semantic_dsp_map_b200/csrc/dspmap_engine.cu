@@ -502,7 +502,7 @@ int dspmap::init(const dspmap_config& c) {
         while (gcd(ck_seg_stride, n_seg) != 1) ++ck_seg_stride;
     }
     CU_TRY(this, d_vstate.alloc(v_pad)); CU_TRY(this, d_res_w.alloc(v_pad)); CU_TRY(this, d_res_tl.alloc(v_pad)); CU_TRY(this, d_mov_mask.alloc(v_pad));
-    CU_TRY(this, d_blk_cnt.alloc(n_occ_blocks)); CU_TRY(this, d_blk_off.alloc(n_occ_blocks)); CU_TRY(this, d_work.alloc(v_pad));
+    CU_TRY(this, d_blk_cnt.alloc(n_occ_blocks)); CU_TRY(this, d_blk_off.alloc(n_occ_blocks)); CU_TRY(this, d_work.alloc(v_pad + (size_t)sm_count * 8 * 8 * 512 + 512));
     CU_TRY(this, cudaMemset(d_vstate.p, 0, v_pad));
     {   // exchange arena
         const int G = c.shard_count;
@@ -777,8 +777,9 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     // ---- O1 occupancy -------------------------------------------------------------------------------------------------
     ResultArrays out{r_idx, r_xyz, r_w, r_track, r_label, r_state, r_free_idx, r_free_xyz};
     OccScratch osc{d_vstate.p, d_res_w.p - (slot_lo >> f.Pb), d_res_tl.p - (slot_lo >> f.Pb), d_mov_mask.p - (slot_lo >> f.Pb), d_blk_cnt.p, d_blk_off.p};
+    CU_TRY(this, cudaMemsetAsync(d_blk_cnt.p, 0, (size_t)n_occ_blocks * sizeof(uint4), stream));
     if (profiling) cudaEventRecord(ev[8], stream);
-    DISPATCH_PB(f.Pb, (k_occ_headers<PB><<<n_occ_blocks, OCC_BLOCK, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, d_cnt.p)));
+    DISPATCH_PB(f.Pb, (k_occ_headers<PB><<<sm_count * 8, OCC_BLOCK, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, n_occ_blocks, d_cnt.p)));
     ++launches;
     if (profiling) cudaEventRecord(ev[9], stream);
     DISPATCH_PB(f.Pb, (k_occ_slots<PB><<<sm_count * 8, 256, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, d_cnt.p)));

@@ -923,58 +923,69 @@ struct OccScratch {
     uint4* blk_off;         // exclusive prefix of blk_cnt
 };
 
+// persistent warps, each streaming 128-voxel pieces (32 lanes x one 16-byte load) of the header plane with the next
+// piece's load already in flight; no block-level synchronisation.  blk_cnt must be zero on entry.
 template <int PB>
 __global__ void __launch_bounds__(OCC_BLOCK)
 k_occ_headers(const __grid_constant__ FrameParams f, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
-              const uint32_t* __restrict__ stamp_z, OccScratch sc, uint32_t* __restrict__ work, Counters* __restrict__ cnt) {
-    __shared__ uint32_t s_free;
-    if (threadIdx.x == 0) s_free = 0;
-    __syncthreads();
+              const uint32_t* __restrict__ stamp_z, OccScratch sc, uint32_t* __restrict__ work, uint32_t n_tiles, Counters* __restrict__ cnt) {
     const uint32_t v_lo = f.z_lo << (f.Xb + f.Yb);
-    const uint32_t v0 = v_lo + blockIdx.x * OCC_TILE + threadIdx.x * OCC_VPT;   // header plane is padded to whole tiles
-    const uint4 h4 = *reinterpret_cast<const uint4*>(st.hdr + v0);
-    const uint32_t hdrs[OCC_VPT] = {h4.x, h4.y, h4.z, h4.w};
-    uint32_t bx0, by, bz;
-    voxel_to_buffer(f, v0, bx0, by, bz);
-    const uint32_t stamp_yz = max(__ldg(stamp_y + by), __ldg(stamp_z + bz));
-    uint32_t sb4 = 0, heavy = 0, n_free = 0;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n_pieces = n_tiles * (OCC_TILE / 128);
+    uint32_t piece = warp;
+    uint4 h4 = make_uint4(0, 0, 0, 0);
+    if (piece < n_pieces) h4 = *reinterpret_cast<const uint4*>(st.hdr + v_lo + piece * 128 + lane_id() * 4);
+    for (; piece < n_pieces; piece += n_warps) {
+        const uint32_t v0 = v_lo + piece * 128 + lane_id() * 4;
+        const uint32_t hdrs[OCC_VPT] = {h4.x, h4.y, h4.z, h4.w};
+        if (piece + n_warps < n_pieces) h4 = *reinterpret_cast<const uint4*>(st.hdr + v0 + (size_t)n_warps * 128);   // prefetch
+        // never-observed voxels (header 0: no time stamp, no live slot) are unknown whatever the slab stamps say
+        const bool any_set = (hdrs[0] | hdrs[1] | hdrs[2] | hdrs[3]) != 0;
+        if (!__any_sync(0xffffffffu, any_set)) {
+            *reinterpret_cast<uint32_t*>(sc.vstate + (v0 - v_lo)) = 0u;
+            continue;
+        }
+        uint32_t sb4 = 0, heavy = 0, n_free = 0;
+        if (any_set) {
+            uint32_t bx0, by, bz;
+            voxel_to_buffer(f, v0, bx0, by, bz);
+            const uint32_t stamp_yz = max(__ldg(stamp_y + by), __ldg(stamp_z + bz));
 #pragma unroll
-    for (int u = 0; u < OCC_VPT; ++u) {
-        const uint32_t hdr = hdrs[u];
-        const uint32_t stamp = max(stamp_yz, __ldg(stamp_x + bx0 + u));
-        const uint32_t ts0 = hdr_ts(hdr);
-        const bool known = ts0 != 0 && !(ts0 < stamp);                  // isVoxelValid, operations.h:824-837
-        const bool hv = hdr_live(hdr) != 0 && (known || (hdr & HDR_MOVABLE));
-        // decided by the header alone: unknown (-1), or known and empty (0: weight sum 0, no guessed weight)
-        sb4 |= (known ? 1u : 0u) << (8 * u);
-        heavy |= (hv ? 1u : 0u) << u;
-        n_free += known && !hv;
-    }
-    *reinterpret_cast<uint32_t*>(sc.vstate + (v0 - v_lo)) = sb4;
-    // append this warp's heavy voxels to the work list (one atomic per warp)
-    const uint32_t nh = __popc(heavy);
-    uint32_t inc = nh;
+            for (int u = 0; u < OCC_VPT; ++u) {
+                const uint32_t hdr = hdrs[u];
+                const uint32_t stamp = max(stamp_yz, __ldg(stamp_x + bx0 + u));
+                const uint32_t ts0 = hdr_ts(hdr);
+                const bool known = ts0 != 0 && !(ts0 < stamp);                  // isVoxelValid, operations.h:824-837
+                const bool hv = hdr_live(hdr) != 0 && (known || (hdr & HDR_MOVABLE));
+                // decided by the header alone: unknown (-1), or known and empty (0: weight sum 0, no guessed weight)
+                sb4 |= (known ? 1u : 0u) << (8 * u);
+                heavy |= (hv ? 1u : 0u) << u;
+                n_free += known && !hv;
+            }
+        }
+        *reinterpret_cast<uint32_t*>(sc.vstate + (v0 - v_lo)) = sb4;
+        if (f.want_free) {
+            n_free = __reduce_add_sync(0xffffffffu, n_free);
+            if (lane_id() == 0 && n_free) atomicAdd(reinterpret_cast<uint32_t*>(sc.blk_cnt + piece / (OCC_TILE / 128)) + 1, n_free);
+        }
+        if (!__any_sync(0xffffffffu, heavy != 0)) continue;
+        // append this warp's heavy voxels to the work list (one atomic per warp)
+        const uint32_t nh = __popc(heavy);
+        uint32_t inc = nh;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane_id() >= (uint32_t)o) inc += n;
-    }
-    const uint32_t warp_total = __shfl_sync(0xffffffffu, inc, 31);
-    n_free = __reduce_add_sync(0xffffffffu, n_free);
-    uint32_t base = 0;
-    if (lane_id() == 31) {
-        if (warp_total) base = atomicAdd(&cnt->n_occ_work, warp_total);
-        if (n_free) atomicAdd(&s_free, n_free);
-    }
-    if (warp_total) {
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane_id() >= (uint32_t)o) inc += n;
+        }
+        const uint32_t warp_total = __shfl_sync(0xffffffffu, inc, 31);
+        uint32_t base = 0;
+        if (lane_id() == 31) base = atomicAdd(&cnt->n_occ_work, warp_total);
         base = __shfl_sync(0xffffffffu, base, 31);
         uint32_t pos = base + inc - nh;
 #pragma unroll
         for (int u = 0; u < OCC_VPT; ++u)
             if ((heavy >> u) & 1u) work[pos++] = v0 + u;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) sc.blk_cnt[blockIdx.x] = make_uint4(0u, f.want_free ? s_free : 0u, 0u, 0u);
 }
 
 template <int PB>
@@ -990,8 +1001,9 @@ k_occ_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* __r
     uint32_t n_nonempty = 0;
     for (uint32_t w0 = warp * G; w0 < n_work; w0 += n_warps * G) {     // warp-uniform trip count
         const uint32_t wi = w0 + g;
-        const bool active = wi < n_work;
-        const uint32_t g_v = active ? work[wi] : v_lo;
+        uint32_t g_v = wi < n_work ? work[wi] : 0xffffffffu;
+        const bool active = g_v != 0xffffffffu;                 // sentinel: unused tail of a reserved chunk
+        if (!active) g_v = v_lo;
         const uint32_t g_hdr = active ? st.hdr[g_v] : 0u;
         const size_t base = (size_t)g_v << PB;
         const bool has = active && sl != 0 && ((g_hdr >> (16 + sl)) & 1u);
@@ -1066,14 +1078,25 @@ __global__ void __launch_bounds__(1024)
 k_occ_scan(OccScratch sc, uint32_t n_blocks, Counters* __restrict__ cnt, Persist* __restrict__ persist, CommView cv) {
     __shared__ uint32_t s_warp[33];
     uint32_t run0 = 0, run1 = 0, run2 = 0;
-    for (uint32_t c = 0; c < n_blocks; c += blockDim.x) {
-        const uint32_t b = c + threadIdx.x;
-        const uint4 v = b < n_blocks ? sc.blk_cnt[b] : make_uint4(0, 0, 0, 0);
+    constexpr int TPT = 4;                                   // tiles per thread
+    for (uint32_t c = 0; c < n_blocks; c += blockDim.x * TPT) {
+        const uint32_t b0 = c + threadIdx.x * TPT;
+        uint4 v[TPT];
+        uint32_t s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+        for (int i = 0; i < TPT; ++i) {
+            v[i] = (b0 + i) < n_blocks ? sc.blk_cnt[b0 + i] : make_uint4(0, 0, 0, 0);
+            s0 += v[i].x; s1 += v[i].y; s2 += v[i].z;
+        }
         uint32_t t0, t1, t2;
-        const uint32_t e0 = block_exclusive_scan(v.x, s_warp, t0);
-        const uint32_t e1 = block_exclusive_scan(v.y, s_warp, t1);
-        const uint32_t e2 = block_exclusive_scan(v.z, s_warp, t2);
-        if (b < n_blocks) sc.blk_off[b] = make_uint4(run0 + e0, run1 + e1, run2 + e2, 0u);
+        uint32_t e0 = run0 + block_exclusive_scan(s0, s_warp, t0);
+        uint32_t e1 = run1 + block_exclusive_scan(s1, s_warp, t1);
+        uint32_t e2 = run2 + block_exclusive_scan(s2, s_warp, t2);
+#pragma unroll
+        for (int i = 0; i < TPT; ++i) {
+            if ((b0 + i) < n_blocks) sc.blk_off[b0 + i] = make_uint4(e0, e1, e2, 0u);
+            e0 += v[i].x; e1 += v[i].y; e2 += v[i].z;
+        }
         run0 += t0; run1 += t1; run2 += t2;
     }
     if (threadIdx.x == 0) { cnt->n_occupied = run0; cnt->n_free = run1; cnt->n_movable = run2; persist->n_movable = run2; }
