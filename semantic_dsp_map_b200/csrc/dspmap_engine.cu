@@ -590,15 +590,19 @@ int dspmap::run_moves(const dspmap_object_move* moves, int n_moves, const int32_
     if (scan_remove) {
         ++launches; k_remove_tracks_scan<<<sm_count * 8, 256, 0, stream>>>(fp, st, d_moves.p, d_cnt.p);
     } else {
-        ++launches; k_move_count<<<1, 1024, 0, stream>>>(d_moves.p, d_movl_track.p, sel_cap, d_persist.p, cv);
-        barrier();   // every rank knows how many particles of each moved track the lower ranks hold
+        if (cv.size > 1) {
+            ++launches; k_move_count<<<1, 1024, 0, stream>>>(d_moves.p, d_movl_track.p, sel_cap, d_persist.p, cv);
+            barrier();   // every rank knows how many particles of each moved track the lower ranks hold
+        }
         ++launches; k_move_prepare<<<1, 1024, 0, stream>>>(d_moves.p, d_movl_track.p, d_movl_seq.p, sel_cap, rand_n, d_cnt.p, d_persist.p, cv,
                                                          cv.move_counts[cv.rank]);
         ++launches; k_move_apply<<<sm_count * 2, 256, 0, stream>>>(fp, d_cnt.p, st, d_moves.p, d_randoms.p, d_persist.p, d_movl_idx.p, d_movl_track.p,
-                                                             d_movl_seq.p, sel_cap, cv, d_mov_out.p);
+                                                             d_movl_seq.p, sel_cap, cv);
         if (n_moves > 0) {
-            ++launches; k_move_publish<<<1, 32, 0, stream>>>(cv, d_mov_out.p);
-            barrier();   // the moved particles bound for this rank have arrived
+            if (cv.size > 1) {
+                ++launches; k_move_publish<<<1, 32, 0, stream>>>(cv, d_cnt.p);
+                barrier();   // the moved particles bound for this rank have arrived
+            }
             ++launches; k_move_bin<<<sm_count * 2, 256, 0, stream>>>(fp, cv, cv.movs[cv.rank], d_counts, d_seq_ref.p, sel_cap, d_keys.p, d_ranks.p,
                                                                d_entry_list.p, d_cnt.p);
             DISPATCH_PB(fp.Pb, (k_move_replay<PB><<<sm_count * 2, 128, 0, stream>>>(fp, st, stx, sty, stz, d_keys.p, d_ranks.p, d_entry_list.p, d_entry_voxel.p, d_cnt.p)));
@@ -702,7 +706,9 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
 
     if (profiling) cudaEventRecord(ev[0], stream);
     // ---- K1a internal depth image ----------------------------------------------------------------------------------
-    ++launches; k_depth_int<<<(npix + 255) / 256, 256, 0, stream>>>(fp, d_depth, stride, d_depth_int.p);
+    const float* depth_int = d_depth_int.p;
+    if ((pre_decimated || !f.boost) && stride == f.W) depth_int = d_depth;      // already the internal image: no copy
+    else { ++launches; k_depth_int<<<(npix + 255) / 256, 256, 0, stream>>>(fp, d_depth, stride, d_depth_int.p); }
     if (profiling) cudaEventRecord(ev[1], stream);
     // ---- P2/P3 object predict / prune ---------------------------------------------------------------------------
     if (n_moves > 0 || n_remove > 0) {
@@ -727,20 +733,27 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
         const int y0 = std::max(f.vb_lo[1] - 1, 0), y1 = std::min(f.vb_hi[1] + 1, (int)f.NY);
         const int z0 = std::max(f.vb_lo[2] - 1, 0), z1 = std::min(f.vb_hi[2] + 1, (int)f.NZ);
         ++launches; k_vertex_mask<<<dim3((words_per_row * 32 + 255) / 256, (y1 - y0 + 1) * (z1 - z0 + 1)), 256, 0, stream>>>(fp, d_vmask.p, words_per_row, y0, y1 - y0 + 1, z0);
-        ++launches; k_sweep_select<<<(v_local + 255) / 256, 256, 0, stream>>>(fp, st, d_vmask.p, words_per_row, d_depth_int.p, d_work.p, d_cnt.p);
-        DISPATCH_PB(f.Pb, (k_sweep_slots<PB><<<sm_count * 8, 256, 0, stream>>>(fp, st, stx, sty, stz, d_work.p, d_depth_int.p, d_pix_count.p, cv, d_cnt.p)));
+        {   // voxels whose vertices m..m+1 can intersect the vertex box [vb_lo, vb_hi]
+            const int3 lo = make_int3(std::max(f.vb_lo[0] - 1, 0), std::max(f.vb_lo[1] - 1, 0), std::max(f.vb_lo[2] - 1, 0));
+            const int3 hi = make_int3(std::min(f.vb_hi[0], (int)f.NX - 1), std::min(f.vb_hi[1], (int)f.NY - 1), std::min(f.vb_hi[2], (int)f.NZ - 1));
+            const int3 n = make_int3(hi.x - lo.x + 1, hi.y - lo.y + 1, hi.z - lo.z + 1);
+            if (n.x > 0 && n.y > 0 && n.z > 0) {
+                ++launches; k_sweep_select<<<dim3((n.x + 255) / 256, n.y * n.z), 256, 0, stream>>>(fp, st, d_vmask.p, words_per_row, depth_int, d_work.p, d_cnt.p, lo, n);
+            }
+        }
+        DISPATCH_PB(f.Pb, (k_sweep_slots<PB><<<sm_count * 8, 256, 0, stream>>>(fp, st, stx, sty, stz, d_work.p, depth_int, d_pix_count.p, cv, d_cnt.p)));
         ++launches;
     }
     // every rank tells every rank how many visible records it wrote into their arenas
-    ++launches; k_publish_pairs<<<1, 32, 0, stream>>>(cv, d_cnt.p);
     if (cv.size > 1) {
+        ++launches; k_publish_pairs<<<1, 32, 0, stream>>>(cv, d_cnt.p);
         barrier();
         ++launches; k_count_remote<<<sm_count * 2, 256, 0, stream>>>(cv, cv.recs[cv.rank], d_counts, d_pix_count.p);
     }
     const int nsb = (npix + SCAN_BLOCK - 1) / SCAN_BLOCK;
     ++launches; k_scan_blocksum<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p);
     ++launches; k_scan_apply<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p, d_pix_offset.p);
-    ++launches; k_fill<<<sm_count * 4, 256, 0, stream>>>(cv, cv.recs[cv.rank], d_counts, d_pix_offset.p, d_pix_count.p, d_csr_key.p);
+    ++launches; k_fill<<<sm_count * 4, 256, 0, stream>>>(cv, cv.recs[cv.rank], d_counts, d_cnt.p, d_pix_offset.p, d_pix_count.p, d_csr_key.p);
     ++launches; k_sort_lists<<<(npix + 255) / 256, 256, 0, stream>>>(fp, d_pix_offset.p, d_csr_key.p);
     ++launches; k_gather_visible<<<sm_count * 4, 256, 0, stream>>>(d_pix_offset.p + npix, cv.recs[cv.rank], d_csr_key.p, d_csr_idx.p, d_vis_pix.p, d_vis_pos.p, d_vis_meta.p);
     if (profiling) cudaEventRecord(ev[3], stream);
@@ -757,7 +770,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     }
     if (n_masks) CU_TRY(this, cudaMemcpyAsync(d_masks.p, p_maskdesc.p, n_masks * sizeof(MaskDesc), cudaMemcpyHostToDevice, stream));
     ++launches; k_project<<<(npix + 255) / 256, 256, 0, stream>>>(fp, d_masks.p, d_static_track.p, d_static_label.p,
-                                                     d_depth_int.p, d_cloud_pos.p, d_cloud_meta.p, d_cnt.p);
+                                                     depth_int, d_cloud_pos.p, d_cloud_meta.p, d_cnt.p);
     if (profiling) cudaEventRecord(ev[4], stream);
     // ---- U3 weight update --------------------------------------------------------------------------------------------
     ++launches; k_ck<<<sm_count * 2, 1024, lut_bytes, stream>>>(fp, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_pix_offset.p, d_vis_pos.p, d_vis_meta.p, cv, ck_seg_stride);
@@ -975,7 +988,7 @@ int dspmap_update(dspmap_t* h, const float* depth, int32_t rows, int32_t cols, i
     }
     if (!h->stage_pool) {
         const char* env = getenv("DSPMAP_STAGE_THREADS");
-        const int want = env ? atoi(env) : 0;   // helper threads for the staging copies; 0 = stage on the calling thread
+        const int want = env ? atoi(env) : 2;   // helper threads for the staging copies; 0 = stage on the calling thread
         h->stage_pool.reset(new StagePool(std::max(0, std::min(want, (int)std::thread::hardware_concurrency() - 1))));
     }
     auto stage_rows = [&](auto* dst, const auto* src, int src_stride, int r0, int r1) {

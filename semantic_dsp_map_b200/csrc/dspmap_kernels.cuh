@@ -33,6 +33,7 @@ struct Counters {
     uint32_t n_sweep_work;     // swept voxels with live slots (work list of the slot pass)
     uint32_t n_occ_work;       // voxels whose occupancy needs the slot records
     uint32_t comm_errors;      // barriers that timed out (sharded maps)
+    uint32_t mov_out[8];       // moved particles sent to each destination rank this frame
 };
 
 // survives across frames
@@ -257,18 +258,19 @@ __device__ __forceinline__ bool corner_visible(const FrameParams& f, const float
 
 __global__ void __launch_bounds__(256)
 k_sweep_select(const __grid_constant__ FrameParams f, Store st, const uint32_t* __restrict__ vmask, uint32_t words_per_row,
-               const float* __restrict__ depth_int, uint32_t* __restrict__ work, Counters* __restrict__ cnt) {
-    const uint32_t v_lo = f.z_lo << (f.Xb + f.Yb), v_hi = f.z_hi << (f.Xb + f.Yb);
-    const uint32_t v = v_lo + blockIdx.x * blockDim.x + threadIdx.x;
+               const float* __restrict__ depth_int, uint32_t* __restrict__ work, Counters* __restrict__ cnt, int3 box_lo, int3 box_n) {
+    // the grid covers only the voxels of the frustum's bounding box, in MAP coordinates: blockIdx.y = (my, mz) row of the
+    // box, x along the threads.  Voxels outside the box touch no in-frustum vertex.
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t mz = (uint32_t)(box_lo.z + (int)(blockIdx.y / (uint32_t)box_n.y)), my = (uint32_t)(box_lo.y + (int)(blockIdx.y % (uint32_t)box_n.y));
+    const uint32_t mx = (uint32_t)(box_lo.x + ix);
     bool swept = false;
-    uint32_t mx = 0, my = 0, mz = 0;
-    if (v < v_hi) {
+    uint32_t v = 0;
+    if (ix < box_n.x) {
         uint32_t bx, by, bz;
-        voxel_to_buffer(f, v, bx, by, bz);
-        buffer_to_map(f, bx, by, bz, mx, my, mz);
-        // a voxel's vertices are m..m+1 per axis: outside the frustum's vertex bounding box nothing can be set
-        if ((int)mx + 1 >= f.vb_lo[0] && (int)mx <= f.vb_hi[0] && (int)my + 1 >= f.vb_lo[1] && (int)my <= f.vb_hi[1] &&
-            (int)mz + 1 >= f.vb_lo[2] && (int)mz <= f.vb_hi[2]) {
+        map_to_buffer(f, (int)mx, (int)my, (int)mz, bx, by, bz);
+        if (bz >= f.z_lo && bz < f.z_hi) {        // this shard's slabs
+            v = buffer_to_voxel(f, bx, by, bz);
             const uint32_t nyp = f.NY + 1;
 #pragma unroll
             for (int c = 0; c < 2; ++c)
@@ -487,10 +489,10 @@ k_count_remote(CommView cv, const VisRec* __restrict__ recs, const uint32_t* __r
 
 // scatter (particle index, record reference) keys into their pixel segments (arrival order; sorted next)
 __global__ void __launch_bounds__(256)
-k_fill(CommView cv, const VisRec* __restrict__ recs, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offset,
-       uint32_t* __restrict__ pix_count, uint64_t* __restrict__ csr_key) {
+k_fill(CommView cv, const VisRec* __restrict__ recs, const uint32_t* __restrict__ counts, const Counters* __restrict__ cnt,
+       const uint32_t* __restrict__ offset, uint32_t* __restrict__ pix_count, uint64_t* __restrict__ csr_key) {
     for (int g = 0; g < cv.size; ++g) {
-        const uint32_t n = min(counts[g * COMM_COUNTS + CC_PAIRS], cv.rec_cap);
+        const uint32_t n = min(g == cv.rank ? cnt->n_pairs : counts[g * COMM_COUNTS + CC_PAIRS], cv.rec_cap);
         const VisRec* seg = recs + (size_t)g * cv.rec_cap;
         for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
             const uint32_t pix = seg[k].pix;
@@ -1227,13 +1229,23 @@ k_move_prepare(const MoveTable* __restrict__ mt, const uint16_t* __restrict__ mo
                const uint32_t* __restrict__ move_counts) {
     __shared__ uint32_t s_offset[MAX_MOVES], s_running[MAX_MOVES];
     __shared__ uint32_t s_wcount[32][MAX_MOVES];
+    __shared__ uint32_t s_local[MAX_MOVES];
     const uint32_t n = min(persist->n_movable, movl_cap);
     const int n_moves = mt->n_moves;
+    if (cv.size == 1) {                        // unsharded: count here (sharded maps ran k_move_count and a barrier)
+        if (threadIdx.x < MAX_MOVES) s_local[threadIdx.x] = 0;
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+            const int mv = find_track(mt->move_track, n_moves, (int)movl_track[k]);
+            if (mv >= 0) atomicAdd(&s_local[mv], 1u);
+        }
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
         uint32_t acc = 0;
         for (int m = 0; m < n_moves; ++m) {
             uint32_t below = 0, all = 0;
-            for (int g = 0; g < cv.size; ++g) { const uint32_t c = move_counts[g * MAX_MOVES + m]; if (g < cv.rank) below += c; all += c; }
+            for (int g = 0; g < cv.size; ++g) { const uint32_t c = cv.size == 1 ? s_local[m] : move_counts[g * MAX_MOVES + m]; if (g < cv.rank) below += c; all += c; }
             s_offset[m] = acc + below;
             s_running[m] = 0;
             acc += all;
@@ -1275,8 +1287,8 @@ k_move_prepare(const MoveTable* __restrict__ mt, const uint16_t* __restrict__ mo
 __global__ void __launch_bounds__(256)
 k_move_apply(const __grid_constant__ FrameParams f, Counters* __restrict__ cnt, Store st, const MoveTable* __restrict__ mt,
              const float* __restrict__ randoms, const Persist* __restrict__ persist, const uint32_t* __restrict__ movl_idx,
-             const uint16_t* __restrict__ movl_track, const uint32_t* __restrict__ movl_seq, uint32_t movl_cap, CommView cv,
-             uint32_t* __restrict__ out_count /*[MAX_RANKS]*/) {
+             const uint16_t* __restrict__ movl_track, const uint32_t* __restrict__ movl_seq, uint32_t movl_cap, CommView cv) {
+    uint32_t* out_count = cnt->mov_out;
     const uint32_t n = min(persist->n_movable, movl_cap);
     const uint32_t cur = cnt->move_cursor0;
     const uint32_t slabs = f.z_hi - f.z_lo;
@@ -1315,9 +1327,9 @@ k_move_apply(const __grid_constant__ FrameParams f, Counters* __restrict__ cnt, 
 }
 
 // tell every destination rank how many moved particles this rank sent it
-__global__ void k_move_publish(CommView cv, uint32_t* __restrict__ out_count) {
+__global__ void k_move_publish(CommView cv, const Counters* __restrict__ cnt) {
     const int p = threadIdx.x;
-    if (p < cv.size) { cv.counts[p][cv.rank * COMM_COUNTS + CC_MOVREC] = out_count[p]; out_count[p] = 0; }
+    if (p < cv.size) cv.counts[p][cv.rank * COMM_COUNTS + CC_MOVREC] = cnt->mov_out[p];
     __threadfence_system();
 }
 
@@ -1327,7 +1339,7 @@ k_move_bin(const __grid_constant__ FrameParams f, CommView cv, const MovRec* __r
            uint32_t* __restrict__ seq_ref, uint32_t seq_cap, uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks,
            uint32_t* __restrict__ entry_list, Counters* __restrict__ cnt) {
     for (int g = 0; g < cv.size; ++g) {
-        const uint32_t n = counts[g * COMM_COUNTS + CC_MOVREC];
+        const uint32_t n = g == cv.rank ? cnt->mov_out[cv.rank] : counts[g * COMM_COUNTS + CC_MOVREC];
         if (n > cv.mov_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->hash_overflow, 1u); }
         const MovRec* seg = movs + (size_t)g * cv.mov_cap;
         for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < min(n, cv.mov_cap); k += gridDim.x * blockDim.x) {
