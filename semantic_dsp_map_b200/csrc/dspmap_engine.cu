@@ -161,7 +161,8 @@ struct dspmap {
     std::string err = "";
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr, side_stream = nullptr;   // side: independent kernels run beside the main chain
+    cudaEvent_t ev_fork[2]{}, ev_join[2]{};
     uint64_t launches = 0;
 
     // host ring state (mc_ring/buffer.h:97-120)
@@ -329,6 +330,9 @@ struct dspmap {
         hr_idx.release(); hr_free_idx.release(); hr_xyz.release(); hr_w.release(); hr_free_xyz.release(); hr_track.release(); hr_label.release(); hr_state.release();
         for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (own_stream) { cudaStreamDestroy(own_stream); own_stream = nullptr; }
+        if (side_stream) { cudaStreamDestroy(side_stream); side_stream = nullptr; }
+        for (auto& e : ev_fork) if (e) { cudaEventDestroy(e); e = nullptr; }
+        for (auto& e : ev_join) if (e) { cudaEventDestroy(e); e = nullptr; }
         stream = nullptr;
     }
 
@@ -398,6 +402,9 @@ int dspmap::init(const dspmap_config& c) {
     sm_count = prop.multiProcessorCount;
     CU_TRY(this, cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
     stream = own_stream;
+    CU_TRY(this, cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+    for (auto& e : ev_fork) CU_TRY(this, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : ev_join) CU_TRY(this, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : ev) CU_TRY(this, cudaEventCreate(&e));
 
     FrameParams& f = fp;
@@ -705,6 +712,15 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     const size_t lut_bytes = PDF_NUM * sizeof(float);
 
     if (profiling) cudaEventRecord(ev[0], stream);
+    // ---- U2a vertex mask: depends on the pose only, so it runs on the side stream beside the depth copy and the moves ------
+    if (f.start_in) {
+        const int y0 = std::max(f.vb_lo[1] - 1, 0), y1 = std::min(f.vb_hi[1] + 1, (int)f.NY);
+        const int z0 = std::max(f.vb_lo[2] - 1, 0), z1 = std::min(f.vb_hi[2] + 1, (int)f.NZ);
+        CU_TRY(this, cudaEventRecord(ev_fork[0], stream));
+        CU_TRY(this, cudaStreamWaitEvent(side_stream, ev_fork[0], 0));
+        ++launches; k_vertex_mask<<<dim3((words_per_row * 32 + 255) / 256, (y1 - y0 + 1) * (z1 - z0 + 1)), 256, 0, side_stream>>>(fp, d_vmask.p, words_per_row, y0, y1 - y0 + 1, z0);
+        CU_TRY(this, cudaEventRecord(ev_join[0], side_stream));
+    }
     // ---- K1a internal depth image ----------------------------------------------------------------------------------
     const float* depth_int = d_depth_int.p;
     if ((pre_decimated || !f.boost) && stride == f.W) depth_int = d_depth;      // already the internal image: no copy
@@ -730,9 +746,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     if (profiling) cudaEventRecord(ev[2], stream);
     // ---- U2 visibility ---------------------------------------------------------------------------------------------
     if (f.start_in) {
-        const int y0 = std::max(f.vb_lo[1] - 1, 0), y1 = std::min(f.vb_hi[1] + 1, (int)f.NY);
-        const int z0 = std::max(f.vb_lo[2] - 1, 0), z1 = std::min(f.vb_hi[2] + 1, (int)f.NZ);
-        ++launches; k_vertex_mask<<<dim3((words_per_row * 32 + 255) / 256, (y1 - y0 + 1) * (z1 - z0 + 1)), 256, 0, stream>>>(fp, d_vmask.p, words_per_row, y0, y1 - y0 + 1, z0);
+        CU_TRY(this, cudaStreamWaitEvent(stream, ev_join[0], 0));   // the vertex mask was computed on the side stream
         {   // voxels whose vertices m..m+1 can intersect the vertex box [vb_lo, vb_hi]
             const int3 lo = make_int3(std::max(f.vb_lo[0] - 1, 0), std::max(f.vb_lo[1] - 1, 0), std::max(f.vb_lo[2] - 1, 0));
             const int3 hi = make_int3(std::min(f.vb_hi[0], (int)f.NX - 1), std::min(f.vb_hi[1], (int)f.NY - 1), std::min(f.vb_hi[2], (int)f.NZ - 1));
@@ -772,6 +786,14 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     ++launches; k_project<<<(npix + 255) / 256, 256, 0, stream>>>(fp, d_masks.p, d_static_track.p, d_static_label.p,
                                                      depth_int, d_cloud_pos.p, d_cloud_meta.p, d_cnt.p);
     if (profiling) cudaEventRecord(ev[4], stream);
+    // ---- B1a birth binning: needs only the labelled points, so it runs on the side stream beside the two stencil passes ----
+    {
+        const int n_ranks = 9 * ((f.H + 2) / 3) * ((f.W + 2) / 3);
+        CU_TRY(this, cudaEventRecord(ev_fork[1], stream));
+        CU_TRY(this, cudaStreamWaitEvent(side_stream, ev_fork[1], 0));
+        ++launches; k_birth_bin<<<(n_ranks + 255) / 256, 256, 0, side_stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_entry_list.p, d_cnt.p);
+        CU_TRY(this, cudaEventRecord(ev_join[1], side_stream));
+    }
     // ---- U3 weight update --------------------------------------------------------------------------------------------
     ++launches; k_ck<<<sm_count * 2, 1024, lut_bytes, stream>>>(fp, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_pix_offset.p, d_vis_pos.p, d_vis_meta.p, cv, ck_seg_stride);
     barrier();   // sharded map: every rank's ck image is complete
@@ -780,8 +802,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     if (profiling) cudaEventRecord(ev[5], stream);
     // ---- B1 birth + resample -----------------------------------------------------------------------------------------
     {
-        const int n_ranks = 9 * ((f.H + 2) / 3) * ((f.W + 2) / 3);
-        ++launches; k_birth_bin<<<(n_ranks + 255) / 256, 256, 0, stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_entry_list.p, d_cnt.p);
+        CU_TRY(this, cudaStreamWaitEvent(stream, ev_join[1], 0));   // the candidates were binned on the side stream
         DISPATCH_PB(f.Pb, (k_birth_replay<PB><<<sm_count * 4, 128, 0, stream>>>(fp, st, stx, sty, stz, d_keys.p, d_ranks.p, d_entry_list.p, d_entry_voxel.p, d_cnt.p)));
         ++launches;
         ++launches; k_birth_write<<<sm_count * 8, 256, 0, stream>>>(fp, st, d_cloud_pos.p, d_cloud_meta.p, d_ranks.p, d_entry_list.p, d_entry_voxel.p, d_cnt.p);
