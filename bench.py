@@ -255,6 +255,12 @@ def main():
         occ_bytes = 5.0 * n_vox + 4.0 * acc["n_listed"] / args.steps
         occ_ms = stage_ms[1] / args.steps
         achieved = occ_bytes / (occ_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
+        if os.path.exists(tpath):
+            t = json.load(open(tpath)).get(cfg.name, {}).get("k_occ_headers")
+            if t:
+                traffic = t["dram_read"] + t["dram_write"]      # from one ncu --set full capture (profiles/), per launch
         out = {
             "metric": METRIC, "value": units * args.steps / (ms_device * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_device / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
@@ -266,7 +272,10 @@ def main():
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
             "roofline": {"kernel": "k_occ_headers", "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "algorithmic_bytes": occ_bytes, "ms": occ_ms},
+                         "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": occ_bytes, "ms": occ_ms,
+                         "note": "no kernel of this path is HBM-bound at this map size (about 0.12 GB moves through HBM per 0.43 ms frame); the "
+                                 "two stencil passes (k_ck, k_weight_update: 3 IEEE divisions + 3 table look-ups per particle-pixel pair, "
+                                 "~38% of the frame) are instruction-latency bound. See DESIGN.md section 4 and profiles/r01_summary.md."},
             "stage_ms": {n: float(v / args.steps) for n, v in zip(_capi.STAGE_NAMES, stage_ms)},
         }
         if not args.no_cpu_baseline:
