@@ -208,7 +208,7 @@ struct dspmap {
     DevBuf<uint32_t> d_csr_idx, d_vis_pix, d_vis_meta, d_seq_ref, d_mov_out;
     DevBuf<float4> d_vis_pos;
     // ordered insertion
-    DevBuf<uint32_t> d_keys, d_ranks;
+    DevBuf<uint32_t> d_keys, d_ranks, d_birth_flags, d_birth_prefix, d_birth_block;
     // object moves
     DevBuf<uint32_t> d_movl_idx, d_movl_seq;
     DevBuf<uint16_t> d_movl_track, d_mov_mask;
@@ -217,7 +217,7 @@ struct dspmap {
     DevBuf<uint32_t> d_res_tl;
     DevBuf<uint4> d_blk_cnt, d_blk_off;
     DevBuf<uint32_t> d_work;
-    uint32_t n_occ_blocks = 0;
+    uint32_t n_occ_blocks = 0, birth_cap1 = 0, birth_shift1 = 0;
     uint32_t ck_seg_stride = 1;
     uint32_t sel_cap = 0;
     // occupancy
@@ -323,7 +323,7 @@ struct dspmap {
         d_static_track.release(); d_static_label.release(); d_fp.release(); d_cnt.release(); d_persist.release(); d_masks.release(); d_moves.release();
         d_depth_in.release(); d_depth_int.release(); d_mask_in.release(); d_cloud_pos.release(); d_cloud_meta.release();
         d_pix_count.release(); d_pix_offset.release(); d_scan_block.release(); d_vmask.release(); d_csr_key.release(); d_seq_ref.release(); d_mov_out.release(); d_csr_idx.release();
-        d_vis_pix.release(); d_vis_meta.release(); d_vis_pos.release(); d_keys.release(); d_ranks.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_work.release();
+        d_vis_pix.release(); d_vis_meta.release(); d_vis_pos.release(); d_keys.release(); d_ranks.release(); d_birth_flags.release(); d_birth_prefix.release(); d_birth_block.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_work.release();
         for (int p = 0; p < MAX_RANKS; ++p) if (peer_base[p] && p != cfg.shard_rank) { cudaIpcCloseMemHandle(peer_base[p]); peer_base[p] = nullptr; }
         arena.release();
         p_depth.release(); p_masks.release(); p_cnt.release(); p_fp.release(); p_stamps.release(); p_maskdesc.release(); p_moves.release();
@@ -498,6 +498,7 @@ int dspmap::init(const dspmap_config& c) {
         uint32_t bcap = 1024, bbits = 10;
         while (bcap < 2 * npix) { bcap <<= 1; ++bbits; }
         f.birth_hash_cap = bcap; f.birth_hash_shift = 32 - bbits;
+        birth_cap1 = bcap; birth_shift1 = 32 - bbits;
     }
     CU_TRY(this, d_keys.alloc(cap)); CU_TRY(this, d_ranks.alloc((size_t)cap * f.topk)); CU_TRY(this, d_entry_list.alloc(cap)); CU_TRY(this, d_entry_voxel.alloc(cap));
 
@@ -577,7 +578,9 @@ int dspmap::apply_params() {
     f.n0 = prm.depth_noise_zero_order; f.n1 = prm.depth_noise_first_order;
     f.sigma_invalid = prm.consider_depth_noise ? prm.depth_noise_zero_order : 0.1f;
     f.zero_center = prm.zero_center ? 1 : 0;
-    f.nb_ptc = prm.nb_ptc_num_per_point;
+    f.nb_ptc = prm.consider_depth_noise ? prm.nb_ptc_num_per_point : 1;
+    // one newborn per point: a table prefix of 2x the pixel count is enough (and cache friendlier); more: the whole table
+    f.birth_hash_cap = f.nb_ptc > 1 ? f.hash_cap : birth_cap1; f.birth_hash_shift = f.nb_ptc > 1 ? f.hash_shift : birth_shift1;
     return DSPMAP_OK;
 }
 
@@ -629,8 +632,13 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     // mask-independent kernels have been launched, so the copy engine and the CPU work under them
     FrameParams& f = fp;
     f.pre_decimated = pre_decimated;
-    if (prm.consider_depth_noise && prm.nb_ptc_num_per_point != 1)
-        return fail(DSPMAP_ERR_UNSUPPORTED, "nb_ptc_num_per_point != 1 with the depth-noise model is not implemented");
+    // the noise path spawns nb particles per point only under the depth-noise model; addNewbornParticleAndResample (no depth
+    // noise) always adds one (semantic_dsp_map.h:1148-1171)
+    const int nb_eff = prm.consider_depth_noise ? prm.nb_ptc_num_per_point : 1;
+    {
+        const long long n_cand = 9ll * ((fp.H + 2) / 3) * ((fp.W + 2) / 3) * nb_eff;
+        if (n_cand >= (1ll << 24)) return fail(DSPMAP_ERR_UNSUPPORTED, "nb_ptc_num_per_point = %d gives %lld birth candidates per frame (limit 2^24)", nb_eff, n_cand);
+    }
     host_result_valid = false;
     T += 1;                                                       // :173
     f.T = T;
@@ -791,7 +799,15 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
         const int n_ranks = 9 * ((f.H + 2) / 3) * ((f.W + 2) / 3);
         CU_TRY(this, cudaEventRecord(ev_fork[1], stream));
         CU_TRY(this, cudaStreamWaitEvent(side_stream, ev_fork[1], 0));
-        ++launches; k_birth_bin<<<(n_ranks + 255) / 256, 256, 0, side_stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_entry_list.p, d_cnt.p);
+        if (f.nb_ptc > 1) {     // number the valid pixels in birth order: they own consecutive draws of the random table
+            if (d_birth_flags.n < (size_t)n_ranks + 1) { CU_TRY(this, d_birth_flags.alloc(n_ranks + 1)); CU_TRY(this, d_birth_prefix.alloc(n_ranks + 1)); CU_TRY(this, d_birth_block.alloc((n_ranks + SCAN_BLOCK - 1) / SCAN_BLOCK)); }
+            const int nb_blocks = (n_ranks + SCAN_BLOCK - 1) / SCAN_BLOCK;
+            ++launches; k_birth_flags<<<(n_ranks + 255) / 256, 256, 0, side_stream>>>(fp, d_cloud_meta.p, d_birth_flags.p, (uint32_t)n_ranks);
+            ++launches; k_scan_blocksum<<<nb_blocks, SCAN_BLOCK, 0, side_stream>>>(d_birth_flags.p, (uint32_t)n_ranks, d_birth_block.p);
+            ++launches; k_scan_apply<<<nb_blocks, SCAN_BLOCK, 0, side_stream>>>(d_birth_flags.p, (uint32_t)n_ranks, d_birth_block.p, d_birth_prefix.p);
+        }
+        ++launches; k_birth_bin<<<(n_ranks * f.nb_ptc + 255) / 256, 256, 0, side_stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_entry_list.p, d_cnt.p,
+                                                                                    d_birth_prefix.p, d_randoms.p, d_persist.p);
         CU_TRY(this, cudaEventRecord(ev_join[1], side_stream));
     }
     // ---- U3 weight update --------------------------------------------------------------------------------------------
@@ -805,7 +821,9 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
         CU_TRY(this, cudaStreamWaitEvent(stream, ev_join[1], 0));   // the candidates were binned on the side stream
         DISPATCH_PB(f.Pb, (k_birth_replay<PB><<<sm_count * 4, 128, 0, stream>>>(fp, st, stx, sty, stz, d_keys.p, d_ranks.p, d_entry_list.p, d_entry_voxel.p, d_cnt.p)));
         ++launches;
-        ++launches; k_birth_write<<<sm_count * 8, 256, 0, stream>>>(fp, st, d_cloud_pos.p, d_cloud_meta.p, d_ranks.p, d_entry_list.p, d_entry_voxel.p, d_cnt.p);
+        ++launches; k_birth_write<<<sm_count * 8, 256, 0, stream>>>(fp, st, d_cloud_pos.p, d_cloud_meta.p, d_ranks.p, d_entry_list.p, d_entry_voxel.p, d_cnt.p,
+                                                                d_birth_prefix.p, d_randoms.p, d_persist.p);
+        if (f.nb_ptc > 1) { ++launches; k_birth_advance_cursor<<<1, 1, 0, stream>>>(fp, d_cnt.p, d_persist.p); }
     }
     if (profiling) cudaEventRecord(ev[6], stream);
     // ---- O1 occupancy -------------------------------------------------------------------------------------------------

@@ -706,25 +706,58 @@ __device__ __forceinline__ int birth_rank_to_pixel(const FrameParams& f, uint32_
     return ((ph / 3) + 3 * a) * f.W + (ph % 3) + 3 * b;
 }
 
-// One thread per birth RANK (not per pixel): the lowest ranks are binned by the first blocks, so by the time the
-// later 3x3 phases arrive most per-voxel lists are full and their cascades end at the first comparison.
-__global__ void __launch_bounds__(256)
-k_birth_bin(const __grid_constant__ FrameParams f, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta, uint32_t* __restrict__ keys,
-            uint32_t* __restrict__ ranks, uint32_t* __restrict__ entry_list, Counters* __restrict__ cnt) {
-    const uint32_t rank = blockIdx.x * blockDim.x + threadIdx.x;
+// birth rank -> pixel; -1 for the padding ranks of image sizes that are not multiples of 3
+__device__ __forceinline__ int birth_rank_pixel_checked(const FrameParams& f, uint32_t rank) {
     const int hc = (f.H + 2) / 3, wc = (f.W + 2) / 3;
-    if (rank >= (uint32_t)(9 * hc * wc)) return;
+    if (rank >= (uint32_t)(9 * hc * wc)) return -1;
     const int b = (int)(rank % (uint32_t)wc), a = (int)((rank / (uint32_t)wc) % (uint32_t)hc), ph = (int)(rank / (uint32_t)(wc * hc));
     const int i = ph / 3 + 3 * a, j = ph % 3 + 3 * b;
-    if (i >= f.H || j >= f.W) return;
-    const int q = i * f.W + j;
+    if (i >= f.H || j >= f.W) return -1;
+    return i * f.W + j;
+}
+
+// Several newborn particles per point (nb_ptc_num_per_point > 1 with the depth-noise model): the reference perturbs each
+// by sigma * three values of its pre-drawn Gaussian table, consumed in birth order (semantic_dsp_map.h:1177-1190;
+// utils/basic_algorithms.h:426-440).  Valid pixel number k (in birth order) owns the draws cursor + 3*(k*nb + n) + 1..3.
+__device__ __forceinline__ float3 newborn_position(const FrameParams& f, const float4 p, uint32_t k_valid, uint32_t n,
+                                                   const float* __restrict__ randoms, uint32_t cursor) {
+    if (f.nb_ptc == 1) return make_float3(p.x + 0.f, p.y + 0.f, p.z + 0.f);       // :1183-1184 zero noise
+    const uint64_t d0 = (uint64_t)cursor + 3ull * ((uint64_t)k_valid * (uint32_t)f.nb_ptc + n);
+    const float n0 = p.w * randoms[(d0 + 1) % f.rand_n], n1 = p.w * randoms[(d0 + 2) % f.rand_n], n2 = p.w * randoms[(d0 + 3) % f.rand_n];
+    return make_float3(p.x + n0, p.y + n1, p.z + n2);
+}
+
+// valid flag of every birth rank (input of the scan that numbers the valid pixels in birth order; nb > 1 only)
+__global__ void __launch_bounds__(256)
+k_birth_flags(const __grid_constant__ FrameParams f, const uint32_t* __restrict__ cloud_meta, uint32_t* __restrict__ flags, uint32_t n_ranks) {
+    const uint32_t rank = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rank >= n_ranks) return;
+    const int q = birth_rank_pixel_checked(f, rank);
+    flags[rank] = (q >= 0 && pt_valid(cloud_meta[q])) ? 1u : 0u;
+}
+
+// One thread per birth candidate = (birth RANK, copy n) — not per pixel: the lowest ranks are binned by the first blocks,
+// so by the time the later 3x3 phases arrive most per-voxel lists are full and their cascades end at the first comparison.
+__global__ void __launch_bounds__(256)
+k_birth_bin(const __grid_constant__ FrameParams f, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta, uint32_t* __restrict__ keys,
+            uint32_t* __restrict__ ranks, uint32_t* __restrict__ entry_list, Counters* __restrict__ cnt,
+            const uint32_t* __restrict__ valid_prefix, const float* __restrict__ randoms, const Persist* __restrict__ persist) {
+    const uint32_t cand = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nb = (uint32_t)f.nb_ptc, rank = cand / nb, n = cand - rank * nb;
+    const int q = birth_rank_pixel_checked(f, rank);
+    if (q < 0) return;
     if (!pt_valid(cloud_meta[q])) return;
-    const float4 p = cloud_pos[q];
+    const float3 p = newborn_position(f, cloud_pos[q], nb > 1 ? valid_prefix[rank] : 0u, n, randoms, persist->cursor_map);
     uint32_t bx, by, bz;
     const uint32_t v = global_pos_to_voxel(f, p.x, p.y, p.z, bx, by, bz);
     if (v == INVALID_INDEX) return;
     if (bz < f.z_lo || bz >= f.z_hi) return;   // another shard owns this voxel
-    topk_insert(f, f.birth_hash_cap, f.birth_hash_shift, v, rank, keys, ranks, entry_list, &cnt->n_birth_voxels, &cnt->hash_overflow);
+    topk_insert(f, f.birth_hash_cap, f.birth_hash_shift, v, cand, keys, ranks, entry_list, &cnt->n_birth_voxels, &cnt->hash_overflow);
+}
+
+// the map's random cursor moves on by three draws per candidate of every valid pixel (nb > 1 only)
+__global__ void k_birth_advance_cursor(const __grid_constant__ FrameParams f, const Counters* __restrict__ cnt, Persist* __restrict__ persist) {
+    persist->cursor_map = (uint32_t)(((uint64_t)persist->cursor_map + 3ull * (uint32_t)f.nb_ptc * cnt->n_valid_points) % f.rand_n);
 }
 
 // ---- per-voxel slot state held in registers while candidates are replayed ------------------------------------------
@@ -869,7 +902,8 @@ k_birth_replay(const __grid_constant__ FrameParams f, Store st, const uint32_t* 
 __global__ void __launch_bounds__(256)
 k_birth_write(const __grid_constant__ FrameParams f, Store st, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta,
               uint32_t* __restrict__ ranks, const uint32_t* __restrict__ entry_list, const uint32_t* __restrict__ entry_voxel,
-              const Counters* __restrict__ cnt) {
+              const Counters* __restrict__ cnt, const uint32_t* __restrict__ valid_prefix, const float* __restrict__ randoms,
+              const Persist* __restrict__ persist) {
     const uint32_t K = f.topk, n = cnt->n_birth_voxels * K;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
         const uint32_t li = t / K, i = t - li * K;
@@ -878,8 +912,9 @@ k_birth_write(const __grid_constant__ FrameParams f, Store st, const float4* __r
         if (a == NO_RANK) continue;
         *r = NO_RANK;
         const uint32_t s = a >> 24, v = entry_voxel[li];
-        const int q = birth_rank_to_pixel(f, a & 0xffffffu);
-        const float4 p = cloud_pos[q];
+        const uint32_t cand = a & 0xffffffu, nb = (uint32_t)f.nb_ptc, rank = cand / nb;
+        const int q = birth_rank_to_pixel(f, rank);
+        const float3 p = newborn_position(f, cloud_pos[q], nb > 1 ? valid_prefix[rank] : 0u, cand - rank * nb, randoms, persist->cursor_map);
         const uint32_t pm = cloud_meta[q];
         const size_t idx = ((size_t)v << f.Pb) + s;
         st.x[idx] = p.x; st.y[idx] = p.y; st.z[idx] = p.z;

@@ -120,12 +120,21 @@ def test_capacity_and_unsupported_errors():
             fr = scene.frame(t)
             m.update(fr.depth, fr.masks, fr.position, fr.orientation)
     assert e.value.rc == -5       # DSPMAP_ERR_CAPACITY
-    # several newborn particles per point with the depth-noise model is not implemented: say so
-    m2 = SemanticDSPMap(dataclasses.replace(cfg, nb_ptc_num_per_point=3))
+    # an absurd number of newborn particles per point exceeds the 2^24 candidate ranks: reported as unsupported
+    m2 = SemanticDSPMap(dataclasses.replace(cfg, nb_ptc_num_per_point=6000))
     fr = scene.frame(0)
     with pytest.raises(_capi.DspMapError) as e:
         m2.update(fr.depth, fr.masks, fr.position, fr.orientation)
     assert e.value.rc == -7       # DSPMAP_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("nb", [2, 3])
+def test_several_noisy_newborn_particles_per_point(nb):
+    # nb_ptc_num_per_point > 1 with the depth-noise model: each copy is perturbed by sigma * table draws, consumed in birth
+    # order (semantic_dsp_map.h:1177-1230); the table is short here so the cursor wraps many times
+    cfg = dataclasses.replace(tiny(BASELINE["B"]), nb_ptc_num_per_point=nb)
+    eng, orc = _pair(cfg)
+    run_pair(eng, orc, Scene(cfg), 8, make_random_table(cfg.seed, 7_919))
 
 
 def test_object_particle_count_matches_the_store():
