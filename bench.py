@@ -56,7 +56,8 @@ def generate_frames(name, n, overrides=None):
     """Frames are a pure function of (config, t); fan the ray casting out over the host cores (before CUDA is touched)."""
     from concurrent.futures import ProcessPoolExecutor
     jobs = [(name, t, overrides or {}) for t in range(n)]
-    workers = max(1, min(os.cpu_count() or 1, 16, n))
+    world = int(os.environ.get("WORLD_SIZE", "1"))      # every rank generates the same frames: share the host cores
+    workers = max(1, min((os.cpu_count() or 1) // world, 16, n))
     if workers == 1:
         return [_gen_frame(j) for j in jobs]
     with ProcessPoolExecutor(workers) as ex:
