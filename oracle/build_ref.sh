@@ -1,0 +1,44 @@
+#!/bin/sh
+# Builds oracle/_ref/libdsp_ref_s<SETTING>.so: the reference's own headers, compiled where they lie under
+# $REF/include, against the stand-in third-party headers of oracle/ref_stubs (see ref_harness.cpp).
+# TEST INFRASTRUCTURE.  Outputs go only into oracle/_ref/ (git-ignored; travels to the GPU box like any built .so).
+#
+#   sh oracle/build_ref.sh [SETTING ...]      default: 3 (the configuration the reference ships, settings.h:22)
+#
+# SETTING 3 compiles the tree exactly as it is.  The reference selects its grid / camera preset with a hard
+# "#define SETTING 3" (include/settings/settings.h:22) that no -D can override, so for another preset the headers are
+# reached through a throw-away directory of SYMLINKS into $REF/include in which only settings/settings.h is a
+# generated file with that one line changed; the directory is deleted after the compile and nothing is copied into
+# the repository.
+set -e
+REF="${REF:-/root/reference}"
+HERE="$(cd "$(dirname "$0")" && pwd)"
+# the system compiler: its libstdc++ is linked dynamically (the /opt/gcc toolchain of this image links it statically, and two
+# static iostream copies in one process do not mix)
+CXX="${REF_CXX:-/usr/bin/g++}"
+# the reference's flags (CMakeLists.txt:5-8: -std=c++17 -O3 -ftree-vectorize -fPIC) with the oracle's two changes:
+# -ffp-contract=off pins the floating-point order, -march=x86-64-v3 instead of -march=native because the .so travels
+FLAGS="-std=c++17 -O3 -ftree-vectorize -march=x86-64-v3 -ffp-contract=off -fPIC -fno-access-control -shared -w"
+[ -d "$REF/include" ] || { echo "build_ref: $REF/include not present, keeping prebuilt oracle/_ref" >&2; exit 0; }
+mkdir -p "$HERE/_ref"
+[ $# -gt 0 ] || set -- 3
+for S in "$@"; do
+    OUT="$HERE/_ref/libdsp_ref_s$S.so"
+    if [ -f "$OUT" ] && [ "$OUT" -nt "$HERE/ref_harness.cpp" ] && [ "$OUT" -nt "$HERE/ref_stubs/Eigen/Dense" ] && \
+       [ "$OUT" -nt "$HERE/ref_stubs/opencv2/opencv.hpp" ] && [ "$OUT" -nt "$HERE/ref_stubs/pcl/point_types.h" ]; then continue; fi
+    if [ "$S" = "3" ]; then
+        INC="$REF/include"
+        TMP=""
+    else
+        TMP="$(mktemp -d)"
+        (cd "$REF/include" && find . -type d) | while read -r d; do mkdir -p "$TMP/$d"; done
+        (cd "$REF/include" && find . -type f) | while read -r f; do ln -s "$REF/include/$f" "$TMP/$f"; done
+        rm "$TMP/settings/settings.h"
+        sed "s/^#define SETTING 3 /#define SETTING $S /" "$REF/include/settings/settings.h" > "$TMP/settings/settings.h"
+        grep -q "^#define SETTING $S " "$TMP/settings/settings.h"
+        INC="$TMP"
+    fi
+    echo "build_ref: SETTING $S -> $OUT"
+    $CXX $FLAGS -I"$HERE/ref_stubs" -I"$INC" -o "$OUT" "$HERE/ref_harness.cpp"
+    [ -z "$TMP" ] || rm -rf "$TMP"
+done

@@ -189,6 +189,8 @@ struct Oracle {
     dspmap_frame_stats stats{};
     uint64_t sweep_set_mismatch = 0;  // |BFS voxel set  xor  in-frustum-vertex voxel set|, reference order only
     uint64_t start_vertex_outside = 0;
+    bool invalid_sigma_set = false;  // orc_set_invalid_sigma: see project()
+    float invalid_sigma_value = 0.f;
     bool diagnostics = false;  // the sweep-set check costs a full pass over the map: off when the oracle is being timed
     double stage_s[8]{};
     std::vector<uint32_t> csr_off, csr_idx;
@@ -482,8 +484,10 @@ struct Oracle {
                 const float d = depth_int[(size_t)i * W + j];
                 // DEFINED UB: the reference copies an uninitialised LabeledPoint for invalid pixels
                 // (:224-232); sigma of such a pixel is read later by updateParticles pass 2
-                // (semantic_dsp_map.h:1047).  The oracle defines it as the zero-depth noise term.
-                const float sigma_invalid = prm.consider_depth_noise ? prm.depth_noise_zero_order : 0.1f;
+                // (semantic_dsp_map.h:1047).  The oracle defines it as the zero-depth noise term.  What an actual
+                // build of the reference reads there is whatever its stack slot holds (0 in oracle/_ref's build);
+                // orc_set_invalid_sigma lets the pin test feed that value in so everything else can be compared.
+                const float sigma_invalid = invalid_sigma_set ? invalid_sigma_value : (prm.consider_depth_noise ? prm.depth_noise_zero_order : 0.1f);
                 if (std::isnan(d) || (double)d < dmin || (double)d > dmax) {  // :228
                     pt.sigma = sigma_invalid; pt.is_valid = 0; cloud[(size_t)i * W + j] = pt; continue;
                 }
@@ -1064,6 +1068,7 @@ uint64_t orc_get_extra(void* h, int which) {
     auto* o = static_cast<Oracle*>(h);
     return which == 0 ? o->sweep_set_mismatch : o->start_vertex_outside;
 }
+void orc_set_invalid_sigma(void* h, float v) { auto* o = static_cast<Oracle*>(h); o->invalid_sigma_set = true; o->invalid_sigma_value = v; }
 void orc_set_diagnostics(void* h, int on) { static_cast<Oracle*>(h)->diagnostics = on != 0; }
 double orc_stage_seconds(void* h, int stage) { return static_cast<Oracle*>(h)->stage_s[stage & 7]; }
 

@@ -34,6 +34,8 @@ def load_oracle():
         lib.orc_get_extra.argtypes = [C.c_void_p, C.c_int]
         lib.orc_set_diagnostics.restype = None
         lib.orc_set_diagnostics.argtypes = [C.c_void_p, C.c_int]
+        lib.orc_set_invalid_sigma.restype = None
+        lib.orc_set_invalid_sigma.argtypes = [C.c_void_p, C.c_float]
         lib.orc_stage_seconds.restype = C.c_double
         lib.orc_stage_seconds.argtypes = [C.c_void_p, C.c_int]
         _lib = lib
@@ -60,6 +62,10 @@ class OracleEngine(Engine):
 
     def set_diagnostics(self, on):
         self.lib.orc_set_diagnostics(self._h, int(on))
+
+    def set_invalid_sigma(self, value):
+        """The sigma an invalid pixel carries (uninitialised in the reference, pointcloud_tools.h:224-232)."""
+        self.lib.orc_set_invalid_sigma(self._h, float(value))
 
     def extra(self, which):
         return int(self.lib.orc_get_extra(self._h, which))
