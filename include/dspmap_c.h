@@ -120,6 +120,9 @@ typedef struct dspmap_result {
     const int8_t*   state;         /* 1 occupied, 2 guessed occupied                   */
     const uint32_t* free_voxel_index;
     const float*    free_xyz;
+    const uint8_t*  rgb;           /* 3 bytes (r, g, b) per entry: the colour getOccupancyResult gives the point
+                                      (semantic_dsp_map.h:1274-1351); zeros until dspmap_set_colors enabled it.
+                                      Free-space points are always (0, 255, 0) (:1371-1373) and carry no array. */
 } dspmap_result;
 
 /* per-frame counters (also the inputs of the roofline accounting) */
@@ -176,6 +179,27 @@ int dspmap_set_label_luts(dspmap_t* h, const uint16_t static_value_to_track[256]
  * GaussianRandomCalculator::calculateGaussianTable (utils/basic_algorithms.h:394-401);
  * injecting it makes runs reproducible.  n must be >= 1. */
 int dspmap_set_random_table(dspmap_t* h, const float* table, uint32_t n);
+
+/* Colouring of the occupied list — the rest of getOccupancyResult (include/semantic_dsp_map.h:1274-1351): jet colour by
+ * height for background voxels, the label table colour for static classes, instance colours for movable tracks, the
+ * evaluation-format packing (label, track >> 8, track & 0xFF), white for guessed voxels, and — unless the evaluation
+ * format is on — the 8-bit RGB -> HSV -> RGB round trip of cv::cvtColor with V scaled by 0.7 for voxels outside the
+ * camera frustum (checkIfPointInFrustum on the voxel corner).  The HSV conversions restate OpenCV's 8-bit algorithm
+ * and are bit-identical to cv2 4.13 on all 2^24 inputs (tests/test_colour_cpu.py). */
+typedef struct dspmap_colors {
+    int32_t enabled;          /* 0: dspmap_result.rgb stays zero (default)                                  */
+    int32_t eval_format;      /* if_out_evaluation_format_ (setVisualizeOptions, semantic_dsp_map.h:130-134) */
+    int32_t scheme;           /* which "#if SETTING" block colours a voxel (semantic_dsp_map.h:1279-1322):
+                                 0 = SETTING 0: every non-background voxel gets its label colour, jet over -z;
+                                 1 = SETTING 1 / 2: static -> label colour, movable -> instance colours, jet over -z;
+                                 3 = SETTING 3: as 1, jet over +y                                            */
+    int32_t background_label; /* g_label_id_map_default["Background"], default-insert semantics (:1276)      */
+    uint8_t label_bgr[256][3];/* g_label_color_map_default[label] as (b, g, r); absent labels read (0,0,0)    */
+    uint8_t instance_map[256];/* color_map_int_256_: a std::random_device shuffle of 0..255 in the reference
+                                 (:45-48), so it is injected.  The reference indexes it with the 16-bit track id
+                                 (out of bounds for ids >= 256); the index is taken modulo 256 here.         */
+} dspmap_colors;
+int dspmap_set_colors(dspmap_t* h, const dspmap_colors* c);
 
 /* ---- the per-frame hot path ---------------------------------------------- */
 

@@ -130,6 +130,64 @@ double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+
+// ---- colouring of the occupied list: semantic_dsp_map.h:1274-1351 -------------------------------------------
+// cv::cvtColor(COLOR_RGB2HSV / COLOR_HSV2RGB) on one CV_8UC3 pixel, restated from OpenCV's published 8-bit algorithm
+// and checked bit for bit against cv2 4.13 on all 2^24 inputs (tests/test_colour_cpu.py): H in [0,180), S and H through
+// 12-bit fixed-point reciprocal tables; back through float sectors with the two "1 - s*h" terms fused and the final
+// scaling truncated.
+inline void rgb_to_hsv_u8(const uint8_t in[3], uint8_t out[3]) {
+    static int sdiv[256], hdiv[256];
+    static bool init = false;
+    if (!init) {
+        sdiv[0] = hdiv[0] = 0;
+        for (int i = 1; i < 256; ++i) {
+            sdiv[i] = (int)lrint((255 << 12) / (1. * i));
+            hdiv[i] = (int)lrint((180 << 12) / (6. * i));
+        }
+        init = true;
+    }
+    const int r = in[0], g = in[1], b = in[2];
+    const int v = std::max(r, std::max(g, b)), vmin = std::min(r, std::min(g, b));
+    const int diff = v - vmin;
+    const int vr = v == r ? -1 : 0, vg = v == g ? -1 : 0;
+    const int s = (diff * sdiv[v] + (1 << 11)) >> 12;
+    int h = (vr & (g - b)) + (~vr & ((vg & (b - r + 2 * diff)) + ((~vg) & (r - g + 4 * diff))));
+    h = (h * hdiv[diff] + (1 << 11)) >> 12;
+    h += h < 0 ? 180 : 0;
+    out[0] = (uint8_t)h; out[1] = (uint8_t)s; out[2] = (uint8_t)v;
+}
+inline void hsv_to_rgb_u8(const uint8_t in[3], uint8_t out[3]) {
+    float h = (float)in[0];
+    const float s = in[1] * (1.f / 255.f), v = in[2] * (1.f / 255.f);
+    float r, g, b;
+    if (in[1] == 0) {
+        r = g = b = v;
+    } else {
+        static const int sector_data[6][3] = {{1, 3, 0}, {1, 0, 2}, {3, 0, 1}, {0, 2, 1}, {0, 1, 3}, {2, 1, 0}};
+        h *= 6.f / 180.f;
+        while (h >= 6.f) h -= 6.f;
+        int sector = (int)floorf(h);
+        h -= (float)sector;
+        if ((unsigned)sector >= 6u) { sector = 0; h = 0.f; }
+        float tab[4];
+        tab[0] = v;
+        tab[1] = v * (1.f - s);
+        tab[2] = v * fmaf(-s, h, 1.f);
+        tab[3] = v * fmaf(-s, 1.f - h, 1.f);
+        b = tab[sector_data[sector][0]]; g = tab[sector_data[sector][1]]; r = tab[sector_data[sector][2]];
+    }
+    auto sat = [](float x) { const float y = floorf(x * 255.f); return (uint8_t)(y < 0.f ? 0.f : (y > 255.f ? 255.f : y)); };
+    out[0] = sat(r); out[1] = sat(g); out[2] = sat(b);
+}
+// color_map_jet_256_, semantic_dsp_map.h:50-63
+inline void jet_256(int i, uint8_t out[3]) {
+    if (i < 64) { out[0] = 0; out[1] = 0; out[2] = (uint8_t)(i * 4); }
+    else if (i < 128) { out[0] = 0; out[1] = (uint8_t)((i - 64) * 4); out[2] = 255; }
+    else if (i < 192) { out[0] = (uint8_t)((i - 128) * 4); out[1] = 255; out[2] = (uint8_t)(255 - (i - 128) * 4); }
+    else { out[0] = 255; out[1] = (uint8_t)(255 - (i - 192) * 4); out[2] = 0; }
+}
+
 // ---- the oracle map ---------------------------------------------------------------------
 
 struct Oracle {
@@ -189,6 +247,9 @@ struct Oracle {
     dspmap_frame_stats stats{};
     uint64_t sweep_set_mismatch = 0;  // |BFS voxel set  xor  in-frustum-vertex voxel set|, reference order only
     uint64_t start_vertex_outside = 0;
+    dspmap_colors colors{};          // orc_set_colors: colouring of the occupied list (semantic_dsp_map.h:1274-1351)
+    std::vector<uint8_t> out_rgb;
+    bool carry_undefined_label = false;  // orc_set_undefined_label_carry: see occupancy()
     bool invalid_sigma_set = false;  // orc_set_invalid_sigma: see project()
     float invalid_sigma_value = 0.f;
     bool diagnostics = false;  // the sweep-set check costs a full pass over the map: off when the oracle is being timed
@@ -904,10 +965,38 @@ struct Oracle {
         stats.n_birth_voxels = (uint32_t)touched.size();
     }
 
+    // ---- semantic_dsp_map.h:1274-1351: the colour of one occupied voxel --------------------------------
+    // pt = the emitted position (camera-relative when zero-centred), corner = the voxel corner in the global frame
+    void colour_of(int state, uint8_t label, uint16_t track, const float pt[3], const float corner[3], uint8_t rgb[3]) const {
+        if (state == 1) {
+            if ((int)label == colors.background_label) {  // :1277-1294 jet by height
+                const float h = colors.scheme == 3 ? (pt[1] + 2.f) : (-pt[2] + 2.f);
+                const int ci = std::min(std::max(static_cast<int>(h * 51.2f), 0), 255);
+                jet_256(ci, rgb);
+                if (colors.eval_format) rgb[0] = rgb[1] = rgb[2] = 0;
+            } else if (colors.scheme == 0 || track > max_movable) {  // :1297-1309 label colour (stored b, g, r)
+                rgb[0] = colors.label_bgr[label][2]; rgb[1] = colors.label_bgr[label][1]; rgb[2] = colors.label_bgr[label][0];
+            } else if (colors.eval_format) {  // :1311-1315
+                rgb[0] = label; rgb[1] = (uint8_t)(track >> 8); rgb[2] = (uint8_t)(track & 0xFF);
+            } else {  // :1317-1319; DEFINED UB: the reference indexes the 256-entry table with the 16-bit track id
+                rgb[0] = 160; rgb[1] = colors.instance_map[track & 0xFF]; rgb[2] = colors.instance_map[label];
+            }
+        } else {  // guessed occupied: white, :1325-1331
+            rgb[0] = rgb[1] = rgb[2] = 255;
+        }
+        if (!colors.eval_format) {  // :1333-1351
+            uint8_t hsv[3];
+            rgb_to_hsv_u8(rgb, hsv);
+            if (!point_in_frustum(corner[0], corner[1], corner[2])) hsv[2] = (uint8_t)(hsv[2] * 0.7f);
+            hsv_to_rgb_u8(hsv, rgb);
+        }
+    }
+
     // ---- O1: semantic_dsp_map.h:1239-1383; operations.h:390-448, 623-648 --------------------
     void occupancy(bool want_free) {
-        out_idx.clear(); out_xyz.clear(); out_w.clear(); out_track.clear(); out_label.clear(); out_state.clear();
+        out_idx.clear(); out_xyz.clear(); out_w.clear(); out_track.clear(); out_label.clear(); out_state.clear(); out_rgb.clear();
         free_idx.clear(); free_xyz.clear();
+        uint8_t carried_label = 0; uint16_t carried_track = 0;
         float inv_ext[16];
         inverse4f(extrinsic, inv_ext);
         const float cam[3] = {inv_ext[3], inv_ext[7], inv_ext[11]};  // :1241
@@ -918,11 +1007,16 @@ struct Oracle {
             const size_t s = (size_t)v << Pb;
             float wsum, gsum = 0.f;
             // DEFINED UB: label/track are uninitialised out-params in the reference when no particle
-            // enters the histogram (semantic_dsp_map.h:1245-1246); defined as 0 here.
-            uint8_t label = 0; uint16_t track = 0;
+            // enters the histogram (semantic_dsp_map.h:1245-1246); defined as 0 here.  A compiled reference
+            // keeps the two variables in one place across loop iterations, so what it actually emits is the
+            // value the most recent voxel assigned (an unknown voxel assigns 0, operations.h:402-408);
+            // orc_set_undefined_label_carry reproduces that for the pin against oracle/_ref.
+            uint8_t label = carry_undefined_label ? carried_label : 0;
+            uint16_t track = carry_undefined_label ? carried_track : 0;
             int state;
             if (!is_voxel_valid(v, bx, by, bz)) {
                 wsum = -1.f;
+                label = 0; track = 0;
             } else {
                 wsum = 0.f;
                 std::map<uint16_t, float> tw;
@@ -949,14 +1043,19 @@ struct Oracle {
             else if (gsum >= OCC_INIT_WEIGHT) state = 2;
             else state = 0;
             voxel_state[v] = (int8_t)state;
+            carried_label = label; carried_track = track;
             if (state > 0 || (want_free && state == 0)) {
                 // voxelIdxToMapFramePos + map_center, operations.h:970-983, 940-944
                 uint32_t mx, my, mz;
                 buffer_to_map(bx, by, bz, mx, my, mz);
                 float p3[3] = {mx * voxel + pmin[0], my * voxel + pmin[1], mz * voxel + pmin[2]};
                 for (int a = 0; a < 3; ++a) p3[a] += map_center[a];
+                const float corner[3] = {p3[0], p3[1], p3[2]};
                 if (prm.zero_center) for (int a = 0; a < 3; ++a) p3[a] = p3[a] - cam[a];
                 if (state > 0) {
+                    uint8_t rgb[3] = {0, 0, 0};
+                    if (colors.enabled) colour_of(state, label, track, p3, corner, rgb);
+                    out_rgb.insert(out_rgb.end(), rgb, rgb + 3);
                     out_idx.push_back(v); out_xyz.insert(out_xyz.end(), p3, p3 + 3); out_w.push_back(wsum);
                     out_track.push_back(track); out_label.push_back(label); out_state.push_back((int8_t)state);
                 } else {
@@ -1060,6 +1159,7 @@ int orc_get_result(void* h, dspmap_result* out) {
     out->voxel_index = o->out_idx.data(); out->xyz = o->out_xyz.data(); out->weight_sum = o->out_w.data();
     out->track_id = o->out_track.data(); out->label_id = o->out_label.data(); out->state = o->out_state.data();
     out->free_voxel_index = o->free_idx.data(); out->free_xyz = o->free_xyz.data();
+    out->rgb = o->out_rgb.data();
     return DSPMAP_OK;
 }
 int orc_get_stats(void* h, dspmap_frame_stats* out) { *out = static_cast<Oracle*>(h)->stats; return DSPMAP_OK; }
@@ -1068,6 +1168,16 @@ uint64_t orc_get_extra(void* h, int which) {
     auto* o = static_cast<Oracle*>(h);
     return which == 0 ? o->sweep_set_mismatch : o->start_vertex_outside;
 }
+int orc_set_colors(void* h, const dspmap_colors* c) {
+    if (!h || !c) return DSPMAP_ERR_INVALID_ARG;
+    if (c->scheme != 0 && c->scheme != 1 && c->scheme != 3) return DSPMAP_ERR_INVALID_ARG;
+    static_cast<Oracle*>(h)->colors = *c;
+    return DSPMAP_OK;
+}
+void orc_set_undefined_label_carry(void* h, int on) { static_cast<Oracle*>(h)->carry_undefined_label = on != 0; }
+// test hooks for the two colour-space conversions (tests/test_colour_cpu.py checks them against cv2)
+void orc_rgb_to_hsv(const uint8_t* in, uint8_t* out, size_t n) { for (size_t i = 0; i < n; ++i) rgb_to_hsv_u8(in + 3 * i, out + 3 * i); }
+void orc_hsv_to_rgb(const uint8_t* in, uint8_t* out, size_t n) { for (size_t i = 0; i < n; ++i) hsv_to_rgb_u8(in + 3 * i, out + 3 * i); }
 void orc_set_invalid_sigma(void* h, float v) { auto* o = static_cast<Oracle*>(h); o->invalid_sigma_set = true; o->invalid_sigma_value = v; }
 void orc_set_diagnostics(void* h, int on) { static_cast<Oracle*>(h)->diagnostics = on != 0; }
 double orc_stage_seconds(void* h, int stage) { return static_cast<Oracle*>(h)->stage_s[stage & 7]; }

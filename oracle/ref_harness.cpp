@@ -231,6 +231,13 @@ int ref_update(const float* depth, int32_t rows, int32_t cols, int32_t row_strid
     return 0;
 }
 
+// test hook: the stand-in cv::cvtColor the reference's colouring runs on here (checked against the real cv2 module)
+void ref_cvt_color(int32_t code, const uint8_t* in, uint8_t* out, uint32_t n) {
+    cv::Mat src(1, static_cast<int>(n), CV_8UC3, const_cast<uint8_t*>(in)), dst;
+    cv::cvtColor(src, dst, code == 0 ? cv::COLOR_RGB2HSV : cv::COLOR_HSV2RGB);
+    std::memcpy(out, dst.data, 3 * static_cast<size_t>(n));
+}
+
 double ref_last_seconds(void) { return g_seconds_last; }
 uint32_t ref_time_stamp(void) { return global_time_stamp; }
 

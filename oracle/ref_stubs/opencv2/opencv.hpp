@@ -1,8 +1,9 @@
 // Stand-in for <opencv2/opencv.hpp> — TEST INFRASTRUCTURE (oracle/_ref build only; see ref_stubs/Eigen/Dense).
 // cv::Mat with at<T>() / clone / zeros, Vec3b, and the two 8-bit colour conversions getOccupancyResult uses
 // (semantic_dsp_map.h:1335-1350).  The conversions restate OpenCV's published 8-bit RGB<->HSV algorithm (H in
-// [0,180), fixed-point division tables with a 12-bit shift; HSV->RGB through float sectors) and are checked
-// exhaustively against the real cv2 module in tests/test_colour_cpu.py.  GUI / resize / colormap entry points
+// [0,180), fixed-point division tables with a 12-bit shift; HSV->RGB through float sectors with the two "1 - s*h" terms
+// fused and the final scaling truncated) and are checked on all 2^24 inputs against the real cv2 4.13 module in
+// tests/test_colour_cpu.py.  GUI / resize / colormap entry points
 // exist only so the reference headers compile; they abort if executed.
 #pragma once
 
@@ -192,15 +193,16 @@ inline void hsv2rgb_u8(uchar hh, uchar ss, uchar vv, uchar out[3]) {
         if (static_cast<unsigned>(sector) >= 6u) { sector = 0; h = 0.f; }
         tab[0] = v;
         tab[1] = v * (1.f - s);
-        tab[2] = v * (1.f - s * h);
-        tab[3] = v * (1.f - s * (1.f - h));
+        tab[2] = v * std::fmaf(-s, h, 1.f);
+        tab[3] = v * std::fmaf(-s, 1.f - h, 1.f);
         b = tab[sector_data[sector][0]];
         g = tab[sector_data[sector][1]];
         r = tab[sector_data[sector][2]];
     }
-    out[0] = saturate_u8(r * 255.f);
-    out[1] = saturate_u8(g * 255.f);
-    out[2] = saturate_u8(b * 255.f);
+    auto sat = [](float x) { const float y = std::floor(x * 255.f); return static_cast<uchar>(y < 0.f ? 0.f : (y > 255.f ? 255.f : y)); };
+    out[0] = sat(r);
+    out[1] = sat(g);
+    out[2] = sat(b);
 }
 }  // namespace hsv_detail
 

@@ -64,7 +64,14 @@ class Result(C.Structure):
         ("count", C.c_uint32), ("free_count", C.c_uint32),
         ("voxel_index", C.c_void_p), ("xyz", C.c_void_p), ("weight_sum", C.c_void_p),
         ("track_id", C.c_void_p), ("label_id", C.c_void_p), ("state", C.c_void_p),
-        ("free_voxel_index", C.c_void_p), ("free_xyz", C.c_void_p),
+        ("free_voxel_index", C.c_void_p), ("free_xyz", C.c_void_p), ("rgb", C.c_void_p),
+    ]
+
+
+class Colors(C.Structure):
+    _fields_ = [
+        ("enabled", C.c_int32), ("eval_format", C.c_int32), ("scheme", C.c_int32), ("background_label", C.c_int32),
+        ("label_bgr", (C.c_uint8 * 3) * 256), ("instance_map", C.c_uint8 * 256),
     ]
 
 
@@ -95,6 +102,7 @@ SYMBOLS = {
     "dspmap_set_params": (C.c_int, [C.c_void_p, C.POINTER(Params)]),
     "dspmap_set_label_luts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_uint16, C.c_uint16]),
     "dspmap_set_random_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "dspmap_set_colors": (C.c_int, [C.c_void_p, C.POINTER(Colors)]),
     "dspmap_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Mask), C.c_int32,
                                 C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(ObjectMove), C.c_int32,
                                 C.POINTER(C.c_int32), C.c_int32, C.c_int32]),

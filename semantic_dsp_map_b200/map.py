@@ -47,6 +47,7 @@ class OccupancyResult:
     state: np.ndarray
     free_voxel_index: np.ndarray
     free_xyz: np.ndarray
+    rgb: np.ndarray = None     # (n, 3) uint8 r, g, b of the occupied points (zeros until set_colors enabled them)
 
 
 _memview = C.pythonapi.PyMemoryView_FromMemory
@@ -111,6 +112,9 @@ class Engine:
         self.check(self._fn("set_label_luts")(self._h, v2t.ctypes.data, tracks.ctypes.data, labels.ctypes.data, len(tracks),
                                               tables.max_movable_instance_id & 0xFFFF, tables.sky_track() & 0xFFFF),
                    "dspmap_set_label_luts")
+
+    def set_colors(self, c: _capi.Colors):
+        self.check(self._fn("set_colors")(self._h, C.byref(c)), "dspmap_set_colors")
 
     def set_random_table(self, table: np.ndarray):
         t = np.ascontiguousarray(table, np.float32)
@@ -180,7 +184,8 @@ class Engine:
             _as_array(r.voxel_index, n, np.uint32, None, copy), _as_array(r.xyz, n, np.float32, (n, 3), copy),
             _as_array(r.weight_sum, n, np.float32, None, copy), _as_array(r.track_id, n, np.uint16, None, copy),
             _as_array(r.label_id, n, np.uint8, None, copy), _as_array(r.state, n, np.int8, None, copy),
-            _as_array(r.free_voxel_index, nf, np.uint32, None, copy), _as_array(r.free_xyz, nf, np.float32, (nf, 3), copy))
+            _as_array(r.free_voxel_index, nf, np.uint32, None, copy), _as_array(r.free_xyz, nf, np.float32, (nf, 3), copy),
+            _as_array(r.rgb, n, np.uint8, (n, 3), copy))
 
     def stats(self) -> dict:
         s = _capi.FrameStats()
@@ -224,6 +229,7 @@ class SemanticDSPMap:
         self._movement = (0.0, 0.0, 0.0, 0.0)
         self._keep = []
         self._eval_format = False
+        self._colors = None
 
     # -- setters, semantic_dsp_map.h:101-166 ----------------------------------------------------------------------------
     def setMapParameters(self, detection_probability, noise_number, nb_ptc_num_per_point, occupancy_threshold, max_obersevation_lost_time,
@@ -246,6 +252,30 @@ class SemanticDSPMap:
         self._params.zero_center = int(bool(visualize_with_zero_center))
         self._eval_format = bool(if_out_evaluation_format)
         self.engine.set_params(self._params)
+        if self._colors is not None:
+            self._colors.eval_format = int(self._eval_format)
+            self.engine.set_colors(self._colors)
+
+    def enable_colors(self, label_bgr=None, instance_map=None, scheme=None):
+        """Turn on the colouring of the occupied list (getOccupancyResult, semantic_dsp_map.h:1274-1351).
+
+        label_bgr: {label_id: (b, g, r)} = g_label_color_map_default (the colour columns of the object-info CSV);
+        instance_map: the 256-entry permutation color_map_int_256_ (a std::random_device shuffle in the reference, so the
+        caller supplies it; default: a fixed seeded permutation); scheme: which ``#if SETTING`` colouring block applies
+        (default: 3 when the ZED2 filters are on, 0 for a map without instances, else 1)."""
+        c = _capi.Colors()
+        c.enabled, c.eval_format = 1, int(self._eval_format)
+        cfg = self.config
+        c.scheme = scheme if scheme is not None else (3 if cfg.zed2_filters else (1 if cfg.consider_instance else 0))
+        c.background_label = self.labels.label_id_of("Background")              # :1276, default-insert semantics
+        for label_id, bgr in (label_bgr or {}).items():
+            for k in range(3):
+                c.label_bgr[int(label_id) & 0xFF][k] = int(bgr[k]) & 0xFF
+        perm = np.random.default_rng(256).permutation(256) if instance_map is None else np.asarray(instance_map)
+        for k in range(256):
+            c.instance_map[k] = int(perm[k]) & 0xFF
+        self._colors = c
+        self.engine.set_colors(c)
 
     def setBeyesianMovementParameters(self, a, b, c, d):
         self._movement = (a, b, c, d)  # object layer (host, out of scope): kept for interface parity

@@ -129,6 +129,11 @@ def run_reference(name):
     return out
 
 
+def csv_colours():
+    """{label_id: (b, g, r)}: the colour columns ref_lib.write_label_csv writes by default."""
+    return {label_id: ((37 * label_id) % 256, (91 * label_id + 13) % 256, (53 * label_id + 101) % 256) for label_id, _, _ in ZED2_ROWS}
+
+
 def colour_permutation():
     """Stands in for the std::random_device shuffle of color_map_int_256_ (semantic_dsp_map.h:45-48)."""
     return np.random.default_rng(7).permutation(256).astype(np.int32)
@@ -146,6 +151,11 @@ def run_oracle(name, move_orders=None, order=0):
     # sigma (semantic_dsp_map.h:1047).  In oracle/_ref's build that stack slot reads 0 when the depth-noise model is on and
     # 0.1 when it is off; the oracle takes the value as a parameter so that everything else is compared bit for bit.
     orc.engine.set_invalid_sigma(0.0 if cfg.consider_depth_noise else 0.1)
+    # likewise label / track of an occupied voxel with an empty histogram are uninitialised out-params
+    # (semantic_dsp_map.h:1245-1246): a compiled reference emits what the previous voxel left there
+    orc.engine.set_undefined_label_carry(True)
+    orc.setVisualizeOptions(cfg.zero_center, spec["eval_format"])
+    orc.enable_colors(label_bgr=csv_colours(), instance_map=colour_permutation())
     scene = Scene(cfg)
     out, seconds = {}, []
     import time
@@ -162,7 +172,7 @@ def run_oracle(name, move_orders=None, order=0):
         zc = cfg.zero_center
         out.update(frame_record(t, e.dump(_capi.DUMP_RING, np.uint32), e.dump(_capi.DUMP_POINTS), e.dump(_capi.DUMP_PIXEL_OFFSETS, np.uint32),
                                 e.dump(_capi.DUMP_PIXEL_LISTS, np.uint32), e.dump(_capi.DUMP_PARTICLES),
-                                np.zeros(0, np.uint32) if zc else r.voxel_index, r.xyz, np.zeros((len(r.xyz), 3), np.uint8),
+                                np.zeros(0, np.uint32) if zc else r.voxel_index, r.xyz, r.rgb,
                                 np.zeros(0, np.uint32) if zc else r.free_voxel_index, r.free_xyz, [k for k, _ in moves], True))
         out[f"f{t}_label"], out[f"f{t}_track"], out[f"f{t}_state"] = r.label_id, r.track_id, r.state
     out["seconds"] = np.asarray(seconds)

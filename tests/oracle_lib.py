@@ -14,7 +14,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "libdsp_oracle.so")
 
 _ORC_SYMBOLS = {k: v for k, v in _capi.SYMBOLS.items()
-                if k in ("dspmap_clear", "dspmap_set_params", "dspmap_set_label_luts", "dspmap_set_random_table", "dspmap_update",
+                if k in ("dspmap_clear", "dspmap_set_params", "dspmap_set_label_luts", "dspmap_set_random_table", "dspmap_set_colors", "dspmap_update",
                          "dspmap_get_result", "dspmap_get_stats", "dspmap_dump")}
 _lib = None
 
@@ -34,6 +34,11 @@ def load_oracle():
         lib.orc_get_extra.argtypes = [C.c_void_p, C.c_int]
         lib.orc_set_diagnostics.restype = None
         lib.orc_set_diagnostics.argtypes = [C.c_void_p, C.c_int]
+        lib.orc_set_undefined_label_carry.restype = None
+        lib.orc_set_undefined_label_carry.argtypes = [C.c_void_p, C.c_int]
+        for fn in (lib.orc_rgb_to_hsv, lib.orc_hsv_to_rgb):
+            fn.restype = None
+            fn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         lib.orc_set_invalid_sigma.restype = None
         lib.orc_set_invalid_sigma.argtypes = [C.c_void_p, C.c_float]
         lib.orc_stage_seconds.restype = C.c_double
@@ -66,6 +71,11 @@ class OracleEngine(Engine):
     def set_invalid_sigma(self, value):
         """The sigma an invalid pixel carries (uninitialised in the reference, pointcloud_tools.h:224-232)."""
         self.lib.orc_set_invalid_sigma(self._h, float(value))
+
+    def set_undefined_label_carry(self, on):
+        """Label / track of an occupied voxel whose histogram is empty: 0 (default) or what the previous voxel left, as a
+        compiled reference does (semantic_dsp_map.h:1245-1246)."""
+        self.lib.orc_set_undefined_label_carry(self._h, int(on))
 
     def extra(self, which):
         return int(self.lib.orc_get_extra(self._h, which))
