@@ -272,6 +272,9 @@ enum {
  * IEEE division on n pseudo-random operand pairs (divisor in [b_lo, b_hi], |dividend| <= a_max) and counts results that
  * differ in any bit */
 int dspmap_selftest_division(dspmap_t* h, uint64_t n, uint64_t seed, float b_lo, float b_hi, float a_max, uint64_t* mismatches);
+/* Every 8-bit triple (a, b, c) = (i >> 16, i >> 8 & 255, i & 255), i < 2^24, through the device's RGB->HSV and HSV->RGB
+ * conversions (the ones dspmap_set_colors uses); each output word packs the three result bytes, first in bits 0..7. */
+int dspmap_selftest_colour(dspmap_t* h, uint32_t* rgb_to_hsv /* 2^24 */, uint32_t* hsv_to_rgb /* 2^24 */);
 /* copies at most cap bytes to dst (host); *n_bytes = full size of the dump */
 int dspmap_dump(dspmap_t* h, int32_t what, void* dst, size_t cap, size_t* n_bytes);
 

@@ -119,6 +119,7 @@ SYMBOLS = {
     "dspmap_comm_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dspmap_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dspmap_selftest_division": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_uint64)]),
+    "dspmap_selftest_colour": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dspmap_dump": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
 }
 

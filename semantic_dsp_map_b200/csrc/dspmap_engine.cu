@@ -224,7 +224,7 @@ struct dspmap {
     // exchange arena (one allocation, exported over CUDA IPC in sharded maps): barrier flags, counts, visible records,
     // incoming moved particles, the ck image and the (global) result arrays
     DevBuf<uint8_t> arena;
-    struct ArenaLayout { size_t flags, counts, move_counts, recs, movs, ck, r_idx, r_xyz, r_w, r_track, r_label, r_state, r_free_idx, r_free_xyz, total; } lay{};
+    struct ArenaLayout { size_t flags, counts, move_counts, recs, movs, ck, r_idx, r_xyz, r_w, r_track, r_label, r_state, r_free_idx, r_free_xyz, r_rgb, total; } lay{};
     CommView cv{};
     uint32_t comm_epoch = 0;
     void* peer_base[MAX_RANKS]{};
@@ -233,6 +233,9 @@ struct dspmap {
     float *r_xyz = nullptr, *r_w = nullptr, *r_free_xyz = nullptr, *d_ck = nullptr;
     uint16_t* r_track = nullptr;
     uint8_t* r_label = nullptr;
+    uint8_t* r_rgb = nullptr;
+    dspmap_colors colors{};            // dspmap_set_colors
+    DevBuf<uint8_t> d_col_tab;         // 768 B label colours (b, g, r) + 256 B instance map
     int8_t* r_state = nullptr;
     uint32_t* d_counts = nullptr;      // this rank's counts[source rank][COMM_COUNTS]
 
@@ -247,7 +250,7 @@ struct dspmap {
     PinBuf<uint32_t> hr_idx, hr_free_idx;
     PinBuf<float> hr_xyz, hr_w, hr_free_xyz;
     PinBuf<uint16_t> hr_track;
-    PinBuf<uint8_t> hr_label;
+    PinBuf<uint8_t> hr_label, hr_rgb;
     PinBuf<int8_t> hr_state;
     bool host_result_valid = false;
     std::unique_ptr<StagePool> stage_pool;
@@ -327,7 +330,7 @@ struct dspmap {
         for (int p = 0; p < MAX_RANKS; ++p) if (peer_base[p] && p != cfg.shard_rank) { cudaIpcCloseMemHandle(peer_base[p]); peer_base[p] = nullptr; }
         arena.release();
         p_depth.release(); p_masks.release(); p_cnt.release(); p_fp.release(); p_stamps.release(); p_maskdesc.release(); p_moves.release();
-        hr_idx.release(); hr_free_idx.release(); hr_xyz.release(); hr_w.release(); hr_free_xyz.release(); hr_track.release(); hr_label.release(); hr_state.release();
+        hr_idx.release(); hr_free_idx.release(); hr_xyz.release(); hr_w.release(); hr_free_xyz.release(); hr_track.release(); hr_label.release(); hr_state.release(); hr_rgb.release();
         for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (own_stream) { cudaStreamDestroy(own_stream); own_stream = nullptr; }
         if (side_stream) { cudaStreamDestroy(side_stream); side_stream = nullptr; }
@@ -350,6 +353,7 @@ struct dspmap {
         uint8_t* r0 = (uint8_t*)(peer_base[0] && have_rank0 >= 0 ? peer_base[0] : arena.p);
         r_idx = (uint32_t*)(r0 + lay.r_idx); r_xyz = (float*)(r0 + lay.r_xyz); r_w = (float*)(r0 + lay.r_w); r_track = (uint16_t*)(r0 + lay.r_track);
         r_label = (uint8_t*)(r0 + lay.r_label); r_state = (int8_t*)(r0 + lay.r_state); r_free_idx = (uint32_t*)(r0 + lay.r_free_idx); r_free_xyz = (float*)(r0 + lay.r_free_xyz);
+        r_rgb = r0 + lay.r_rgb;
     }
     int barrier() {
         if (cfg.shard_count == 1) return DSPMAP_OK;
@@ -509,6 +513,7 @@ int dspmap::init(const dspmap_config& c) {
         ck_seg_stride = std::max<uint32_t>(1, (uint32_t)(n_seg * 0.6180339887));
         while (gcd(ck_seg_stride, n_seg) != 1) ++ck_seg_stride;
     }
+    CU_TRY(this, d_col_tab.alloc(1024)); CU_TRY(this, cudaMemset(d_col_tab.p, 0, 1024));
     CU_TRY(this, d_vstate.alloc(v_pad)); CU_TRY(this, d_res_w.alloc(v_pad)); CU_TRY(this, d_res_tl.alloc(v_pad)); CU_TRY(this, d_mov_mask.alloc(v_pad));
     CU_TRY(this, d_blk_cnt.alloc(n_occ_blocks)); CU_TRY(this, d_blk_off.alloc(n_occ_blocks)); CU_TRY(this, d_work.alloc(v_pad + (size_t)sm_count * 8 * 8 * 512 + 512));
     CU_TRY(this, cudaMemset(d_vstate.p, 0, v_pad));
@@ -522,6 +527,7 @@ int dspmap::init(const dspmap_config& c) {
         const size_t Vg = f.V;   // rank 0 receives the global result
         lay.r_idx = take(Vg * 4); lay.r_xyz = take(Vg * 12); lay.r_w = take(Vg * 4); lay.r_track = take(Vg * 2); lay.r_label = take(Vg); lay.r_state = take(Vg);
         lay.r_free_idx = take(Vg * 4); lay.r_free_xyz = take(Vg * 12);
+        lay.r_rgb = take(Vg * 3);
         lay.total = off;
         CU_TRY(this, arena.alloc(lay.total));
         CU_TRY(this, cudaMemset(arena.p, 0, lay.flags + 64 * 4 + (size_t)MAX_RANKS * COMM_COUNTS * 4 + (size_t)MAX_RANKS * MAX_MOVES * 4 + 1024));
@@ -578,6 +584,7 @@ int dspmap::apply_params() {
     f.n0 = prm.depth_noise_zero_order; f.n1 = prm.depth_noise_first_order;
     f.sigma_invalid = prm.consider_depth_noise ? prm.depth_noise_zero_order : 0.1f;
     f.zero_center = prm.zero_center ? 1 : 0;
+    f.col_enabled = colors.enabled ? 1 : 0; f.col_eval = colors.eval_format ? 1 : 0; f.col_scheme = colors.scheme; f.col_background = colors.background_label;
     f.nb_ptc = prm.consider_depth_noise ? prm.nb_ptc_num_per_point : 1;
     // one newborn per point: a table prefix of 2x the pixel count is enough (and cache friendlier); more: the whole table
     f.birth_hash_cap = f.nb_ptc > 1 ? f.hash_cap : birth_cap1; f.birth_hash_shift = f.nb_ptc > 1 ? f.hash_shift : birth_shift1;
@@ -827,7 +834,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     }
     if (profiling) cudaEventRecord(ev[6], stream);
     // ---- O1 occupancy -------------------------------------------------------------------------------------------------
-    ResultArrays out{r_idx, r_xyz, r_w, r_track, r_label, r_state, r_free_idx, r_free_xyz};
+    ResultArrays out{r_idx, r_xyz, r_w, r_track, r_label, r_state, r_free_idx, r_free_xyz, r_rgb};
     OccScratch osc{d_vstate.p, d_res_w.p - (slot_lo >> f.Pb), d_res_tl.p - (slot_lo >> f.Pb), d_mov_mask.p - (slot_lo >> f.Pb), d_blk_cnt.p, d_blk_off.p};
     CU_TRY(this, cudaMemsetAsync(d_blk_cnt.p, 0, (size_t)n_occ_blocks * sizeof(uint4), stream));
     if (profiling) cudaEventRecord(ev[8], stream);
@@ -838,7 +845,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     ++launches;
     ++launches; k_occ_scan<<<1, 1024, 0, stream>>>(osc, n_occ_blocks, d_cnt.p, d_persist.p, cv);
     barrier();   // the lower ranks' totals are this rank's base offsets
-    DISPATCH_PB(f.Pb, (k_occ_emit<PB><<<n_occ_blocks, OCC_BLOCK, 0, stream>>>(fp, st, osc, out, d_movl_idx.p, d_movl_track.p, sel_cap, cv, d_counts)));
+    DISPATCH_PB(f.Pb, (k_occ_emit<PB><<<n_occ_blocks, OCC_BLOCK, 0, stream>>>(fp, st, osc, out, d_movl_idx.p, d_movl_track.p, sel_cap, cv, d_counts, d_col_tab.p)));
     ++launches;
     barrier();   // rank 0 holds the whole result
     if (profiling) cudaEventRecord(ev[7], stream);
@@ -887,6 +894,7 @@ int dspmap::fetch_result_to_host() {
     CU_TRY(this, hr_idx.reserve(std::max<size_t>(n, 1))); CU_TRY(this, hr_xyz.reserve(std::max<size_t>(3 * n, 1)));
     CU_TRY(this, hr_w.reserve(std::max<size_t>(n, 1))); CU_TRY(this, hr_track.reserve(std::max<size_t>(n, 1)));
     CU_TRY(this, hr_label.reserve(std::max<size_t>(n, 1))); CU_TRY(this, hr_state.reserve(std::max<size_t>(n, 1)));
+    CU_TRY(this, hr_rgb.reserve(std::max<size_t>(3 * n, 1)));
     if (n) {
         CU_TRY(this, cudaMemcpyAsync(hr_idx.p, r_idx, n * 4, cudaMemcpyDeviceToHost, stream));
         CU_TRY(this, cudaMemcpyAsync(hr_xyz.p, r_xyz, n * 12, cudaMemcpyDeviceToHost, stream));
@@ -894,6 +902,8 @@ int dspmap::fetch_result_to_host() {
         CU_TRY(this, cudaMemcpyAsync(hr_track.p, r_track, n * 2, cudaMemcpyDeviceToHost, stream));
         CU_TRY(this, cudaMemcpyAsync(hr_label.p, r_label, n, cudaMemcpyDeviceToHost, stream));
         CU_TRY(this, cudaMemcpyAsync(hr_state.p, r_state, n, cudaMemcpyDeviceToHost, stream));
+        if (fp.col_enabled) CU_TRY(this, cudaMemcpyAsync(hr_rgb.p, r_rgb, 3 * n, cudaMemcpyDeviceToHost, stream));
+        else memset(hr_rgb.p, 0, 3 * n);
     }
     if (nf) {
         CU_TRY(this, hr_free_idx.reserve(nf)); CU_TRY(this, hr_free_xyz.reserve(3 * nf));
@@ -971,6 +981,18 @@ int dspmap_set_random_table(dspmap_t* h, const float* table, uint32_t n) {
     CU_TRY(h, cudaMemcpy(h->d_randoms.p, table, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
     h->rand_n = n;
     return DSPMAP_OK;
+}
+
+int dspmap_set_colors(dspmap_t* h, const dspmap_colors* c) {
+    if (!h || !c) return DSPMAP_ERR_INVALID_ARG;
+    if (c->scheme != 0 && c->scheme != 1 && c->scheme != 3) return h->fail(DSPMAP_ERR_INVALID_ARG, "colour scheme %d (0, 1 or 3)", c->scheme);
+    CU_TRY(h, cudaSetDevice(h->device));
+    h->colors = *c;
+    uint8_t tab[1024];
+    memcpy(tab, c->label_bgr, 768);
+    memcpy(tab + 768, c->instance_map, 256);
+    CU_TRY(h, cudaMemcpy(h->d_col_tab.p, tab, sizeof(tab), cudaMemcpyHostToDevice));
+    return h->apply_params();
 }
 
 static int check_frame_args(dspmap_t* h, const float* depth, int32_t rows, int32_t cols, int32_t row_stride, const dspmap_mask* masks,
@@ -1072,6 +1094,7 @@ int dspmap_get_result(dspmap_t* h, dspmap_result* out) {
     out->free_count = h->fp.want_free ? h->result_nf : 0;
     out->voxel_index = h->hr_idx.p; out->xyz = h->hr_xyz.p; out->weight_sum = h->hr_w.p; out->track_id = h->hr_track.p;
     out->label_id = h->hr_label.p; out->state = h->hr_state.p; out->free_voxel_index = h->hr_free_idx.p; out->free_xyz = h->hr_free_xyz.p;
+    out->rgb = h->hr_rgb.p;
     return DSPMAP_OK;
 }
 
@@ -1081,6 +1104,7 @@ int dspmap_get_result_device(dspmap_t* h, dspmap_result* out) {
     out->free_count = h->fp.want_free ? h->result_nf : 0;
     out->voxel_index = h->r_idx; out->xyz = h->r_xyz; out->weight_sum = h->r_w; out->track_id = h->r_track;
     out->label_id = h->r_label; out->state = h->r_state; out->free_voxel_index = h->r_free_idx; out->free_xyz = h->r_free_xyz;
+    out->rgb = h->r_rgb;
     return DSPMAP_OK;
 }
 
@@ -1161,6 +1185,21 @@ int dspmap_selftest_division(dspmap_t* h, uint64_t n, uint64_t seed, float b_lo,
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     cudaFree(d);
     *mismatches = out;
+    return DSPMAP_OK;
+}
+
+int dspmap_selftest_colour(dspmap_t* h, uint32_t* rgb_to_hsv, uint32_t* hsv_to_rgb) {
+    if (!h || !rgb_to_hsv || !hsv_to_rgb) return DSPMAP_ERR_INVALID_ARG;
+    CU_TRY(h, cudaSetDevice(h->device));
+    uint32_t* d = nullptr;
+    const size_t n = (size_t)1 << 24;
+    CU_TRY(h, cudaMalloc(&d, 2 * n * sizeof(uint32_t)));
+    k_selftest_colour<<<h->sm_count * 8, 256, 0, h->stream>>>(d);
+    cudaError_t e = cudaMemcpyAsync(rgb_to_hsv, d, n * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hsv_to_rgb, d + n, n * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    CU_TRY(h, e);
     return DSPMAP_OK;
 }
 

@@ -949,7 +949,90 @@ constexpr uint32_t VS_MOVABLE = 4u;
 struct ResultArrays {
     uint32_t* voxel_index; float* xyz; float* weight_sum; uint16_t* track_id; uint8_t* label_id; int8_t* state;
     uint32_t* free_voxel_index; float* free_xyz;
+    uint8_t* rgb;           // 3 bytes per occupied entry (written when FrameParams::col_enabled)
 };
+
+// ---- colour of one occupied voxel: getOccupancyResult, semantic_dsp_map.h:1274-1351 ------------------------------
+// The two conversions restate cv::cvtColor on one CV_8UC3 pixel (H in [0,180); S and H through 12-bit fixed-point
+// reciprocals, rounded to nearest like OpenCV's tables; back through float sectors with the two "1 - s*h" terms FUSED
+// and the final scaling truncated) — bit-identical to cv2 4.13 on all 2^24 inputs (tests/test_colour_cpu.py pins the
+// oracle's copy of the same arithmetic, tests/test_colour_gpu.py this one).
+__device__ __forceinline__ int fixed_recip12(int num, int den) {   // lrint((num << 12) / (double)den), den >= 1
+    // the quotient is never at an exact .5 (num << 12 is even, ties need an odd numerator over 2*den), so
+    // round-half-up in integers equals the reference's round-half-even
+    const long long n2 = ((long long)num << 13) + den;
+    return (int)(n2 / (2 * den));
+}
+__device__ __forceinline__ void rgb_to_hsv_u8(int r, int g, int b, int& h, int& s, int& v) {
+    v = max(r, max(g, b));
+    const int vmin = min(r, min(g, b)), diff = v - vmin;
+    const int vr = v == r ? -1 : 0, vg = v == g ? -1 : 0;
+    const int sdiv = v ? fixed_recip12(255, v) : 0;
+    const int hdiv = diff ? fixed_recip12(180, 6 * diff) : 0;
+    s = (diff * sdiv + (1 << 11)) >> 12;
+    h = (vr & (g - b)) + (~vr & ((vg & (b - r + 2 * diff)) + ((~vg) & (r - g + 4 * diff))));
+    h = (h * hdiv + (1 << 11)) >> 12;
+    h += h < 0 ? 180 : 0;
+}
+__device__ __forceinline__ void hsv_to_rgb_u8(int hh, int ss, int vv, int& r, int& g, int& b) {
+    float h = (float)hh;
+    const float s = __fmul_rn((float)ss, 1.f / 255.f), v = __fmul_rn((float)vv, 1.f / 255.f);
+    float fr, fg, fb;
+    if (ss == 0) {
+        fr = fg = fb = v;
+    } else {
+        h = __fmul_rn(h, 6.f / 180.f);
+        while (h >= 6.f) h = __fsub_rn(h, 6.f);
+        int sector = (int)floorf(h);
+        h = __fsub_rn(h, (float)sector);
+        if ((unsigned)sector >= 6u) { sector = 0; h = 0.f; }
+        const float t0 = v, t1 = __fmul_rn(v, __fsub_rn(1.f, s)), t2 = __fmul_rn(v, __fmaf_rn(-s, h, 1.f)),
+                    t3 = __fmul_rn(v, __fmaf_rn(-s, __fsub_rn(1.f, h), 1.f));
+        // sector table of OpenCV: (b, g, r) = tab[{1,3,0}, {1,0,2}, {3,0,1}, {0,2,1}, {0,1,3}, {2,1,0}]
+        switch (sector) {
+            case 0: fb = t1; fg = t3; fr = t0; break;
+            case 1: fb = t1; fg = t0; fr = t2; break;
+            case 2: fb = t3; fg = t0; fr = t1; break;
+            case 3: fb = t0; fg = t2; fr = t1; break;
+            case 4: fb = t0; fg = t1; fr = t3; break;
+            default: fb = t2; fg = t1; fr = t0; break;
+        }
+    }
+    r = min(max((int)floorf(__fmul_rn(fr, 255.f)), 0), 255);
+    g = min(max((int)floorf(__fmul_rn(fg, 255.f)), 0), 255);
+    b = min(max((int)floorf(__fmul_rn(fb, 255.f)), 0), 255);
+}
+// col_tab: 768 bytes label colours (b, g, r per label) followed by the 256-entry instance map
+__device__ __forceinline__ uint32_t voxel_colour(const FrameParams& f, const uint8_t* __restrict__ col_tab, int state, uint32_t label, uint32_t track,
+                                                 float px, float py, float pz, float cx, float cy, float cz) {
+    int r, g, b;
+    if (state == 1) {
+        if ((int)label == f.col_background) {                       // :1277-1294 jet by height (color_map_jet_256_, :50-63)
+            const float hgt = f.col_scheme == 3 ? (py + 2.f) : (-pz + 2.f);
+            const int ci = min(max((int)(hgt * 51.2f), 0), 255);
+            if (ci < 64) { r = 0; g = 0; b = ci * 4; }
+            else if (ci < 128) { r = 0; g = (ci - 64) * 4; b = 255; }
+            else if (ci < 192) { r = (ci - 128) * 4; g = 255; b = 255 - (ci - 128) * 4; }
+            else { r = 255; g = 255 - (ci - 192) * 4; b = 0; }
+            if (f.col_eval) r = g = b = 0;
+        } else if (f.col_scheme == 0 || track > f.max_movable) {    // :1297-1309 label colour, stored (b, g, r)
+            b = col_tab[3 * label]; g = col_tab[3 * label + 1]; r = col_tab[3 * label + 2];
+        } else if (f.col_eval) {                                    // :1311-1315
+            r = (int)label; g = (int)(track >> 8); b = (int)(track & 0xffu);
+        } else {                                                    // :1317-1319 (table index taken modulo 256)
+            r = 160; g = col_tab[768 + (track & 0xffu)]; b = col_tab[768 + label];
+        }
+    } else {                                                        // guessed occupied: white, :1325-1331
+        r = g = b = 255;
+    }
+    if (!f.col_eval) {                                              // :1333-1351
+        int h, s, v;
+        rgb_to_hsv_u8(r, g, b, h, s, v);
+        if (!point_in_frustum(f, cx, cy, cz)) v = (int)((float)v * 0.7f) & 0xff;
+        hsv_to_rgb_u8(h, s, v, r, g, b);
+    }
+    return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
+}
 
 struct OccScratch {
     uint8_t* vstate;        // V bytes
@@ -1147,7 +1230,8 @@ k_occ_scan(OccScratch sc, uint32_t n_blocks, Counters* __restrict__ cnt, Persist
 template <int PB>
 __global__ void __launch_bounds__(OCC_BLOCK)
 k_occ_emit(const __grid_constant__ FrameParams f, Store st, OccScratch sc, ResultArrays out, uint32_t* __restrict__ movl_idx,
-           uint16_t* __restrict__ movl_track, uint32_t movl_cap, CommView cv, const uint32_t* __restrict__ counts) {
+           uint16_t* __restrict__ movl_track, uint32_t movl_cap, CommView cv, const uint32_t* __restrict__ counts,
+           const uint8_t* __restrict__ col_tab) {
     __shared__ uint32_t s_warp[33];
     // sharded map: `out` is rank 0's result arrays; this rank's entries start after the lower ranks' (ascending storage index)
     uint32_t base_occ = 0, base_free = 0;
@@ -1185,6 +1269,7 @@ k_occ_emit(const __grid_constant__ FrameParams f, Store st, OccScratch sc, Resul
             buffer_to_map(f, bx0 + u, by, bz, mx, my, mz);
             float p0 = (float)mx * f.voxel + f.pmin[0], p1 = (float)my * f.voxel + f.pmin[1], p2 = (float)mz * f.voxel + f.pmin[2];
             p0 += f.map_center[0]; p1 += f.map_center[1]; p2 += f.map_center[2];
+            const float c0 = p0, c1 = p1, c2 = p2;                  // the voxel corner in the global frame
             if (f.zero_center) { p0 = p0 - f.cam[0]; p1 = p1 - f.cam[1]; p2 = p2 - f.cam[2]; }
             if (is_occ) {
                 const uint32_t pos = pos_occ++;
@@ -1195,6 +1280,10 @@ k_occ_emit(const __grid_constant__ FrameParams f, Store st, OccScratch sc, Resul
                 out.track_id[pos] = (uint16_t)(tl & 0xffffu);
                 out.label_id[pos] = (uint8_t)((tl >> 16) & 0xffu);
                 out.state[pos] = (int8_t)((int)stt - 1);
+                if (f.col_enabled) {
+                    const uint32_t c = voxel_colour(f, col_tab, (int)stt - 1, (tl >> 16) & 0xffu, tl & 0xffffu, p0, p1, p2, c0, c1, c2);
+                    out.rgb[3 * (size_t)pos + 0] = (uint8_t)c; out.rgb[3 * (size_t)pos + 1] = (uint8_t)(c >> 8); out.rgb[3 * (size_t)pos + 2] = (uint8_t)(c >> 16);
+                }
             } else {
                 const uint32_t pos = pos_free++;
                 out.free_voxel_index[pos] = v;
@@ -1522,6 +1611,18 @@ __global__ void k_selftest_invdiv(uint64_t n, uint64_t seed, float b_lo, float b
         if (__float_as_uint(q1) != __float_as_uint(q2)) ++local;
     }
     if (local) atomicAdd(mismatches, (unsigned long long)local);
+}
+
+// all 2^24 8-bit triples through both colour-space conversions; out = 2 x 2^24 packed (c0 | c1 << 8 | c2 << 16) words
+__global__ void k_selftest_colour(uint32_t* __restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (1u << 24); i += gridDim.x * blockDim.x) {
+        const int a = (int)(i >> 16), b = (int)((i >> 8) & 255u), c = (int)(i & 255u);
+        int h, s, v, r, g, bb;
+        rgb_to_hsv_u8(a, b, c, h, s, v);
+        out[i] = (uint32_t)(h & 255) | ((uint32_t)s << 8) | ((uint32_t)v << 16);
+        hsv_to_rgb_u8(a, b, c, r, g, bb);
+        out[(1u << 24) + i] = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)bb << 16);
+    }
 }
 
 }  // namespace dspk

@@ -42,7 +42,7 @@ def compare_frame(eng_map, orc_map, res_e, res_o, frame, stages=True, particles=
         pe, po = e.dump(_capi.DUMP_PARTICLES).view(PARTICLE), o.dump(_capi.DUMP_PARTICLES).view(PARTICLE)
         assert_same("particles", pe, po, frame)
     assert_same("voxel_state", e.dump(_capi.DUMP_VOXEL_STATE, np.int8), o.dump(_capi.DUMP_VOXEL_STATE, np.int8), frame)
-    for name in ("voxel_index", "xyz", "weight_sum", "track_id", "label_id", "state", "free_voxel_index", "free_xyz"):
+    for name in ("voxel_index", "xyz", "weight_sum", "track_id", "label_id", "state", "free_voxel_index", "free_xyz", "rgb"):
         assert_same("result." + name, getattr(res_e, name), getattr(res_o, name), frame)
     se, so = e.stats(), o.stats()
     for k in COUNT_STATS:
