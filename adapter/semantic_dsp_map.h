@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <random>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -44,11 +45,13 @@ struct DspLabelTables {
     std::unordered_map<std::string, int> label_id_static;     // g_label_id_map_static
     std::unordered_map<std::string, int> label_to_instance;   // g_label_to_instance_id_map_default
     std::map<int, std::string> instance_to_label;             // g_instance_id_to_label_map_default
+    std::unordered_map<int, cv::Vec3b> label_color;           // g_label_color_map_default, (b, g, r)
     int max_movable_instance_id = 65523;                      // g_max_movable_object_instance_id
 
-    void addRow(int id, const std::string& name, int instance_id) {   // object_info_handler.h:51-86
+    void addRow(int id, const std::string& name, int instance_id, int color_b = 0, int color_g = 0, int color_r = 0) {   // object_info_handler.h:51-86
         label_id[name] = id;
         label_id_reversed[id] = name;
+        label_color[id] = cv::Vec3b((unsigned char)color_b, (unsigned char)color_g, (unsigned char)color_r);
         if (instance_id > 0) {
             label_id_static[name] = id;
             label_to_instance[name] = instance_id;
@@ -65,7 +68,12 @@ public:
     explicit SemanticDSPMap(const dspmap_config& cfg, const DspLabelTables& labels = DspLabelTables()) : cfg_(cfg), labels_(labels) {
         if (dspmap_create(&cfg_, &h_) != DSPMAP_OK) { std::fprintf(stderr, "dspmap_create failed\n"); std::exit(-1); }   // reference: exit(-1), operations.h:57
         prm_ = dspmap_params{0.95f, 0.1f, 3, 0.2f, 1.0f, 5, 0.1f, 0.0f, 0.1f, 0, 0, 0};   // ctor defaults, reference :25-43
+        for (int i = 0; i < 256; ++i) color_map_int_256_[i] = (uint8_t)i;                       // reference :45-48: a random shuffle of 0..255
+        std::random_device rd;
+        std::mt19937 gen(rd());
+        for (int i = 255; i > 0; --i) { std::uniform_int_distribution<int> dist(0, i); std::swap(color_map_int_256_[i], color_map_int_256_[dist(gen)]); }
         pushLabels();
+        pushColors();
     }
     ~SemanticDSPMap() { dspmap_destroy(h_); }
     SemanticDSPMap(const SemanticDSPMap&) = delete;
@@ -90,7 +98,10 @@ public:
     void setVisualizeOptions(bool visualize_with_zero_center, bool if_out_evaluation_format = false) {   // reference :130-134
         prm_.zero_center = visualize_with_zero_center; if_out_evaluation_format_ = if_out_evaluation_format;
         dspmap_set_params(h_, &prm_);
+        pushColors();
     }
+    // the instance colour permutation (color_map_int_256_); random per process in the reference, settable here for reproducible output
+    void setInstanceColorMap(const uint8_t map256[256]) { for (int i = 0; i < 256; ++i) color_map_int_256_[i] = map256[i]; pushColors(); }
     void setBeyesianMovementParameters(double, double, double, double) {}                        // object layer (host), reference :142-150
     void setOccupancyThreshold(float t) { prm_.occupancy_threshold = t; dspmap_set_params(h_, &prm_); }   // reference :153-156
     void setDepthNoiseModelParameters(float first_order, float zero_order) {                     // reference :161-166
@@ -133,9 +144,7 @@ public:
         for (uint32_t i = 0; i < r.count; ++i) {                                                  // reference :1274-1351
             pcl::PointXYZRGB pt;
             pt.x = r.xyz[3 * i]; pt.y = r.xyz[3 * i + 1]; pt.z = r.xyz[3 * i + 2];
-            if (r.state[i] == 2) { pt.r = pt.g = pt.b = 255; }                                   // guessed occupied: white (:1326-1330)
-            else if (if_out_evaluation_format_) { pt.r = r.label_id[i]; pt.g = r.track_id[i] >> 8; pt.b = r.track_id[i] & 0xFF; }   // :1311-1315
-            else { pt.r = 160; pt.g = (uint8_t)(r.track_id[i] * 37u); pt.b = (uint8_t)(r.label_id[i] * 29u); }   // colour maps: next (§8 f1)
+            pt.r = r.rgb[3 * i]; pt.g = r.rgb[3 * i + 1]; pt.b = r.rgb[3 * i + 2];               // coloured on the device (dspmap_set_colors)
             occupied_point_cloud->push_back(pt);
         }
         for (uint32_t i = 0; i < r.free_count; ++i) {                                             // reference :1354-1376
@@ -165,8 +174,21 @@ private:
                               (uint16_t)DspLabelTables::getOr0(labels_.label_to_instance, std::string("Sky")));   // pointcloud_tools.h:236
     }
 
+    void pushColors() {   // reference :1274-1351; which "#if SETTING" block applies follows from the configuration
+        dspmap_colors c{};
+        c.enabled = 1;
+        c.eval_format = if_out_evaluation_format_;
+        c.scheme = cfg_.zed2_filters ? 3 : (cfg_.consider_instance ? 1 : 0);
+        c.background_label = DspLabelTables::getOr0(labels_.label_id, std::string("Background"));   // :1276, operator[] default-insert
+        for (const auto& kv : labels_.label_color)
+            if (kv.first >= 0 && kv.first < 256) for (int k = 0; k < 3; ++k) c.label_bgr[kv.first][k] = kv.second[k];
+        for (int i = 0; i < 256; ++i) c.instance_map[i] = color_map_int_256_[i];
+        dspmap_set_colors(h_, &c);
+    }
+
     dspmap_config cfg_;
     DspLabelTables labels_;
+    uint8_t color_map_int_256_[256];
     dspmap_params prm_{};
     dspmap_t* h_ = nullptr;
     int max_obersevation_lost_time_ = 0;

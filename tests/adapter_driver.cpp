@@ -1,5 +1,5 @@
-// Drives adapter/semantic_dsp_map.h the way src/mapping.cpp does (mapping.cpp:135-140, 273), against stand-ins for
-// Eigen / OpenCV / PCL.  Prints one line per frame: "<frame> <n_occupied> <fnv1a of the occupied voxel positions>".
+// Drives adapter/semantic_dsp_map.h the way src/mapping.cpp does (mapping.cpp:135-140, 273), against the stand-ins for
+// Eigen / OpenCV / PCL in oracle/ref_stubs (the same ones the reference itself is compiled against for the parity pin).  Prints one line per frame: "<frame> <n_occupied> <fnv1a of the occupied voxel positions>".
 #include "../adapter/semantic_dsp_map.h"
 
 #include <cmath>
@@ -20,15 +20,15 @@ int main(int argc, char** argv) {
     dsp_map_.setBeyesianMovementParameters(0.1, 0.9, 0.3, 0.1);
     dsp_map_.setDepthNoiseModelParameters(0.02f, 0.3f);
     for (int t = 0; t < frames; ++t) {
-        cv::Mat depth(96, 160, sizeof(float));
+        cv::Mat depth(96, 160, CV_32FC1);
         float* d = reinterpret_cast<float*>(depth.data);
         for (int i = 0; i < 96; ++i)
             for (int j = 0; j < 160; ++j) d[i * 160 + j] = i > 52 ? 1.5f * 66.f / (float)(i - 47) : 3.5f;   // ground plane + wall
         std::vector<MaskKpts> ins_seg;
-        MaskKpts st; st.track_id = 65535; st.label = "static"; st.mask = cv::Mat(96, 160, 1);
+        MaskKpts st; st.track_id = 65535; st.label = "static"; st.mask = cv::Mat(96, 160, CV_8UC1);
         std::memset(st.mask.data, 0, 96 * 160);
         ins_seg.push_back(st);
-        MaskKpts car; car.track_id = 3; car.label = "Vehicle"; car.mask = cv::Mat(96, 160, 1);
+        MaskKpts car; car.track_id = 3; car.label = "Vehicle"; car.mask = cv::Mat(96, 160, CV_8UC1);
         std::memset(car.mask.data, 0, 96 * 160);
         for (int i = 30; i < 50; ++i) for (int j = 60; j < 90; ++j) car.mask.data[i * 160 + j] = 255;
         ins_seg.push_back(car);

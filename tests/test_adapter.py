@@ -14,7 +14,7 @@ EXE = os.path.join(ROOT, "tests", "adapter_driver")
 
 def build_driver():
     lib_dir = os.path.join(ROOT, "semantic_dsp_map_b200")
-    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(ROOT, "tests", "adapter_stubs"), "-I" + os.path.join(ROOT, "include"),
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(ROOT, "oracle", "ref_stubs"), "-I" + os.path.join(ROOT, "include"),
            os.path.join(ROOT, "tests", "adapter_driver.cpp"), "-o", EXE, "-L" + lib_dir, "-l:libdspmap_b200.so", "-Wl,-rpath," + lib_dir]
     subprocess.check_call(cmd)
 
@@ -45,6 +45,8 @@ def test_adapter_matches_python_mirror():
                     depth_noise_zero_order=0.3, consider_depth_noise=True, use_independent_filter=False, zero_center=False)
     labels = LabelTables.from_rows([(0, "background", 65535), (1, "road", 65534), (14, "Vehicle", -1)])
     m = SemanticDSPMap(cfg, labels)
+    m.setVisualizeOptions(False, True)          # like the driver: evaluation format
+    m.enable_colors()
     i = np.arange(96, dtype=np.float32)[:, None] * np.ones((1, 160), np.float32)
     with np.errstate(divide="ignore"):
         depth = np.where(i > 52, np.float32(1.5) * np.float32(66.0) / (i - np.float32(47.0)), np.float32(3.5)).astype(np.float32)
@@ -53,7 +55,7 @@ def test_adapter_matches_python_mirror():
     for t, line in enumerate(out):
         r = m.update(depth, [MaskKpts(65535, "static", np.zeros((96, 160), np.uint8)), MaskKpts(3, "Vehicle", car)],
                      [0.0, 0.0, 0.1 * t], [1.0, 0.0, 0.0, 0.0])
-        red = np.where(r.state == 2, 255, r.label_id).astype(np.int64)
+        red = r.rgb[:, 0].astype(np.int64)
         f, n, h = line.split()
         assert int(f) == t and int(n) == len(r.voxel_index), (line, len(r.voxel_index))
         assert int(h, 16) == _fnv(r.xyz, red), line
