@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <map>
 #include <random>
+#include <set>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -79,7 +80,7 @@ public:
     SemanticDSPMap(const SemanticDSPMap&) = delete;
     SemanticDSPMap& operator=(const SemanticDSPMap&) = delete;
 
-    void clear() { dspmap_clear(h_); }                                                          // reference :74-81
+    void clear() { dspmap_clear(h_); known_objects_.clear(); born_tracks_.clear(); }                                                          // reference :74-81
     void setTemplatePath(std::string) {}                                                         // template matching: out of scope
     void setMapParameters(float detection_probability, float noise_number, int nb_ptc_num_per_point, float occupancy_threshold,
                           int max_obersevation_lost_time, float forgetting_rate = 1.f, int max_forget_count = 5,
@@ -132,6 +133,7 @@ public:
                 for (int a = 0; a < 3; ++a) { if (k[a] < mn[a]) mn[a] = k[a]; if (k[a] > mx[a]) mx[a] = k[a]; }
             for (int a = 0; a < 3; ++a) { d.bbox_min[a] = mn[a] - 1.0; d.bbox_max[a] = mx[a] + 1.0; }
         }
+        appendFloatingTracks(ins_seg_result);
         const double pos[3] = {camera_position.x(), camera_position.y(), camera_position.z()};
         const double quat[4] = {camera_orientation.w(), camera_orientation.x(), camera_orientation.y(), camera_orientation.z()};
         const int rc = dspmap_update(h_, reinterpret_cast<const float*>(depth_value_mat.data), depth_value_mat.rows, depth_value_mat.cols,
@@ -174,6 +176,32 @@ private:
                               (uint16_t)DspLabelTables::getOr0(labels_.label_to_instance, std::string("Sky")));   // pointcloud_tools.h:236
     }
 
+    // reference :712-737 ("floating objects"): after the moves and removals of a frame, every track that owns particles in
+    // obj_ptc_hash_map (particles register at birth when track <= g_max_movable_object_instance_id, :1160-1162) without being
+    // a tracked object (object_tracking_hash_map, filled by objectLevelUpdate only under g_consider_instance, :346-364) is
+    // removed with all its particles - e.g. pixels of a movable CLASS of the static mask (instance id -1 -> track 0,
+    // pointcloud_tools.h:137-138) live for one frame.  Mirrors just enough of ObjectSet's bookkeeping to name those tracks.
+    void appendFloatingTracks(const std::vector<MaskKpts>& ins_seg_result) {
+        if (cfg_.consider_instance)
+            for (const MaskKpts& m : ins_seg_result)
+                if (m.label != "static" && m.track_id <= labels_.max_movable_instance_id) { known_objects_.insert(m.track_id); born_tracks_.insert(m.track_id); }
+        for (const auto& mv : moves_) known_objects_.insert(mv.track_id);
+        for (int32_t t : remove_) { known_objects_.erase(t); born_tracks_.erase(t); }
+        std::set<int> candidates = born_tracks_;
+        for (int v = 0; v < 256; ++v) {   // tracks the static-mask look-up can produce (pointcloud_tools.h:137-138)
+            auto it = labels_.label_id_reversed.find(v + 1);
+            const int t = it == labels_.label_id_reversed.end() ? 0 : DspLabelTables::getOr0(labels_.label_to_instance, it->second);
+            if (t <= labels_.max_movable_instance_id) candidates.insert(t);
+        }
+        for (int t : candidates) {
+            if (known_objects_.count(t)) continue;
+            bool listed = false;
+            for (int32_t r : remove_) listed |= r == t;
+            if (!listed) remove_.push_back(t);
+            born_tracks_.erase(t);
+        }
+    }
+
     void pushColors() {   // reference :1274-1351; which "#if SETTING" block applies follows from the configuration
         dspmap_colors c{};
         c.enabled = 1;
@@ -189,6 +217,7 @@ private:
     dspmap_config cfg_;
     DspLabelTables labels_;
     uint8_t color_map_int_256_[256];
+    std::set<int> known_objects_, born_tracks_;
     dspmap_params prm_{};
     dspmap_t* h_ = nullptr;
     int max_obersevation_lost_time_ = 0;

@@ -280,6 +280,16 @@ def main():
                                  "~38% of the frame) are instruction-latency bound. See DESIGN.md section 4 and profiles/r01_summary.md."},
             "stage_ms": {n: float(v / args.steps) for n, v in zip(_capi.STAGE_NAMES, stage_ms)},
         }
+        # The north-star's "fused predict+update kernel" charged with SURVEY.md section 8(d)'s layout-independent numerator
+        # (24 B per slot of every swept voxel + 8 B per updated particle + 24 B per internal pixel) over the time of the
+        # visibility + weight-update stages (CUDA events inside the engine).  The engine does NOT move those bytes - the header
+        # plane lets it open only non-empty voxels - so this is the dense formulation's yardstick, not achieved DRAM traffic.
+        pu_bytes = (24.0 * cfg.n_slots / cfg.n_voxels * acc["n_swept"] + 8.0 * acc["n_vis"]) / args.steps + 24.0 * cfg.internal_size[0] * cfg.internal_size[1]
+        pu_ms = (stage_ms[3] + stage_ms[4]) / args.steps
+        out["roofline_predict_update"] = {"kernels": "k_vertex_mask..k_gather_visible + k_ck + k_weight_update", "bound": "hbm", "unit": "GB/s",
+                                          "algorithmic_bytes": pu_bytes, "ms": pu_ms, "achieved": pu_bytes / (pu_ms * 1e-3) / 1e9, "peak": peak,
+                                          "frac": pu_bytes / (pu_ms * 1e-3) / 1e9 / peak,
+                                          "note": "SURVEY 8(d) numerator of the dense formulation; the stencil passes are instruction-bound (profiles/)"}
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.config, frames)
         print(json.dumps(out))

@@ -39,6 +39,8 @@ for S in "$@"; do
         INC="$TMP"
     fi
     echo "build_ref: SETTING $S -> $OUT"
-    $CXX $FLAGS -I"$HERE/ref_stubs" -I"$INC" -o "$OUT" "$HERE/ref_harness.cpp"
+    # SETTING 0 declares a 3.2 GB static particle array (docs/trouble_shooting.md:3-18): it only links with the medium code model
+    MODEL=""; [ "$S" != "0" ] || MODEL="-mcmodel=medium"
+    $CXX $FLAGS $MODEL -I"$HERE/ref_stubs" -I"$INC" -o "$OUT" "$HERE/ref_harness.cpp"
     [ -z "$TMP" ] || rm -rf "$TMP"
 done

@@ -233,6 +233,11 @@ class SemanticDSPMap:
         self._keep = []
         self._eval_format = False
         self._colors = None
+        # mirror of ObjectSet's two tables as far as the hot path reads them (object_layer.h:345-425): which movable tracks
+        # are tracked objects, and which tracks can own particles without being one ("floating", semantic_dsp_map.h:712-737)
+        self._known_objects = set()
+        self._born_tracks = set()
+        self._refresh_lut_tracks()
 
     # -- setters, semantic_dsp_map.h:101-166 ----------------------------------------------------------------------------
     def setMapParameters(self, detection_probability, noise_number, nb_ptc_num_per_point, occupancy_threshold, max_obersevation_lost_time,
@@ -293,6 +298,33 @@ class SemanticDSPMap:
 
     def clear(self):
         self.engine.clear()
+        self._known_objects.clear()          # object_set_.clear(), semantic_dsp_map.h:74-81
+        self._born_tracks.clear()
+
+    def _refresh_lut_tracks(self):
+        max_movable = self.labels.max_movable_instance_id
+        self._lut_movable_tracks = {int(t) for t in np.unique(self.labels.static_value_to_track()) if int(t) <= max_movable}
+
+    def _floating_tracks(self, ins_seg_result, moves, remove_tracks):
+        """semantic_dsp_map.h:712-737 ("floating objects"): after the moves and the removals of a frame, every track that owns
+        particles in obj_ptc_hash_map but has no entry in object_tracking_hash_map is removed with all its particles.  Particles
+        enter obj_ptc_hash_map at birth when their track id is <= g_max_movable_object_instance_id (:1160-1162); objects enter
+        object_tracking_hash_map when objectLevelUpdate sees their mask (:346-364), which only runs with g_consider_instance.
+        Hence e.g. in static mode the pixels of a movable CLASS of the static mask (instance id -1 -> track 0,
+        pointcloud_tools.h:137-138) live for exactly one frame.  Returns the tracks to append to this frame's removals."""
+        max_movable = self.labels.max_movable_instance_id
+        if self.config.consider_instance:
+            for m in ins_seg_result:
+                if m.label != "static" and m.track_id <= max_movable:
+                    self._known_objects.add(int(m.track_id))
+                    self._born_tracks.add(int(m.track_id))
+        for track, _ in moves:
+            self._known_objects.add(int(track))
+        for track in remove_tracks:
+            self._known_objects.discard(int(track))
+        floating = sorted((self._lut_movable_tracks | self._born_tracks) - self._known_objects - {int(t) for t in remove_tracks})
+        self._born_tracks -= set(floating) | {int(t) for t in remove_tracks}
+        return floating
 
     # -- host evaluation of the string-keyed parts of generateLabeledPointCloud ---------------------------------------------
     def lower_masks(self, ins_seg_result: Sequence[MaskKpts]):
@@ -325,6 +357,7 @@ class SemanticDSPMap:
             depth = np.ascontiguousarray(depth)
         self._keep = [depth]
         masks = self.lower_masks(ins_seg_result)
+        remove_tracks = list(remove_tracks) + self._floating_tracks(ins_seg_result, moves, remove_tracks)
         self.engine.update_raw("update", depth.ctypes.data, depth.shape[0], depth.shape[1], depth.strides[0] // 4, masks,
                                camera_position, camera_orientation, moves, remove_tracks, if_get_freespace)
         return self.engine.result_arrays(copy_result)

@@ -57,6 +57,8 @@ def test_oracle_reproduces_the_reference_bit_for_bit(name):
 @pytest.mark.parametrize("name", sorted(G.SCENARIOS))
 def test_live_reference_reproduces_the_committed_fixtures(name):
     spec = G.SCENARIOS[name]
+    if spec["setting"] == 0 and not os.environ.get("DSPMAP_SLOW_TESTS"):
+        pytest.skip("SETTING 0 keeps a 3.2 GB particle array: the live re-run takes over a minute (set DSPMAP_SLOW_TESTS=1)")
     if not have_ref(spec["setting"]):
         pytest.skip("oracle/_ref/libdsp_ref_s%d.so not built (needs /root/reference at build time)" % spec["setting"])
     want = load(name)
