@@ -15,6 +15,9 @@
 #include <cstdlib>
 #include <ctime>
 #include <atomic>
+#if defined(__AVX2__)
+#include <immintrin.h>
+#endif
 #include <condition_variable>
 #include <functional>
 #include <memory>
@@ -74,11 +77,11 @@ void inverse4f(const float m[16], float o[16]) {
 // image and of every mask are independent).  Workers sleep on a condition variable between frames.
 class StagePool {
 public:
-    explicit StagePool(int n_workers) {
+    explicit StagePool(int n_workers, int spin_us = 200) : spin_us_(spin_us) {
         for (int i = 0; i < n_workers; ++i) workers_.emplace_back([this] { loop(); });
     }
     ~StagePool() {
-        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        { std::lock_guard<std::mutex> lk(mu_); stop_.store(true); }
         cv_.notify_all();
         for (auto& t : workers_) t.join();
     }
@@ -87,44 +90,59 @@ public:
         if (n <= 0) return;
         {
             std::lock_guard<std::mutex> lk(mu_);
-            fn_ = &fn; n_ = n; next_.store(0); pending_.store(n); ++epoch_;
+            fn_ = &fn; n_.store(n); next_.store(0); pending_.store(n);
+            epoch_.fetch_add(1, std::memory_order_release);
         }
-        cv_.notify_all();
+        if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
         work();
-        std::unique_lock<std::mutex> lk(mu_);
-        done_cv_.wait(lk, [this] { return pending_.load() == 0; });
+        while (pending_.load(std::memory_order_acquire) != 0) cpu_relax();   // the tail of a staging copy is microseconds
         fn_ = nullptr;
     }
 
 private:
+    static void cpu_relax() {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
     void work() {
         for (;;) {
             const int i = next_.fetch_add(1);
-            if (i >= n_) break;
+            if (i >= n_.load(std::memory_order_acquire)) break;
             (*fn_)(i);
-            if (pending_.fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk(mu_); done_cv_.notify_all(); }
+            pending_.fetch_sub(1, std::memory_order_acq_rel);
         }
     }
+    // A frame stages twice within ~0.1 ms (depth, then the masks under the sweep): after a job the workers keep polling for
+    // the next one for a short while before they block on the condition variable, so the second job starts without a wake-up.
     void loop() {
         uint64_t seen = 0;
         for (;;) {
-            {
-                std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return stop_ || epoch_ != seen; });
-                if (stop_) return;
-                seen = epoch_;
+            const auto t0 = std::chrono::steady_clock::now();
+            int spins = 0;
+            while (!stop_.load(std::memory_order_acquire) && epoch_.load(std::memory_order_acquire) == seen) {
+                cpu_relax();
+                if ((++spins & 255) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(spin_us_)) {
+                    std::unique_lock<std::mutex> lk(mu_);
+                    sleepers_.fetch_add(1, std::memory_order_acq_rel);
+                    cv_.wait(lk, [&] { return stop_.load() || epoch_.load(std::memory_order_acquire) != seen; });
+                    sleepers_.fetch_sub(1, std::memory_order_acq_rel);
+                    break;
+                }
             }
+            if (stop_.load(std::memory_order_acquire)) return;
+            seen = epoch_.load(std::memory_order_acquire);   // fn_ / n_ were written before the epoch was released
             work();
         }
     }
     std::vector<std::thread> workers_;
     std::mutex mu_;
-    std::condition_variable cv_, done_cv_;
+    std::condition_variable cv_;
     const std::function<void(int)>* fn_ = nullptr;
-    int n_ = 0;
-    std::atomic<int> next_{0}, pending_{0};
-    uint64_t epoch_ = 0;
-    bool stop_ = false;
+    std::atomic<int> n_{0}, next_{0}, pending_{0}, sleepers_{0};
+    std::atomic<uint64_t> epoch_{0};
+    std::atomic<bool> stop_{false};
+    const int spin_us_;
 };
 
 template <typename T>
@@ -253,6 +271,7 @@ struct dspmap {
     PinBuf<uint8_t> hr_label, hr_rgb;
     PinBuf<int8_t> hr_state;
     bool host_result_valid = false;
+    double t_frame_begin = 0, trace_issue_ms = 0, trace_wait_ms = 0;   // DSPMAP_TRACE
     std::unique_ptr<StagePool> stage_pool;
 
     Counters last{};
@@ -631,6 +650,12 @@ int dspmap::run_moves(const dspmap_object_move* moves, int n_moves, const int32_
     return DSPMAP_OK;
 }
 
+static double host_now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 // SemanticDSPMap::update (semantic_dsp_map.h:170-251) -> subObjectLevelUpdate (:576-955)
 int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const dspmap_mask* masks, int n_masks, const double pos[3],
                   const double quat[4], const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove,
@@ -647,6 +672,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
         if (n_cand >= (1ll << 24)) return fail(DSPMAP_ERR_UNSUPPORTED, "nb_ptc_num_per_point = %d gives %lld birth candidates per frame (limit 2^24)", nb_eff, n_cand);
     }
     host_result_valid = false;
+    t_frame_begin = host_now_ms();
     T += 1;                                                       // :173
     f.T = T;
     apply_params();
@@ -853,7 +879,13 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     CU_TRY(this, cudaMemcpyAsync(p_stamps.p + (f.NX + f.NY + f.NZ), d_pix_offset.p + npix, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     CU_TRY(this, cudaMemcpyAsync(p_stamps.p + (f.NX + f.NY + f.NZ) + 1, d_counts, (size_t)MAX_RANKS * COMM_COUNTS * 4, cudaMemcpyDeviceToHost, stream));
     CU_TRY(this, cudaGetLastError());
+    static const bool trace_frame = getenv("DSPMAP_TRACE") != nullptr;
+    const double t_issued = trace_frame ? host_now_ms() : 0.0;
     CU_TRY(this, cudaStreamSynchronize(stream));
+    if (trace_frame) {   // host time to issue the frame's launches vs time left waiting for the device afterwards
+        trace_issue_ms += t_issued - t_frame_begin; trace_wait_ms += host_now_ms() - t_issued;
+        if ((T % 16) == 0) { fprintf(stderr, "[dspmap] frame %u: issue %.3f ms, wait %.3f ms (mean of 16)\n", T, trace_issue_ms / 16, trace_wait_ms / 16); trace_issue_ms = trace_wait_ms = 0; }
+    }
     last = *p_cnt.p;
 
     stats.time_stamp = T;
@@ -1019,11 +1051,6 @@ int dspmap_update_device(dspmap_t* h, const float* d_depth, int32_t rows, int32_
     return h->frame(d_depth, rows, cols, row_stride, masks, n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove, want_freespace, 0);
 }
 
-static double host_now_ms() {
-    timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
-}
 
 int dspmap_update(dspmap_t* h, const float* depth, int32_t rows, int32_t cols, int32_t row_stride, const dspmap_mask* masks,
                   int32_t n_masks, const double position[3], const double orientation_wxyz[4], const dspmap_object_move* moves,
@@ -1049,26 +1076,54 @@ int dspmap_update(dspmap_t* h, const float* depth, int32_t rows, int32_t cols, i
     }
     if (!h->stage_pool) {
         const char* env = getenv("DSPMAP_STAGE_THREADS");
-        const int want = env ? atoi(env) : 2;   // helper threads for the staging copies; 0 = stage on the calling thread
-        h->stage_pool.reset(new StagePool(std::max(0, std::min(want, (int)std::thread::hardware_concurrency() - 1))));
+        const int want = env ? atoi(env) : 6;   // helper threads for the staging copies; 0 = stage on the calling thread
+        const char* spin = getenv("DSPMAP_STAGE_SPIN_US");   // how long an idle helper polls for the next job before it sleeps
+        h->stage_pool.reset(new StagePool(std::max(0, std::min(want, (int)std::thread::hardware_concurrency() - 1)), spin ? atoi(spin) : 200));
     }
+    // drow[j] = srow[2 j]: the BOOST_MODE column decimation of manualResize (pointcloud_tools.h:1104-1133)
+    auto take_even = [](auto* drow, const auto* srow, int n) {
+        int j = 0;
+#if defined(__AVX2__)
+        if constexpr (sizeof(*drow) == 1) {
+            const __m256i lo = _mm256_set1_epi16(0x00ff);
+            for (; j + 32 <= n; j += 32) {
+                const __m256i a = _mm256_and_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(srow + 2 * j)), lo);
+                const __m256i b = _mm256_and_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(srow + 2 * j + 32)), lo);
+                const __m256i p = _mm256_permute4x64_epi64(_mm256_packus_epi16(a, b), 0xd8);
+                _mm256_storeu_si256(reinterpret_cast<__m256i*>(drow + j), p);
+            }
+        } else if constexpr (sizeof(*drow) == 4) {
+            const __m256i idx = _mm256_setr_epi32(0, 2, 4, 6, 0, 2, 4, 6);
+            for (; j + 8 <= n; j += 8) {
+                const __m256 a = _mm256_permutevar8x32_ps(_mm256_loadu_ps(reinterpret_cast<const float*>(srow + 2 * j)), idx);
+                const __m256 b = _mm256_permutevar8x32_ps(_mm256_loadu_ps(reinterpret_cast<const float*>(srow + 2 * j + 8)), idx);
+                _mm256_storeu_ps(reinterpret_cast<float*>(drow + j), _mm256_permute2f128_ps(a, b, 0x20));
+            }
+        }
+#endif
+        for (; j < n; ++j) drow[j] = srow[2 * j];
+    };
     auto stage_rows = [&](auto* dst, const auto* src, int src_stride, int r0, int r1) {
         for (int i = r0; i < r1; ++i) {
             const int si = f.boost ? std::min((int)((float)i * 2.0f), rows - 1) : i;
             const auto* srow = src + (size_t)si * src_stride;
             auto* drow = dst + (size_t)i * scols;
-            if (f.boost && 2 * scols <= cols) for (int j = 0; j < scols; ++j) drow[j] = srow[2 * j];   // src = 2j exactly: vectorisable
+            if (f.boost && 2 * scols <= cols) take_even(drow, srow, scols);                             // src = 2j exactly
             else if (f.boost) for (int j = 0; j < scols; ++j) drow[j] = srow[src_col[j]];
             else memcpy(drow, srow, (size_t)scols * sizeof(*dst));
         }
     };
     // depth first: the sweep and the pixel lists need nothing else, so the GPU starts while the masks are still being staged
-    const int depth_parts = 4;
+    const int depth_parts = 8;
     h->stage_pool->run(depth_parts, [&](int t) { stage_rows(h->p_depth.p, depth, row_stride, srows * t / depth_parts, srows * (t + 1) / depth_parts); });
     CU_TRY(h, cudaMemcpyAsync(h->d_depth_in.p, h->p_depth.p, npix * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     const std::function<int(dspmap_mask*)> late_masks = [&](dspmap_mask* dmv) -> int {
         if (!n_masks) return DSPMAP_OK;
-        h->stage_pool->run(n_masks, [&](int m) { stage_rows(h->p_masks.p + (size_t)m * npix, masks[m].data, masks[m].row_stride, 0, srows); });
+        const int parts = 2;   // row blocks per mask: enough tasks to keep every helper busy
+        h->stage_pool->run(n_masks * parts, [&](int t) {
+            const int m = t / parts, b = t % parts;
+            stage_rows(h->p_masks.p + (size_t)m * npix, masks[m].data, masks[m].row_stride, srows * b / parts, srows * (b + 1) / parts);
+        });
         for (int m = 0; m < n_masks; ++m) { dmv[m].data = h->d_mask_in.p + (size_t)m * npix; dmv[m].row_stride = scols; }
         CU_TRY(h, cudaMemcpyAsync(h->d_mask_in.p, h->p_masks.p, npix * n_masks, cudaMemcpyHostToDevice, h->stream));
         return DSPMAP_OK;
