@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import argparse
 import ctypes as C
+import gc
 import json
 import os
 import subprocess
@@ -205,6 +206,8 @@ def main():
     for k in range(args.warmup):
         step_device(k)
     barrier()
+    gc.collect()
+    gc.disable()          # a cyclic-GC pass inside a 50 ms timed region would be a tenth of it; re-enabled after the last timed step
     sampler = ClockSampler(local)
     sampler.start()
     l0 = launches()
@@ -242,6 +245,7 @@ def main():
     e3.record(stream)
     barrier()
     ms_e2e = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
+    gc.enable()
 
     t = torch.tensor([ms_device, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:

@@ -844,7 +844,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
         CU_TRY(this, cudaEventRecord(ev_join[1], side_stream));
     }
     // ---- U3 weight update --------------------------------------------------------------------------------------------
-    ++launches; k_ck<<<sm_count * 2, 1024, lut_bytes, stream>>>(fp, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_pix_offset.p, d_vis_pos.p, d_vis_meta.p, cv, ck_seg_stride);
+    ++launches; k_ck<<<sm_count, 1024, lut_bytes, stream>>>(fp, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_pix_offset.p, d_vis_pos.p, d_vis_meta.p, cv, ck_seg_stride, d_cnt.p);
     barrier();   // sharded map: every rank's ck image is complete
     ++launches; k_weight_update<<<sm_count * 2, 1024, lut_bytes, stream>>>(fp, d_pix_offset.p + npix, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_ck, d_csr_idx.p,
                                                              d_vis_pix.p, d_vis_pos.p, d_vis_meta.p, st);
@@ -922,11 +922,14 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
 
 int dspmap::fetch_result_to_host() {
     if (host_result_valid) return DSPMAP_OK;
+    // pinned result buffers grow in big steps (cudaMallocHost takes milliseconds: not something to do every few frames)
+    const size_t grain = (size_t)1 << 18;
     const size_t n = result_n, nf = fp.want_free ? result_nf : 0;
-    CU_TRY(this, hr_idx.reserve(std::max<size_t>(n, 1))); CU_TRY(this, hr_xyz.reserve(std::max<size_t>(3 * n, 1)));
-    CU_TRY(this, hr_w.reserve(std::max<size_t>(n, 1))); CU_TRY(this, hr_track.reserve(std::max<size_t>(n, 1)));
-    CU_TRY(this, hr_label.reserve(std::max<size_t>(n, 1))); CU_TRY(this, hr_state.reserve(std::max<size_t>(n, 1)));
-    CU_TRY(this, hr_rgb.reserve(std::max<size_t>(3 * n, 1)));
+    const size_t n_cap = (std::max<size_t>(n, 1) + grain - 1) / grain * grain;
+    CU_TRY(this, hr_idx.reserve(n_cap)); CU_TRY(this, hr_xyz.reserve(3 * n_cap));
+    CU_TRY(this, hr_w.reserve(n_cap)); CU_TRY(this, hr_track.reserve(n_cap));
+    CU_TRY(this, hr_label.reserve(n_cap)); CU_TRY(this, hr_state.reserve(n_cap));
+    CU_TRY(this, hr_rgb.reserve(3 * n_cap));
     if (n) {
         CU_TRY(this, cudaMemcpyAsync(hr_idx.p, r_idx, n * 4, cudaMemcpyDeviceToHost, stream));
         CU_TRY(this, cudaMemcpyAsync(hr_xyz.p, r_xyz, n * 12, cudaMemcpyDeviceToHost, stream));
@@ -938,7 +941,8 @@ int dspmap::fetch_result_to_host() {
         else memset(hr_rgb.p, 0, 3 * n);
     }
     if (nf) {
-        CU_TRY(this, hr_free_idx.reserve(nf)); CU_TRY(this, hr_free_xyz.reserve(3 * nf));
+        const size_t nf_cap = (nf + grain - 1) / grain * grain;
+        CU_TRY(this, hr_free_idx.reserve(nf_cap)); CU_TRY(this, hr_free_xyz.reserve(3 * nf_cap));
         CU_TRY(this, cudaMemcpyAsync(hr_free_idx.p, r_free_idx, nf * 4, cudaMemcpyDeviceToHost, stream));
         CU_TRY(this, cudaMemcpyAsync(hr_free_xyz.p, r_free_xyz, nf * 12, cudaMemcpyDeviceToHost, stream));
     }

@@ -33,6 +33,7 @@ struct Counters {
     uint32_t n_sweep_work;     // swept voxels with live slots (work list of the slot pass)
     uint32_t n_occ_work;       // voxels whose occupancy needs the slot records
     uint32_t comm_errors;      // barriers that timed out (sharded maps)
+    uint32_t ck_next;          // k_ck: next 32-pixel segment to hand out (dynamic work distribution)
     uint32_t mov_out[8];       // moved particles sent to each destination rank this frame
 };
 
@@ -542,21 +543,50 @@ __device__ __forceinline__ void stage_lut(const float* __restrict__ lut) {
     __syncthreads();
 }
 
+// one entry of the list-ordered particle copies (k_gather_visible)
+struct VisElem { float4 p; uint32_t m; };
+__device__ __forceinline__ VisElem ld_vis(const float4* __restrict__ vis_pos, const uint32_t* __restrict__ vis_meta, uint32_t k) {
+    VisElem e;
+    e.p = vis_pos[k];
+    e.m = vis_meta[k];
+    return e;
+}
+
+// The sum of one observation pixel runs over its window row by row and, inside a row, over a contiguous range of the
+// list-ordered particle copies: a strictly sequential chain (the float sum must keep the reference's order), one scattered
+// 16-byte load per step and lane.  Pixels near the horizon have 4-5x the average number of steps, so a warp's time is
+// (steps) x (latency of one step), and the kernel's time is its slowest warp's.  The loads are therefore software-pipelined:
+// list entries two steps ahead, the first two entries of the NEXT row while the current row is processed, and the row
+// offsets two rows ahead - a step no longer waits for L2.
 template <bool FAST>
 __device__ __forceinline__ float ck_pixel(const FrameParams& f, const float4 o, const uint32_t otrack, int i, int j,
                                           const uint32_t* __restrict__ offset, const float4* __restrict__ vis_pos,
                                           const uint32_t* __restrict__ vis_meta) {
     const InvDiv sigma(o.w);
     const int r = f.win_r;
-    const int j0 = max(j - r, 0), j1 = min(j + r, f.W - 1);
+    const int j0 = max(j - r, 0), j1 = min(j + r, f.W - 1) + 1;
+    const int i0 = max(i - r, 0), i1 = min(i + r, f.H - 1);
     float acc = 0.f;
-    for (int ni = max(i - r, 0); ni <= min(i + r, f.H - 1); ++ni) {
-        const uint32_t kb = offset[ni * f.W + j0], ke = offset[ni * f.W + j1 + 1];
+    uint32_t kb = offset[i0 * f.W + j0], ke = offset[i0 * f.W + j1];
+    uint32_t kbn = 0, ken = 0;
+    if (i0 < i1) { kbn = offset[(i0 + 1) * f.W + j0]; ken = offset[(i0 + 1) * f.W + j1]; }
+    VisElem e0{}, e1{};
+    if (kb < ke) e0 = ld_vis(vis_pos, vis_meta, kb);
+    if (kb + 1 < ke) e1 = ld_vis(vis_pos, vis_meta, kb + 1);
+    for (int ni = i0; ni <= i1; ++ni) {
+        VisElem n0{}, n1{};
+        if (kbn < ken) n0 = ld_vis(vis_pos, vis_meta, kbn);
+        if (kbn + 1 < ken) n1 = ld_vis(vis_pos, vis_meta, kbn + 1);
+        uint32_t kbnn = 0, kenn = 0;
+        if (ni + 2 <= i1) { kbnn = offset[(ni + 2) * f.W + j0]; kenn = offset[(ni + 2) * f.W + j1]; }
         for (uint32_t k = kb; k < ke; ++k) {
-            const uint32_t pm = vis_meta[k];
+            VisElem nx{};
+            if (k + 2 < ke) nx = ld_vis(vis_pos, vis_meta, k + 2);
+            const uint32_t pm = e0.m;
+            const float4 p = e0.p;
+            e0 = e1; e1 = nx;
             const bool same = (pm & 0xffffu) == otrack;
             if (f.indep && !same) continue;
-            const float4 p = vis_pos[k];
             float gk = query_pdf<FAST>(p.x, o.x, sigma) * query_pdf<FAST>(p.y, o.y, sigma) * query_pdf<FAST>(p.z, o.z, sigma);
             if (!f.indep) {
                 gk *= forgetting_factor(f, pm >> 16);
@@ -564,22 +594,28 @@ __device__ __forceinline__ float ck_pixel(const FrameParams& f, const float4 o, 
             }
             acc += p.w * gk;
         }
+        e0 = n0; e1 = n1;
+        kb = kbn; ke = ken; kbn = kbnn; ken = kenn;
     }
     return acc;
 }
 
-__global__ void __launch_bounds__(1024, 2)
+__global__ void __launch_bounds__(1024, 1)
 k_ck(const __grid_constant__ FrameParams f, const float* __restrict__ lut, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta,
      const uint32_t* __restrict__ offset, const float4* __restrict__ vis_pos, const uint32_t* __restrict__ vis_meta,
-     CommView cv, uint32_t seg_stride) {
+     CommView cv, uint32_t seg_stride, Counters* __restrict__ cnt) {
     stage_lut(lut);
     const int npix = f.W * f.H;
     const uint32_t n_seg = (uint32_t)(npix + 31) / 32;
-    // a warp takes 32-pixel segments w, w + n_warps, ...; the index maps to an image segment through a stride coprime
-    // with the segment count, so the (very uneven) per-pixel work of neighbouring image rows spreads over all SMs
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    // sharded map: rank r evaluates every size-th segment and writes its values into every rank's ck image
-    for (uint32_t t = warp * (uint32_t)cv.size + (uint32_t)cv.rank; t < n_seg; t += n_warps * (uint32_t)cv.size) {
+    // Warps draw 32-pixel segments from a shared counter (the per-pixel work is very uneven).  The drawn index maps to an
+    // image segment through a stride coprime with the segment count, so neighbouring image rows spread over all SMs.
+    // Sharded map: rank r evaluates every size-th segment and writes its values into every rank's ck image.
+    for (;;) {
+        uint32_t c = 0;
+        if (lane_id() == 0) c = atomicAdd(&cnt->ck_next, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        const uint32_t t = c * (uint32_t)cv.size + (uint32_t)cv.rank;
+        if (t >= n_seg) break;
         const int q = (int)((uint32_t)(((uint64_t)t * seg_stride) % n_seg) * 32u + lane_id());
         if (q >= npix) continue;
         const uint32_t om = cloud_meta[q];
