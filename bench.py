@@ -144,6 +144,9 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    # the engine's host staging helpers (pageable -> pinned copies of dspmap_update) poll between jobs: share the host cores
+    # between the ranks of one box instead of letting every rank start its default of six
+    os.environ.setdefault("DSPMAP_STAGE_THREADS", str(max(1, min(6, (os.cpu_count() or 1) // world - 2))))
     from semantic_dsp_map_b200 import BASELINE, Engine, SemanticDSPMap, _capi, connect_shards, make_random_table
     cfg = BASELINE[args.config]
     n_frames = args.warmup + args.steps
