@@ -7,6 +7,7 @@ from .configs import BASELINE, SETTINGS, MapConfig, tiny
 from .labels import LabelTables, ZED2_ROWS
 from .map import Engine, MaskKpts, OccupancyResult, SemanticDSPMap, connect_shards
 from .synth import Frame, Scene, make_random_table
+from . import wire  # noqa: E402,F401
 
 __all__ = ["BASELINE", "SETTINGS", "MapConfig", "tiny", "LabelTables", "ZED2_ROWS", "Engine", "MaskKpts", "OccupancyResult",
            "SemanticDSPMap", "connect_shards", "Frame", "Scene", "make_random_table"]
