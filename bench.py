@@ -110,6 +110,7 @@ def run_reference(args, cfg_name):
     steps, warmup = min(args.steps, 20), min(args.warmup, 5)
     frames = generate_frames(cfg_name, warmup + steps)
     m = oracle_map(cfg, order=0)
+    m.enable_colors()
     m.engine.set_random_table(make_random_table(cfg.seed))
     for fr in frames[:warmup]:
         m.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves, remove_tracks=fr.remove_tracks)
@@ -170,6 +171,7 @@ def main():
         connect_shards(m, gather)
     else:
         m = SemanticDSPMap(cfg, device=local)
+    m.enable_colors()                       # the reference colours every emitted point (getOccupancyResult): so do both arms
     eng = m.engine
     units = 1 if sharded else world          # maps updated per step by the whole job
     eng.set_random_table(make_random_table(cfg.seed))
@@ -244,7 +246,7 @@ def main():
         # results are read where dspmap_get_result leaves them: the handle's pinned host buffers (valid until the next update)
         res = m.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves, remove_tracks=fr.remove_tracks, copy_result=False)
         h2d += fr.depth.nbytes + sum(mk.mask.nbytes for mk in fr.masks)
-        d2h += sum(a.nbytes for a in (res.voxel_index, res.xyz, res.weight_sum, res.track_id, res.label_id, res.state)) + 80
+        d2h += sum(a.nbytes for a in (res.voxel_index, res.xyz, res.weight_sum, res.track_id, res.label_id, res.state, res.rgb)) + 80
     e3.record(stream)
     barrier()
     ms_e2e = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
@@ -313,6 +315,7 @@ def cpu_baseline(cfg_name, frames, warmup=3, steps=12):
     cfg = BASELINE[cfg_name]
     steps = min(steps, len(frames) - warmup)
     m = oracle_map(cfg, order=0)
+    m.enable_colors()
     m.engine.set_random_table(make_random_table(cfg.seed))
     for fr in frames[:warmup]:
         m.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves, remove_tracks=fr.remove_tracks)
