@@ -385,7 +385,8 @@ struct dspmap {
     int run_moves(const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove, bool scan_remove);
     int frame(const float* d_depth, int rows, int cols, int stride, const dspmap_mask* masks, int n_masks, const double pos[3],
               const double quat[4], const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove,
-              int want_free, int pre_decimated, const std::function<int(dspmap_mask*)>* late_masks = nullptr);
+              int want_free, int pre_decimated, const std::function<int(dspmap_mask*)>* late_masks = nullptr,
+              const std::function<int()>* late_depth = nullptr);
     int fetch_result_to_host();
 };
 
@@ -659,7 +660,9 @@ static double host_now_ms() {
 // SemanticDSPMap::update (semantic_dsp_map.h:170-251) -> subObjectLevelUpdate (:576-955)
 int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const dspmap_mask* masks, int n_masks, const double pos[3],
                   const double quat[4], const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove,
-                  int want_free, int pre_decimated, const std::function<int(dspmap_mask*)>* late_masks) {
+                  int want_free, int pre_decimated, const std::function<int(dspmap_mask*)>* late_masks, const std::function<int()>* late_depth) {
+    // late_depth: the depth image is not on the device yet; the callback (host staging + H2D enqueue) runs after the vertex
+    // mask and the object moves - which need the pose only - have been launched, so the GPU works while the host stages.
     // late_masks: the mask images are not on the device yet; the callback (host staging + H2D enqueue) runs after the
     // mask-independent kernels have been launched, so the copy engine and the CPU work under them
     FrameParams& f = fp;
@@ -753,6 +756,8 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     const size_t lut_bytes = PDF_NUM * sizeof(float);
 
     if (profiling) cudaEventRecord(ev[0], stream);
+    const bool depth_kernel = !((pre_decimated || !f.boost) && stride == f.W);
+    if (late_depth && depth_kernel) { const int rc = (*late_depth)(); if (rc != DSPMAP_OK) return rc; late_depth = nullptr; }
     // ---- U2a vertex mask: depends on the pose only, so it runs on the side stream beside the depth copy and the moves ------
     if (f.start_in) {
         const int y0 = std::max(f.vb_lo[1] - 1, 0), y1 = std::min(f.vb_hi[1] + 1, (int)f.NY);
@@ -784,6 +789,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
             if (rc != DSPMAP_OK) return rc;
         }
     }
+    if (late_depth) { const int rc = (*late_depth)(); if (rc != DSPMAP_OK) return rc; }
     if (profiling) cudaEventRecord(ev[2], stream);
     // ---- U2 visibility ---------------------------------------------------------------------------------------------
     if (f.start_in) {
@@ -1117,10 +1123,14 @@ int dspmap_update(dspmap_t* h, const float* depth, int32_t rows, int32_t cols, i
             else memcpy(drow, srow, (size_t)scols * sizeof(*dst));
         }
     };
-    // depth first: the sweep and the pixel lists need nothing else, so the GPU starts while the masks are still being staged
-    const int depth_parts = 8;
-    h->stage_pool->run(depth_parts, [&](int t) { stage_rows(h->p_depth.p, depth, row_stride, srows * t / depth_parts, srows * (t + 1) / depth_parts); });
-    CU_TRY(h, cudaMemcpyAsync(h->d_depth_in.p, h->p_depth.p, npix * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    // depth first: the sweep and the pixel lists need nothing else, so the GPU starts while the masks are still being staged;
+    // and even the depth is staged only after the pose-only work (vertex mask, object moves) has been launched
+    const std::function<int()> late_depth = [&]() -> int {
+        const int depth_parts = 8;
+        h->stage_pool->run(depth_parts, [&](int t) { stage_rows(h->p_depth.p, depth, row_stride, srows * t / depth_parts, srows * (t + 1) / depth_parts); });
+        CU_TRY(h, cudaMemcpyAsync(h->d_depth_in.p, h->p_depth.p, npix * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        return DSPMAP_OK;
+    };
     const std::function<int(dspmap_mask*)> late_masks = [&](dspmap_mask* dmv) -> int {
         if (!n_masks) return DSPMAP_OK;
         const int parts = 2;   // row blocks per mask: enough tasks to keep every helper busy
@@ -1134,7 +1144,7 @@ int dspmap_update(dspmap_t* h, const float* depth, int32_t rows, int32_t cols, i
     };
     const double t_b = trace ? host_now_ms() : 0.0;
     rc = h->frame(h->d_depth_in.p, rows, cols, scols, dm.data(), n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove,
-                  want_freespace, f.boost ? 1 : 0, &late_masks);
+                  want_freespace, f.boost ? 1 : 0, &late_masks, &late_depth);
     if (rc != DSPMAP_OK) return rc;
     const double t_c = trace ? host_now_ms() : 0.0;
     rc = h->fetch_result_to_host();
