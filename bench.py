@@ -96,35 +96,64 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(self.samples)}
 
 
-def run_reference(args, cfg_name):
-    """The reference's own CPU implementation of the path: the oracle in the reference's iteration order (BFS sweep,
-    unordered_set object sets), single thread like the shipped code (semantic_dsp_map.h:749 calls the non-MT BFS)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def cpu_reference(cfg_name):
+    """The CPU implementation the baselines time, as (step(frame) -> seconds, kind, description).
+
+    kind "reference": the reference's OWN hot-path code, compiled from /root/reference/include by oracle/build_ref.sh with the
+    benchmark's grid constants (oracle/_ref/libdsp_ref_sB.so; third-party headers replaced by the stand-ins of oracle/ref_stubs,
+    see oracle/ref_harness.cpp) - available for config B.  kind "port": the oracle (oracle/dsp_oracle.cpp, pinned bit for bit to
+    that build) in the reference's iteration order.  Both are single-threaded like the shipped code
+    (semantic_dsp_map.h:749 calls the non-MT BFS)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from semantic_dsp_map_b200 import BASELINE, make_random_table
-    from oracle_lib import oracle_map
     cfg = BASELINE[cfg_name]
-    # bounded: the CPU path runs at about 1 frame/s on this config
-    steps, warmup = min(args.steps, 20), min(args.warmup, 5)
-    frames = generate_frames(cfg_name, warmup + steps)
+    import ref_lib
+    if cfg_name == "B" and ref_lib.have_ref("B"):
+        import tempfile
+        with tempfile.TemporaryDirectory() as td:
+            csv = os.path.join(td, "object_info.csv")
+            ref_lib.write_label_csv(csv)
+            ref = ref_lib.RefMap(cfg, csv, setting="B", eval_format=False)
+        ref.set_random_table(make_random_table(cfg.seed))
+        ref.set_color_map(np.random.default_rng(256).permutation(256))
+
+        def step(fr):
+            ref.update(fr.depth, fr.masks, fr.position, fr.orientation, False, fr.moves, fr.remove_tracks, fetch=False)
+            return ref.seconds()          # time inside the reference call (input Mats copied like cv_bridge::toCvCopy, then update())
+        return step, "reference", "the reference's own code (oracle/_ref/libdsp_ref_sB.so: unmodified headers, benchmark grid constants, stand-in Eigen/OpenCV/PCL)"
+    from oracle_lib import oracle_map
     m = oracle_map(cfg, order=0)
     m.enable_colors()
     m.engine.set_random_table(make_random_table(cfg.seed))
+
+    def step(fr):
+        t0 = time.perf_counter()
+        m.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves, remove_tracks=fr.remove_tracks)
+        return time.perf_counter() - t0
+    return step, "port", "oracle/dsp_oracle.cpp in the reference's iteration order"
+
+
+def run_reference(args, cfg_name):
+    """The reference's own CPU implementation of the path, single thread like the shipped code."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from semantic_dsp_map_b200 import BASELINE
+    cfg = BASELINE[cfg_name]
+    # bounded: the CPU path runs at about 1-2 frames/s on this config
+    steps, warmup = min(args.steps, 20), min(args.warmup, 5)
+    frames = generate_frames(cfg_name, warmup + steps)
+    step, kind, what = cpu_reference(cfg_name)
     for fr in frames[:warmup]:
-        m.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves, remove_tracks=fr.remove_tracks)
-    t0 = time.perf_counter()
-    for fr in frames[warmup:]:
-        m.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves, remove_tracks=fr.remove_tracks)
-    dt = time.perf_counter() - t0
+        step(fr)
+    dt = sum(step(fr) for fr in frames[warmup:])
     fps = steps / dt
-    sample = f"frames {warmup}..{warmup + steps - 1} of the seeded sequence after {warmup} untimed frames (requested steps={args.steps}, warmup={args.warmup}; bounded)"
+    sample = f"frames {warmup}..{warmup + steps - 1} of the seeded sequence after {warmup} untimed frames (requested steps={args.steps}, warmup={args.warmup}; bounded); {what}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg.name, "grid": "256x64x256 voxels x 8 slots", "image": "1280x720 -> 640x360 internal"},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -308,23 +337,14 @@ def main():
 
 
 def cpu_baseline(cfg_name, frames, warmup=3, steps=12):
-    """The oracle in the reference's own iteration order, one thread, on the first frames of the same sequence."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from semantic_dsp_map_b200 import BASELINE, make_random_table
-    from oracle_lib import oracle_map
-    cfg = BASELINE[cfg_name]
+    """The CPU implementation (see cpu_reference), one thread, on the first frames of the same sequence."""
     steps = min(steps, len(frames) - warmup)
-    m = oracle_map(cfg, order=0)
-    m.enable_colors()
-    m.engine.set_random_table(make_random_table(cfg.seed))
+    step, kind, what = cpu_reference(cfg_name)
     for fr in frames[:warmup]:
-        m.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves, remove_tracks=fr.remove_tracks)
-    t0 = time.perf_counter()
-    for fr in frames[warmup:warmup + steps]:
-        m.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves, remove_tracks=fr.remove_tracks)
-    dt = time.perf_counter() - t0
-    return {"value": steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"frames {warmup}..{warmup + steps - 1} of the same seeded sequence (map still filling; the CPU path slows as it fills)",
+        step(fr)
+    dt = sum(step(fr) for fr in frames[warmup:warmup + steps])
+    return {"value": steps / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"frames {warmup}..{warmup + steps - 1} of the same seeded sequence (map still filling; the CPU path slows as it fills); {what}",
             "host_cores_available": os.cpu_count()}
 
 

@@ -25,7 +25,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-from semantic_dsp_map_b200 import SETTINGS, Scene, _capi, make_random_table  # noqa: E402
+from semantic_dsp_map_b200 import BASELINE, SETTINGS, Scene, _capi, make_random_table  # noqa: E402
 from semantic_dsp_map_b200.labels import ZED2_ROWS  # noqa: E402
 from parity import PARTICLE, POINT  # noqa: E402
 
@@ -53,11 +53,15 @@ SCENARIOS = {
     # SETTING 0 (KITTI-360 preset, settings.h:32-52): static mode (g_consider_instance false), 256^3 voxels x 8 slots (a 3.2 GB
     # particle array), independent filters, display colours of the "#if SETTING == 0" block (label colour for every class)
     "s0_kitti360_static": dict(setting=0, n_frames=2, overrides=dict(zero_center=False), eval_format=False),
+    # BASELINE.json's benchmark configuration (the ZED2 preset with 256 x 64 x 256 voxels x 8 slots) -
+    # the build bench.py times as the CPU baseline
+    "sB_benchmark_config": dict(setting="B", n_frames=2, overrides=dict(), eval_format=False),
 }
 
 
 def scenario_config(spec):
-    return dataclasses.replace(SETTINGS[spec["setting"]], **spec["overrides"])
+    base = BASELINE["B"] if spec["setting"] == "B" else SETTINGS[spec["setting"]]
+    return dataclasses.replace(base, **spec["overrides"])
 
 
 def scenario_frame(scene, spec, t):
@@ -186,7 +190,7 @@ def main():
     from ref_lib import have_ref, run_scenario_subprocess
     for name, spec in SCENARIOS.items():
         if not have_ref(spec["setting"]):
-            print(name, "skipped: oracle/_ref/libdsp_ref_s%d.so not built" % spec["setting"])
+            print(name, "skipped: oracle/_ref/libdsp_ref_s%s.so not built" % spec["setting"])
             continue
         out = run_scenario_subprocess("make_ref_golden", "run_reference", name)
         path = os.path.join(HERE, "ref_" + name + ".npz")

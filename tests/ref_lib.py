@@ -91,7 +91,7 @@ class RefMap:
         assert a.size == 256
         self.lib.ref_set_color_map(a.ctypes.data)
 
-    def update(self, depth, masks, position, orientation, if_get_freespace=False, moves=(), remove_tracks=()):
+    def update(self, depth, masks, position, orientation, if_get_freespace=False, moves=(), remove_tracks=(), fetch=True):
         depth = np.ascontiguousarray(depth, np.float32)
         keep = []
         marr = (RefMask * max(len(masks), 1))()
@@ -114,7 +114,7 @@ class RefMap:
         rc = self.lib.ref_update(depth.ctypes.data, depth.shape[0], depth.shape[1], depth.strides[0] // 4, marr, len(masks), pos, quat, mv, len(moves),
                                  rm, len(remove_tracks), int(bool(if_get_freespace)))
         assert rc == 0
-        return self.clouds()
+        return self.clouds() if fetch else None
 
     def clouds(self):
         out = {}

@@ -60,7 +60,7 @@ def test_live_reference_reproduces_the_committed_fixtures(name):
     if spec["setting"] == 0 and not os.environ.get("DSPMAP_SLOW_TESTS"):
         pytest.skip("SETTING 0 keeps a 3.2 GB particle array: the live re-run takes over a minute (set DSPMAP_SLOW_TESTS=1)")
     if not have_ref(spec["setting"]):
-        pytest.skip("oracle/_ref/libdsp_ref_s%d.so not built (needs /root/reference at build time)" % spec["setting"])
+        pytest.skip("oracle/_ref/libdsp_ref_s%s.so not built (needs /root/reference at build time)" % spec["setting"])
     want = load(name)
     got = run_scenario_subprocess("make_ref_golden", "run_reference", name)
     for k in want.files:
