@@ -96,6 +96,19 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(self.samples)}
 
 
+class _StdoutToStderr:
+    """The reference chats on std::cout (setters, warnings): keep this process's stdout to the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def cpu_reference(cfg_name):
     """The CPU implementation the baselines time, as (step(frame) -> seconds, kind, description).
 
@@ -110,15 +123,16 @@ def cpu_reference(cfg_name):
     import ref_lib
     if cfg_name == "B" and ref_lib.have_ref("B"):
         import tempfile
-        with tempfile.TemporaryDirectory() as td:
+        with tempfile.TemporaryDirectory() as td, _StdoutToStderr():
             csv = os.path.join(td, "object_info.csv")
             ref_lib.write_label_csv(csv)
             ref = ref_lib.RefMap(cfg, csv, setting="B", eval_format=False)
-        ref.set_random_table(make_random_table(cfg.seed))
-        ref.set_color_map(np.random.default_rng(256).permutation(256))
+            ref.set_random_table(make_random_table(cfg.seed))
+            ref.set_color_map(np.random.default_rng(256).permutation(256))
 
         def step(fr):
-            ref.update(fr.depth, fr.masks, fr.position, fr.orientation, False, fr.moves, fr.remove_tracks, fetch=False)
+            with _StdoutToStderr():
+                ref.update(fr.depth, fr.masks, fr.position, fr.orientation, False, fr.moves, fr.remove_tracks, fetch=False)
             return ref.seconds()          # time inside the reference call (input Mats copied like cv_bridge::toCvCopy, then update())
         return step, "reference", "the reference's own code (oracle/_ref/libdsp_ref_sB.so: unmodified headers, benchmark grid constants, stand-in Eigen/OpenCV/PCL)"
     from oracle_lib import oracle_map
