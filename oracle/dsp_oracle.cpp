@@ -256,7 +256,7 @@ struct Oracle {
     uint64_t start_vertex_outside = 0;
     dspmap_colors colors{};          // orc_set_colors: colouring of the occupied list (semantic_dsp_map.h:1274-1351)
     std::vector<uint8_t> out_rgb;
-    bool carry_undefined_label = false;  // orc_set_undefined_label_carry: see occupancy()
+    bool carry_undefined_label = true;   // orc_set_undefined_label_carry: see occupancy()
     bool invalid_sigma_set = false;  // orc_set_invalid_sigma: see project()
     float invalid_sigma_value = 0.f;
     bool diagnostics = false;  // the sweep-set check costs a full pass over the map: off when the oracle is being timed
@@ -1014,10 +1014,11 @@ struct Oracle {
             const size_t s = (size_t)v << Pb;
             float wsum, gsum = 0.f;
             // DEFINED UB: label/track are uninitialised out-params in the reference when no particle
-            // enters the histogram (semantic_dsp_map.h:1245-1246); defined as 0 here.  A compiled reference
-            // keeps the two variables in one place across loop iterations, so what it actually emits is the
-            // value the most recent voxel assigned (an unknown voxel assigns 0, operations.h:402-408);
-            // orc_set_undefined_label_carry reproduces that for the pin against oracle/_ref.
+            // enters the histogram (semantic_dsp_map.h:1245-1246).  A compiled reference keeps the two
+            // variables in one place across loop iterations, so what it actually emits is the value the most
+            // recent voxel in storage order assigned (an unknown voxel assigns 0, operations.h:402-408; the
+            // very first voxel starts from 0).  That is the definition here and in the engine (verified
+            // against oracle/_ref); orc_set_undefined_label_carry(0) gives plain zeros instead.
             uint8_t label = carry_undefined_label ? carried_label : 0;
             uint16_t track = carry_undefined_label ? carried_track : 0;
             int state;

@@ -981,6 +981,7 @@ constexpr int OCC_TILE = OCC_BLOCK * OCC_VPT;
 constexpr int MAX_P = 16;
 // state byte: bits 0..1 = state + 1 (0 unknown, 1 free, 2 occupied, 3 guessed occupied), bit 2 = holds movable particles
 constexpr uint32_t VS_MOVABLE = 4u;
+constexpr uint32_t VS_ASSIGNS = 8u;     // the voxel's label histogram had a positive entry: it assigned (label, track), res_tl holds them
 
 struct ResultArrays {
     uint32_t* voxel_index; float* xyz; float* weight_sum; uint16_t* track_id; uint8_t* label_id; int8_t* state;
@@ -1214,7 +1215,10 @@ k_occ_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* __r
                 else if (gs >= OCC_INIT_WEIGHT) state = 2;
                 else state = 0;
                 sb = (uint32_t)(state + 1);
-                if (state > 0) { sc.res_w[g_v] = ws; sc.res_tl[g_v] = best_w > 0.f ? best_tl : 0u; atomicAdd(tile_cnt + 0, 1u); }
+                // label / track are out-parameters the reference assigns only when the histogram has a positive entry
+                // (operations.h:439-446); otherwise the caller's variables keep what an earlier voxel left (see k_occ_emit)
+                if (best_w > 0.f) { sb |= VS_ASSIGNS; sc.res_tl[g_v] = best_tl; }
+                if (state > 0) { sc.res_w[g_v] = ws; atomicAdd(tile_cnt + 0, 1u); }
                 else if (f.want_free) atomicAdd(tile_cnt + 1, 1u);
                 n_nonempty += (b_nonvac & gmask) != 0;
             }
@@ -1309,7 +1313,22 @@ k_occ_emit(const __grid_constant__ FrameParams f, Store st, OccScratch sc, Resul
             if (f.zero_center) { p0 = p0 - f.cam[0]; p1 = p1 - f.cam[1]; p2 = p2 - f.cam[2]; }
             if (is_occ) {
                 const uint32_t pos = pos_occ++;
-                const uint32_t tl = sc.res_tl[v];
+                // getOccupancyResult declares label / track once per loop iteration WITHOUT initialising them
+                // (semantic_dsp_map.h:1245-1246) and determineIfVoxelOccupied leaves them untouched when every particle of the
+                // voxel was pruned in the same call: a compiled reference then emits what the most recent voxel in storage
+                // order assigned - an unknown voxel assigns (0, 0) (operations.h:402-408), a voxel with a positive histogram
+                // entry its arg-max.  Rare (a handful of voxels per frame at low thresholds): walk back over the state bytes.
+                // A sharded map does not look across its slab boundary (defined as (0, 0) there, like the very first voxel).
+                uint32_t tl = 0;
+                if (((sb4 >> (8 * u)) & VS_ASSIGNS) != 0) tl = sc.res_tl[v];
+                else {
+                    for (uint32_t b = v; b > v_lo;) {
+                        --b;
+                        const uint32_t sbb = sc.vstate[b - v_lo];
+                        if ((sbb & 3u) == 0u) break;                                 // unknown voxel: (0, 0)
+                        if (sbb & VS_ASSIGNS) { tl = sc.res_tl[b]; break; }
+                    }
+                }
                 out.voxel_index[pos] = v;
                 out.xyz[3 * (size_t)pos + 0] = p0; out.xyz[3 * (size_t)pos + 1] = p1; out.xyz[3 * (size_t)pos + 2] = p2;
                 out.weight_sum[pos] = sc.res_w[v];

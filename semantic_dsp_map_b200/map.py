@@ -56,14 +56,18 @@ _memview.argtypes = [C.c_void_p, C.c_ssize_t, C.c_int]
 
 
 def _as_array(ptr, count, dtype, shape=None, copy=True):
+    """count entries of `dtype` (rows of shape[1] entries when `shape` is given) at address `ptr`, as a numpy view or copy."""
+    width = shape[1] if shape else 1
     if count == 0 or not ptr:
-        return np.zeros((0,) + tuple(shape[1:]) if shape else (0,), dtype)
-    n = count * (int(np.prod(shape[1:])) if shape else 1)
-    buf = _memview(ptr, n * np.dtype(dtype).itemsize, 0x100)   # PyBUF_READ
-    a = np.frombuffer(buf, dtype=dtype, count=n)
+        return np.zeros((0, width) if shape else (0,), dtype)
+    n = count * width
+    a = np.frombuffer(_memview(ptr, n * _ITEMSIZE[dtype], 0x100), dtype, n)   # 0x100 = PyBUF_READ
     if copy:
         a = a.copy()
-    return a.reshape((count,) + tuple(shape[1:])) if shape else a
+    return a.reshape(count, width) if shape else a
+
+
+_ITEMSIZE = {np.uint32: 4, np.float32: 4, np.uint16: 2, np.uint8: 1, np.int8: 1}
 
 
 class Engine:

@@ -158,9 +158,6 @@ def run_oracle(name, move_orders=None, order=0):
     # sigma (semantic_dsp_map.h:1047).  In oracle/_ref's build that stack slot reads 0 when the depth-noise model is on and
     # 0.1 when it is off; the oracle takes the value as a parameter so that everything else is compared bit for bit.
     orc.engine.set_invalid_sigma(0.0 if cfg.consider_depth_noise else 0.1)
-    # likewise label / track of an occupied voxel with an empty histogram are uninitialised out-params
-    # (semantic_dsp_map.h:1245-1246): a compiled reference emits what the previous voxel left there
-    orc.engine.set_undefined_label_carry(True)
     orc.setVisualizeOptions(cfg.zero_center, spec["eval_format"])
     orc.enable_colors(label_bgr=csv_colours(), instance_map=colour_permutation())
     scene = Scene(cfg)
