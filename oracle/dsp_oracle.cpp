@@ -571,7 +571,8 @@ struct Oracle {
                 for (int r = 0; r < 3; ++r) pg[r] = ((R[r * 3 + 0] * pc[0] + R[r * 3 + 1] * pc[1]) + R[r * 3 + 2] * pc[2]) + pos[r];
 
                 // sigma, :285-289.  DEFINED UB: the bbox-gated background branch (:256-272) leaves sigma
-                // uninitialised in the reference; the oracle assigns the noise model there too.
+                // uninitialised in the reference; the oracle assigns the noise model there too (a compiled reference
+                // reads the same stack slot as for invalid pixels: orc_set_invalid_sigma covers both sites).
                 const float sigma = prm.consider_depth_noise ? (prm.depth_noise_zero_order + prm.depth_noise_first_order * d) : 0.1f;
 
                 if (cfg.zed2_filters && cfg.consider_instance && inst < max_movable) {  // :254-273
@@ -579,7 +580,7 @@ struct Oracle {
                     const double x0 = bmin[0][inst], x1 = bmax[0][inst], y0 = bmin[1][inst], y1 = bmax[1][inst], z0 = bmin[2][inst], z1 = bmax[2][inst];
                     if (pg[0] < x0 || pg[0] > x1 || pg[1] < y0 || pg[1] > y1 || pg[2] < z0 || pg[2] > z1) {
                         pt.x = (float)pg[0]; pt.y = (float)pg[1]; pt.z = (float)pg[2];
-                        pt.sigma = sigma; pt.label_id = 0; pt.track_id = 65535; pt.is_valid = 1;
+                        pt.sigma = invalid_sigma_set ? invalid_sigma_value : sigma; pt.label_id = 0; pt.track_id = 65535; pt.is_valid = 1;
                         cloud[(size_t)i * W + j] = pt; ++n_valid; continue;
                     }
                 }

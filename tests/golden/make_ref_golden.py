@@ -50,6 +50,10 @@ SCENARIOS = {
                                         overrides=dict(zero_center=False, nb_ptc_num_per_point=3, use_independent_filter=True)),
     # SETTING 2 (Virtual KITTI 2 preset, settings.h:79-98): no BOOST_MODE, 11x11 update window, 8 slots, no ZED2 filters
     "s2_vkitti2": dict(setting=2, n_frames=3, overrides=dict(zero_center=False), eval_format=True),
+    # the camera backs away diagonally (-x, +y, -z: every axis scrolls the other way and wraps) while rolling and pitching:
+    # negative ring steps (operations.h:1131-1181, 1196-1230) and a general quaternion; the depth images no longer match the
+    # pose, which parity does not need
+    "s3_backward_diagonal_rotating": dict(setting=3, n_frames=6, overrides=dict(zero_center=True), eval_format=True, trajectory="backward"),
     # SETTING 0 (KITTI-360 preset, settings.h:32-52): static mode (g_consider_instance false), 256^3 voxels x 8 slots (a 3.2 GB
     # particle array), independent filters, display colours of the "#if SETTING == 0" block (label colour for every class)
     "s0_kitti360_static": dict(setting=0, n_frames=2, overrides=dict(zero_center=False), eval_format=False),
@@ -71,6 +75,10 @@ def scenario_frame(scene, spec, t):
         h, w = cls.shape
         cls[: h // 6, : w // 3] = V_SKY
         cls[h // 2:, w // 2: w // 2 + w // 10] = V_PERSON
+    if spec.get("trajectory") == "backward":
+        fr.position = np.array([-0.9 * t, 0.23 * t, -1.7 * t + 0.4], np.float64)
+        q = np.array([np.cos(0.07 * t), 0.3 * np.sin(0.07 * t), np.sin(0.11 * t) * 0.2 + 0.05, -0.25 * np.sin(0.05 * t)], np.float64)
+        fr.orientation = q / np.linalg.norm(q)
     fr.remove_tracks = list(spec.get("remove_at", {}).get(t, []))
     if fr.remove_tracks:
         fr.moves = [(k, T) for k, T in fr.moves if k not in fr.remove_tracks]
