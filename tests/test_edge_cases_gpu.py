@@ -193,3 +193,27 @@ def test_same_inputs_same_bits():
         rb = b.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves)
     np.testing.assert_array_equal(a.engine.dump(_capi.DUMP_PARTICLES), b.engine.dump(_capi.DUMP_PARTICLES))
     np.testing.assert_array_equal(ra.weight_sum.view(np.uint32), rb.weight_sum.view(np.uint32))
+
+
+class _BackwardScene:
+    """The seeded scene with the camera backing away diagonally while rolling and pitching: negative ring steps on every axis,
+    wrap-around, a general quaternion and pixels the ZED2 bounding-box gate turns into background (same trajectory as the
+    reference-pin scenario s3_backward_diagonal_rotating)."""
+
+    def __init__(self, cfg):
+        self.scene = Scene(cfg)
+
+    def frame(self, t):
+        fr = self.scene.frame(t)
+        fr.position = np.array([-0.9 * t, 0.23 * t, -1.7 * t + 0.4], np.float64)
+        q = np.array([np.cos(0.07 * t), 0.3 * np.sin(0.07 * t), np.sin(0.11 * t) * 0.2 + 0.05, -0.25 * np.sin(0.05 * t)], np.float64)
+        fr.orientation = q / np.linalg.norm(q)
+        return fr
+
+
+@pytest.mark.parametrize("base", ["B", "C"])
+def test_backward_diagonal_rotating_trajectory(base):
+    cfg = tiny(BASELINE[base])
+    eng, orc = SemanticDSPMap(cfg), oracle_map(cfg)
+    run_pair(eng, orc, _BackwardScene(cfg), 8, make_random_table(cfg.seed, 50_000), want_free=True)
+    assert eng.engine.stats()["n_occupied"] > 0
