@@ -233,7 +233,9 @@ struct dspmap {
     DevBuf<uint8_t> d_vstate;
     DevBuf<float> d_res_w;
     DevBuf<uint32_t> d_res_tl;
-    DevBuf<uint4> d_blk_cnt, d_blk_off;
+    DevBuf<uint4> d_blk_cnt, d_blk_off, d_chunk_tot, d_chunk_base;
+    DevBuf<uint32_t> d_tile_list;
+    uint32_t n_occ_chunks = 0;
     DevBuf<uint32_t> d_work;
     uint32_t n_occ_blocks = 0, birth_cap1 = 0, birth_shift1 = 0;
     uint32_t ck_seg_stride = 1;
@@ -345,7 +347,7 @@ struct dspmap {
         d_static_track.release(); d_static_label.release(); d_fp.release(); d_cnt.release(); d_persist.release(); d_masks.release(); d_moves.release();
         d_depth_in.release(); d_depth_int.release(); d_mask_in.release(); d_cloud_pos.release(); d_cloud_meta.release();
         d_pix_count.release(); d_pix_offset.release(); d_scan_block.release(); d_vmask.release(); d_csr_key.release(); d_seq_ref.release(); d_mov_out.release(); d_csr_idx.release();
-        d_vis_pix.release(); d_vis_meta.release(); d_vis_pos.release(); d_keys.release(); d_ranks.release(); d_birth_flags.release(); d_birth_prefix.release(); d_birth_block.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_work.release();
+        d_vis_pix.release(); d_vis_meta.release(); d_vis_pos.release(); d_keys.release(); d_ranks.release(); d_birth_flags.release(); d_birth_prefix.release(); d_birth_block.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_chunk_tot.release(); d_chunk_base.release(); d_tile_list.release(); d_work.release();
         for (int p = 0; p < MAX_RANKS; ++p) if (peer_base[p] && p != cfg.shard_rank) { cudaIpcCloseMemHandle(peer_base[p]); peer_base[p] = nullptr; }
         arena.release();
         p_depth.release(); p_masks.release(); p_cnt.release(); p_fp.release(); p_stamps.release(); p_maskdesc.release(); p_moves.release();
@@ -535,6 +537,10 @@ int dspmap::init(const dspmap_config& c) {
     }
     CU_TRY(this, d_col_tab.alloc(1024)); CU_TRY(this, cudaMemset(d_col_tab.p, 0, 1024));
     CU_TRY(this, d_vstate.alloc(v_pad)); CU_TRY(this, d_res_w.alloc(v_pad)); CU_TRY(this, d_res_tl.alloc(v_pad)); CU_TRY(this, d_mov_mask.alloc(v_pad));
+    n_occ_chunks = (n_occ_blocks + OCC_SCAN_CHUNK - 1) / OCC_SCAN_CHUNK;
+    CU_TRY(this, d_chunk_tot.alloc(n_occ_chunks + 1)); CU_TRY(this, d_chunk_base.alloc(n_occ_chunks));
+    CU_TRY(this, cudaMemset(d_chunk_tot.p, 0, (n_occ_chunks + 1) * sizeof(uint4))); CU_TRY(this, cudaMemset(d_chunk_base.p, 0, n_occ_chunks * sizeof(uint4)));
+    CU_TRY(this, d_tile_list.alloc((size_t)n_occ_chunks * OCC_SCAN_CHUNK));
     CU_TRY(this, d_blk_cnt.alloc(n_occ_blocks)); CU_TRY(this, d_blk_off.alloc(n_occ_blocks)); CU_TRY(this, d_work.alloc(v_pad + (size_t)sm_count * 8 * 8 * 512 + 512));
     CU_TRY(this, cudaMemset(d_vstate.p, 0, v_pad));
     {   // exchange arena
@@ -867,7 +873,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     if (profiling) cudaEventRecord(ev[6], stream);
     // ---- O1 occupancy -------------------------------------------------------------------------------------------------
     ResultArrays out{r_idx, r_xyz, r_w, r_track, r_label, r_state, r_free_idx, r_free_xyz, r_rgb};
-    OccScratch osc{d_vstate.p, d_res_w.p - (slot_lo >> f.Pb), d_res_tl.p - (slot_lo >> f.Pb), d_mov_mask.p - (slot_lo >> f.Pb), d_blk_cnt.p, d_blk_off.p};
+    OccScratch osc{d_vstate.p, d_res_w.p - (slot_lo >> f.Pb), d_res_tl.p - (slot_lo >> f.Pb), d_mov_mask.p - (slot_lo >> f.Pb), d_blk_cnt.p, d_blk_off.p, d_chunk_tot.p, d_chunk_base.p, d_tile_list.p};
     CU_TRY(this, cudaMemsetAsync(d_blk_cnt.p, 0, (size_t)n_occ_blocks * sizeof(uint4), stream));
     if (profiling) cudaEventRecord(ev[8], stream);
     DISPATCH_PB(f.Pb, (k_occ_headers<PB><<<sm_count * 8, OCC_BLOCK, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, n_occ_blocks, d_cnt.p)));
@@ -875,9 +881,13 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     if (profiling) cudaEventRecord(ev[9], stream);
     DISPATCH_PB(f.Pb, (k_occ_slots<PB><<<sm_count * 8, 256, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, d_cnt.p)));
     ++launches;
-    ++launches; k_occ_scan<<<1, 1024, 0, stream>>>(osc, n_occ_blocks, d_cnt.p, d_persist.p, cv);
+    ++launches; k_occ_scan<<<n_occ_chunks, 1024, 0, stream>>>(osc, n_occ_blocks, d_cnt.p, d_persist.p, cv);
     barrier();   // the lower ranks' totals are this rank's base offsets
-    DISPATCH_PB(f.Pb, (k_occ_emit<PB><<<n_occ_blocks, OCC_BLOCK, 0, stream>>>(fp, st, osc, out, d_movl_idx.p, d_movl_track.p, sel_cap, cv, d_counts, d_col_tab.p)));
+    {
+        const int use_list = n_occ_chunks > 1;
+        const uint32_t emit_grid = use_list ? std::min<uint32_t>(n_occ_blocks, (uint32_t)sm_count * 8) : n_occ_blocks;
+        DISPATCH_PB(f.Pb, (k_occ_emit<PB><<<emit_grid, OCC_BLOCK, 0, stream>>>(fp, st, osc, out, d_movl_idx.p, d_movl_track.p, sel_cap, cv, d_counts, d_col_tab.p, n_occ_chunks, use_list)));
+    }
     ++launches;
     barrier();   // rank 0 holds the whole result
     if (profiling) cudaEventRecord(ev[7], stream);

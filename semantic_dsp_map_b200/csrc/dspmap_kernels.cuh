@@ -978,6 +978,8 @@ k_birth_write(const __grid_constant__ FrameParams f, Store st, const float4* __r
 constexpr int OCC_BLOCK = 256;
 constexpr int OCC_VPT = 4;                       // voxels per thread (one 16-byte header load)
 constexpr int OCC_TILE = OCC_BLOCK * OCC_VPT;
+constexpr int OCC_SCAN_TPT = 4;                  // tiles per thread of the tile-count scan
+constexpr int OCC_SCAN_CHUNK = 1024 * OCC_SCAN_TPT;   // tiles per scan block
 constexpr int MAX_P = 16;
 // state byte: bits 0..1 = state + 1 (0 unknown, 1 free, 2 occupied, 3 guessed occupied), bit 2 = holds movable particles
 constexpr uint32_t VS_MOVABLE = 4u;
@@ -1076,8 +1078,12 @@ struct OccScratch {
     float* res_w;           // V, written for emitted voxels only
     uint32_t* res_tl;       // V, track | label << 16
     uint16_t* mov_mask;     // V, slots holding live particles of movable tracks (written where VS_MOVABLE)
-    uint4* blk_cnt;         // per block: occupied, free, movable particles
-    uint4* blk_off;         // exclusive prefix of blk_cnt
+    uint4* blk_cnt;         // per tile: occupied, free, movable particles
+    uint4* blk_off;         // exclusive prefix of blk_cnt inside the tile's scan chunk (OCC_SCAN_CHUNK tiles)
+    uint4* chunk_tot;       // per scan chunk: totals (x, y, z) and number of non-empty tiles (w); one extra entry at the end:
+                            // x = ticket counter of the "last block finishes" step, y = total number of non-empty tiles
+    uint4* chunk_base;      // per scan chunk: exclusive prefix of chunk_tot
+    uint32_t* tile_list;    // non-empty tiles, ascending inside each chunk's own segment [chunk * OCC_SCAN_CHUNK, ...)
 };
 
 // persistent warps, each streaming 128-voxel pieces (32 lanes x one 16-byte load) of the header plane with the next
@@ -1236,50 +1242,71 @@ k_occ_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* __r
 // exclusive scan of the per-block (occupied, free, movable) counts; single block, any number of tiles
 __global__ void __launch_bounds__(1024)
 k_occ_scan(OccScratch sc, uint32_t n_blocks, Counters* __restrict__ cnt, Persist* __restrict__ persist, CommView cv) {
+    // one block per chunk of OCC_SCAN_CHUNK tiles (a 256 x 64 x 256 map is one chunk, 1024 x 128 x 1024 thirty-two): offsets
+    // inside the chunk, the chunk's totals, and the block that finishes last turns the totals into chunk bases
     __shared__ uint32_t s_warp[33];
-    uint32_t run0 = 0, run1 = 0, run2 = 0;
-    constexpr int TPT = 4;                                   // tiles per thread
-    for (uint32_t c = 0; c < n_blocks; c += blockDim.x * TPT) {
-        const uint32_t b0 = c + threadIdx.x * TPT;
-        uint4 v[TPT];
-        uint32_t s0 = 0, s1 = 0, s2 = 0;
+    __shared__ uint32_t s_last;
+    constexpr int TPT = OCC_SCAN_TPT;
+    const uint32_t b0 = blockIdx.x * OCC_SCAN_CHUNK + threadIdx.x * TPT;
+    uint4 v[TPT];
+    uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
-        for (int i = 0; i < TPT; ++i) {
-            v[i] = (b0 + i) < n_blocks ? sc.blk_cnt[b0 + i] : make_uint4(0, 0, 0, 0);
-            s0 += v[i].x; s1 += v[i].y; s2 += v[i].z;
-        }
-        uint32_t t0, t1, t2;
-        uint32_t e0 = run0 + block_exclusive_scan(s0, s_warp, t0);
-        uint32_t e1 = run1 + block_exclusive_scan(s1, s_warp, t1);
-        uint32_t e2 = run2 + block_exclusive_scan(s2, s_warp, t2);
-#pragma unroll
-        for (int i = 0; i < TPT; ++i) {
-            if ((b0 + i) < n_blocks) sc.blk_off[b0 + i] = make_uint4(e0, e1, e2, 0u);
-            e0 += v[i].x; e1 += v[i].y; e2 += v[i].z;
-        }
-        run0 += t0; run1 += t1; run2 += t2;
+    for (int i = 0; i < TPT; ++i) {
+        v[i] = (b0 + i) < n_blocks ? sc.blk_cnt[b0 + i] : make_uint4(0, 0, 0, 0);
+        s0 += v[i].x; s1 += v[i].y; s2 += v[i].z; s3 += (v[i].x | v[i].y | v[i].z) != 0;
     }
-    if (threadIdx.x == 0) { cnt->n_occupied = run0; cnt->n_free = run1; cnt->n_movable = run2; persist->n_movable = run2; }
-    if ((int)threadIdx.x < cv.size) {      // every rank learns every rank's totals (the emit pass needs the lower ranks')
-        uint32_t* row = cv.counts[threadIdx.x] + cv.rank * COMM_COUNTS;
-        row[CC_OCC] = run0; row[CC_FREE] = run1;
+    uint32_t t0, t1, t2, t3;
+    uint32_t e0 = block_exclusive_scan(s0, s_warp, t0);
+    uint32_t e1 = block_exclusive_scan(s1, s_warp, t1);
+    uint32_t e2 = block_exclusive_scan(s2, s_warp, t2);
+    const bool multi = gridDim.x > 1;                         // a small map is one chunk: no list, no hand-over between blocks
+    uint32_t e3 = 0;
+    t3 = 0;
+    if (multi) e3 = block_exclusive_scan(s3, s_warp, t3);
+#pragma unroll
+    for (int i = 0; i < TPT; ++i) {
+        if ((b0 + i) < n_blocks) sc.blk_off[b0 + i] = make_uint4(e0, e1, e2, 0u);
+        if (multi && (v[i].x | v[i].y | v[i].z) != 0) sc.tile_list[blockIdx.x * OCC_SCAN_CHUNK + e3++] = b0 + i;   // the emit pass visits only these
+        e0 += v[i].x; e1 += v[i].y; e2 += v[i].z;
+    }
+    uint32_t* tail = reinterpret_cast<uint32_t*>(sc.chunk_tot + gridDim.x);
+    if (threadIdx.x == 0) {
+        sc.chunk_tot[blockIdx.x] = make_uint4(t0, t1, t2, t3);
+        s_last = 1u;
+        if (multi) {
+            __threadfence();
+            const uint32_t ticket = atomicAdd(tail, 1u);
+            s_last = ticket == gridDim.x - 1;
+        }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) {
+        uint32_t run0 = 0, run1 = 0, run2 = 0, run3 = 0;
+        for (uint32_t c = 0; c < gridDim.x; ++c) {
+            const volatile uint32_t* tot = reinterpret_cast<const volatile uint32_t*>(sc.chunk_tot + c);
+            sc.chunk_base[c] = make_uint4(run0, run1, run2, run3);
+            run0 += tot[0]; run1 += tot[1]; run2 += tot[2]; run3 += tot[3];
+        }
+        tail[0] = 0u;                                             // the ticket counter is ready for the next frame
+        tail[1] = run3;                                           // length of the non-empty tile list
+        cnt->n_occupied = run0; cnt->n_free = run1; cnt->n_movable = run2; persist->n_movable = run2;
+        for (int p = 0; p < cv.size; ++p) {   // every rank learns every rank's totals (the emit pass needs the lower ranks')
+            uint32_t* row = cv.counts[p] + cv.rank * COMM_COUNTS;
+            row[CC_OCC] = run0; row[CC_FREE] = run1;
+        }
     }
     __threadfence_system();
 }
 
+// one tile (OCC_TILE voxels) of the ordered emission; every thread of the block takes part in the two scans
 template <int PB>
-__global__ void __launch_bounds__(OCC_BLOCK)
-k_occ_emit(const __grid_constant__ FrameParams f, Store st, OccScratch sc, ResultArrays out, uint32_t* __restrict__ movl_idx,
-           uint16_t* __restrict__ movl_track, uint32_t movl_cap, CommView cv, const uint32_t* __restrict__ counts,
-           const uint8_t* __restrict__ col_tab) {
-    __shared__ uint32_t s_warp[33];
-    // sharded map: `out` is rank 0's result arrays; this rank's entries start after the lower ranks' (ascending storage index)
-    uint32_t base_occ = 0, base_free = 0;
-    for (int g = 0; g < cv.rank; ++g) { base_occ += counts[g * COMM_COUNTS + CC_OCC]; base_free += counts[g * COMM_COUNTS + CC_FREE]; }
-    const uint4 cntb = sc.blk_cnt[blockIdx.x];
-    if ((cntb.x | cntb.y | cntb.z) == 0) return;          // nothing to emit from this tile
+__device__ __forceinline__ void occ_emit_tile(const FrameParams& f, const Store& st, const OccScratch& sc, const ResultArrays& out,
+                                              uint32_t* __restrict__ movl_idx, uint16_t* __restrict__ movl_track, uint32_t movl_cap,
+                                              const uint8_t* __restrict__ col_tab, uint32_t tile, uint32_t base_occ, uint32_t base_free, uint32_t* s_warp, bool use_list) {
     const uint32_t v_lo = f.z_lo << (f.Xb + f.Yb);
-    const uint32_t v0 = v_lo + blockIdx.x * OCC_TILE + threadIdx.x * OCC_VPT;
+    const uint32_t v0 = v_lo + tile * OCC_TILE + threadIdx.x * OCC_VPT;
     const uint32_t sb4 = *reinterpret_cast<const uint32_t*>(sc.vstate + (v0 - v_lo));
     uint32_t n_occ = 0, n_free = 0, n_mov = 0;
     uint32_t mmask[OCC_VPT];
@@ -1294,9 +1321,11 @@ k_occ_emit(const __grid_constant__ FrameParams f, Store st, OccScratch sc, Resul
     uint32_t tot_a, tot_b;
     const uint32_t ex_a = block_exclusive_scan(n_occ | (n_free << 16), s_warp, tot_a);   // <= 1024 each
     const uint32_t ex_b = block_exclusive_scan(n_mov, s_warp, tot_b);
-    if ((n_occ | n_free | n_mov) == 0) return;
-    const uint4 off = sc.blk_off[blockIdx.x];
-    uint32_t pos_occ = base_occ + off.x + (ex_a & 0xffffu), pos_free = base_free + off.y + (ex_a >> 16), pos_mov = off.z + ex_b;
+    if ((n_occ | n_free | n_mov) == 0) return;                // after the scans: no barrier follows inside this tile
+    const uint4 off = sc.blk_off[tile];
+    uint4 cb = make_uint4(0u, 0u, 0u, 0u);
+    if (use_list) cb = sc.chunk_base[tile / OCC_SCAN_CHUNK];   // a one-chunk map has base 0
+    uint32_t pos_occ = base_occ + cb.x + off.x + (ex_a & 0xffffu), pos_free = base_free + cb.y + off.y + (ex_a >> 16), pos_mov = cb.z + off.z + ex_b;
     uint32_t bx0, by, bz;
     voxel_to_buffer(f, v0, bx0, by, bz);
 #pragma unroll
@@ -1353,6 +1382,36 @@ k_occ_emit(const __grid_constant__ FrameParams f, Store st, OccScratch sc, Resul
             if (pos_mov < movl_cap) { movl_idx[pos_mov] = (uint32_t)idx; movl_track[pos_mov] = (uint16_t)meta_track(st.meta[idx]); }
             ++pos_mov;
         }
+    }
+}
+
+// Small maps (one scan chunk): one block per tile, empty tiles leave after one load - every tile in flight at once.
+// Large maps (mostly unknown or empty tiles, where launching a block per tile costs more than the work): a single wave of
+// blocks takes the non-empty tiles round-robin from the list the scan left; list entry g lives in the segment of the chunk
+// whose base covers it.
+template <int PB>
+__global__ void __launch_bounds__(OCC_BLOCK)
+k_occ_emit(const __grid_constant__ FrameParams f, Store st, OccScratch sc, ResultArrays out, uint32_t* __restrict__ movl_idx,
+           uint16_t* __restrict__ movl_track, uint32_t movl_cap, CommView cv, const uint32_t* __restrict__ counts,
+           const uint8_t* __restrict__ col_tab, uint32_t n_chunks, int use_list) {
+    __shared__ uint32_t s_warp[33];
+    // sharded map: `out` is rank 0's result arrays; this rank's entries start after the lower ranks' (ascending storage index)
+    uint32_t base_occ = 0, base_free = 0;
+    for (int g = 0; g < cv.rank; ++g) { base_occ += counts[g * COMM_COUNTS + CC_OCC]; base_free += counts[g * COMM_COUNTS + CC_FREE]; }
+    if (!use_list) {
+        const uint4 cntb = sc.blk_cnt[blockIdx.x];
+        if ((cntb.x | cntb.y | cntb.z) == 0) return;          // nothing to emit from this tile
+        occ_emit_tile<PB>(f, st, sc, out, movl_idx, movl_track, movl_cap, col_tab, blockIdx.x, base_occ, base_free, s_warp, false);
+        __threadfence_system();
+        return;
+    }
+    const uint32_t n_list = reinterpret_cast<const uint32_t*>(sc.chunk_tot + n_chunks)[1];
+    uint32_t c = 0;
+    for (uint32_t g = blockIdx.x; g < n_list; g += gridDim.x) {
+        while (c + 1 < n_chunks && sc.chunk_base[c + 1].w <= g) ++c;                  // g only grows
+        const uint32_t tile = sc.tile_list[c * OCC_SCAN_CHUNK + (g - sc.chunk_base[c].w)];
+        occ_emit_tile<PB>(f, st, sc, out, movl_idx, movl_track, movl_cap, col_tab, tile, base_occ, base_free, s_warp, true);
+        __syncthreads();      // s_warp is reused by the next tile
     }
     __threadfence_system();
 }
