@@ -217,3 +217,14 @@ def test_backward_diagonal_rotating_trajectory(base):
     eng, orc = SemanticDSPMap(cfg), oracle_map(cfg)
     run_pair(eng, orc, _BackwardScene(cfg), 8, make_random_table(cfg.seed, 50_000), want_free=True)
     assert eng.engine.stats()["n_occupied"] > 0
+
+
+def test_multi_chunk_occupancy_pass_matches_oracle():
+    """512 x 64 x 512 voxels = 16384 occupancy tiles = four scan chunks: the tile-count scan hands over between blocks and the
+    emit pass runs from the non-empty-tile list (the path large maps take); free space on, so most tiles emit."""
+    cfg = dataclasses.replace(tiny(BASELINE["B"]), voxel_bits=(9, 6, 9))
+    eng, orc = SemanticDSPMap(cfg), oracle_map(cfg)
+    for m in (eng, orc):
+        m.enable_colors()
+    run_pair(eng, orc, Scene(cfg), 4, make_random_table(cfg.seed, 50_000), want_free=True, stages=False, particles=False)
+    assert eng.engine.stats()["n_occupied"] > 0

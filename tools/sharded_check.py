@@ -25,12 +25,16 @@ def main():
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--same-gpu", action="store_true")
     ap.add_argument("--full", action="store_true", help="full-size config instead of the tiny variant")
+    ap.add_argument("--grid", default="", help="voxel bits x,y,z overriding the (tiny) config's grid, e.g. 9,6,9")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     dist.init_process_group("gloo")
     device = 0 if args.same_gpu else int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(device)
     cfg = BASELINE[args.config] if args.full else tiny(BASELINE[args.config])
+    if args.grid:
+        import dataclasses
+        cfg = dataclasses.replace(cfg, voxel_bits=tuple(int(b) for b in args.grid.split(",")))
     m = SemanticDSPMap(cfg, device=device, shard_rank=rank, shard_count=world)
 
     def gather(obj):
