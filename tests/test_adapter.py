@@ -60,3 +60,39 @@ def test_adapter_matches_python_mirror():
         assert int(f) == t and int(n) == len(r.voxel_index), (line, len(r.voxel_index))
         assert int(h, 16) == _fnv(r.xyz, red), line
     assert int(out[-1].split()[1]) > 0
+
+
+@pytest.mark.gpu
+def test_same_caller_source_against_the_reference_header_and_against_the_adapter():
+    """tests/dropin_driver.cpp is ONE caller source (the node's call sequence on 1280x720 frames, SETTING 3).  Compiled against
+    the reference's own semantic_dsp_map.h it produced tests/golden/dropin_reference.npz (tests/golden/make_dropin_golden.py);
+    compiled against adapter/semantic_dsp_map.h and run on the GPU it must emit the same occupied clouds: same colours on
+    the same voxels, and - the engine sums each pixel's particle list in canonical instead of BFS order, which can move a
+    weight sum across the occupancy threshold by an ulp - at most 1 % of the voxels differing."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_dropin_golden as G
+    lib_dir = os.path.join(ROOT, "semantic_dsp_map_b200")
+    exe, out = os.path.join(ROOT, "tests", "dropin_adapter"), os.path.join(ROOT, "tests", "dropin_adapter.bin")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-w", "-I" + os.path.join(ROOT, "oracle", "ref_stubs"), "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "dropin_driver.cpp"), "-o", exe, "-L" + lib_dir, "-l:libdspmap_b200.so", "-Wl,-rpath," + lib_dir])
+    try:
+        subprocess.run([exe, str(G.FRAMES), out], check=True, capture_output=True, timeout=300)
+        clouds = G.read_clouds(out)
+    finally:
+        for p in (exe, out, out + ".csv"):
+            if os.path.exists(p):
+                os.remove(p)
+    want = np.load(os.path.join(ROOT, "tests", "golden", "dropin_reference.npz"))
+    counts = np.asarray([len(c) for c in clouds])
+    assert len(counts) == len(want["counts"]) and want["counts"][-1] > 1000
+    assert np.all(np.abs(counts - want["counts"]) <= 0.01 * np.maximum(want["counts"], 1)), (counts, want["counts"])
+    key = lambda a: {tuple(v) for v in a.tolist()}  # noqa: E731
+    got_lat, ref_lat = G.lattice(clouds[-1]["xyz"]), want["last_lattice"]
+    a, b = key(got_lat), key(ref_lat)
+    assert len(a ^ b) <= 0.01 * len(b), (len(a ^ b), len(b))
+    col_a = {tuple(v): tuple(c) for v, c in zip(got_lat.tolist(), clouds[-1]["rgb"].tolist())}
+    col_b = {tuple(v): tuple(c) for v, c in zip(ref_lat.tolist(), want["last_rgb"].tolist())}
+    common = a & b
+    differing = sum(col_a[v] != col_b[v] for v in common)
+    assert differing <= 0.002 * len(common), (differing, len(common))
