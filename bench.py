@@ -342,7 +342,7 @@ def main():
                                           "algorithmic_bytes": pu_bytes, "ms": pu_ms, "achieved": pu_bytes / (pu_ms * 1e-3) / 1e9, "peak": peak,
                                           "frac": pu_bytes / (pu_ms * 1e-3) / 1e9 / peak,
                                           "note": "SURVEY 8(d) numerator of the dense formulation; the stencil passes are instruction-bound (profiles/)"}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is a rank-0, N = 1 measurement
             out["cpu_baseline"] = cpu_baseline(args.config, frames)
         print(json.dumps(out))
     if world > 1:
