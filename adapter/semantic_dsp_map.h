@@ -18,17 +18,19 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
 #include <map>
 #include <random>
 #include <set>
+#include <sstream>
 #include <string>
 #include <unordered_map>
 #include <vector>
 
 #include "dspmap_c.h"
 
-// reference include/utils/tracking_result_handler.h:15-26
-struct BBox2D { int x = 0, y = 0, width = 0, height = 0; };
+// reference include/utils/data_base.h:24-30 and include/utils/tracking_result_handler.h:15-26 (src/mapping.cpp:216-219 writes bbox.x1 .. y2)
+struct BBox2D { int x1 = 0, y1 = 0, x2 = 0, y2 = 0; };
 struct MaskKpts {
     int track_id = 0;
     std::string label;
@@ -61,11 +63,80 @@ struct DspLabelTables {
         }
     }
     template <class M, class K> static int getOr0(const M& m, const K& k) { auto it = m.find(k); return it == m.end() ? 0 : it->second; }
+
+    // the tables the reference starts with when no CSV is read (include/utils/data_base.h:108-232)
+    static DspLabelTables builtin() {
+        DspLabelTables t;
+        struct Row { int id; const char* name; int inst; int b, g, r; };
+        static const Row rows[] = {{0, "Background", 65535, 0, 0, 0}, {2, "Terrain", 65534, 200, 0, 210}, {3, "Sky", 65533, 255, 200, 90},
+                                   {4, "Tree", 65532, 0, 199, 0}, {5, "Vegetation", 65531, 0, 240, 90}, {6, "Building", 65530, 140, 140, 140},
+                                   {7, "Road", 65529, 100, 60, 100}, {8, "GuardRail", 65528, 255, 100, 250}, {9, "TrafficSign", 65527, 0, 255, 255},
+                                   {10, "TrafficLight", 65526, 0, 200, 200}, {11, "Pole", 65525, 0, 130, 255}, {12, "Misc", 65524, 80, 80, 80},
+                                   {13, "Truck", -1, 60, 60, 160}, {14, "Car", -1, 80, 127, 255}, {15, "Person", -1, 139, 139, 0}};
+        for (const Row& r : rows) t.addRow(r.id, r.name, r.inst, r.b, r.g, r.r);
+        t.max_movable_instance_id = 65523;
+        return t;
+    }
+};
+
+// The reference keeps its label tables in namespace-scope globals that ObjectInfoHandler::readObjectInfo rewrites
+// (include/utils/data_base.h:108-232; include/utils/object_info_handler.h:28-91) and that the map reads at every frame.
+// Same arrangement here: one process-wide table set with a version stamp; the map re-sends its look-up tables to the engine
+// when the stamp moved (src/mapping.cpp constructs the map BEFORE it reads the CSV, :71 vs :89-93).
+struct DspLabelGlobals {
+    DspLabelTables tables = DspLabelTables::builtin();
+    unsigned version = 1;
+};
+inline DspLabelGlobals& dspLabelGlobals() { static DspLabelGlobals g; return g; }
+
+// reference include/utils/object_info_handler.h:20-152
+class ObjectInfoHandler {
+public:
+    void readObjectInfo(const std::string& file_path) {
+        if (file_path.substr(file_path.find_last_of(".") + 1) != "csv") {                       // :31-35
+            std::fprintf(stderr, "The file path is not a csv file. Will use default settings in data_base.h\n");
+            return;
+        }
+        std::ifstream file(file_path);
+        std::string line;
+        std::getline(file, line);                                                                // header line, :138
+        DspLabelTables t;
+        t.max_movable_instance_id = 65535;                                                       // :49
+        while (std::getline(file, line)) {
+            std::stringstream ss(line);
+            std::string item[6];
+            for (auto& it : item) std::getline(ss, it, ',');
+            t.addRow(std::stoi(item[0]), item[1], std::stoi(item[2]), std::stoi(item[3]), std::stoi(item[4]), std::stoi(item[5]));
+        }
+        dspLabelGlobals().tables = t;
+        ++dspLabelGlobals().version;
+        std::printf("Object information csv file read successfully. File: %s\n g_max_movable_object_instance_id = %d\n", file_path.c_str(), t.max_movable_instance_id);
+    }
+};
+
+// reference include/utils/tracking_result_handler.h:28-34
+class TrackingResultHandler {
+public:
+    std::vector<MaskKpts> tracking_result;
 };
 
 class SemanticDSPMap {
 public:
-    // compile-time constants of the reference (include/settings/settings.h) become this runtime config
+    // The compile-time constants of the reference (include/settings/settings.h) become a runtime config.  The default
+    // constructor - the one src/mapping.cpp:71 uses - takes defaultConfig(), which starts as the configuration the
+    // reference ships (SETTING 3, settings.h:100-119, 136-143) and can be overwritten before the map is constructed.
+    static dspmap_config& defaultConfig() {
+        static dspmap_config c = [] {
+            dspmap_config d{};
+            d.voxel_bits_x = 7; d.voxel_bits_y = 5; d.voxel_bits_z = 7; d.slot_bits = 2; d.voxel_size = 0.15f;
+            d.fx = d.fy = 527.8191528320312f; d.cx = 633.9357299804688f; d.cy = 366.3338623046875f;
+            d.image_width = 1280; d.image_height = 720; d.boost_mode = 1; d.depth_min = 0.3f; d.depth_max = 15.f;
+            d.consider_instance = 1; d.zed2_filters = 1; d.shard_count = 1;
+            return d;
+        }();
+        return c;
+    }
+    SemanticDSPMap() : SemanticDSPMap(defaultConfig(), dspLabelGlobals().tables) { follow_globals_ = true; labels_version_ = dspLabelGlobals().version; }
     explicit SemanticDSPMap(const dspmap_config& cfg, const DspLabelTables& labels = DspLabelTables()) : cfg_(cfg), labels_(labels) {
         if (dspmap_create(&cfg_, &h_) != DSPMAP_OK) { std::fprintf(stderr, "dspmap_create failed\n"); std::exit(-1); }   // reference: exit(-1), operations.h:57
         prm_ = dspmap_params{0.95f, 0.1f, 3, 0.2f, 1.0f, 5, 0.1f, 0.0f, 0.1f, 0, 0, 0};   // ctor defaults, reference :25-43
@@ -118,6 +189,12 @@ public:
     void update(cv::Mat& depth_value_mat, std::vector<MaskKpts>& ins_seg_result, Eigen::Vector3d& camera_position,
                 Eigen::Quaterniond& camera_orientation, pcl::PointCloud<pcl::PointXYZRGB>::Ptr& occupied_point_cloud,
                 pcl::PointCloud<pcl::PointXYZRGB>::Ptr& freespace_point_cloud, bool if_get_freespace = false, double = 0.0) {
+        if (follow_globals_ && labels_version_ != dspLabelGlobals().version) {   // readObjectInfo ran since the tables were sent
+            labels_ = dspLabelGlobals().tables;
+            labels_version_ = dspLabelGlobals().version;
+            pushLabels();
+            pushColors();
+        }
         std::vector<dspmap_mask> masks(ins_seg_result.size());
         for (size_t i = 0; i < ins_seg_result.size(); ++i) {
             MaskKpts& m = ins_seg_result[i];
@@ -218,6 +295,8 @@ private:
     DspLabelTables labels_;
     uint8_t color_map_int_256_[256];
     std::set<int> known_objects_, born_tracks_;
+    bool follow_globals_ = false;
+    unsigned labels_version_ = 0;
     dspmap_params prm_{};
     dspmap_t* h_ = nullptr;
     int max_obersevation_lost_time_ = 0;

@@ -3,7 +3,7 @@
 // It drives the class the way src/mapping.cpp does (readObjectInfo :89-93, the five setters :135-140 with the values of
 // cfg/options_zed2.yaml, update() :273) on procedurally generated 1280x720 frames - the configuration the reference
 // ships (SETTING 3) - and writes every frame's occupied cloud (x, y, z, r, g, b) to a file.  The one place the two builds
-// differ is the construction of the map, the hunk INTEGRATION.md section 2 shows.
+// differ is the header they include: the adapter's default constructor takes the shipped SETTING 3 configuration.
 // Objects carry two key points only, so the reference's object layer (objectLevelUpdate, out of scope) registers them
 // (semantic_dsp_map.h:346-364) but never estimates a motion (:377 needs four), and no random numbers are drawn.
 #ifdef USE_REFERENCE
@@ -41,30 +41,9 @@ int main(int argc, char** argv) {
     const std::string csv_path = std::string(out_path) + ".csv";
     { std::ofstream f(csv_path); f << kCsv; }
 
-#ifdef USE_REFERENCE
-    ObjectInfoHandler object_info_handler;                    // src/mapping.cpp:89-93
+    SemanticDSPMap dsp_map_;                                  // src/mapping.cpp:71: a default-constructed member ...
+    ObjectInfoHandler object_info_handler;                    // ... and only then the label CSV, :89-93
     object_info_handler.readObjectInfo(csv_path);
-    SemanticDSPMap dsp_map_;
-#else
-    dspmap_config cfg{};                                      // include/settings/settings.h:100-119 (SETTING 3) at run time
-    cfg.voxel_bits_x = 7; cfg.voxel_bits_y = 5; cfg.voxel_bits_z = 7; cfg.slot_bits = 2; cfg.voxel_size = 0.15f;
-    cfg.fx = cfg.fy = 527.8191528320312f; cfg.cx = 633.9357299804688f; cfg.cy = 366.3338623046875f;
-    cfg.image_width = 1280; cfg.image_height = 720; cfg.boost_mode = 1; cfg.depth_min = 0.3f; cfg.depth_max = 15.f;
-    cfg.consider_instance = 1; cfg.zed2_filters = 1; cfg.shard_count = 1;
-    DspLabelTables labels;
-    {
-        std::ifstream f(csv_path);
-        std::string line;
-        std::getline(f, line);
-        while (std::getline(f, line)) {                       // the loop of object_info_handler.h:51-86
-            std::stringstream ss(line);
-            std::string item[6];
-            for (auto& it : item) std::getline(ss, it, ',');
-            labels.addRow(std::stoi(item[0]), item[1], std::stoi(item[2]), std::stoi(item[3]), std::stoi(item[4]), std::stoi(item[5]));
-        }
-    }
-    SemanticDSPMap dsp_map_(cfg, labels);
-#endif
     // src/mapping.cpp:135-140 with cfg/options_zed2.yaml
     dsp_map_.setMapParameters(0.8f, 0.2f, 1, 0.15f, 20, 1.f, 5, 0.6f, 0.5f);
     dsp_map_.setMapOptions(true, false);

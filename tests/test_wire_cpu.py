@@ -78,3 +78,31 @@ def test_record_file_round_trip_and_image_errors():
     bad.encoding = "bgr8"
     with pytest.raises(wire.WireError):
         bad.array("32FC1")
+
+
+def test_cpp_decoder_of_the_adapter_reads_the_same_bytes(tmp_path):
+    """adapter/mask_group_wire.h (the C++ twin an integrator would use) on the reference-serialised message."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "wire_driver")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-w", "-I" + os.path.join(root, "oracle", "ref_stubs"), "-I" + os.path.join(root, "include"),
+                           "-I" + os.path.join(root, "adapter"), os.path.join(root, "tests", "wire_driver.cpp"), "-o", exe,
+                           "-L" + os.path.join(root, "semantic_dsp_map_b200"), "-l:libdspmap_b200.so", "-Wl,-rpath," + os.path.join(root, "semantic_dsp_map_b200")])
+    group = open(GOLDEN, "rb").read()
+    depth = np.full((12, 20), 2.5, np.float32)
+
+    def run(depth_seq):
+        files = {}
+        for name, blob in (("depth", wire.encode_image(wire.image_from_array(depth, "32FC1", wire.Header(depth_seq, 10, 0, "zed2")))),
+                           ("pose", wire.encode_pose_stamped(wire.Header(depth_seq, 1700000001, 500000000, "map"), [1.0, 2.0, 3.0], [0.5, 0.1, 0.2, 0.3])), ("group", group)):
+            files[name] = str(tmp_path / name)
+            open(files[name], "wb").write(blob)
+        return subprocess.run([exe, files["depth"], files["pose"], files["group"]], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+
+    assert run(1) == ["dropped"] and run(9) == ["dropped"]                     # seq < 2; seq mismatch (the golden group has seq 7)
+    out = run(7)
+    ex = G.example()
+    assert out[0] == "seq 7 stamp 1700000001.500 depth 12x20 d00 2.500 pos 1.0 2.0 3.0 quat 0.5 0.1 0.2 0.3"
+    assert out[1] == "object static 65535 mask 12x20 sum %d kpts 0" % int(ex["objects"][0]["mask"].sum())
+    assert out[2] == "object Vehicle 3 mask 12x20 sum %d kpts 4" % int(ex["objects"][1]["mask"].sum())
+    assert len(out) == 3                                                        # "person": key-point counts differ -> skipped
