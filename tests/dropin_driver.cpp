@@ -75,8 +75,8 @@ int main(int argc, char** argv) {
         std::vector<MaskKpts> ins_seg(2);
         ins_seg[0].track_id = 65535; ins_seg[0].label = "static"; ins_seg[0].mask = cls;
         ins_seg[1].track_id = 3; ins_seg[1].label = "Vehicle"; ins_seg[1].mask = car;
-        ins_seg[1].kpts_current.push_back(Eigen::Vector3d(-0.2, 0.0, 4.0));
-        ins_seg[1].kpts_current.push_back(Eigen::Vector3d(1.3, 1.5, 5.0));
+        ins_seg[1].kpts_current.push_back(Eigen::Vector3d(-0.25, 0.0, 4.0));   // exact in float32: the wire format carries float32 key points
+        ins_seg[1].kpts_current.push_back(Eigen::Vector3d(1.25, 1.5, 5.0));
         ins_seg[1].kpts_previous = ins_seg[1].kpts_current;
         Eigen::Vector3d pos(0.0, 0.0, cam_z);
         Eigen::Quaterniond q(1.0, 0.0, 0.0, 0.0);

@@ -1,0 +1,159 @@
+"""tests/golden/node_reference.npz: what the REFERENCE'S OWN NODE publishes on a recorded replay.
+
+/root/reference/src/mapping.cpp is compiled UNMODIFIED against the reference's own include/semantic_dsp_map.h (ROS / yaml-cpp /
+cv_bridge from tests/ros_stubs, Eigen / OpenCV / PCL from oracle/ref_stubs), started like `rosrun semantic_dsp_map mapping
+options.yaml object_info.csv`, and fed a replay file of (depth Image, PoseStamped, MaskGroup) triples in ROS 1 wire format
+(semantic_dsp_map_b200/wire.py).  The clouds it publishes on "occupied_point" are the fixture.  tests/test_adapter.py runs the
+same node source compiled against adapter/semantic_dsp_map.h (tests/_built/mapping_node_b200, built by __graft_entry__.build())
+on the same replay on the GPU and compares.  Build container only:
+
+    python tests/golden/make_node_golden.py
+"""
+import os
+import struct
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from semantic_dsp_map_b200 import wire  # noqa: E402
+
+FRAMES = 4
+FIRST_SEQ = 2          # src/mapping.cpp:166 drops depth images with header.seq < 2
+REC = np.dtype([("xyz", "<f4", 3), ("rgb", "u1", 3)])
+
+OPTIONS_YAML = """\
+depth_image_topic: /camera/depth_repub
+camera_pose_topic: /camera/pose_repub
+mask_group_topic: /mask_group_super_glued
+frame_id: zed2
+visualize_with_zero_center: false
+if_out_evaluation_format: true   # label colours: the instance colour map of the reference is std::random_device-seeded
+if_output_freespace: false
+beyesian_movement_distance_threshold: 0.2
+beyesian_movement_decrement: 0.05
+beyesian_movement_increment: 0.2
+beyesian_movement_probability_threshold: 0.3
+if_consider_depth_noise: true
+if_use_independent_filter: false
+match_score_threshold: 0.6
+max_obersevation_lost_time: 20
+nb_ptc_num_per_point: 1
+noise_number: 0.2
+detection_probability: 0.8
+occupancy_threshold: 0.15
+depth_noise_model_first_order: 0.02
+depth_noise_model_zero_order: 0.3
+forgetting_rate: 1
+max_forget_count: 5
+id_transition_probability: 0.5
+"""
+
+OBJECT_INFO_CSV = (
+    "label_id,label,instance_id(-1 means not fixed),color_b,color_g,color_r\n"
+    "0,background,65535,0,0,0\n1,road,65534,128,64,128\n2,sidewalk,65533,232,35,244\n3,building,65532,70,70,70\n4,wall,65531,156,102,102\n"
+    "5,fence,65530,153,153,190\n6,pole,65529,153,153,153\n7,traffic_light,65528,30,170,250\n8,traffic_sign,65527,0,220,220\n"
+    "9,vegetation,65526,35,142,107\n10,terrain,65525,152,251,152\n11,sky,65524,180,130,70\n12,person,-1,60,20,220\n13,rider,65522,0,0,255\n"
+    "14,Vehicle,-1,142,0,0\n15,truck,65521,70,0,0\n")
+
+
+def scene(t):
+    """Frame t of the scene of tests/dropin_driver.cpp, in the same float32 arithmetic: a ground plane 1.5 m below the camera, a
+    wall 7 m ahead of the start, a 1.5 x 1.5 m box face at 4 m, a sprinkle of far pixels; the camera advances 0.3 m a frame."""
+    f32 = np.float32
+    H, W = 720, 1280
+    fx, cx, cy = f32(527.8191528320312), f32(633.9357299804688), f32(366.3338623046875)
+    cam_z = 0.3 * t
+    wall, box = f32(7.0 - cam_z), f32(4.0 - cam_z)
+    i = np.arange(H, dtype=f32)[:, None]
+    j = np.arange(W, dtype=f32)[None, :]
+    ry = np.broadcast_to((i - cy) / fx, (H, W))
+    rx = np.broadcast_to((j - cx) / fx, (H, W))
+    d = np.full((H, W), wall, f32)
+    c = np.full((H, W), 3, np.uint8)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ground = f32(1.5) / ry
+    road = (ry > f32(1e-6)) & (ground < d)
+    d = np.where(road, ground, d).astype(f32)
+    c[road] = 0
+    bx, by = rx * box, ry * box
+    hit = (box > f32(0.5)) & (bx > f32(-0.2)) & (bx < f32(1.3)) & (by > f32(0.0)) & (by < f32(1.5)) & (box < d)
+    d = np.where(hit, box, d).astype(f32)
+    c[hit] = 13
+    car = np.where(hit, 255, 0).astype(np.uint8)
+    ii, jj = np.arange(H)[:, None], np.arange(W)[None, :]
+    d[(ii * 131 + jj * 17 + t * 7) % 97 == 0] = f32(16.0)
+    return d, c, car, cam_z
+
+
+def write_package(td):
+    """The package directory ros::package::getPath returns (cfg/ with the options and the label CSV) and the replay file."""
+    os.makedirs(os.path.join(td, "cfg"), exist_ok=True)
+    with open(os.path.join(td, "cfg", "options.yaml"), "w") as f:
+        f.write(OPTIONS_YAML)
+    with open(os.path.join(td, "cfg", "object_info.csv"), "w") as f:
+        f.write(OBJECT_INFO_CSV)
+    rec = os.path.join(td, "replay_in.bin")
+    kp = np.asarray([[-0.25, 0.0, 4.0], [1.25, 1.5, 5.0]], np.float32)
+    with open(rec, "wb") as f:
+        for t in range(FRAMES):
+            d, c, car, cam_z = scene(t)
+            ns = int(round(0.1 * t * 1e9))
+            h = wire.Header(FIRST_SEQ + t, ns // 10**9, ns % 10**9, "zed2")
+            group = wire.MaskGroup(h, [
+                wire.WireObject("static", 65535, wire.image_from_array(c, "mono8", h), (0, 0, 0), (0, 0, 0), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32)),
+                wire.WireObject("Vehicle", 3, wire.image_from_array(car, "mono8", h), (0, 0, 0), (0, 0, 0), kp, kp)])
+            wire.write_record(f, wire.encode_image(wire.image_from_array(d, "32FC1", h)), wire.encode_pose_stamped(h, (0.0, 0.0, cam_z), (1.0, 0.0, 0.0, 0.0)),
+                              wire.encode_mask_group(group))
+    return rec
+
+
+def read_published(path, topic="occupied_point"):
+    """The clouds the node published (tests/ros_stubs/sensor_msgs/PointCloud2.h writes them), in order, for one topic."""
+    b = open(path, "rb").read()
+    pos, out = 0, []
+    while pos < len(b):
+        (tl,) = struct.unpack_from("<I", b, pos)
+        name = b[pos + 4:pos + 4 + tl].decode()
+        (n,) = struct.unpack_from("<I", b, pos + 4 + tl)
+        pos += 8 + tl
+        if name == topic:
+            out.append(np.frombuffer(b, REC, n, pos).copy())
+        pos += n * REC.itemsize
+    return out
+
+
+def run_node(exe, td):
+    rec = write_package(td)
+    out = os.path.join(td, "published.bin")
+    env = dict(os.environ, DSPMAP_REPLAY_PACKAGE_PATH=td, DSPMAP_REPLAY_IN=rec, DSPMAP_REPLAY_OUT=out)
+    subprocess.run([exe, "options.yaml", "object_info.csv"], env=env, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=900)
+    return read_published(out)
+
+
+def lattice(xyz, voxel=0.15):
+    return np.round(np.asarray(xyz, np.float64) / voxel).astype(np.int16)
+
+
+def main():
+    with tempfile.TemporaryDirectory() as td:
+        exe = os.path.join(td, "mapping_node_ref")
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-w", "-I" + os.path.join(ROOT, "tests", "ros_stubs"),
+                               "-I" + os.path.join(ROOT, "oracle", "ref_stubs"), "-I/root/reference/include", "/root/reference/src/mapping.cpp", "-o", exe])
+        clouds = run_node(exe, td)
+    last = clouds[-1]
+    path = os.path.join(HERE, "node_reference.npz")
+    np.savez_compressed(path, counts=np.asarray([len(c) for c in clouds], np.int64), last_lattice=lattice(last["xyz"]), last_rgb=last["rgb"])
+    print([len(c) for c in clouds], os.path.getsize(path), "bytes")
+    drop = np.load(os.path.join(HERE, "dropin_reference.npz"))
+    same = (np.array_equal(drop["counts"], [len(c) for c in clouds]) and np.array_equal(drop["last_lattice"], lattice(last["xyz"]))
+            and np.array_equal(drop["last_rgb"], last["rgb"]))
+    print("identical to dropin_reference.npz (same scene through the direct caller):", same)
+
+
+if __name__ == "__main__":
+    main()

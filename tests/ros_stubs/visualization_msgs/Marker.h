@@ -1,0 +1,3 @@
+#pragma once
+#include <ros/ros.h>
+namespace visualization_msgs { struct Marker {}; }
