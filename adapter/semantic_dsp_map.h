@@ -6,8 +6,10 @@
 // loops: label look-ups, bbox from key points, the track-id wrap.  Nothing here touches particles, pixels or voxels.
 //
 // Needs the same third-party headers as the reference (Eigen, OpenCV, PCL).  The object layer
-// (objectLevelUpdate, reference :306-566) is out of scope for the engine: an integrator keeps the reference's
-// object_layer.h and passes what it decides through setObjectMoves() before update().
+// (objectLevelUpdate, reference :306-566: a handful of objects, key-point Kabsch, moving-or-not filter, coasting) runs on
+// the host in dsp_object_tracker.h, fed from update() like the reference does; its per-frame product (one rigid matrix per
+// moving object, tracks to drop) goes to the engine with the frame.  An integrator with an object layer of their own calls
+// setObjectMoves() before update() instead, which switches the built-in one off.
 #pragma once
 #include <Eigen/Dense>
 #include <opencv2/opencv.hpp>
@@ -28,6 +30,7 @@
 #include <vector>
 
 #include "dspmap_c.h"
+#include "dsp_object_tracker.h"
 
 // reference include/utils/data_base.h:24-30 and include/utils/tracking_result_handler.h:15-26 (src/mapping.cpp:216-219 writes bbox.x1 .. y2)
 struct BBox2D { int x1 = 0, y1 = 0, x2 = 0, y2 = 0; };
@@ -146,12 +149,14 @@ public:
         for (int i = 255; i > 0; --i) { std::uniform_int_distribution<int> dist(0, i); std::swap(color_map_int_256_[i], color_map_int_256_[dist(gen)]); }
         pushLabels();
         pushColors();
+        setGaussianTableSeed(rd());                                                              // reference :65 -> basic_algorithms.h:394-402
+        configureTracker(cfg_.zed2_filters ? dsp_adapter::ObjectTracker::kBoxKeypoints : dsp_adapter::ObjectTracker::kMatchedKeypoints);
     }
     ~SemanticDSPMap() { dspmap_destroy(h_); }
     SemanticDSPMap(const SemanticDSPMap&) = delete;
     SemanticDSPMap& operator=(const SemanticDSPMap&) = delete;
 
-    void clear() { dspmap_clear(h_); known_objects_.clear(); born_tracks_.clear(); }                                                          // reference :74-81
+    void clear() { dspmap_clear(h_); known_objects_.clear(); born_tracks_.clear(); tracker_.clear(); step_ = 0; }                                                          // reference :74-81
     void setTemplatePath(std::string) {}                                                         // template matching: out of scope
     void setMapParameters(float detection_probability, float noise_number, int nb_ptc_num_per_point, float occupancy_threshold,
                           int max_obersevation_lost_time, float forgetting_rate = 1.f, int max_forget_count = 5,
@@ -172,23 +177,42 @@ public:
         dspmap_set_params(h_, &prm_);
         pushColors();
     }
+    // The table of N(0, 0.05) draws that moved and noisy-newborn particles are jittered with (gaussian_randoms,
+    // utils/basic_algorithms.h:377-402: 10^6 draws of std::normal_distribution<> from a std::random_device-seeded mt19937).
+    // Random per process in the reference; a fixed seed here makes runs reproducible.
+    void setGaussianTableSeed(uint32_t seed) {
+        std::mt19937 gen(seed);
+        std::normal_distribution<> d(0, 0.05);                                                   // prediction_stddev_, reference :40
+        std::vector<float> table(1000000);
+        for (float& v : table) v = (float)d(gen);
+        dspmap_set_random_table(h_, table.data(), (uint32_t)table.size());
+    }
     // the instance colour permutation (color_map_int_256_); random per process in the reference, settable here for reproducible output
     void setInstanceColorMap(const uint8_t map256[256]) { for (int i = 0; i < 256; ++i) color_map_int_256_[i] = map256[i]; pushColors(); }
-    void setBeyesianMovementParameters(double, double, double, double) {}                        // object layer (host), reference :142-150
+    void setBeyesianMovementParameters(double distance_threshold, double probability_threshold, double increment, double decrement) {   // reference :142-150
+        tracker_.setMovementFilter(distance_threshold, probability_threshold, increment, decrement);
+    }
+    // Which "#if SETTING" flavour of the reference's object layer to follow (default: box key points when the configuration
+    // is the ZED2 one, matched key points otherwise); kAlwaysMoving is the SETTING 1 rule.
+    void setObjectLayerMode(dsp_adapter::ObjectTracker::Mode mode) { configureTracker(mode); }
+    void setObjectLayerSeed(uint32_t seed) { tracker_.setSeed(seed); }
+    const dsp_adapter::ObjectTracker& objectTracker() const { return tracker_; }
     void setOccupancyThreshold(float t) { prm_.occupancy_threshold = t; dspmap_set_params(h_, &prm_); }   // reference :153-156
     void setDepthNoiseModelParameters(float first_order, float zero_order) {                     // reference :161-166
         prm_.depth_noise_first_order = first_order; prm_.depth_noise_zero_order = zero_order;
         dspmap_set_params(h_, &prm_);
     }
-    // what the integrator's object layer decided for the coming frame (rigid motion per moving track, tracks to drop)
+    // what an integrator's OWN object layer decided for the coming frame (rigid motion per moving track, tracks to drop);
+    // the first call switches the built-in object layer off for good
     void setObjectMoves(const std::vector<dspmap_object_move>& moves, const std::vector<int32_t>& remove_tracks) {
-        moves_ = moves; remove_ = remove_tracks;
+        moves_ = moves; remove_ = remove_tracks; external_object_layer_ = true;
     }
 
     // reference :170-251.  Unlike the reference the caller's depth/mask Mats are NOT resized in place.
     void update(cv::Mat& depth_value_mat, std::vector<MaskKpts>& ins_seg_result, Eigen::Vector3d& camera_position,
                 Eigen::Quaterniond& camera_orientation, pcl::PointCloud<pcl::PointXYZRGB>::Ptr& occupied_point_cloud,
-                pcl::PointCloud<pcl::PointXYZRGB>::Ptr& freespace_point_cloud, bool if_get_freespace = false, double = 0.0) {
+                pcl::PointCloud<pcl::PointXYZRGB>::Ptr& freespace_point_cloud, bool if_get_freespace = false, double time_stamp_double = 0.0) {
+        ++step_;                                                                                 // global_time_stamp, reference :173
         if (follow_globals_ && labels_version_ != dspLabelGlobals().version) {   // readObjectInfo ran since the tables were sent
             labels_ = dspLabelGlobals().tables;
             labels_version_ = dspLabelGlobals().version;
@@ -210,9 +234,13 @@ public:
                 for (int a = 0; a < 3; ++a) { if (k[a] < mn[a]) mn[a] = k[a]; if (k[a] > mx[a]) mx[a] = k[a]; }
             for (int a = 0; a < 3; ++a) { d.bbox_min[a] = mn[a] - 1.0; d.bbox_max[a] = mx[a] + 1.0; }
         }
-        appendFloatingTracks(ins_seg_result);
         const double pos[3] = {camera_position.x(), camera_position.y(), camera_position.z()};
         const double quat[4] = {camera_orientation.w(), camera_orientation.x(), camera_orientation.y(), camera_orientation.z()};
+        if (cfg_.consider_instance && !external_object_layer_) runObjectLayer(ins_seg_result, pos, quat, time_stamp_double);   // reference :188-190, 588-704
+        if (cfg_.consider_instance)   // pointcloud_tools.h:168 reads g_label_id_map_default with operator[]: an unknown label of a
+            for (const MaskKpts& m : ins_seg_result)   // non-static mask is known from the next frame on, with id 0
+                if (m.label != "static") labels_.label_id.emplace(m.label, 0);
+        appendFloatingTracks(ins_seg_result);
         const int rc = dspmap_update(h_, reinterpret_cast<const float*>(depth_value_mat.data), depth_value_mat.rows, depth_value_mat.cols,
                                      (int32_t)(depth_value_mat.step / sizeof(float)), masks.data(), (int32_t)masks.size(), pos, quat,
                                      moves_.data(), (int32_t)moves_.size(), remove_.data(), (int32_t)remove_.size(), if_get_freespace);
@@ -261,9 +289,15 @@ private:
     void appendFloatingTracks(const std::vector<MaskKpts>& ins_seg_result) {
         if (cfg_.consider_instance)
             for (const MaskKpts& m : ins_seg_result)
-                if (m.label != "static" && m.track_id <= labels_.max_movable_instance_id) { known_objects_.insert(m.track_id); born_tracks_.insert(m.track_id); }
-        for (const auto& mv : moves_) known_objects_.insert(mv.track_id);
-        for (int32_t t : remove_) { known_objects_.erase(t); born_tracks_.erase(t); }
+                if (m.label != "static" && m.track_id <= labels_.max_movable_instance_id) {
+                    born_tracks_.insert(m.track_id);
+                    if (external_object_layer_) known_objects_.insert(m.track_id);
+                }
+        if (external_object_layer_) {
+            for (const auto& mv : moves_) known_objects_.insert(mv.track_id);
+            for (int32_t t : remove_) known_objects_.erase(t);
+        }
+        for (int32_t t : remove_) born_tracks_.erase(t);
         std::set<int> candidates = born_tracks_;
         for (int v = 0; v < 256; ++v) {   // tracks the static-mask look-up can produce (pointcloud_tools.h:137-138)
             auto it = labels_.label_id_reversed.find(v + 1);
@@ -271,12 +305,45 @@ private:
             if (t <= labels_.max_movable_instance_id) candidates.insert(t);
         }
         for (int t : candidates) {
-            if (known_objects_.count(t)) continue;
+            if (external_object_layer_ ? known_objects_.count(t) > 0 : tracker_.isTracked(t)) continue;
             bool listed = false;
             for (int32_t r : remove_) listed |= r == t;
             if (!listed) remove_.push_back(t);
             born_tracks_.erase(t);
+            tracker_.forget(t);
         }
+    }
+
+    void configureTracker(dsp_adapter::ObjectTracker::Mode mode) {
+        const double scale = cfg_.boost_mode ? 0.5 : 1.0;                                        // settings.h:128-143 (float products of the reference)
+        dsp_adapter::ObjectTracker::Camera cam{(double)(float)(scale * cfg_.fx), (double)(float)(scale * cfg_.fy), (double)(float)(scale * cfg_.cx),
+                                               (double)(float)(scale * cfg_.cy), (int)(scale * cfg_.image_width), (int)(scale * cfg_.image_height)};
+        const int biggest = std::max(std::max(cfg_.voxel_bits_x, cfg_.voxel_bits_y), cfg_.voxel_bits_z);   // mc_ring/buffer.h:31-32
+        tracker_.configure(mode, cam, (double)(cfg_.voxel_size * (float)(1 << (biggest - 1))) * 1.2);    // reference :356
+    }
+
+    // objectLevelUpdate (reference :306-566) on this frame's tracking result, then the head of subObjectLevelUpdate
+    // (:588-704): the moves and drops of the frame
+    void runObjectLayer(const std::vector<MaskKpts>& ins_seg_result, const double pos[3], const double quat[4], double time_stamp) {
+        std::vector<dsp_adapter::ObjectTracker::Observation> seen;
+        for (const MaskKpts& m : ins_seg_result) {
+            if (m.track_id > labels_.max_movable_instance_id || m.label == "static") continue;   // reference :317
+            dsp_adapter::ObjectTracker::Observation o;
+            o.track_id = m.track_id;
+            auto it = labels_.label_id.find(m.label);
+            o.label_known = it != labels_.label_id.end();
+            o.label_id = o.label_known ? it->second : 0;
+            for (const auto& k : m.kpts_current) o.kpts_current.push_back({k[0], k[1], k[2]});
+            for (const auto& k : m.kpts_previous) o.kpts_previous.push_back({k[0], k[1], k[2]});
+            seen.push_back(std::move(o));
+        }
+        tracker_.observe(seen, pos, quat, time_stamp, step_);
+        std::vector<dsp_adapter::ObjectTracker::Move> mv;
+        std::vector<int> dropped;
+        tracker_.plan(step_, max_obersevation_lost_time_, mv, dropped);
+        moves_.clear(); remove_.clear();
+        for (const auto& m : mv) { dspmap_object_move d; d.track_id = m.track_id; for (int k = 0; k < 16; ++k) d.t[k] = m.t[k]; moves_.push_back(d); }
+        for (int t : dropped) remove_.push_back(t);
     }
 
     void pushColors() {   // reference :1274-1351; which "#if SETTING" block applies follows from the configuration
@@ -299,9 +366,12 @@ private:
     unsigned labels_version_ = 0;
     dspmap_params prm_{};
     dspmap_t* h_ = nullptr;
-    int max_obersevation_lost_time_ = 0;
+    int max_obersevation_lost_time_ = 5;                                                       // reference :30
     float match_score_threshold_ = 0.5f;
     bool if_out_evaluation_format_ = false;
     std::vector<dspmap_object_move> moves_;
     std::vector<int32_t> remove_;
+    dsp_adapter::ObjectTracker tracker_;
+    bool external_object_layer_ = false;
+    uint32_t step_ = 0;
 };

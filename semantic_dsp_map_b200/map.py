@@ -241,6 +241,7 @@ class SemanticDSPMap:
         # are tracked objects, and which tracks can own particles without being one ("floating", semantic_dsp_map.h:712-737)
         self._known_objects = set()
         self._born_tracks = set()
+        self._met_labels = set()
         self._refresh_lut_tracks()
 
     # -- setters, semantic_dsp_map.h:101-166 ----------------------------------------------------------------------------
@@ -304,24 +305,35 @@ class SemanticDSPMap:
         self.engine.clear()
         self._known_objects.clear()          # object_set_.clear(), semantic_dsp_map.h:74-81
         self._born_tracks.clear()
+        self._met_labels.clear()
 
     def _refresh_lut_tracks(self):
         max_movable = self.labels.max_movable_instance_id
         self._lut_movable_tracks = {int(t) for t in np.unique(self.labels.static_value_to_track()) if int(t) <= max_movable}
 
-    def _floating_tracks(self, ins_seg_result, moves, remove_tracks):
+    def _floating_tracks(self, ins_seg_result, moves, remove_tracks, camera_position=(0.0, 0.0, 0.0)):
         """semantic_dsp_map.h:712-737 ("floating objects"): after the moves and the removals of a frame, every track that owns
         particles in obj_ptc_hash_map but has no entry in object_tracking_hash_map is removed with all its particles.  Particles
         enter obj_ptc_hash_map at birth when their track id is <= g_max_movable_object_instance_id (:1160-1162); objects enter
-        object_tracking_hash_map when objectLevelUpdate sees their mask (:346-364), which only runs with g_consider_instance.
+        object_tracking_hash_map when objectLevelUpdate sees their mask (:346-364), which only runs with g_consider_instance,
+        and only when the label is known (:330-334; pointcloud_tools.h:168 default-inserts an unknown label, so it is known
+        from the next frame on) and some key point lies within 1.2 x the map's half size of the camera (:348-360: an object
+        reported WITHOUT key points is never registered).
         Hence e.g. in static mode the pixels of a movable CLASS of the static mask (instance id -1 -> track 0,
         pointcloud_tools.h:137-138) live for exactly one frame.  Returns the tracks to append to this frame's removals."""
         max_movable = self.labels.max_movable_instance_id
         if self.config.consider_instance:
+            half = float(np.float32(self.config.voxel_size) * np.float32(1 << (max(self.config.voxel_bits) - 1))) * 1.2
+            cam = np.asarray(camera_position, np.float64).reshape(3)
             for m in ins_seg_result:
                 if m.label != "static" and m.track_id <= max_movable:
-                    self._known_objects.add(int(m.track_id))
                     self._born_tracks.add(int(m.track_id))
+                    if int(m.track_id) in self._known_objects or not (m.label in self.labels.label_id_map or m.label in self._met_labels):
+                        continue
+                    k = np.asarray(m.kpts_current, np.float64).reshape(-1, 3)
+                    if len(k) and np.abs(k - cam).max(axis=1).min() <= half:
+                        self._known_objects.add(int(m.track_id))
+            self._met_labels.update(m.label for m in ins_seg_result if m.label != "static")
         for track, _ in moves:
             self._known_objects.add(int(track))
         for track in remove_tracks:
@@ -361,7 +373,7 @@ class SemanticDSPMap:
             depth = np.ascontiguousarray(depth)
         self._keep = [depth]
         masks = self.lower_masks(ins_seg_result)
-        remove_tracks = list(remove_tracks) + self._floating_tracks(ins_seg_result, moves, remove_tracks)
+        remove_tracks = list(remove_tracks) + self._floating_tracks(ins_seg_result, moves, remove_tracks, camera_position)
         self.engine.update_raw("update", depth.ctypes.data, depth.shape[0], depth.shape[1], depth.strides[0] // 4, masks,
                                camera_position, camera_orientation, moves, remove_tracks, if_get_freespace)
         return self.engine.result_arrays(copy_result)

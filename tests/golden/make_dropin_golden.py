@@ -14,6 +14,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 FRAMES = 4
+MOVING_FRAMES = 11                 # scene "moving" of tests/dropin_driver.cpp: the whole object layer runs (Kabsch, filter, coasting, drop)
+MOVING_KEPT = (2, 6, 8, 9, 10)     # frames whose clouds are kept in dropin_reference_moving.npz
 REC = np.dtype([("xyz", "<f4", 3), ("rgb", "u1", 3)])
 
 
@@ -39,6 +41,13 @@ def main():
                                "-I" + os.path.join(ROOT, "oracle", "ref_stubs"), "-I/root/reference/include", os.path.join(ROOT, "tests", "dropin_driver.cpp"), "-o", exe])
         subprocess.check_call([exe, str(FRAMES), out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         clouds = read_clouds(out)
+        subprocess.check_call([exe, str(MOVING_FRAMES), out, "moving"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        moving = read_clouds(out)
+    kept = {}
+    for t in MOVING_KEPT:
+        kept[f"lattice_{t}"], kept[f"rgb_{t}"] = lattice(moving[t]["xyz"]), moving[t]["rgb"]
+    np.savez_compressed(os.path.join(HERE, "dropin_reference_moving.npz"), counts=np.asarray([len(c) for c in moving], np.int64), **kept)
+    print("moving:", [len(c) for c in moving], os.path.getsize(os.path.join(HERE, "dropin_reference_moving.npz")), "bytes")
     last = clouds[-1]
     np.savez_compressed(os.path.join(HERE, "dropin_reference.npz"), counts=np.asarray([len(c) for c in clouds], np.int64),
                         last_lattice=lattice(last["xyz"]), last_rgb=last["rgb"])

@@ -1,0 +1,106 @@
+// Scenarios for the object-layer pin (TEST INFRASTRUCTURE): sequences of tracking results (track id, label, 3-D key points),
+// camera poses and time stamps, generated identically for the reference harness (reference_harness.cpp, the reference's own
+// objectLevelUpdate / ObjectSet driven through SemanticDSPMap::update) and for the adapter's tracker (tracker_harness.cpp).
+#pragma once
+#include <cmath>
+#include <string>
+#include <vector>
+
+namespace scen {
+struct Obj { int track_id; std::string label; std::vector<std::array<double, 3>> kpts; };
+struct Frame { double pos[3]; double quat_wxyz[4]; double time_stamp; std::vector<Obj> objects; };
+struct Scenario { std::string name; int max_lost; std::vector<Frame> frames; int setting = 3; };   // setting: the reference preset the scenario is meant for
+
+inline std::vector<std::array<double, 3>> box(double x, double y, double z, double yaw) {
+    // four corners of a 1.8 x 1.5 x 4.2 m box (two along the width, one along the length, one up), rotated about +y
+    const double c = std::cos(yaw), s = std::sin(yaw);
+    const double local[4][3] = {{-0.9, 0.0, -2.1}, {0.9, 0.0, -2.1}, {-0.9, 0.0, 2.1}, {-0.9, -1.5, -2.1}};
+    std::vector<std::array<double, 3>> out;
+    for (auto& l : local) out.push_back({x + c * l[0] + s * l[2], y + l[1], z - s * l[0] + c * l[2]});
+    return out;
+}
+inline std::vector<std::array<double, 3>> cloud8(double x, double y, double z, double yaw, double outlier) {
+    // eight matched feature points on a car-sized body (SETTING 1 / 2: Superpoint matches); the last one is off by `outlier` metres
+    const double c = std::cos(yaw), s = std::sin(yaw);
+    const double local[8][3] = {{-0.9, 0.0, -2.1}, {0.9, -0.2, -2.0}, {-0.8, -0.4, 2.1}, {-0.9, -1.5, -1.7}, {0.7, -1.2, 1.9}, {0.2, -0.7, 0.3}, {0.9, -0.1, 1.2}, {-0.3, -1.1, -0.9}};
+    std::vector<std::array<double, 3>> out;
+    for (auto& l : local) out.push_back({x + c * l[0] + s * l[2], y + l[1], z - s * l[0] + c * l[2]});
+    out[7][0] += outlier;
+    return out;
+}
+inline Frame frame(double t, double cam_z) { Frame f{{0.0, 0.0, cam_z}, {1.0, 0.0, 0.0, 0.0}, t, {}}; return f; }
+
+inline std::vector<Scenario> all() {
+    std::vector<Scenario> out;
+    {   // a car driving across at 0.5 m / frame, lost after frame 7, coasting, dropped
+        Scenario s{"translating_then_lost", 3, {}};
+        for (int t = 0; t < 14; ++t) { Frame f = frame(0.1 * t, 0.05 * t); if (t <= 7) f.objects.push_back({5, "Vehicle", box(-3.0 + 0.5 * t, 1.0, 8.0, 0.0)}); s.frames.push_back(f); }
+        out.push_back(s);
+    }
+    {   // turning while driving: Kabsch must recover a rotation about +y; two objects, one parked
+        Scenario s{"turning_and_parked", 20, {}};
+        for (int t = 0; t < 12; ++t) {
+            Frame f = frame(0.1 * t, 0.0);
+            f.objects.push_back({9, "Vehicle", box(-2.0 + 0.4 * t, 1.0, 9.0 + 0.2 * t, 0.07 * t)});
+            f.objects.push_back({2, "person", box(3.0, 1.0, 6.0, 0.3)});
+            s.frames.push_back(f);
+        }
+        out.push_back(s);
+    }
+    {   // key frame refresh after 2 s; slow creep below the movement threshold, then a burst
+        Scenario s{"creep_then_burst_long", 20, {}};
+        for (int t = 0; t < 40; ++t) {
+            Frame f = frame(0.1 * t, 0.0);
+            const double x = t < 25 ? 0.01 * t : 0.25 + 0.6 * (t - 25);
+            f.objects.push_back({7, "Vehicle", box(-4.0 + x, 1.0, 10.0, 0.0)});
+            s.frames.push_back(f);
+        }
+        out.push_back(s);
+    }
+    {   // quirks: an object too far to be added, an unknown label, the last key point leaving the view, a two-key-point report
+        Scenario s{"far_unknown_outofview_short", 4, {}};
+        for (int t = 0; t < 10; ++t) {
+            Frame f = frame(0.1 * t, 0.0);
+            f.objects.push_back({11, "Vehicle", box(0.0, 1.0, 40.0 - 4.0 * t, 0.0)});           // far at first (1.2 x half map = 11.52 m)
+            f.objects.push_back({12, "Unicorn", box(1.0, 1.0, 7.0, 0.0)});
+            auto k = box(-2.0 + 0.6 * t, 1.0, 6.0, 0.0);
+            if (t >= 5) k[3] = {k[3][0], k[3][1] - 30.0, k[3][2]};                               // the last key point far above the image
+            f.objects.push_back({13, "Vehicle", k});
+            auto two = box(2.0 + 0.3 * t, 1.0, 9.0, 0.0); two.resize(2);
+            f.objects.push_back({14, "Vehicle", t % 2 ? two : box(2.0 + 0.3 * t, 1.0, 9.0, 0.0)});
+            s.frames.push_back(f);
+        }
+        out.push_back(s);
+    }
+    {   // irregular time stamps, a gap longer than a second while lost, then re-observed
+        Scenario s{"irregular_time_reappear", 6, {}};
+        const double ts[] = {0.0, 0.1, 0.25, 0.3, 0.5, 0.55, 2.0, 2.1, 2.2, 2.3, 2.4, 2.5};
+        for (int t = 0; t < 12; ++t) {
+            Frame f = frame(ts[t], 0.02 * t);
+            if (t < 5 || t > 8) f.objects.push_back({21, "Vehicle", box(-3.0 + 0.45 * t, 1.0, 7.5, 0.02 * t)});
+            s.frames.push_back(f);
+        }
+        out.push_back(s);
+    }
+    {   // SETTING 2: matched key points (previous -> current), one gross outlier every third frame, a stretch of too few points, a stop
+        Scenario s{"matched_keypoints_outlier", 5, {}, 2};
+        for (int t = 0; t < 16; ++t) {
+            Frame f = frame(0.1 * t, 0.0);
+            const double x = t < 10 ? 0.35 * t : 3.5;
+            auto k = cloud8(-2.0 + x, 1.0, 9.0 + 0.1 * x, 0.03 * std::min(t, 10), t % 3 == 2 ? 1.7 : 0.0);
+            if (t == 6 || t == 7) k.resize(4);
+            if (t != 12 && t != 13) f.objects.push_back({4, "Vehicle", k});
+            s.frames.push_back(f);
+        }
+        out.push_back(s);
+    }
+    return out;
+}
+// key points of the same track in the previous frame (what the tracking node sends as kpts_last); the current ones when there are none
+inline std::vector<std::array<double, 3>> previous(const Scenario& s, size_t frame_index, const Obj& o) {
+    if (frame_index > 0)
+        for (const Obj& p : s.frames[frame_index - 1].objects)
+            if (p.track_id == o.track_id && p.kpts.size() == o.kpts.size()) return p.kpts;
+    return o.kpts;
+}
+}  // namespace scen

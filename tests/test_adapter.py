@@ -143,3 +143,49 @@ def test_the_reference_node_itself_on_the_engine_publishes_the_reference_clouds(
     common = a & b
     differing = sum(col_a[v] != col_b[v] for v in common)
     assert differing <= 0.002 * len(common), (differing, len(common))
+
+
+@pytest.mark.gpu
+def test_moving_object_through_the_adapter_object_layer_matches_the_reference():
+    """Scene "moving" of tests/dropin_driver.cpp: a box with four 3-D key points slides 0.125 m a frame, is lost after frame 6,
+    coasts on its estimated velocity and is dropped after three unobserved steps - the reference's whole object layer
+    (objectLevelUpdate, Kabsch on the key points, moving-or-not filter, prediction, removal; semantic_dsp_map.h:306-566,
+    588-704), which the adapter runs on the host (adapter/dsp_object_tracker.h) and hands to the engine as moves / removals.
+    The reference jitters every moved particle with draws from a std::random_device-seeded table, so two runs of the
+    reference itself differ by up to 3.6 % of the voxels; the comparison with tests/golden/dropin_reference_moving.npz is
+    statistical: the Vehicle voxels (evaluation format: red = label 14) must sit where the reference's sit, frame by frame,
+    and be gone when the reference drops them; the static part of the cloud must agree to 1.5 %."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_dropin_golden as G
+    lib_dir = os.path.join(ROOT, "semantic_dsp_map_b200")
+    exe, out = os.path.join(ROOT, "tests", "dropin_adapter_moving"), os.path.join(ROOT, "tests", "dropin_adapter_moving.bin")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-w", "-I" + os.path.join(ROOT, "oracle", "ref_stubs"), "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "dropin_driver.cpp"), "-o", exe, "-L" + lib_dir, "-l:libdspmap_b200.so", "-Wl,-rpath," + lib_dir])
+    try:
+        subprocess.run([exe, str(G.MOVING_FRAMES), out, "moving"], check=True, capture_output=True, timeout=300)
+        clouds = G.read_clouds(out)
+    finally:
+        for p in (exe, out, out + ".csv"):
+            if os.path.exists(p):
+                os.remove(p)
+    want = np.load(os.path.join(ROOT, "tests", "golden", "dropin_reference_moving.npz"))
+    counts = np.asarray([len(c) for c in clouds])
+    assert len(counts) == G.MOVING_FRAMES
+    assert np.all(np.abs(counts - want["counts"]) <= 0.02 * np.maximum(want["counts"], 1)), (counts, want["counts"])
+    key = lambda a: {tuple(v) for v in a.tolist()}  # noqa: E731
+    seen_vehicle = 0
+    for t in G.MOVING_KEPT:
+        lat, rgb = G.lattice(clouds[t]["xyz"]), clouds[t]["rgb"]
+        ref_lat, ref_rgb = want[f"lattice_{t}"], want[f"rgb_{t}"]
+        veh, ref_veh = lat[rgb[:, 0] == 14], ref_lat[ref_rgb[:, 0] == 14]
+        if len(ref_veh) == 0:
+            assert len(veh) == 0, (t, len(veh))                         # dropped with all its particles
+        else:
+            seen_vehicle += 1
+            assert abs(len(veh) - len(ref_veh)) <= 0.2 * len(ref_veh), (t, len(veh), len(ref_veh))
+            assert np.all(np.abs(veh.mean(0) - ref_veh.mean(0)) <= 0.6), (t, veh.mean(0), ref_veh.mean(0))   # in voxels; the box moves 0.83 voxels a frame
+            assert np.all(np.abs(veh.min(0) - ref_veh.min(0)) <= 2) and np.all(np.abs(veh.max(0) - ref_veh.max(0)) <= 2), t
+        a, b = key(lat[rgb[:, 0] != 14]), key(ref_lat[ref_rgb[:, 0] != 14])
+        assert len(a ^ b) <= 0.015 * len(b), (t, len(a ^ b), len(b))
+    assert seen_vehicle >= 3
