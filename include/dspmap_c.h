@@ -278,6 +278,59 @@ int dspmap_selftest_colour(dspmap_t* h, uint32_t* rgb_to_hsv /* 2^24 */, uint32_
 /* copies at most cap bytes to dst (host); *n_bytes = full size of the dump */
 int dspmap_dump(dspmap_t* h, int32_t what, void* dst, size_t cap, size_t* n_bytes);
 
+/* ---- object layer (host only: no GPU, no map handle needed) -----------------------------
+ * What the reference decides per frame about its handful of tracked objects before it touches
+ * a particle: objectLevelUpdate (semantic_dsp_map.h:306-566: register / update / coast objects;
+ * Kabsch + 3-point RANSAC on the key points, utils/basic_algorithms.h:56-195; moving-or-not
+ * filter and constant-velocity prediction, object_layer.h:94-258, 467-566) and the head of
+ * subObjectLevelUpdate (:588-704: which objects move by which matrix, which are dropped).
+ * Its product per frame - `moves` and `dropped` - is what dspmap_update() takes.
+ * Implementation: adapter/dsp_object_tracker.h (the C++ adapter uses it directly). */
+typedef struct dspmap_objects dspmap_objects_t;
+
+enum {                       /* which "#if SETTING" flavour of the reference's object layer  */
+    DSPMAP_OBJECTS_STATIC = 0,            /* SETTING 0: objects never move                   */
+    DSPMAP_OBJECTS_ALWAYS_MOVING = 1,     /* SETTING 1: matched key points, every update moves */
+    DSPMAP_OBJECTS_MATCHED_KEYPOINTS = 2, /* SETTING 2: matched key points + movement filter  */
+    DSPMAP_OBJECTS_BOX_KEYPOINTS = 3      /* SETTING 3: four 3-D box key points per object    */
+};
+
+/* one non-static entry of ins_seg_result (utils/tracking_result_handler.h:15-26) with
+ * track_id <= g_max_movable_object_instance_id, after the id wrap of semantic_dsp_map.h:179-186 */
+typedef struct dspmap_object_observation {
+    int32_t track_id;
+    int32_t label_known;          /* label found in g_label_id_map_default (:330-334)        */
+    int32_t label_id;
+    int32_t n_kpts;
+    const double* kpts_current;   /* n_kpts x 3, global frame                                */
+    const double* kpts_previous;  /* n_kpts x 3 (matched key points) or NULL = same as current */
+} dspmap_object_observation;
+
+/* cfg: grid bits, voxel size, intrinsics, image size and boost mode are read (map extent for the
+ * "too far to register" rule :356, internal camera for the out-of-view rule :1421-1442) */
+int  dspmap_objects_create(const dspmap_config* cfg, int32_t mode, dspmap_objects_t** out);
+void dspmap_objects_destroy(dspmap_objects_t* o);
+int  dspmap_objects_clear(dspmap_objects_t* o);                       /* object_set_.clear(), :74-81 */
+/* setBeyesianMovementParameters, semantic_dsp_map.h:142-148 */
+int  dspmap_objects_set_movement_filter(dspmap_objects_t* o, double distance_threshold, double probability_threshold,
+                                        double increment, double decrement);
+/* the reference seeds its RANSAC from std::random_device; fixed by default here */
+int  dspmap_objects_set_seed(dspmap_objects_t* o, uint32_t seed);
+/* One frame: objectLevelUpdate on the observations, then the move / drop decisions of the frame.
+ * max_lost = max_obersevation_lost_time (setMapParameters :101).  Returns DSPMAP_ERR_CAPACITY when
+ * an output array is too small (n_moves / n_dropped then hold the needed sizes; state is updated). */
+int  dspmap_objects_step(dspmap_objects_t* o, const dspmap_object_observation* observations, int32_t n_observations,
+                         const double position[3], const double orientation_wxyz[4], double time_stamp, int32_t max_lost,
+                         dspmap_object_move* moves, int32_t moves_cap, int32_t* n_moves,
+                         int32_t* dropped, int32_t dropped_cap, int32_t* n_dropped);
+/* state of one object after the last step: tracked (in object_tracking_hash_map), has_flag
+ * (rigidbody_moved_vec not empty), moving, moved_probability, t16 = rigidbody_tmatrix_vec[0]
+ * (row-major double 4x4; untouched while has_flag is 0).  Any output may be NULL. */
+int  dspmap_objects_query(dspmap_objects_t* o, int32_t track_id, int32_t* tracked, int32_t* has_flag, int32_t* moving,
+                          double* moved_probability, double* t16);
+/* a "floating" track (:712-737) loses its stored key points */
+int  dspmap_objects_forget(dspmap_objects_t* o, int32_t track_id);
+
 #ifdef __cplusplus
 }
 #endif

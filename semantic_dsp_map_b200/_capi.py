@@ -59,6 +59,11 @@ class ObjectMove(C.Structure):
     _fields_ = [("track_id", C.c_int32), ("t", C.c_float * 16)]
 
 
+class ObjectObservation(C.Structure):
+    _fields_ = [("track_id", C.c_int32), ("label_known", C.c_int32), ("label_id", C.c_int32), ("n_kpts", C.c_int32),
+                ("kpts_current", C.c_void_p), ("kpts_previous", C.c_void_p)]
+
+
 class Result(C.Structure):
     _fields_ = [
         ("count", C.c_uint32), ("free_count", C.c_uint32),
@@ -121,6 +126,18 @@ SYMBOLS = {
     "dspmap_selftest_division": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_uint64)]),
     "dspmap_selftest_colour": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dspmap_dump": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    # host object layer (no GPU needed)
+    "dspmap_objects_create": (C.c_int, [C.POINTER(Config), C.c_int32, C.POINTER(C.c_void_p)]),
+    "dspmap_objects_destroy": (None, [C.c_void_p]),
+    "dspmap_objects_clear": (C.c_int, [C.c_void_p]),
+    "dspmap_objects_set_movement_filter": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "dspmap_objects_set_seed": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "dspmap_objects_step": (C.c_int, [C.c_void_p, C.POINTER(ObjectObservation), C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double,
+                                      C.c_int32, C.POINTER(ObjectMove), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32,
+                                      C.POINTER(C.c_int32)]),
+    "dspmap_objects_query": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                                       C.POINTER(C.c_double)]),
+    "dspmap_objects_forget": (C.c_int, [C.c_void_p, C.c_int32]),
 }
 
 _lib = None

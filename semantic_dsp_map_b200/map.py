@@ -233,7 +233,9 @@ class SemanticDSPMap:
         self._params = config.c_params()
         self.engine.set_params(self._params)
         self.engine.set_label_luts(self.labels)
-        self._movement = (0.0, 0.0, 0.0, 0.0)
+        self._movement = (0.1, 0.69, 0.1, 0.15)          # constructor defaults, semantic_dsp_map.h:36-39
+        self.max_obersevation_lost_time = 5              # :30
+        self.objects = None                              # host object layer, created at the first update() that needs it
         self._keep = []
         self._eval_format = False
         self._colors = None
@@ -290,8 +292,29 @@ class SemanticDSPMap:
         self._colors = c
         self.engine.set_colors(c)
 
-    def setBeyesianMovementParameters(self, a, b, c, d):
-        self._movement = (a, b, c, d)  # object layer (host, out of scope): kept for interface parity
+    def setBeyesianMovementParameters(self, distance_threshold, probability_threshold, increment, decrement):   # semantic_dsp_map.h:142-148
+        self._movement = (distance_threshold, probability_threshold, increment, decrement)
+        if self.objects is not None:
+            self.objects.set_movement_filter(*self._movement)
+
+    def _object_layer(self):
+        if self.objects is None:
+            from .objects import ObjectLayer
+            self.objects = ObjectLayer(self.config)
+            self.objects.set_movement_filter(*self._movement)
+        return self.objects
+
+    def _run_object_layer(self, ins_seg_result, camera_position, camera_orientation, time_stamp):
+        """objectLevelUpdate on this frame's tracking result, then the move / drop decisions (semantic_dsp_map.h:188-190,
+        306-566, 588-704) - on the host, through the C ABI's object layer."""
+        max_movable = self.labels.max_movable_instance_id
+        obs = []
+        for m in ins_seg_result:
+            if m.label == "static" or m.track_id > max_movable:                      # :317
+                continue
+            known = m.label in self.labels.label_id_map or m.label in self._met_labels
+            obs.append((m.track_id, known, self.labels.label_id_of(m.label), m.kpts_current, m.kpts_previous))
+        return self._object_layer().step(obs, camera_position, camera_orientation, time_stamp, self.max_obersevation_lost_time)
 
     def setDepthNoiseModelParameters(self, first_order, zero_order):
         self._params.depth_noise_first_order, self._params.depth_noise_zero_order = first_order, zero_order
@@ -306,12 +329,14 @@ class SemanticDSPMap:
         self._known_objects.clear()          # object_set_.clear(), semantic_dsp_map.h:74-81
         self._born_tracks.clear()
         self._met_labels.clear()
+        if self.objects is not None:
+            self.objects.clear()
 
     def _refresh_lut_tracks(self):
         max_movable = self.labels.max_movable_instance_id
         self._lut_movable_tracks = {int(t) for t in np.unique(self.labels.static_value_to_track()) if int(t) <= max_movable}
 
-    def _floating_tracks(self, ins_seg_result, moves, remove_tracks, camera_position=(0.0, 0.0, 0.0)):
+    def _floating_tracks(self, ins_seg_result, moves, remove_tracks, camera_position=(0.0, 0.0, 0.0), builtin=False):
         """semantic_dsp_map.h:712-737 ("floating objects"): after the moves and the removals of a frame, every track that owns
         particles in obj_ptc_hash_map but has no entry in object_tracking_hash_map is removed with all its particles.  Particles
         enter obj_ptc_hash_map at birth when their track id is <= g_max_movable_object_instance_id (:1160-1162); objects enter
@@ -322,6 +347,16 @@ class SemanticDSPMap:
         Hence e.g. in static mode the pixels of a movable CLASS of the static mask (instance id -1 -> track 0,
         pointcloud_tools.h:137-138) live for exactly one frame.  Returns the tracks to append to this frame's removals."""
         max_movable = self.labels.max_movable_instance_id
+        if builtin:   # the object layer itself says which tracks are objects
+            if self.config.consider_instance:
+                self._born_tracks.update(int(m.track_id) for m in ins_seg_result if m.label != "static" and m.track_id <= max_movable)
+                self._met_labels.update(m.label for m in ins_seg_result if m.label != "static")
+            self._born_tracks -= {int(t) for t in remove_tracks}
+            floating = sorted(t for t in (self._lut_movable_tracks | self._born_tracks) if not self.objects.is_tracked(t) and t not in remove_tracks)
+            for t in floating:
+                self.objects.forget(t)
+            self._born_tracks -= set(floating)
+            return floating
         if self.config.consider_instance:
             half = float(np.float32(self.config.voxel_size) * np.float32(1 << (max(self.config.voxel_bits) - 1))) * 1.2
             cam = np.asarray(camera_position, np.float64).reshape(3)
@@ -362,10 +397,12 @@ class SemanticDSPMap:
 
     # -- semantic_dsp_map.h:170-251 -----------------------------------------------------------------------------------------
     def update(self, depth_value_mat: np.ndarray, ins_seg_result: Sequence[MaskKpts], camera_position, camera_orientation,
-               if_get_freespace: bool = False, time_stamp_double: float = 0.0, moves=(), remove_tracks=(),
+               if_get_freespace: bool = False, time_stamp_double: float = 0.0, moves=None, remove_tracks=(),
                copy_result: bool = True) -> OccupancyResult:
-        """One frame.  ``camera_orientation`` is (w, x, y, z).  ``moves`` = [(track_id, 4x4)], ``remove_tracks`` = [track_id]:
-        what the host-side object layer (objectLevelUpdate, out of scope) decided for this frame."""
+        """One frame.  ``camera_orientation`` is (w, x, y, z).  With ``moves=None`` (default) the object layer of the
+        reference (objectLevelUpdate) runs on the host from the masks' key points and ``time_stamp_double``, like in the
+        reference.  A caller with an object layer of their own passes ``moves`` = [(track_id, 4x4)] and ``remove_tracks`` =
+        [track_id] instead (an empty list = "no object moves this frame")."""
         depth = np.asarray(depth_value_mat)
         if depth.dtype != np.float32 or depth.ndim != 2:
             raise TypeError("depth must be a 2-D float32 array (CV_32FC1, metres)")
@@ -373,7 +410,12 @@ class SemanticDSPMap:
             depth = np.ascontiguousarray(depth)
         self._keep = [depth]
         masks = self.lower_masks(ins_seg_result)
-        remove_tracks = list(remove_tracks) + self._floating_tracks(ins_seg_result, moves, remove_tracks, camera_position)
+        builtin = moves is None
+        if builtin:
+            moves, dropped = self._run_object_layer(ins_seg_result, camera_position, camera_orientation, time_stamp_double) if self.config.consider_instance else ([], [])
+            self._object_layer()
+            remove_tracks = list(remove_tracks) + dropped
+        remove_tracks = list(remove_tracks) + self._floating_tracks(ins_seg_result, moves, remove_tracks, camera_position, builtin)
         self.engine.update_raw("update", depth.ctypes.data, depth.shape[0], depth.shape[1], depth.strides[0] // 4, masks,
                                camera_position, camera_orientation, moves, remove_tracks, if_get_freespace)
         return self.engine.result_arrays(copy_result)

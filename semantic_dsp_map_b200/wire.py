@@ -248,11 +248,12 @@ def read_records(f):
 
 def replay(dsp_map, records, if_get_freespace=False, moves_for=None):
     """Feed recorded (depth, pose, mask group) triples through ``SemanticDSPMap.update`` the way the node does; yields
-    (seq, OccupancyResult).  ``moves_for(frame) -> (moves, remove_tracks)`` stands in for the object layer."""
+    (seq, OccupancyResult).  ``moves_for(frame) -> (moves, remove_tracks)`` replaces the built-in host object layer with the
+    caller's own; by default the map runs objectLevelUpdate itself from the key points and the pose time stamp, like the node."""
     for rec in records:
         fr = to_frame(*rec)
         if fr is None:
             continue
-        moves, remove = moves_for(fr) if moves_for else ((), ())
+        moves, remove = moves_for(fr) if moves_for else (None, ())
         yield fr.seq, dsp_map.update(fr.depth, fr.tracking_result, fr.position, fr.orientation, if_get_freespace, fr.time_stamp, moves=moves,
                                      remove_tracks=remove)

@@ -23,6 +23,8 @@ sys.path.insert(0, ROOT)
 from semantic_dsp_map_b200 import wire  # noqa: E402
 
 FRAMES = 4
+MOVING_FRAMES = 11                 # scene "moving" of tests/dropin_driver.cpp (the object layer runs: Kabsch, filter, coasting, drop)
+MOVING_KEPT = (2, 6, 8, 9, 10)
 FIRST_SEQ = 2          # src/mapping.cpp:166 drops depth images with header.seq < 2
 REC = np.dtype([("xyz", "<f4", 3), ("rgb", "u1", 3)])
 
@@ -41,7 +43,7 @@ beyesian_movement_probability_threshold: 0.3
 if_consider_depth_noise: true
 if_use_independent_filter: false
 match_score_threshold: 0.6
-max_obersevation_lost_time: 20
+max_obersevation_lost_time: {max_lost}
 nb_ptc_num_per_point: 1
 noise_number: 0.2
 detection_probability: 0.8
@@ -61,13 +63,17 @@ OBJECT_INFO_CSV = (
     "14,Vehicle,-1,142,0,0\n15,truck,65521,70,0,0\n")
 
 
-def scene(t):
-    """Frame t of the scene of tests/dropin_driver.cpp, in the same float32 arithmetic: a ground plane 1.5 m below the camera, a
-    wall 7 m ahead of the start, a 1.5 x 1.5 m box face at 4 m, a sprinkle of far pixels; the camera advances 0.3 m a frame."""
+def scene(t, moving=False):
+    """Frame t of the scenes of tests/dropin_driver.cpp, in the same float32 arithmetic: a ground plane 1.5 m below the camera, a
+    wall 7 m ahead of the start, a 1.5 x 1.5 m box face at 4 m, a sprinkle of far pixels; the camera advances 0.3 m a frame.
+    moving: the box slides 0.125 m a frame (camera 0.125 m a frame), four key points, detection lost after frame 6.
+    Returns depth, static class image, box mask, camera z, key points (None when the box is not detected)."""
     f32 = np.float32
     H, W = 720, 1280
     fx, cx, cy = f32(527.8191528320312), f32(633.9357299804688), f32(366.3338623046875)
-    cam_z = 0.3 * t
+    cam_z = 0.125 * t if moving else 0.3 * t
+    box_x = f32(0.125) * f32(t) if moving else f32(0.0)
+    box_seen = (not moving) or t <= 6
     wall, box = f32(7.0 - cam_z), f32(4.0 - cam_z)
     i = np.arange(H, dtype=f32)[:, None]
     j = np.arange(W, dtype=f32)[None, :]
@@ -80,33 +86,37 @@ def scene(t):
     road = (ry > f32(1e-6)) & (ground < d)
     d = np.where(road, ground, d).astype(f32)
     c[road] = 0
-    bx, by = rx * box, ry * box
+    bx, by = rx * box - box_x, ry * box
     hit = (box > f32(0.5)) & (bx > f32(-0.2)) & (bx < f32(1.3)) & (by > f32(0.0)) & (by < f32(1.5)) & (box < d)
     d = np.where(hit, box, d).astype(f32)
-    c[hit] = 13
-    car = np.where(hit, 255, 0).astype(np.uint8)
+    c[hit] = 13 if box_seen else 3
+    car = np.where(hit & box_seen, 255, 0).astype(np.uint8)
     ii, jj = np.arange(H)[:, None], np.arange(W)[None, :]
     d[(ii * 131 + jj * 17 + t * 7) % 97 == 0] = f32(16.0)
-    return d, c, car, cam_z
+    b = float(box_x)
+    kp = None
+    if box_seen:
+        kp = [[b - 0.25, 0.0, 4.0], [b - 0.125, 0.0, 4.0], [b + 1.25, 1.5, 5.0], [b - 0.25, 0.5, 4.5]] if moving else [[-0.25, 0.0, 4.0], [1.25, 1.5, 5.0]]
+    return d, c, car, cam_z, (None if kp is None else np.asarray(kp, np.float32))
 
 
-def write_package(td):
+def write_package(td, moving=False):
     """The package directory ros::package::getPath returns (cfg/ with the options and the label CSV) and the replay file."""
     os.makedirs(os.path.join(td, "cfg"), exist_ok=True)
     with open(os.path.join(td, "cfg", "options.yaml"), "w") as f:
-        f.write(OPTIONS_YAML)
+        f.write(OPTIONS_YAML.format(max_lost=3 if moving else 20))
     with open(os.path.join(td, "cfg", "object_info.csv"), "w") as f:
         f.write(OBJECT_INFO_CSV)
     rec = os.path.join(td, "replay_in.bin")
-    kp = np.asarray([[-0.25, 0.0, 4.0], [1.25, 1.5, 5.0]], np.float32)
     with open(rec, "wb") as f:
-        for t in range(FRAMES):
-            d, c, car, cam_z = scene(t)
+        for t in range(MOVING_FRAMES if moving else FRAMES):
+            d, c, car, cam_z, kp = scene(t, moving)
             ns = int(round(0.1 * t * 1e9))
             h = wire.Header(FIRST_SEQ + t, ns // 10**9, ns % 10**9, "zed2")
             group = wire.MaskGroup(h, [
-                wire.WireObject("static", 65535, wire.image_from_array(c, "mono8", h), (0, 0, 0), (0, 0, 0), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32)),
-                wire.WireObject("Vehicle", 3, wire.image_from_array(car, "mono8", h), (0, 0, 0), (0, 0, 0), kp, kp)])
+                wire.WireObject("static", 65535, wire.image_from_array(c, "mono8", h), (0, 0, 0), (0, 0, 0), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))])
+            if kp is not None:
+                group.objects.append(wire.WireObject("Vehicle", 3, wire.image_from_array(car, "mono8", h), (0, 0, 0), (0, 0, 0), kp, kp))
             wire.write_record(f, wire.encode_image(wire.image_from_array(d, "32FC1", h)), wire.encode_pose_stamped(h, (0.0, 0.0, cam_z), (1.0, 0.0, 0.0, 0.0)),
                               wire.encode_mask_group(group))
     return rec
@@ -127,8 +137,8 @@ def read_published(path, topic="occupied_point"):
     return out
 
 
-def run_node(exe, td):
-    rec = write_package(td)
+def run_node(exe, td, moving=False):
+    rec = write_package(td, moving)
     out = os.path.join(td, "published.bin")
     env = dict(os.environ, DSPMAP_REPLAY_PACKAGE_PATH=td, DSPMAP_REPLAY_IN=rec, DSPMAP_REPLAY_OUT=out)
     subprocess.run([exe, "options.yaml", "object_info.csv"], env=env, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=900)
@@ -145,6 +155,13 @@ def main():
         subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-w", "-I" + os.path.join(ROOT, "tests", "ros_stubs"),
                                "-I" + os.path.join(ROOT, "oracle", "ref_stubs"), "-I/root/reference/include", "/root/reference/src/mapping.cpp", "-o", exe])
         clouds = run_node(exe, td)
+        with tempfile.TemporaryDirectory() as td2:
+            moving = run_node(exe, td2, moving=True)
+    kept = {}
+    for t in MOVING_KEPT:
+        kept[f"lattice_{t}"], kept[f"rgb_{t}"] = lattice(moving[t]["xyz"]), moving[t]["rgb"]
+    np.savez_compressed(os.path.join(HERE, "node_reference_moving.npz"), counts=np.asarray([len(c) for c in moving], np.int64), **kept)
+    print("moving:", [len(c) for c in moving], os.path.getsize(os.path.join(HERE, "node_reference_moving.npz")), "bytes")
     last = clouds[-1]
     path = os.path.join(HERE, "node_reference.npz")
     np.savez_compressed(path, counts=np.asarray([len(c) for c in clouds], np.int64), last_lattice=lattice(last["xyz"]), last_rgb=last["rgb"])

@@ -12,6 +12,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "object_layer")
 EXE = os.path.join(ROOT, "tests", "_built", "tracker_harness")
+LIB_DIR = os.path.join(ROOT, "semantic_dsp_map_b200")
 T_TOL = 1e-9
 
 
@@ -26,11 +27,15 @@ def golden():
     return out
 
 
-@pytest.fixture(scope="module")
-def harness():
+@pytest.fixture(scope="module", params=["c_abi", "direct_header"])
+def harness(request):
+    """c_abi: the dspmap_objects_* entry points of libdspmap_b200.so (host only, no GPU needed); direct_header: the C++ header
+    the way adapter/semantic_dsp_map.h uses it."""
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", os.path.join(SRC, "tracker_harness.cpp"), "-o", EXE])
-    return EXE
+    exe = EXE + "_" + request.param
+    extra = ["-DDIRECT_HEADER"] if request.param == "direct_header" else ["-L" + LIB_DIR, "-l:libdspmap_b200.so", "-Wl,-rpath," + LIB_DIR]
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", os.path.join(SRC, "tracker_harness.cpp"), "-o", exe] + extra)
+    return exe
 
 
 GOLDEN = golden()
@@ -52,6 +57,17 @@ def test_object_layer_follows_the_reference(harness, name):
         moving += "moving=1" in w
         dropped += "absent" in w
     assert moving > 0                              # every scenario has a moving object: the comparison is not vacuous
+    if harness.endswith("c_abi"):                  # the moves handed to dspmap_update are the float casts of the moving objects' matrices
+        moves = [ln.split() for ln in r.stderr.splitlines() if ln.startswith("MOVE ")]
+        drops = [ln.split() for ln in r.stderr.splitlines() if ln.startswith("DROP ")]
+        state = {(w.split()[1], w.split()[2]): w.split() for w in want}
+        assert len(moves) == sum("moving=1" in w for w in want)
+        for _, t, track, tx, ty, tz in moves:
+            ws = state[(t, track)]
+            assert ws[5] == "moving=1"
+            assert [float(tx), float(ty), float(tz)] == pytest.approx([float(ws[10]), float(ws[14]), float(ws[18])], abs=1e-6)
+        for _, t, track in drops:                  # a dropped object is absent from that frame on
+            assert state[(t, track)][3] == "absent" and state[(str(int(t) - 1), track)][5] == "moving=1"
 
 
 def test_scenarios_cover_the_branches():
