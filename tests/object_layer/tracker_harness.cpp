@@ -27,8 +27,10 @@ int main(int argc, char** argv) {
         if (s.setting == 3)   // SETTING 3 as shipped: boost mode halves the intrinsics (settings.h:100-119, 136-143); 1.2 x half of the 128-voxel axis
             tr.configure(ObjectTracker::kBoxKeypoints, {(double)(0.5f * 527.8191528320312f), (double)(0.5f * 527.8191528320312f), (double)(0.5f * 633.9357299804688f),
                                                         (double)(0.5f * 366.3338623046875f), 640, 360}, (double)(0.15f * 64) * 1.2);
-        else                  // SETTING 2 (settings.h:79-98): Virtual KITTI 2 camera, 0.2 m voxels, 256-voxel axes
+        else if (s.setting == 2)   // SETTING 2 (settings.h:79-98): Virtual KITTI 2 camera, 0.2 m voxels, 256-voxel axes
             tr.configure(ObjectTracker::kMatchedKeypoints, {725.0087, 725.0087, 620.5, 187.0, 1242, 375}, (double)(0.2f * 128) * 1.2);
+        else                       // SETTING 1 (settings.h:55-77): CODA camera, 0.15 m voxels, 256-voxel axes
+            tr.configure(ObjectTracker::kAlwaysMoving, {569.8286, 565.4818, 439.2660, 360.5810, 960, 540}, (double)(0.15f * 128) * 1.2);
         tr.setMovementFilter(0.2, 0.3, 0.2, 0.05);
         uint32_t step = 0;
 #else
@@ -37,12 +39,15 @@ int main(int argc, char** argv) {
             cfg.voxel_bits_x = 7; cfg.voxel_bits_y = 5; cfg.voxel_bits_z = 7; cfg.slot_bits = 2; cfg.voxel_size = 0.15f;
             cfg.fx = cfg.fy = 527.8191528320312f; cfg.cx = 633.9357299804688f; cfg.cy = 366.3338623046875f;
             cfg.image_width = 1280; cfg.image_height = 720; cfg.boost_mode = 1;
-        } else {
+        } else if (s.setting == 2) {
             cfg.voxel_bits_x = 8; cfg.voxel_bits_y = 7; cfg.voxel_bits_z = 8; cfg.slot_bits = 3; cfg.voxel_size = 0.2f;
             cfg.fx = cfg.fy = 725.0087f; cfg.cx = 620.5f; cfg.cy = 187.f; cfg.image_width = 1242; cfg.image_height = 375; cfg.boost_mode = 0;
+        } else {
+            cfg.voxel_bits_x = 8; cfg.voxel_bits_y = 8; cfg.voxel_bits_z = 7; cfg.slot_bits = 2; cfg.voxel_size = 0.15f;
+            cfg.fx = 569.8286f; cfg.fy = 565.4818f; cfg.cx = 439.2660f; cfg.cy = 360.5810f; cfg.image_width = 960; cfg.image_height = 540; cfg.boost_mode = 0;
         }
         dspmap_objects_t* tr = nullptr;
-        if (dspmap_objects_create(&cfg, s.setting == 3 ? DSPMAP_OBJECTS_BOX_KEYPOINTS : DSPMAP_OBJECTS_MATCHED_KEYPOINTS, &tr) != DSPMAP_OK) return 3;
+        if (dspmap_objects_create(&cfg, s.setting, &tr) != DSPMAP_OK) return 3;   // DSPMAP_OBJECTS_* = the reference's SETTING number
         dspmap_objects_set_movement_filter(tr, 0.2, 0.3, 0.2, 0.05);
 #endif
         int t = 0;
