@@ -63,7 +63,7 @@ OBJECT_INFO_CSV = (
     "14,Vehicle,-1,142,0,0\n15,truck,65521,70,0,0\n")
 
 
-def scene(t, moving=False):
+def scene(t, moving=False, cam_step=None):
     """Frame t of the scenes of tests/dropin_driver.cpp, in the same float32 arithmetic: a ground plane 1.5 m below the camera, a
     wall 7 m ahead of the start, a 1.5 x 1.5 m box face at 4 m, a sprinkle of far pixels; the camera advances 0.3 m a frame.
     moving: the box slides 0.125 m a frame (camera 0.125 m a frame), four key points, detection lost after frame 6.
@@ -71,7 +71,7 @@ def scene(t, moving=False):
     f32 = np.float32
     H, W = 720, 1280
     fx, cx, cy = f32(527.8191528320312), f32(633.9357299804688), f32(366.3338623046875)
-    cam_z = 0.125 * t if moving else 0.3 * t
+    cam_z = (0.125 if moving else 0.3) * t if cam_step is None else cam_step * t
     box_x = f32(0.125) * f32(t) if moving else f32(0.0)
     box_seen = (not moving) or t <= 6
     wall, box = f32(7.0 - cam_z), f32(4.0 - cam_z)
@@ -100,7 +100,7 @@ def scene(t, moving=False):
     return d, c, car, cam_z, (None if kp is None else np.asarray(kp, np.float32))
 
 
-def write_package(td, moving=False):
+def write_package(td, moving=False, frames=None, cam_step=None):
     """The package directory ros::package::getPath returns (cfg/ with the options and the label CSV) and the replay file."""
     os.makedirs(os.path.join(td, "cfg"), exist_ok=True)
     with open(os.path.join(td, "cfg", "options.yaml"), "w") as f:
@@ -109,8 +109,8 @@ def write_package(td, moving=False):
         f.write(OBJECT_INFO_CSV)
     rec = os.path.join(td, "replay_in.bin")
     with open(rec, "wb") as f:
-        for t in range(MOVING_FRAMES if moving else FRAMES):
-            d, c, car, cam_z, kp = scene(t, moving)
+        for t in range(frames or (MOVING_FRAMES if moving else FRAMES)):
+            d, c, car, cam_z, kp = scene(t, moving, cam_step)
             ns = int(round(0.1 * t * 1e9))
             h = wire.Header(FIRST_SEQ + t, ns // 10**9, ns % 10**9, "zed2")
             group = wire.MaskGroup(h, [
@@ -137,12 +137,13 @@ def read_published(path, topic="occupied_point"):
     return out
 
 
-def run_node(exe, td, moving=False):
-    rec = write_package(td, moving)
+def run_node(exe, td, moving=False, rec=None, want_log=False):
+    rec = rec or write_package(td, moving)
     out = os.path.join(td, "published.bin")
     env = dict(os.environ, DSPMAP_REPLAY_PACKAGE_PATH=td, DSPMAP_REPLAY_IN=rec, DSPMAP_REPLAY_OUT=out)
-    subprocess.run([exe, "options.yaml", "object_info.csv"], env=env, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=900)
-    return read_published(out)
+    r = subprocess.run([exe, "options.yaml", "object_info.csv"], env=env, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=900, text=True)
+    clouds = read_published(out)
+    return (clouds, r.stderr) if want_log else clouds
 
 
 def lattice(xyz, voxel=0.15):

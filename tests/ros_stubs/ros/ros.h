@@ -7,6 +7,7 @@
 // topic, a u32 point count, then x, y, z as f32 and r, g, b as u8 per point).
 #pragma once
 #include <chrono>
+#include <cstdarg>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -19,9 +20,24 @@
 #include <string>
 #include <vector>
 
-#define ROS_INFO_THROTTLE(period, ...) do { } while (0)
+// The node reports its own timing through ROS_INFO_THROTTLE (src/mapping.cpp:279-280: time cost of the last update() and the
+// running average).  The stand-in keeps the LAST message per call site and prints them when the process ends.
+#define ROS_INFO_THROTTLE(period, ...) do { static ros::replay_detail::LastMessage _m; _m.set(__VA_ARGS__); } while (0)
 #define ROS_INFO(...) do { std::printf(__VA_ARGS__); std::printf("\n"); } while (0)
 #define ROS_ERROR(...) do { std::fprintf(stderr, __VA_ARGS__); std::fprintf(stderr, "\n"); } while (0)
+
+namespace ros { namespace replay_detail {
+struct LastMessage {
+    char text[256] = {0};
+    void set(const char* fmt, ...) __attribute__((format(printf, 2, 3))) {
+        va_list ap;
+        va_start(ap, fmt);
+        std::vsnprintf(text, sizeof text, fmt, ap);
+        va_end(ap);
+    }
+    ~LastMessage() { if (text[0]) std::fprintf(stderr, "[last ROS_INFO_THROTTLE] %s\n", text); }
+};
+}}  // namespace ros::replay_detail
 
 namespace boost {
 template <typename T> using shared_ptr = std::shared_ptr<T>;
