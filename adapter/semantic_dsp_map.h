@@ -144,7 +144,12 @@ public:
         if (dspmap_create(&cfg_, &h_) != DSPMAP_OK) { std::fprintf(stderr, "dspmap_create failed\n"); std::exit(-1); }   // reference: exit(-1), operations.h:57
         prm_ = dspmap_params{0.95f, 0.1f, 3, 0.2f, 1.0f, 5, 0.1f, 0.0f, 0.1f, 0, 0, 0};   // ctor defaults, reference :25-43
         for (int i = 0; i < 256; ++i) color_map_int_256_[i] = (uint8_t)i;                       // reference :45-48: a random shuffle of 0..255
-        std::random_device rd;
+        // The reference draws its instance colours and its jitter table from std::random_device.  DSPMAP_ADAPTER_SEED in the
+        // environment replaces that entropy by a fixed seed (reproducible runs: tests, regression comparisons).
+        std::random_device rd_device;
+        const char* fixed_seed = std::getenv("DSPMAP_ADAPTER_SEED");
+        std::mt19937 seed_source(fixed_seed ? (uint32_t)std::strtoul(fixed_seed, nullptr, 10) : rd_device());
+        auto rd = [&seed_source]() { return (uint32_t)seed_source(); };
         std::mt19937 gen(rd());
         for (int i = 255; i > 0; --i) { std::uniform_int_distribution<int> dist(0, i); std::swap(color_map_int_256_[i], color_map_int_256_[dist(gen)]); }
         pushLabels();

@@ -36,6 +36,9 @@ def main():
                 out[name] = "failed: " + (e.stderr or "").strip().splitlines()[-1]
                 continue
             wall = time.time() - t0
+            if os.environ.get("NODE_TIMING_LOG"):            # e.g. with DSPMAP_TRACE=1: the engine's issue / wait times per frame
+                with open(os.environ["NODE_TIMING_LOG"] + "." + name, "w") as f:
+                    f.write(log)
             m = re.search(r"Average time cost: ([0-9.eE+-]+) s", log)
             out[name] = {"average_update_s": float(m.group(1)) if m else None, "process_wall_s": round(wall, 3), "clouds": len(clouds),
                          "last_cloud_points": int(len(clouds[-1])) if clouds else 0}
