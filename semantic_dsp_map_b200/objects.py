@@ -29,9 +29,12 @@ class ObjectLayer:
         self._dropped = (C.c_int32 * 64)()
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            self._lib.dspmap_objects_destroy(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                self._lib.dspmap_objects_destroy(self._h)
+                self._h = None
+        except Exception:      # interpreter shutdown: the library may already be gone
+            pass
 
     def _check(self, rc, where):
         if rc != 0:

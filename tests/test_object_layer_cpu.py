@@ -75,3 +75,41 @@ def test_scenarios_cover_the_branches():
     assert "absent" in text and "has_flag=0" in text and "moving=0 p=" in text and "moving=1" in text
     # a recovered rotation: some matrix has an off-diagonal rotation term well away from zero
     assert any(abs(float(ln.split()[9])) > 0.05 for ln in text.splitlines() if len(ln.split()) > 9)
+
+
+def test_python_wrapper_of_the_object_layer():
+    """semantic_dsp_map_b200/objects.py over dspmap_objects_* (no GPU): a box translating 0.3 m a frame is registered, found
+    moving with the right matrix, coasts when lost and is dropped after max_lost steps; a far object is never registered."""
+    import numpy as np
+    from semantic_dsp_map_b200 import SETTINGS
+    from semantic_dsp_map_b200.objects import BOX_KEYPOINTS, ObjectLayer
+    ol = ObjectLayer(SETTINGS[3])
+    assert ol.mode == BOX_KEYPOINTS
+    ol.set_movement_filter(0.2, 0.3, 0.2, 0.05)
+    base = np.array([[-0.9, 1.0, 5.9], [0.9, 1.0, 5.9], [-0.9, 1.0, 10.1], [-0.9, -0.5, 5.9]])
+    far = base + [0.0, 0.0, 100.0]
+    pos, quat = [0.0, 0.0, 0.0], [1.0, 0.0, 0.0, 0.0]
+    for t in range(5):
+        k = base + [0.3 * t, 0.0, 0.0]
+        moves, dropped = ol.step([(4, True, 14, k, None), (9, True, 14, far, None)], pos, quat, 0.1 * t, 3)
+        assert dropped == [] and not ol.is_tracked(9)
+        if t == 0:
+            assert moves == [] and ol.query(4) == dict(tracked=True, has_flag=False, moving=False, moved_probability=0.5, matrix=None)
+        else:
+            (track, T), = moves
+            assert track == 4 and T.dtype == np.float32
+            assert np.allclose(T, [[1, 0, 0, 0.3], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], atol=1e-6)
+    q = ol.query(4)
+    assert q["moving"] and np.allclose(q["matrix"][:3, 3], [0.3, 0, 0], atol=1e-12)
+    seen_drop = False
+    for t in range(5, 9):                                   # lost: coasts on the estimated velocity, then is dropped
+        moves, dropped = ol.step([], pos, quat, 0.1 * t, 3)
+        if dropped:
+            assert dropped == [4] and moves == [] and not ol.is_tracked(4)
+            seen_drop = True
+            break
+        (track, T), = moves
+        assert track == 4 and np.allclose(T[:3, :3], np.eye(3)) and T[0, 3] > 0.25   # pure translation (object_layer.h:190)
+    assert seen_drop
+    ol.clear()
+    assert not ol.is_tracked(4)
