@@ -19,6 +19,10 @@ _DEFAULT_ROWS = [
     (9, "TrafficSign", 65527), (10, "TrafficLight", 65526), (11, "Pole", 65525), (12, "Misc", 65524),
     (13, "Truck", -1), (14, "Car", -1), (15, "Person", -1),
 ]
+# include/utils/data_base.h:198-232 — g_label_color_map_default of the built-in tables, label id -> (b, g, r)
+_DEFAULT_COLORS = {0: (0, 0, 0), 2: (200, 0, 210), 3: (255, 200, 90), 4: (0, 199, 0), 5: (0, 240, 90), 6: (140, 140, 140), 7: (100, 60, 100),
+                   8: (255, 100, 250), 9: (0, 255, 255), 10: (0, 200, 200), 11: (0, 130, 255), 12: (80, 80, 80), 13: (60, 60, 160), 14: (80, 127, 255),
+                   15: (139, 139, 0)}
 
 # cfg/object_info_zed2.csv of the reference (label_id, label, instance_id); colours are not on the hot path
 ZED2_ROWS = [
@@ -39,6 +43,7 @@ class LabelTables:
     label_to_instance: dict = field(default_factory=dict)        # g_label_to_instance_id_map_default
     instance_to_label: dict = field(default_factory=dict)        # g_instance_id_to_label_map_default
     movable_label_ids: set = field(default_factory=set)          # g_movable_object_label_ids_set
+    label_colors: dict = field(default_factory=dict)             # g_label_color_map_default: label id -> (b, g, r)
     max_movable_instance_id: int = 65523                         # g_max_movable_object_instance_id
 
     @classmethod
@@ -54,14 +59,18 @@ class LabelTables:
             else:
                 t.movable_label_ids.add(label_id)
         t.max_movable_instance_id = 65523
+        t.label_colors = dict(_DEFAULT_COLORS)
         return t
 
     @classmethod
     def from_rows(cls, rows) -> "LabelTables":
-        """object_info_handler.h:51-86: rebuild every table from (label_id, label, instance_id) rows."""
+        """object_info_handler.h:51-86: rebuild every table from (label_id, label, instance_id[, color_b, color_g, color_r]) rows."""
         t = cls()
         max_movable = 65535
-        for label_id, name, inst in rows:
+        for row in rows:
+            label_id, name, inst = row[:3]
+            if len(row) >= 6:
+                t.label_colors[label_id] = (int(row[3]) & 0xFF, int(row[4]) & 0xFF, int(row[5]) & 0xFF)   # cv::Vec3b(b, g, r), :56
             t.label_id_map[name] = label_id
             t.label_id_map_reversed[label_id] = name
             if inst > 0:
@@ -86,7 +95,7 @@ class LabelTables:
             next(rd)  # header line is skipped (object_info_handler.h:138)
             for r in rd:
                 if r:
-                    rows.append((int(r[0]), r[1], int(r[2])))
+                    rows.append((int(r[0]), r[1], int(r[2])) + tuple(int(v) for v in r[3:6]))
         return cls.from_rows(rows)
 
     # ---- what the hot path evaluates per pixel, folded into LUTs -------------------------------

@@ -274,7 +274,8 @@ class SemanticDSPMap:
     def enable_colors(self, label_bgr=None, instance_map=None, scheme=None):
         """Turn on the colouring of the occupied list (getOccupancyResult, semantic_dsp_map.h:1274-1351).
 
-        label_bgr: {label_id: (b, g, r)} = g_label_color_map_default (the colour columns of the object-info CSV);
+        label_bgr: {label_id: (b, g, r)} = g_label_color_map_default (default: the colour columns of the object-info CSV the
+        label tables were read from, or the built-in colours);
         instance_map: the 256-entry permutation color_map_int_256_ (a std::random_device shuffle in the reference, so the
         caller supplies it; default: a fixed seeded permutation); scheme: which ``#if SETTING`` colouring block applies
         (default: 3 when the ZED2 filters are on, 0 for a map without instances, else 1)."""
@@ -283,7 +284,7 @@ class SemanticDSPMap:
         cfg = self.config
         c.scheme = scheme if scheme is not None else (3 if cfg.zed2_filters else (1 if cfg.consider_instance else 0))
         c.background_label = self.labels.label_id_of("Background")              # :1276, default-insert semantics
-        for label_id, bgr in (label_bgr or {}).items():
+        for label_id, bgr in (self.labels.label_colors if label_bgr is None else label_bgr).items():
             for k in range(3):
                 c.label_bgr[int(label_id) & 0xFF][k] = int(bgr[k]) & 0xFF
         perm = np.random.default_rng(256).permutation(256) if instance_map is None else np.asarray(instance_map)
