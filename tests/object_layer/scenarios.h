@@ -94,6 +94,29 @@ inline std::vector<Scenario> all() {
         }
         out.push_back(s);
     }
+    {   // a dozen objects on pseudo-random courses (fixed LCG): different speeds and headings, detections dropping out and coming
+        // back, objects entering from beyond the registration range, parked ones, turns
+        Scenario s{"traffic_of_twelve", 5, {}};
+        uint32_t lcg = 12345u;
+        auto rnd = [&lcg]() { lcg = lcg * 1664525u + 1013904223u; return (double)(lcg >> 8) / (double)(1u << 24); };   // [0, 1)
+        struct Car { double x, z, heading, speed, turn; int first, gap_from, gap_to; };
+        std::vector<Car> cars;
+        for (int c = 0; c < 12; ++c)
+            cars.push_back({-8.0 + 16.0 * rnd(), 4.0 + 14.0 * rnd(), 6.283185307179586 * rnd(), c % 4 == 3 ? 0.0 : 0.05 + 0.6 * rnd(), (rnd() - 0.5) * 0.12,
+                            (int)(6 * rnd()), 8 + (int)(10 * rnd()), 0});
+        for (auto& c : cars) c.gap_to = c.gap_from + 1 + (int)(7 * rnd());
+        for (int t = 0; t < 36; ++t) {
+            Frame f = frame(0.1 * t + (t % 5 == 4 ? 0.03 : 0.0), 0.04 * t);
+            for (size_t c = 0; c < cars.size(); ++c) {
+                Car& car = cars[c];
+                car.x += car.speed * std::sin(car.heading); car.z += car.speed * std::cos(car.heading); car.heading += car.turn;
+                if (t < car.first || (t >= car.gap_from && t < car.gap_to)) continue;
+                f.objects.push_back({30 + (int)c, c % 5 == 0 ? "person" : "Vehicle", box(car.x, 1.0, car.z, car.heading)});
+            }
+            s.frames.push_back(f);
+        }
+        out.push_back(s);
+    }
     // No SETTING 1 scenario: the reference does not compile with that preset (settings.h:74 and :150 both define
     // g_depth_error_stddev_at_one_meter), so its "every updated object is moving" rule (object_layer.h:482-483) cannot be pinned.
     return out;

@@ -84,3 +84,17 @@ def test_oracle_rejects_wrong_image_size():
         assert e.rc == -3
     else:
         raise AssertionError("expected DSPMAP_ERR_IMAGE_SIZE")
+
+
+def test_label_tables_keep_the_colour_columns(tmp_path):
+    """g_label_color_map_default: built-in colours (utils/data_base.h:216-232) and the colour columns of an object-info CSV
+    (object_info_handler.h:56), as (b, g, r); enable_colors() sends them to the engine by default."""
+    from semantic_dsp_map_b200 import LabelTables
+    b = LabelTables.builtin()
+    assert b.label_colors[7] == (100, 60, 100) and b.label_colors[14] == (80, 127, 255) and len(b.label_colors) == 15
+    p = tmp_path / "object_info.csv"
+    p.write_text("label_id,label,instance_id(-1 means not fixed),color_b,color_g,color_r\n0,background,65535,0,0,0\n1,road,65534,128,64,128\n14,Vehicle,-1,142,0,0\n")
+    t = LabelTables.read_object_info(str(p))
+    assert t.label_colors == {0: (0, 0, 0), 1: (128, 64, 128), 14: (142, 0, 0)}
+    assert t.max_movable_instance_id == 65533 and t.label_id_map["Vehicle"] == 14
+    assert LabelTables.from_rows([(1, "road", 65534)]).label_colors == {}          # rows without colour columns: no colours
