@@ -100,6 +100,63 @@ def scene(t, moving=False, cam_step=None):
     return d, c, car, cam_z, (None if kp is None else np.asarray(kp, np.float32))
 
 
+QUIRK_FRAMES = 6
+
+
+def quirk_frame(t):
+    """Frame t of the "quirks" replay: a static world (no object ever moves, so the reference draws no random numbers and its
+    output is reproducible bit for bit) seen from a camera that yaws, climbs and side-steps, with the label quirks of the
+    path in the static mask - the "sky" class (value 10: removed by the ZED2 sky filter only if the table has a label spelt
+    "Sky", pointcloud_tools.h:236), a movable CLASS (value 11, "person": instance id -1 -> track 0, floating, lives one frame),
+    a value outside the table (200) - and two detections: one with two key points (registered, never moved) and one WITHOUT key
+    points (never registered: its particles are floating and die every frame).  (A detection with a label the table does not
+    know is left out: the optimised build of the reference node segfaults on it once its mask covers pixels - not under
+    AddressSanitizer, so some layout-dependent undefined behaviour; the object layer's handling of unknown labels is pinned
+    separately in tests/test_object_layer_cpu.py.)  Returns depth, class image, [(label, track, mask, key
+    points)], position, orientation (w, x, y, z)."""
+    f32 = np.float32
+    H, W = 720, 1280
+    i = np.arange(H, dtype=f32)[:, None]
+    j = np.arange(W, dtype=f32)[None, :]
+    d = (f32(2.5) + f32(0.004) * i + f32(0.002) * j + f32(0.15) * f32(t)).astype(f32) * np.ones((H, W), f32)
+    d[(np.arange(H)[:, None] * 37 + np.arange(W)[None, :] * 11 + t * 5) % 53 == 0] = f32(16.0)      # far
+    d[(np.arange(H)[:, None] * 29 + np.arange(W)[None, :] * 13 + t * 3) % 211 == 0] = f32(0.1)      # too close: invalid
+    c = np.zeros((H, W), np.uint8)
+    c[:, 200:520] = 3
+    c[:160, :] = 10            # sky band
+    c[400:520, 600:760] = 11   # a person CLASS in the static mask
+    c[600:, 900:] = 200        # a value the table does not have
+    c[300:360, 0:200] = 9
+    def box(r0, r1, c0, c1):
+        m = np.zeros((H, W), np.uint8)
+        m[r0:r1, c0:c1] = 255
+        return m
+    objects = [("Vehicle", 5, box(250, 420, 800, 1000), np.asarray([[1.0, -0.5, 4.0], [2.5, 1.0, 6.5]], np.float32)),
+               ("Vehicle", 6, box(450, 600, 300, 480), np.zeros((0, 3), np.float32))]
+    yaw = 0.04 * t
+    return d, c, objects, (0.1 * t, -0.03 * t, 0.2 * t), (float(np.cos(yaw / 2)), 0.0, float(np.sin(yaw / 2)), 0.0)
+
+
+def write_quirk_package(td):
+    os.makedirs(os.path.join(td, "cfg"), exist_ok=True)
+    with open(os.path.join(td, "cfg", "options.yaml"), "w") as f:
+        f.write(OPTIONS_YAML.format(max_lost=20))
+    with open(os.path.join(td, "cfg", "object_info.csv"), "w") as f:
+        f.write(OBJECT_INFO_CSV)
+    rec = os.path.join(td, "replay_quirks.bin")
+    none = np.zeros((0, 3), np.float32)
+    with open(rec, "wb") as f:
+        for t in range(QUIRK_FRAMES):
+            d, c, objects, pos, quat = quirk_frame(t)
+            ns = int(round(0.1 * t * 1e9))
+            h = wire.Header(FIRST_SEQ + t, ns // 10**9, ns % 10**9, "zed2")
+            group = wire.MaskGroup(h, [wire.WireObject("static", 65535, wire.image_from_array(c, "mono8", h), (0, 0, 0), (0, 0, 0), none, none)])
+            for label, track, mask, kp in objects:
+                group.objects.append(wire.WireObject(label, track, wire.image_from_array(mask, "mono8", h), (0, 0, 0), (0, 0, 0), kp, kp))
+            wire.write_record(f, wire.encode_image(wire.image_from_array(d, "32FC1", h)), wire.encode_pose_stamped(h, pos, quat), wire.encode_mask_group(group))
+    return rec
+
+
 def write_package(td, moving=False, frames=None, cam_step=None):
     """The package directory ros::package::getPath returns (cfg/ with the options and the label CSV) and the replay file."""
     os.makedirs(os.path.join(td, "cfg"), exist_ok=True)
@@ -158,6 +215,15 @@ def main():
         clouds = run_node(exe, td)
         with tempfile.TemporaryDirectory() as td2:
             moving = run_node(exe, td2, moving=True)
+        with tempfile.TemporaryDirectory() as td3:
+            quirks = run_node(exe, td3, rec=write_quirk_package(td3))
+            again = run_node(exe, td3, rec=os.path.join(td3, "replay_quirks.bin"))
+    assert all(np.array_equal(a, b) for a, b in zip(quirks, again)), "the reference node is not reproducible on the quirks replay"
+    qk = {}
+    for t in (1, QUIRK_FRAMES - 1):
+        qk[f"lattice_{t}"], qk[f"rgb_{t}"] = lattice(quirks[t]["xyz"]), quirks[t]["rgb"]
+    np.savez_compressed(os.path.join(HERE, "node_reference_quirks.npz"), counts=np.asarray([len(c) for c in quirks], np.int64), **qk)
+    print("quirks:", [len(c) for c in quirks], os.path.getsize(os.path.join(HERE, "node_reference_quirks.npz")), "bytes")
     kept = {}
     for t in MOVING_KEPT:
         kept[f"lattice_{t}"], kept[f"rgb_{t}"] = lattice(moving[t]["xyz"]), moving[t]["rgb"]

@@ -69,3 +69,35 @@ def test_static_replay_on_the_oracle_equals_the_reference_node_exactly():
     got = np.concatenate([G.lattice(last.xyz).astype(np.int32), last.rgb.astype(np.int32)], axis=1)
     ref = np.concatenate([want["last_lattice"].astype(np.int32), want["last_rgb"].astype(np.int32)], axis=1)
     assert np.array_equal(got, ref)                                                 # same order too: ascending storage index
+
+
+def test_quirks_replay_on_the_oracle_equals_the_reference_node_exactly():
+    """A yawing, climbing, side-stepping camera over a static world with the label quirks of the path in the static mask ("sky"
+    spelt unlike the filter's "Sky", a movable class, a value outside the table), far and too-close pixels, a detection with two
+    key points (registered, never moved) and one without key points (never registered: floating, its particles live one
+    frame).  Nothing moves, so the reference draws no random numbers: EXACT equality with the reference node's clouds."""
+    with tempfile.TemporaryDirectory() as td:
+        rec = G.write_quirk_package(td)
+        labels = LabelTables.read_object_info(os.path.join(td, "cfg", "object_info.csv"))
+        m = oracle_map(SETTINGS[3], labels, order=0)
+        m.engine.set_undefined_label_carry(True)
+        # the two places where the reference reads uninitialised memory (DESIGN 6): sigma of an invalid pixel and of a pixel the
+        # bounding-box gate turned into background - a compiled reference reads 0 there when the depth-noise model is on
+        m.engine.set_invalid_sigma(0.0)
+        m.setMapParameters(0.8, 0.2, 1, 0.15, 20, 1.0, 5, 0.6, 0.5)
+        m.setMapOptions(True, False)
+        m.setVisualizeOptions(False, True)
+        m.setBeyesianMovementParameters(0.2, 0.3, 0.2, 0.05)
+        m.setDepthNoiseModelParameters(0.02, 0.3)
+        m.enable_colors()
+        m.engine.set_random_table(make_random_table(7))
+        with open(rec, "rb") as f:
+            results = [r for _, r in wire.replay(m, wire.read_records(f))]
+        assert m.objects.is_tracked(5) and not m.objects.is_tracked(6)
+    want = np.load(os.path.join(ROOT, "tests", "golden", "node_reference_quirks.npz"))
+    assert [len(r.voxel_index) for r in results] == want["counts"].tolist()
+    assert want["counts"][-1] > 5000
+    for t in (1, G.QUIRK_FRAMES - 1):
+        got = np.concatenate([G.lattice(results[t].xyz).astype(np.int32), results[t].rgb.astype(np.int32)], axis=1)
+        ref = np.concatenate([want[f"lattice_{t}"].astype(np.int32), want[f"rgb_{t}"].astype(np.int32)], axis=1)
+        assert np.array_equal(got, ref), t
