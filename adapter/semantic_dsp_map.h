@@ -171,15 +171,15 @@ public:
         prm_.forgetting_rate = forgetting_rate; prm_.max_forget_count = max_forget_count;
         prm_.id_transition_probability = id_transition_probability;
         max_obersevation_lost_time_ = max_obersevation_lost_time; match_score_threshold_ = match_score_threshold;
-        dspmap_set_params(h_, &prm_);
+        pushParams();
     }
     void setMapOptions(bool if_consider_depth_noise, bool if_use_independent_filter) {          // reference :121-126
         prm_.consider_depth_noise = if_consider_depth_noise; prm_.use_independent_filter = if_use_independent_filter;
-        dspmap_set_params(h_, &prm_);
+        pushParams();
     }
     void setVisualizeOptions(bool visualize_with_zero_center, bool if_out_evaluation_format = false) {   // reference :130-134
         prm_.zero_center = visualize_with_zero_center; if_out_evaluation_format_ = if_out_evaluation_format;
-        dspmap_set_params(h_, &prm_);
+        pushParams();
         pushColors();
     }
     // The table of N(0, 0.05) draws that moved and noisy-newborn particles are jittered with (gaussian_randoms,
@@ -190,7 +190,7 @@ public:
         std::normal_distribution<> d(0, 0.05);                                                   // prediction_stddev_, reference :40
         std::vector<float> table(1000000);
         for (float& v : table) v = (float)d(gen);
-        dspmap_set_random_table(h_, table.data(), (uint32_t)table.size());
+        checked(dspmap_set_random_table(h_, table.data(), (uint32_t)table.size()), "dspmap_set_random_table");
     }
     // the instance colour permutation (color_map_int_256_); random per process in the reference, settable here for reproducible output
     void setInstanceColorMap(const uint8_t map256[256]) { for (int i = 0; i < 256; ++i) color_map_int_256_[i] = map256[i]; pushColors(); }
@@ -202,10 +202,10 @@ public:
     void setObjectLayerMode(dsp_adapter::ObjectTracker::Mode mode) { configureTracker(mode); }
     void setObjectLayerSeed(uint32_t seed) { tracker_.setSeed(seed); }
     const dsp_adapter::ObjectTracker& objectTracker() const { return tracker_; }
-    void setOccupancyThreshold(float t) { prm_.occupancy_threshold = t; dspmap_set_params(h_, &prm_); }   // reference :153-156
+    void setOccupancyThreshold(float t) { prm_.occupancy_threshold = t; pushParams(); }   // reference :153-156
     void setDepthNoiseModelParameters(float first_order, float zero_order) {                     // reference :161-166
         prm_.depth_noise_first_order = first_order; prm_.depth_noise_zero_order = zero_order;
-        dspmap_set_params(h_, &prm_);
+        pushParams();
     }
     // what an integrator's OWN object layer decided for the coming frame (rigid motion per moving track, tracks to drop);
     // the first call switches the built-in object layer off for good
@@ -232,7 +232,9 @@ public:
                 m.track_id = m.track_id % labels_.max_movable_instance_id;
             }
             dspmap_mask& d = masks[i];
+            if (m.mask.type() != CV_8UC1) { std::fprintf(stderr, "mask %zu is not CV_8UC1: frame dropped\n", i); moves_.clear(); return; }
             d.data = m.mask.data; d.row_stride = (int32_t)m.mask.step; d.is_static = m.label == "static";
+            d.rows = m.mask.rows; d.cols = m.mask.cols;                                           // checked against the depth image by the engine
             d.track_id = m.track_id; d.label_id = DspLabelTables::getOr0(labels_.label_id, m.label);
             double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {DBL_MIN, DBL_MIN, DBL_MIN};     // pointcloud_tools.h:178-199
             for (const auto& k : m.kpts_current)
@@ -249,8 +251,11 @@ public:
         const int rc = dspmap_update(h_, reinterpret_cast<const float*>(depth_value_mat.data), depth_value_mat.rows, depth_value_mat.cols,
                                      (int32_t)(depth_value_mat.step / sizeof(float)), masks.data(), (int32_t)masks.size(), pos, quat,
                                      moves_.data(), (int32_t)moves_.size(), remove_.data(), (int32_t)remove_.size(), if_get_freespace);
-        moves_.clear(); remove_.clear();
-        if (rc != DSPMAP_OK) { std::fprintf(stderr, "dspmap_update: %s\n", dspmap_last_error(h_)); return; }   // reference: no error channel
+        moves_.clear();
+        // reference: no error channel.  A refused frame changed nothing in the engine (arguments are validated before any state
+        // is touched), so the tracks that were due for removal stay queued and go with the next frame.
+        if (rc != DSPMAP_OK) { std::fprintf(stderr, "dspmap_update: %s\n", dspmap_last_error(h_)); return; }
+        remove_.clear();
         dspmap_result r;
         if (dspmap_get_result(h_, &r) != DSPMAP_OK) return;
         for (uint32_t i = 0; i < r.count; ++i) {                                                  // reference :1274-1351
@@ -268,8 +273,27 @@ public:
     }
 
     dspmap_t* handle() { return h_; }
+    // follow a COMPILED reference where it reads an uninitialised sigma (dspmap_params.uninit_sigma_mode); not in the reference's API
+    void followCompiledReferenceSigma(bool on, float value = 0.f) { prm_.uninit_sigma_mode = on; prm_.uninit_sigma_value = value; pushParams(); }
 
 private:
+    // every setter of the C ABI can refuse its argument; the reference has no error channel, so: clamp what the engine's
+    // tables cannot hold (the reference's own forgetting table has five entries, basic_algorithms.h:33), say so, and treat
+    // anything else like the constructor treats a failed create (exit(-1), mc_ring/operations.h:57)
+    void checked(int rc, const char* what) {
+        if (rc == DSPMAP_OK) return;
+        std::fprintf(stderr, "%s: %s\n", what, dspmap_last_error(h_));
+        std::exit(-1);
+    }
+    void pushParams() {
+        dspmap_params p = prm_;
+        if (p.max_forget_count > 5 || p.max_forget_count < 0) {
+            std::fprintf(stderr, "max_forget_count %d clamped to 0..5 (size of the forgetting table)\n", p.max_forget_count);
+            p.max_forget_count = p.max_forget_count < 0 ? 0 : 5;
+        }
+        if (p.nb_ptc_num_per_point < 1) { std::fprintf(stderr, "nb_ptc_num_per_point %d raised to 1\n", p.nb_ptc_num_per_point); p.nb_ptc_num_per_point = 1; }
+        checked(dspmap_set_params(h_, &p), "dspmap_set_params");
+    }
     void pushLabels() {
         uint16_t v2t[256];
         for (int v = 0; v < 256; ++v) {   // pointcloud_tools.h:137-138 with operator[] default-insert semantics
@@ -282,8 +306,8 @@ private:
             tracks.push_back((uint16_t)kv.first);
             labs.push_back((uint8_t)DspLabelTables::getOr0(labels_.label_id_static, kv.second));
         }
-        dspmap_set_label_luts(h_, v2t, tracks.data(), labs.data(), (int32_t)tracks.size(), (uint16_t)labels_.max_movable_instance_id,
-                              (uint16_t)DspLabelTables::getOr0(labels_.label_to_instance, std::string("Sky")));   // pointcloud_tools.h:236
+        checked(dspmap_set_label_luts(h_, v2t, tracks.data(), labs.data(), (int32_t)tracks.size(), (uint16_t)labels_.max_movable_instance_id,
+                              (uint16_t)DspLabelTables::getOr0(labels_.label_to_instance, std::string("Sky"))), "dspmap_set_label_luts");   // pointcloud_tools.h:236
     }
 
     // reference :712-737 ("floating objects"): after the moves and removals of a frame, every track that owns particles in
@@ -360,7 +384,7 @@ private:
         for (const auto& kv : labels_.label_color)
             if (kv.first >= 0 && kv.first < 256) for (int k = 0; k < 3; ++k) c.label_bgr[kv.first][k] = kv.second[k];
         for (int i = 0; i < 256; ++i) c.instance_map[i] = color_map_int_256_[i];
-        dspmap_set_colors(h_, &c);
+        checked(dspmap_set_colors(h_, &c), "dspmap_set_colors");
     }
 
     dspmap_config cfg_;

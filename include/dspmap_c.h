@@ -83,6 +83,13 @@ typedef struct dspmap_params {
     int32_t consider_depth_noise;      /* g_if_consider_depth_noise            */
     int32_t use_independent_filter;    /* g_if_use_independent_filter          */
     int32_t zero_center;               /* visualize_with_zero_center_ (output positions minus camera) */
+    /* The reference never initialises LabeledPoint::sigma for an invalid pixel and for a pixel the ZED2 bounding-box
+     * gate turned into background (utils/pointcloud_tools.h:224-232, 256-272); updateParticles reads it
+     * (semantic_dsp_map.h:985, 1047).  0 (default): both sites get the depth-noise model's value (defined behaviour).
+     * 1: both sites carry uninit_sigma_value instead - what a COMPILED reference reads there (0.0 in the GCC builds of
+     * oracle/build_ref.sh and of the reference node), so that a replay follows the shipped binary voxel for voxel. */
+    int32_t uninit_sigma_mode;
+    float   uninit_sigma_value;
 } dspmap_params;
 
 /* one segmentation mask: reference MaskKpts (utils/tracking_result_handler.h:15-26),
@@ -95,6 +102,9 @@ typedef struct dspmap_mask {
     int32_t label_id;      /* g_label_id_map_default[MaskKpts.label]                    */
     double  bbox_min[3];   /* min over kpts_current - 1 m (pointcloud_tools.h:178-199)  */
     double  bbox_max[3];   /* max over kpts_current + 1 m; used only when zed2_filters  */
+    int32_t rows, cols;    /* size of the mask image; must equal the depth image's (else DSPMAP_ERR_IMAGE_SIZE: the
+                              reference iterates over the mask's own size, pointcloud_tools.h:203-212, the engine
+                              indexes masks with depth coordinates).  0, 0 = not stated: the caller vouches for it */
 } dspmap_mask;
 
 /* rigid motion of one tracked object for this frame: what objectLevelUpdate (host,
@@ -266,7 +276,12 @@ enum {
     DSPMAP_DUMP_CK = 5,       /* Hi*Wi f32: ck*Pd+kappa, 0 where the pixel is invalid     */
     DSPMAP_DUMP_RING = 6,     /* ring state: 3 i32 moved steps, 3 i32 equivalent steps, 3 f32 map centre,
                                  then stamps x,y,z as u32                                  */
-    DSPMAP_DUMP_VOXEL_STATE = 7 /* V i8: -1 unknown, 0 free, 1 occupied, 2 guessed          */
+    DSPMAP_DUMP_VOXEL_STATE = 7, /* V i8: -1 unknown, 0 free, 1 occupied, 2 guessed          */
+    DSPMAP_DUMP_PARTICLES_HASH = 8 /* one u64: order-independent digest of the DSPMAP_DUMP_PARTICLES records (for maps whose
+                                 store is too large to dump): sum over particle index i of
+                                 mix(mix(mix(i * 0x9E3779B97F4A7C15 + (x | y << 32)) ^ (z | w << 32)) + tail), x..w the float
+                                 bit patterns, tail the record's last 8 bytes as a little-endian u64, mix = the splitmix64
+                                 finaliser.  A sharded map returns the sum over its own slabs (add the ranks' values). */
 };
 /* test hook: evaluates the engine's hoisted-reciprocal division (csrc/dspmap_device.cuh InvDiv) against the compiler's
  * IEEE division on n pseudo-random operand pairs (divisor in [b_lo, b_hi], |dividend| <= a_max) and counts results that
@@ -318,11 +333,15 @@ int  dspmap_objects_set_movement_filter(dspmap_objects_t* o, double distance_thr
 int  dspmap_objects_set_seed(dspmap_objects_t* o, uint32_t seed);
 /* One frame: objectLevelUpdate on the observations, then the move / drop decisions of the frame.
  * max_lost = max_obersevation_lost_time (setMapParameters :101).  Returns DSPMAP_ERR_CAPACITY when
- * an output array is too small (n_moves / n_dropped then hold the needed sizes; state is updated). */
+ * an output array is too small: n_moves / n_dropped then hold the needed sizes, the tracker HAS stepped, and the
+ * frame's plan stays available - fetch it with dspmap_objects_last_plan into larger arrays (do not step again). */
 int  dspmap_objects_step(dspmap_objects_t* o, const dspmap_object_observation* observations, int32_t n_observations,
                          const double position[3], const double orientation_wxyz[4], double time_stamp, int32_t max_lost,
                          dspmap_object_move* moves, int32_t moves_cap, int32_t* n_moves,
                          int32_t* dropped, int32_t dropped_cap, int32_t* n_dropped);
+/* the move / drop decisions of the last dspmap_objects_step again (same outputs, no state change) */
+int  dspmap_objects_last_plan(dspmap_objects_t* o, dspmap_object_move* moves, int32_t moves_cap, int32_t* n_moves,
+                              int32_t* dropped, int32_t dropped_cap, int32_t* n_dropped);
 /* state of one object after the last step: tracked (in object_tracking_hash_map), has_flag
  * (rigidbody_moved_vec not empty), moving, moved_probability, t16 = rigidbody_tmatrix_vec[0]
  * (row-major double 4x4; untouched while has_flag is 0).  Any output may be NULL. */

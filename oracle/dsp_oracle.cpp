@@ -555,6 +555,8 @@ struct Oracle {
                 // (semantic_dsp_map.h:1047).  The oracle defines it as the zero-depth noise term.  What an actual
                 // build of the reference reads there is whatever its stack slot holds (0 in oracle/_ref's build);
                 // orc_set_invalid_sigma lets the pin test feed that value in so everything else can be compared.
+                const bool invalid_sigma_set = this->invalid_sigma_set || prm.uninit_sigma_mode != 0;      // test knob, or the C-ABI flag (dspmap_params)
+                const float invalid_sigma_value = this->invalid_sigma_set ? this->invalid_sigma_value : prm.uninit_sigma_value;
                 const float sigma_invalid = invalid_sigma_set ? invalid_sigma_value : (prm.consider_depth_noise ? prm.depth_noise_zero_order : 0.1f);
                 if (std::isnan(d) || (double)d < dmin || (double)d > dmax) {  // :228
                     pt.sigma = sigma_invalid; pt.is_valid = 0; cloud[(size_t)i * W + j] = pt; continue;
@@ -1203,6 +1205,19 @@ int orc_dump(void* h, int32_t what, void* dst, size_t cap, size_t* n_bytes) {
         case DSPMAP_DUMP_PIXEL_LISTS: o->build_csr(); src = o->csr_idx.data(); n = o->csr_idx.size() * 4; break;
         case DSPMAP_DUMP_CK: src = o->ck.data(); n = o->ck.size() * 4; break;
         case DSPMAP_DUMP_VOXEL_STATE: src = o->voxel_state.data(); n = o->voxel_state.size(); break;
+        case DSPMAP_DUMP_PARTICLES_HASH: {   // include/dspmap_c.h: digest of the records above, for maps too large to dump
+            auto mix = [](uint64_t z) { z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); };
+            uint64_t sum = 0;
+            for (size_t i = 0; i < o->store.size(); ++i) {
+                uint64_t w[3];
+                memcpy(w, &o->store[i], 24);
+                sum += mix(mix(mix((uint64_t)i * 0x9E3779B97F4A7C15ull + w[0]) ^ w[1]) + w[2]);
+            }
+            tmp.resize(8);
+            memcpy(tmp.data(), &sum, 8);
+            src = tmp.data(); n = 8;
+            break;
+        }
         case DSPMAP_DUMP_RING: {
             tmp.resize(4 * (9 + o->NX + o->NY + o->NZ));
             uint8_t* w = tmp.data();

@@ -13,13 +13,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdspmap_b200.so")
 
 DSPMAP_OK = 0
+DSPMAP_ERR_CAPACITY = -5
 ERRORS = {
     0: "OK", -1: "INVALID_ARG", -2: "CONFIG", -3: "IMAGE_SIZE", -4: "CUDA", -5: "CAPACITY",
     -6: "NO_DEVICE", -7: "UNSUPPORTED", -8: "COMM",
 }
 COMM_HANDLE_BYTES = 128
 
-DUMP_POINTS, DUMP_PARTICLES, DUMP_PIXEL_OFFSETS, DUMP_PIXEL_LISTS, DUMP_CK, DUMP_RING, DUMP_VOXEL_STATE = 1, 2, 3, 4, 5, 6, 7
+DUMP_POINTS, DUMP_PARTICLES, DUMP_PIXEL_OFFSETS, DUMP_PIXEL_LISTS, DUMP_CK, DUMP_RING, DUMP_VOXEL_STATE, DUMP_PARTICLES_HASH = 1, 2, 3, 4, 5, 6, 7, 8
 
 
 class Config(C.Structure):
@@ -44,6 +45,7 @@ class Params(C.Structure):
         ("depth_noise_first_order", C.c_float), ("depth_noise_zero_order", C.c_float),
         ("consider_depth_noise", C.c_int32), ("use_independent_filter", C.c_int32),
         ("zero_center", C.c_int32),
+        ("uninit_sigma_mode", C.c_int32), ("uninit_sigma_value", C.c_float),
     ]
 
 
@@ -52,6 +54,7 @@ class Mask(C.Structure):
         ("data", C.c_void_p), ("row_stride", C.c_int32), ("is_static", C.c_int32),
         ("track_id", C.c_int32), ("label_id", C.c_int32),
         ("bbox_min", C.c_double * 3), ("bbox_max", C.c_double * 3),
+        ("rows", C.c_int32), ("cols", C.c_int32),
     ]
 
 
@@ -135,6 +138,7 @@ SYMBOLS = {
     "dspmap_objects_step": (C.c_int, [C.c_void_p, C.POINTER(ObjectObservation), C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double,
                                       C.c_int32, C.POINTER(ObjectMove), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32,
                                       C.POINTER(C.c_int32)]),
+    "dspmap_objects_last_plan": (C.c_int, [C.c_void_p, C.POINTER(ObjectMove), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
     "dspmap_objects_query": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double),
                                        C.POINTER(C.c_double)]),
     "dspmap_objects_forget": (C.c_int, [C.c_void_p, C.c_int32]),

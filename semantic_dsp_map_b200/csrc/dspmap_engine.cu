@@ -75,6 +75,12 @@ void inverse4f(const float m[16], float o[16]) {
 
 // A few persistent host threads for the pageable -> pinned staging copies of dspmap_update (row blocks of the depth
 // image and of every mask are independent).  Workers sleep on a condition variable between frames.
+//
+// Work items are handed out as TICKETS: one 64-bit counter holding (job generation << 32 | next item).  A ticket names
+// the job it was drawn for, the job's (function, item count) live in a two-entry table indexed by generation parity, and
+// run() does not return before every thread that may hold a ticket of its job has left work() (the `active_` count) - so
+// a helper that is descheduled between drawing a ticket and looking at the job can neither run an item of the NEXT job
+// nor touch a function object that has gone out of scope.
 class StagePool {
 public:
     explicit StagePool(int n_workers, int spin_us = 200) : spin_us_(spin_us) {
@@ -88,30 +94,38 @@ public:
     // runs fn(i) for i in [0, n) on the workers and the calling thread; returns when all are done
     void run(int n, const std::function<void(int)>& fn) {
         if (n <= 0) return;
+        const uint64_t gen = (ticket_.load(std::memory_order_relaxed) >> 32) + 1;
         {
             std::lock_guard<std::mutex> lk(mu_);
-            fn_ = &fn; n_.store(n); next_.store(0); pending_.store(n);
-            epoch_.fetch_add(1, std::memory_order_release);
+            Job& j = jobs_[gen & 1];
+            j.fn = &fn; j.n = n;
+            pending_.store(n, std::memory_order_relaxed);
+            ticket_.store(gen << 32, std::memory_order_release);          // publishes the job
         }
         if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
         work();
-        while (pending_.load(std::memory_order_acquire) != 0) cpu_relax();   // the tail of a staging copy is microseconds
-        fn_ = nullptr;
+        // the tail of a staging copy is microseconds: spin.  active_ == 0: nobody is left inside work() with a ticket of this job
+        while (pending_.load(std::memory_order_acquire) != 0 || active_.load(std::memory_order_acquire) != 0) cpu_relax();
     }
 
 private:
+    struct Job { const std::function<void(int)>* fn = nullptr; int n = 0; };
     static void cpu_relax() {
 #if defined(__x86_64__)
         __builtin_ia32_pause();
 #endif
     }
     void work() {
+        active_.fetch_add(1, std::memory_order_acq_rel);
         for (;;) {
-            const int i = next_.fetch_add(1);
-            if (i >= n_.load(std::memory_order_acquire)) break;
-            (*fn_)(i);
+            const uint64_t t = ticket_.fetch_add(1, std::memory_order_acq_rel);
+            const Job& j = jobs_[(t >> 32) & 1];                          // the job this ticket was drawn for
+            const int i = (int)(uint32_t)t;
+            if ((t >> 32) == 0 || i >= j.n) break;
+            (*j.fn)(i);
             pending_.fetch_sub(1, std::memory_order_acq_rel);
         }
+        active_.fetch_sub(1, std::memory_order_acq_rel);
     }
     // A frame stages twice within ~0.1 ms (depth, then the masks under the sweep): after a job the workers keep polling for
     // the next one for a short while before they block on the condition variable, so the second job starts without a wake-up.
@@ -120,27 +134,27 @@ private:
         for (;;) {
             const auto t0 = std::chrono::steady_clock::now();
             int spins = 0;
-            while (!stop_.load(std::memory_order_acquire) && epoch_.load(std::memory_order_acquire) == seen) {
+            while (!stop_.load(std::memory_order_acquire) && (ticket_.load(std::memory_order_acquire) >> 32) == seen) {
                 cpu_relax();
                 if ((++spins & 255) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(spin_us_)) {
                     std::unique_lock<std::mutex> lk(mu_);
                     sleepers_.fetch_add(1, std::memory_order_acq_rel);
-                    cv_.wait(lk, [&] { return stop_.load() || epoch_.load(std::memory_order_acquire) != seen; });
+                    cv_.wait(lk, [&] { return stop_.load() || (ticket_.load(std::memory_order_acquire) >> 32) != seen; });
                     sleepers_.fetch_sub(1, std::memory_order_acq_rel);
                     break;
                 }
             }
             if (stop_.load(std::memory_order_acquire)) return;
-            seen = epoch_.load(std::memory_order_acquire);   // fn_ / n_ were written before the epoch was released
+            seen = ticket_.load(std::memory_order_acquire) >> 32;
             work();
         }
     }
     std::vector<std::thread> workers_;
     std::mutex mu_;
     std::condition_variable cv_;
-    const std::function<void(int)>* fn_ = nullptr;
-    std::atomic<int> n_{0}, next_{0}, pending_{0}, sleepers_{0};
-    std::atomic<uint64_t> epoch_{0};
+    Job jobs_[2];
+    std::atomic<uint64_t> ticket_{0};
+    std::atomic<int> pending_{0}, active_{0}, sleepers_{0};
     std::atomic<bool> stop_{false};
     const int spin_us_;
 };
@@ -223,7 +237,9 @@ struct dspmap {
     DevBuf<uint32_t> d_vmask;
     uint32_t words_per_row = 0, n_vwords = 0;
     DevBuf<uint64_t> d_csr_key;
-    DevBuf<uint32_t> d_csr_idx, d_vis_pix, d_vis_meta, d_seq_ref, d_mov_out;
+    DevBuf<uint32_t> d_csr_idx, d_seq_ref, d_mov_out;
+    DevBuf<uint32_t> d_row_order;      // image rows by listed particles in their window, descending (k_ck_row_order)
+    DevBuf<uint2> d_vis_mp;            // list-ordered {track | forget << 16, pixel}
     DevBuf<float4> d_vis_pos;
     // ordered insertion
     DevBuf<uint32_t> d_keys, d_ranks, d_birth_flags, d_birth_prefix, d_birth_block;
@@ -238,8 +254,7 @@ struct dspmap {
     uint32_t n_occ_chunks = 0;
     DevBuf<uint32_t> d_work;
     uint32_t n_occ_blocks = 0, birth_cap1 = 0, birth_shift1 = 0;
-    uint32_t ck_seg_stride = 1;
-    uint32_t sel_cap = 0;
+    uint32_t sel_cap = 0, seq_cap = 0;
     // occupancy
     // exchange arena (one allocation, exported over CUDA IPC in sharded maps): barrier flags, counts, visible records,
     // incoming moved particles, the ck image and the (global) result arrays
@@ -250,7 +265,8 @@ struct dspmap {
     void* peer_base[MAX_RANKS]{};
     bool comm_connected = false;
     uint32_t *r_idx = nullptr, *r_free_idx = nullptr;
-    float *r_xyz = nullptr, *r_w = nullptr, *r_free_xyz = nullptr, *d_ck = nullptr;
+    float *r_xyz = nullptr, *r_w = nullptr, *r_free_xyz = nullptr;
+    float2* d_ck = nullptr;           // {ck * Pd + kappa, refined reciprocal} per internal pixel
     uint16_t* r_track = nullptr;
     uint8_t* r_label = nullptr;
     uint8_t* r_rgb = nullptr;
@@ -347,7 +363,7 @@ struct dspmap {
         d_static_track.release(); d_static_label.release(); d_fp.release(); d_cnt.release(); d_persist.release(); d_masks.release(); d_moves.release();
         d_depth_in.release(); d_depth_int.release(); d_mask_in.release(); d_cloud_pos.release(); d_cloud_meta.release();
         d_pix_count.release(); d_pix_offset.release(); d_scan_block.release(); d_vmask.release(); d_csr_key.release(); d_seq_ref.release(); d_mov_out.release(); d_csr_idx.release();
-        d_vis_pix.release(); d_vis_meta.release(); d_vis_pos.release(); d_keys.release(); d_ranks.release(); d_birth_flags.release(); d_birth_prefix.release(); d_birth_block.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_chunk_tot.release(); d_chunk_base.release(); d_tile_list.release(); d_work.release();
+        d_vis_mp.release(); d_row_order.release(); d_vis_pos.release(); d_keys.release(); d_ranks.release(); d_birth_flags.release(); d_birth_prefix.release(); d_birth_block.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_chunk_tot.release(); d_chunk_base.release(); d_tile_list.release(); d_work.release();
         for (int p = 0; p < MAX_RANKS; ++p) if (peer_base[p] && p != cfg.shard_rank) { cudaIpcCloseMemHandle(peer_base[p]); peer_base[p] = nullptr; }
         arena.release();
         p_depth.release(); p_masks.release(); p_cnt.release(); p_fp.release(); p_stamps.release(); p_maskdesc.release(); p_moves.release();
@@ -367,10 +383,10 @@ struct dspmap {
         for (int p = 0; p < G; ++p) {
             uint8_t* b = (uint8_t*)(peer_base[p] ? peer_base[p] : arena.p);
             cv.flags[p] = (uint32_t*)(b + lay.flags); cv.counts[p] = (uint32_t*)(b + lay.counts); cv.move_counts[p] = (uint32_t*)(b + lay.move_counts);
-            cv.recs[p] = (VisRec*)(b + lay.recs); cv.movs[p] = (MovRec*)(b + lay.movs); cv.ck[p] = (float*)(b + lay.ck);
+            cv.recs[p] = (VisRec*)(b + lay.recs); cv.movs[p] = (MovRec*)(b + lay.movs); cv.ck[p] = (float2*)(b + lay.ck);
         }
         uint8_t* mine = arena.p;
-        d_ck = (float*)(mine + lay.ck); d_counts = (uint32_t*)(mine + lay.counts);
+        d_ck = (float2*)(mine + lay.ck); d_counts = (uint32_t*)(mine + lay.counts);
         uint8_t* r0 = (uint8_t*)(peer_base[0] && have_rank0 >= 0 ? peer_base[0] : arena.p);
         r_idx = (uint32_t*)(r0 + lay.r_idx); r_xyz = (float*)(r0 + lay.r_xyz); r_w = (float*)(r0 + lay.r_w); r_track = (uint16_t*)(r0 + lay.r_track);
         r_label = (uint8_t*)(r0 + lay.r_label); r_state = (int8_t*)(r0 + lay.r_state); r_free_idx = (uint32_t*)(r0 + lay.r_free_idx); r_free_xyz = (float*)(r0 + lay.r_free_xyz);
@@ -384,7 +400,7 @@ struct dspmap {
     int init(const dspmap_config& c);
     int clear_device();
     int apply_params();
-    int run_moves(const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove, bool scan_remove);
+    int run_moves(const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove, bool scan_remove, int slot);
     int frame(const float* d_depth, int rows, int cols, int stride, const dspmap_mask* masks, int n_masks, const double pos[3],
               const double quat[4], const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove,
               int want_free, int pre_decimated, const std::function<int(dspmap_mask*)>* late_masks = nullptr,
@@ -507,12 +523,13 @@ int dspmap::init(const dspmap_config& c) {
     // capacity of ONE rank's visible-record segment; the pixel lists hold the records of all ranks
     f.vis_cap = (uint32_t)std::min<size_t>(usable, c.max_visible ? (size_t)c.max_visible : (size_t)4 << 20);
     const size_t list_cap = (size_t)f.vis_cap * c.shard_count;
-    CU_TRY(this, d_csr_key.alloc(list_cap)); CU_TRY(this, d_csr_idx.alloc(list_cap)); CU_TRY(this, d_vis_pix.alloc(list_cap));
-    CU_TRY(this, d_vis_meta.alloc(list_cap)); CU_TRY(this, d_vis_pos.alloc(list_cap));
+    CU_TRY(this, d_csr_key.alloc(list_cap)); CU_TRY(this, d_csr_idx.alloc(list_cap));
+    CU_TRY(this, d_vis_mp.alloc(list_cap)); CU_TRY(this, d_vis_pos.alloc(list_cap)); CU_TRY(this, d_row_order.alloc(f.H));
 
     sel_cap = (uint32_t)std::min<size_t>(usable, (size_t)1 << 20);
     CU_TRY(this, d_movl_idx.alloc(sel_cap)); CU_TRY(this, d_movl_seq.alloc(sel_cap)); CU_TRY(this, d_movl_track.alloc(sel_cap));
-    CU_TRY(this, d_seq_ref.alloc(sel_cap)); CU_TRY(this, d_mov_out.alloc(MAX_RANKS));
+    seq_cap = (size_t)sel_cap * c.shard_count >= ((size_t)1 << 24) ? (1u << 24) : sel_cap * (uint32_t)c.shard_count;   // sequence numbers are global (and 24 bits in the rank lists)
+    CU_TRY(this, d_seq_ref.alloc(seq_cap)); CU_TRY(this, d_mov_out.alloc(MAX_RANKS));
     CU_TRY(this, cudaMemset(d_mov_out.p, 0, MAX_RANKS * sizeof(uint32_t)));
 
     // hash table for ordered insertion: >= 2x the larger candidate population (pixels, moved particles)
@@ -529,12 +546,6 @@ int dspmap::init(const dspmap_config& c) {
     CU_TRY(this, d_keys.alloc(cap)); CU_TRY(this, d_ranks.alloc((size_t)cap * f.topk)); CU_TRY(this, d_entry_list.alloc(cap)); CU_TRY(this, d_entry_voxel.alloc(cap));
 
     n_occ_blocks = (uint32_t)(v_pad / OCC_TILE);
-    {   // a stride coprime with the number of 32-pixel segments, near the golden ratio of it (k_ck's segment shuffle)
-        const uint32_t n_seg = (uint32_t)(npix + 31) / 32;
-        auto gcd = [](uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; };
-        ck_seg_stride = std::max<uint32_t>(1, (uint32_t)(n_seg * 0.6180339887));
-        while (gcd(ck_seg_stride, n_seg) != 1) ++ck_seg_stride;
-    }
     CU_TRY(this, d_col_tab.alloc(1024)); CU_TRY(this, cudaMemset(d_col_tab.p, 0, 1024));
     CU_TRY(this, d_vstate.alloc(v_pad)); CU_TRY(this, d_res_w.alloc(v_pad)); CU_TRY(this, d_res_tl.alloc(v_pad)); CU_TRY(this, d_mov_mask.alloc(v_pad));
     n_occ_chunks = (n_occ_blocks + OCC_SCAN_CHUNK - 1) / OCC_SCAN_CHUNK;
@@ -549,7 +560,7 @@ int dspmap::init(const dspmap_config& c) {
         auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
         lay.flags = take(64 * 4); lay.counts = take((size_t)MAX_RANKS * COMM_COUNTS * 4); lay.move_counts = take((size_t)MAX_RANKS * MAX_MOVES * 4);
         lay.recs = take((size_t)G * f.vis_cap * sizeof(VisRec)); lay.movs = take((size_t)G * sel_cap * sizeof(MovRec));
-        lay.ck = take(npix * 4);
+        lay.ck = take(npix * 8);
         const size_t Vg = f.V;   // rank 0 receives the global result
         lay.r_idx = take(Vg * 4); lay.r_xyz = take(Vg * 12); lay.r_w = take(Vg * 4); lay.r_track = take(Vg * 2); lay.r_label = take(Vg); lay.r_state = take(Vg);
         lay.r_free_idx = take(Vg * 4); lay.r_free_xyz = take(Vg * 12);
@@ -575,8 +586,13 @@ int dspmap::init(const dspmap_config& c) {
         }
         CU_TRY(this, cudaMemcpy(d_lut.p, lut.data(), PDF_NUM * sizeof(float), cudaMemcpyHostToDevice));
     }
-    CU_TRY(this, cudaFuncSetAttribute(k_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, PDF_NUM * (int)sizeof(float)));
-    CU_TRY(this, cudaFuncSetAttribute(k_weight_update, cudaFuncAttributeMaxDynamicSharedMemorySize, PDF_NUM * (int)sizeof(float)));
+    if (f.win_r > CK_MAX_R) return fail(DSPMAP_ERR_CONFIG, "window_half %d: at most %d", f.win_r, CK_MAX_R);
+#define SET_SMEM(K, BYTES) CU_TRY(this, cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES)))
+    SET_SMEM((k_ck<0, false>), CK_SMEM_BYTES); SET_SMEM((k_ck<3, false>), CK_SMEM_BYTES); SET_SMEM((k_ck<5, false>), CK_SMEM_BYTES);
+    SET_SMEM((k_ck<0, true>), CK_SMEM_BYTES); SET_SMEM((k_ck<3, true>), CK_SMEM_BYTES); SET_SMEM((k_ck<5, true>), CK_SMEM_BYTES);
+    SET_SMEM((k_weight_update<0, false>), WU_SMEM_BYTES); SET_SMEM((k_weight_update<3, false>), WU_SMEM_BYTES); SET_SMEM((k_weight_update<5, false>), WU_SMEM_BYTES);
+    SET_SMEM((k_weight_update<0, true>), WU_SMEM_BYTES); SET_SMEM((k_weight_update<3, true>), WU_SMEM_BYTES); SET_SMEM((k_weight_update<5, true>), WU_SMEM_BYTES);
+#undef SET_SMEM
 
     for (int a = 0; a < 3; ++a) { moved[a] = 0; equiv[a] = 0; map_center[a] = 0.f; ego_center[a] = 0.f; last_pos[a] = 0.f; }
     return clear_device();
@@ -608,7 +624,8 @@ int dspmap::apply_params() {
     f.occ_thr = prm.occupancy_threshold; f.max_forget = prm.max_forget_count;
     f.depth_noise = prm.consider_depth_noise ? 1 : 0; f.indep = prm.use_independent_filter ? 1 : 0;
     f.n0 = prm.depth_noise_zero_order; f.n1 = prm.depth_noise_first_order;
-    f.sigma_invalid = prm.consider_depth_noise ? prm.depth_noise_zero_order : 0.1f;
+    f.sigma_invalid = prm.uninit_sigma_mode ? prm.uninit_sigma_value : (prm.consider_depth_noise ? prm.depth_noise_zero_order : 0.1f);
+    f.sigma_gated_set = prm.uninit_sigma_mode ? 1 : 0;
     f.zero_center = prm.zero_center ? 1 : 0;
     f.col_enabled = colors.enabled ? 1 : 0; f.col_eval = colors.eval_format ? 1 : 0; f.col_scheme = colors.scheme; f.col_background = colors.background_label;
     f.nb_ptc = prm.consider_depth_noise ? prm.nb_ptc_num_per_point : 1;
@@ -619,38 +636,38 @@ int dspmap::apply_params() {
 
 // moveParticlesInSetsByTransformations + removeObjectByTrackID (mc_ring/operations.h:321-362; object_layer.h:414-425)
 // scan_remove: the movable list no longer describes the store (second phase of a move-then-remove frame)
-int dspmap::run_moves(const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove, bool scan_remove) {
-    if (n_moves > MAX_MOVES || n_remove > MAX_MOVES) return fail(DSPMAP_ERR_CAPACITY, "at most %d moves and %d removals per frame", MAX_MOVES, MAX_MOVES);
-    MoveTable& mt = *p_moves.p;
-    memset(&mt, 0, sizeof mt);
+int dspmap::run_moves(const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove, bool scan_remove, int slot) {
+    // one staging table per call of a frame (slot): nothing waits for an earlier table's copy to finish
+    MoveTable& mt = p_moves.p[slot];
     mt.n_moves = n_moves; mt.n_remove = n_remove;
     for (int i = 0; i < n_moves; ++i) { mt.move_track[i] = moves[i].track_id; memcpy(mt.t[i], moves[i].t, 12 * sizeof(float)); }
     for (int i = 0; i < n_remove; ++i) mt.remove_track[i] = remove_tracks[i];
-    CU_TRY(this, cudaMemcpyAsync(d_moves.p, &mt, sizeof mt, cudaMemcpyHostToDevice, stream));
+    MoveTable* d_mt = d_moves.p + slot;
+    CU_TRY(this, cudaMemcpyAsync(d_mt, &mt, sizeof mt, cudaMemcpyHostToDevice, stream));
     const uint32_t* stx = d_stamps.p;
     const uint32_t* sty = d_stamps.p + fp.NX;
     const uint32_t* stz = d_stamps.p + fp.NX + fp.NY;
     if (scan_remove) {
-        ++launches; k_remove_tracks_scan<<<sm_count * 8, 256, 0, stream>>>(fp, st, d_moves.p, d_cnt.p);
+        ++launches; k_remove_tracks_scan<<<sm_count * 8, 256, 0, stream>>>(fp, st, d_mt, d_cnt.p);
     } else {
         if (cv.size > 1) {
-            ++launches; k_move_count<<<1, 1024, 0, stream>>>(d_moves.p, d_movl_track.p, sel_cap, d_persist.p, cv);
+            ++launches; k_move_count<<<1, 1024, 0, stream>>>(d_mt, d_movl_track.p, sel_cap, d_persist.p, cv);
             barrier();   // every rank knows how many particles of each moved track the lower ranks hold
         }
-        ++launches; k_move_prepare<<<1, 1024, 0, stream>>>(d_moves.p, d_movl_track.p, d_movl_seq.p, sel_cap, rand_n, d_cnt.p, d_persist.p, cv,
+        ++launches; k_move_prepare<<<1, 1024, 0, stream>>>(d_mt, d_movl_track.p, d_movl_seq.p, sel_cap, rand_n, d_cnt.p, d_persist.p, cv,
                                                          cv.move_counts[cv.rank]);
-        ++launches; k_move_apply<<<sm_count * 2, 256, 0, stream>>>(fp, d_cnt.p, st, d_moves.p, d_randoms.p, d_persist.p, d_movl_idx.p, d_movl_track.p,
+        ++launches; k_move_apply<<<sm_count * 2, 256, 0, stream>>>(fp, d_cnt.p, st, d_mt, d_randoms.p, d_persist.p, d_movl_idx.p, d_movl_track.p,
                                                              d_movl_seq.p, sel_cap, cv);
         if (n_moves > 0) {
             if (cv.size > 1) {
                 ++launches; k_move_publish<<<1, 32, 0, stream>>>(cv, d_cnt.p);
                 barrier();   // the moved particles bound for this rank have arrived
             }
-            ++launches; k_move_bin<<<sm_count * 2, 256, 0, stream>>>(fp, cv, cv.movs[cv.rank], d_counts, d_seq_ref.p, sel_cap, d_keys.p, d_ranks.p,
+            ++launches; k_move_bin<<<sm_count * 2, 256, 0, stream>>>(fp, cv, cv.movs[cv.rank], d_counts, d_seq_ref.p, seq_cap, d_keys.p, d_ranks.p,
                                                                d_entry_list.p, d_cnt.p);
             DISPATCH_PB(fp.Pb, (k_move_replay<PB><<<sm_count * 2, 128, 0, stream>>>(fp, st, stx, sty, stz, d_keys.p, d_ranks.p, d_entry_list.p, d_entry_voxel.p, d_cnt.p)));
             ++launches;
-            ++launches; k_move_write<<<sm_count * 2, 256, 0, stream>>>(fp, st, cv.movs[cv.rank], d_seq_ref.p, d_ranks.p, d_entry_list.p, d_entry_voxel.p, d_cnt.p);
+            ++launches; k_move_write<<<sm_count * 2, 256, 0, stream>>>(fp, st, cv.movs[cv.rank], d_seq_ref.p, seq_cap, d_ranks.p, d_entry_list.p, d_entry_voxel.p, d_cnt.p);
         }
     }
     CU_TRY(this, cudaGetLastError());
@@ -680,6 +697,9 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
         const long long n_cand = 9ll * ((fp.H + 2) / 3) * ((fp.W + 2) / 3) * nb_eff;
         if (n_cand >= (1ll << 24)) return fail(DSPMAP_ERR_UNSUPPORTED, "nb_ptc_num_per_point = %d gives %lld birth candidates per frame (limit 2^24)", nb_eff, n_cand);
     }
+    // everything that can refuse the frame is checked BEFORE the time stamp, the ring or the store are touched
+    if (n_moves > MAX_MOVES) return fail(DSPMAP_ERR_CAPACITY, "%d object moves in one frame (limit %d); nothing was changed", n_moves, MAX_MOVES);
+    if (!comm_connected) return fail(DSPMAP_ERR_COMM, "sharded map: call dspmap_comm_connect on every rank before the first update");
     host_result_valid = false;
     t_frame_begin = host_now_ms();
     T += 1;                                                       // :173
@@ -745,8 +765,6 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     f.want_free = want_free ? 1 : 0; f.want_state = 0;
     f.rand_n = rand_n;
 
-    if (!comm_connected) return fail(DSPMAP_ERR_COMM, "sharded map: call dspmap_comm_connect on every rank before the first update");
-
     // ---- uploads -------------------------------------------------------------------------------------------
     if (stamps_dirty) {
         uint32_t* s = p_stamps.p;
@@ -759,7 +777,6 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     const uint32_t* sty = d_stamps.p + f.NX;
     const uint32_t* stz = d_stamps.p + f.NX + f.NY;
     const int npix = f.W * f.H;
-    const size_t lut_bytes = PDF_NUM * sizeof(float);
 
     if (profiling) cudaEventRecord(ev[0], stream);
     const bool depth_kernel = !((pre_decimated || !f.boost) && stride == f.W);
@@ -787,11 +804,20 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
             for (int k = 0; k < n_moves; ++k) also_moved |= moves[k].track_id == remove_tracks[i];
             (also_moved ? rm_after : rm_now).push_back(remove_tracks[i]);
         }
-        int rc = run_moves(moves, n_moves, rm_now.data(), (int)rm_now.size(), false);
-        if (rc != DSPMAP_OK) return rc;
-        if (!rm_after.empty()) {
-            CU_TRY(this, cudaStreamSynchronize(stream));   // the move table staging buffer is reused
-            rc = run_moves(nullptr, 0, rm_after.data(), (int)rm_after.size(), true);
+        // the reference has no limit on removals per frame (every unregistered detection is one): they are independent, so
+        // they go MAX_MOVES at a time, the first batch together with the moves
+        const int nb_now = std::max(1, ((int)rm_now.size() + MAX_MOVES - 1) / MAX_MOVES), nb_after = ((int)rm_after.size() + MAX_MOVES - 1) / MAX_MOVES;
+        CU_TRY(this, p_moves.reserve(nb_now + nb_after));
+        if (d_moves.n < (size_t)(nb_now + nb_after)) { CU_TRY(this, cudaStreamSynchronize(stream)); CU_TRY(this, d_moves.alloc(nb_now + nb_after)); }
+        int slot = 0;
+        for (int b = 0; b < nb_now; ++b, ++slot) {
+            const int lo = b * MAX_MOVES, n = std::min((int)rm_now.size() - lo, MAX_MOVES);
+            const int rc = run_moves(b == 0 ? moves : nullptr, b == 0 ? n_moves : 0, rm_now.data() + lo, std::max(n, 0), false, slot);
+            if (rc != DSPMAP_OK) return rc;
+        }
+        for (int b = 0; b < nb_after; ++b, ++slot) {
+            const int lo = b * MAX_MOVES, n = std::min((int)rm_after.size() - lo, MAX_MOVES);
+            const int rc = run_moves(nullptr, 0, rm_after.data() + lo, n, true, slot);
             if (rc != DSPMAP_OK) return rc;
         }
     }
@@ -820,9 +846,10 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     const int nsb = (npix + SCAN_BLOCK - 1) / SCAN_BLOCK;
     ++launches; k_scan_blocksum<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p);
     ++launches; k_scan_apply<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p, d_pix_offset.p);
+    ++launches; k_ck_row_order<<<1, 1024, (size_t)f.H * sizeof(uint32_t), stream>>>(fp, d_pix_offset.p, d_row_order.p);
     ++launches; k_fill<<<sm_count * 4, 256, 0, stream>>>(cv, cv.recs[cv.rank], d_counts, d_cnt.p, d_pix_offset.p, d_pix_count.p, d_csr_key.p);
     ++launches; k_sort_lists<<<(npix + 255) / 256, 256, 0, stream>>>(fp, d_pix_offset.p, d_csr_key.p);
-    ++launches; k_gather_visible<<<sm_count * 4, 256, 0, stream>>>(d_pix_offset.p + npix, cv.recs[cv.rank], d_csr_key.p, d_csr_idx.p, d_vis_pix.p, d_vis_pos.p, d_vis_meta.p);
+    ++launches; k_gather_visible<<<sm_count * 4, 256, 0, stream>>>(d_pix_offset.p + npix, cv.recs[cv.rank], d_csr_key.p, d_csr_idx.p, d_vis_pos.p, d_vis_mp.p);
     if (profiling) cudaEventRecord(ev[3], stream);
     // ---- K1 projection + labels (needs the masks) -----------------------------------------------------------------------
     std::vector<dspmap_mask> mask_copy(masks, masks + n_masks);
@@ -856,10 +883,20 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
         CU_TRY(this, cudaEventRecord(ev_join[1], side_stream));
     }
     // ---- U3 weight update --------------------------------------------------------------------------------------------
-    ++launches; k_ck<<<sm_count, 1024, lut_bytes, stream>>>(fp, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_pix_offset.p, d_vis_pos.p, d_vis_meta.p, cv, ck_seg_stride, d_cnt.p);
+#define DISPATCH_R1(r, CALL)                                    \
+    switch (r) {                                                \
+        case 3: { constexpr int RT = 3; CALL; break; }          \
+        case 5: { constexpr int RT = 5; CALL; break; }          \
+        default: { constexpr int RT = 0; CALL; break; }         \
+    }
+#define DISPATCH_R(r, CALL)                                     \
+    if (f.indep) { constexpr bool INDEP = true; DISPATCH_R1(r, CALL) } else { constexpr bool INDEP = false; DISPATCH_R1(r, CALL) }
+    DISPATCH_R(f.win_r, (k_ck<RT, INDEP><<<sm_count, CK_WARPS * 32, CK_SMEM_BYTES, stream>>>(fp, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_pix_offset.p, d_vis_pos.p, d_vis_mp.p, d_row_order.p, cv, d_cnt.p)));
+    ++launches;
     barrier();   // sharded map: every rank's ck image is complete
-    ++launches; k_weight_update<<<sm_count * 2, 1024, lut_bytes, stream>>>(fp, d_pix_offset.p + npix, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_ck, d_csr_idx.p,
-                                                             d_vis_pix.p, d_vis_pos.p, d_vis_meta.p, st);
+    DISPATCH_R(f.win_r, (k_weight_update<RT, INDEP><<<sm_count, WU_THREADS, WU_SMEM_BYTES, stream>>>(fp, d_pix_offset.p + npix, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_ck, d_csr_idx.p,
+                                                                                  d_vis_pos.p, d_vis_mp.p, st)));
+    ++launches;
     if (profiling) cudaEventRecord(ev[5], stream);
     // ---- B1 birth + resample -----------------------------------------------------------------------------------------
     {
@@ -1057,8 +1094,11 @@ static int check_frame_args(dspmap_t* h, const float* depth, int32_t rows, int32
     // the reference indexes with the compile-time size and reads out of bounds otherwise (semantic_dsp_map.h:212-221 vs :974-979)
     if (rows != h->cfg.image_height || cols != h->cfg.image_width || row_stride < cols)
         return h->fail(DSPMAP_ERR_IMAGE_SIZE, "depth is %dx%d (stride %d), map is configured for %dx%d", rows, cols, row_stride, h->cfg.image_height, h->cfg.image_width);
-    for (int m = 0; m < n_masks; ++m)
+    for (int m = 0; m < n_masks; ++m) {
         if (!masks[m].data || masks[m].row_stride < cols) return h->fail(DSPMAP_ERR_IMAGE_SIZE, "mask %d: null data or stride < width", m);
+        if ((masks[m].rows || masks[m].cols) && (masks[m].rows != rows || masks[m].cols != cols))
+            return h->fail(DSPMAP_ERR_IMAGE_SIZE, "mask %d is %dx%d, the depth image %dx%d", m, masks[m].rows, masks[m].cols, rows, cols);
+    }
     return DSPMAP_OK;
 }
 
@@ -1323,6 +1363,18 @@ int dspmap_dump(dspmap_t* h, int32_t what, void* dst, size_t cap, size_t* n_byte
             }
             break;
         }
+        case DSPMAP_DUMP_PARTICLES_HASH: {
+            unsigned long long* d = nullptr;
+            CU_TRY(h, cudaMalloc(&d, sizeof(unsigned long long)));
+            CU_TRY(h, cudaMemset(d, 0, sizeof(unsigned long long)));
+            k_store_hash<<<h->sm_count * 16, 256, 0, h->stream>>>(h->st, h->slot_lo, h->n_slots_local, (uint32_t)f.Pb, d);
+            tmp.resize(8);
+            const cudaError_t e = cudaMemcpyAsync(tmp.data(), d, 8, cudaMemcpyDeviceToHost, h->stream);
+            const cudaError_t e2 = cudaStreamSynchronize(h->stream);
+            cudaFree(d);
+            CU_TRY(h, e); CU_TRY(h, e2);
+            break;
+        }
         case DSPMAP_DUMP_PIXEL_OFFSETS:
             tmp.resize((npix + 1) * 4);
             CU_TRY(h, pull(tmp.data(), h->d_pix_offset.p, tmp.size()));
@@ -1335,7 +1387,7 @@ int dspmap_dump(dspmap_t* h, int32_t what, void* dst, size_t cap, size_t* n_byte
         }
         case DSPMAP_DUMP_CK:
             tmp.resize(npix * 4);
-            CU_TRY(h, pull(tmp.data(), h->d_ck, tmp.size()));
+            CU_TRY(h, cudaMemcpy2D(tmp.data(), 4, h->d_ck, 8, 4, npix, cudaMemcpyDeviceToHost));     // the .x of every {ck, reciprocal} pair
             break;
         case DSPMAP_DUMP_RING: {
             tmp.resize(4 * (9 + f.NX + f.NY + f.NZ));

@@ -84,7 +84,7 @@ struct CommView {
     uint32_t* counts[MAX_RANKS];       // peer p's counts[source rank][COMM_COUNTS]
     VisRec* recs[MAX_RANKS];           // peer p's visible-record arena: [source rank][rec_cap]
     MovRec* movs[MAX_RANKS];           // peer p's incoming moved particles: [source rank][mov_cap]
-    float* ck[MAX_RANKS];              // peer p's ck image
+    float2* ck[MAX_RANKS];             // peer p's ck image: {ck * Pd + kappa, its refined reciprocal}
     uint32_t* move_counts[MAX_RANKS];  // peer p's per-move particle counts: [source rank][MAX_MOVES]
 };
 
@@ -179,10 +179,10 @@ k_project(const __grid_constant__ FrameParams f, const MaskDesc* __restrict__ ma
                 }
                 background = pg[0] < b0[0] || pg[0] > b1[0] || pg[1] < b0[1] || pg[1] > b1[1] || pg[2] < b0[2] || pg[2] > b1[2];
             }
-            if (background) { label = 0; track = 65535u; }
+            if (background) { label = 0; track = 65535u; }       // sigma is never assigned on this branch of the reference (:256-272)
             else if (inst > f.max_movable) label = lut_static_label[inst];                           // :277-279
             else label = owner >= 0 ? ((uint32_t)masks[owner].label_id & 0xffu) : 0u;                 // :281
-            pos = make_float4((float)pg[0], (float)pg[1], (float)pg[2], sigma);                       // :298-300
+            pos = make_float4((float)pg[0], (float)pg[1], (float)pg[2], (background && f.sigma_gated_set) ? f.sigma_invalid : sigma);   // :298-300
             meta = track | (label << 16) | (1u << 24);
             valid = true;
         }
@@ -521,180 +521,24 @@ k_sort_lists(const __grid_constant__ FrameParams f, const uint32_t* __restrict__
 // lay the listed particles out in list order for the two stencil passes (from the records, not from the store)
 __global__ void __launch_bounds__(256)
 k_gather_visible(const uint32_t* __restrict__ n_visible, const VisRec* __restrict__ recs, const uint64_t* __restrict__ csr_key,
-                 uint32_t* __restrict__ csr_idx, uint32_t* __restrict__ vis_pix, float4* __restrict__ vis_pos, uint32_t* __restrict__ vis_meta) {
+                 uint32_t* __restrict__ csr_idx, float4* __restrict__ vis_pos, uint2* __restrict__ vis_mp) {
     const uint32_t n = *n_visible;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint64_t key = csr_key[k];
         const uint4* r = reinterpret_cast<const uint4*>(recs + (uint32_t)key);
         const uint4 lo = r[0], hi = r[1];
         csr_idx[k] = (uint32_t)(key >> 32);
-        vis_pix[k] = lo.x;
         vis_pos[k] = make_float4(__uint_as_float(lo.z), __uint_as_float(lo.w), __uint_as_float(hi.x), __uint_as_float(hi.y));
-        vis_meta[k] = hi.z;
+        vis_mp[k] = make_uint2(hi.z, lo.x);          // {track | forget << 16, pixel}
     }
 }
 
 // =====================================================================================================
-// U3a  ck_accumulate  replaces SemanticDSPMap::updateParticles pass 1 (semantic_dsp_map.h:973-1037)
-// one thread per observation pixel; window rows are contiguous CSR ranges; Gaussian LUT in shared memory.
+// U3  the two stencil passes of updateParticles (k_ck, k_weight_update): dspmap_stencil.cuh
 // =====================================================================================================
-__device__ __forceinline__ void stage_lut(const float* __restrict__ lut) {
-    for (int i = threadIdx.x; i < PDF_NUM / 4; i += blockDim.x) reinterpret_cast<float4*>(s_lut)[i] = reinterpret_cast<const float4*>(lut)[i];
-    __syncthreads();
-}
-
-// one entry of the list-ordered particle copies (k_gather_visible)
-struct VisElem { float4 p; uint32_t m; };
-__device__ __forceinline__ VisElem ld_vis(const float4* __restrict__ vis_pos, const uint32_t* __restrict__ vis_meta, uint32_t k) {
-    VisElem e;
-    e.p = vis_pos[k];
-    e.m = vis_meta[k];
-    return e;
-}
-
-// The sum of one observation pixel runs over its window row by row and, inside a row, over a contiguous range of the
-// list-ordered particle copies: a strictly sequential chain (the float sum must keep the reference's order), one scattered
-// 16-byte load per step and lane.  Pixels near the horizon have 4-5x the average number of steps, so a warp's time is
-// (steps) x (latency of one step), and the kernel's time is its slowest warp's.  The loads are therefore software-pipelined:
-// list entries two steps ahead, the first two entries of the NEXT row while the current row is processed, and the row
-// offsets two rows ahead - a step no longer waits for L2.
-template <bool FAST>
-__device__ __forceinline__ float ck_pixel(const FrameParams& f, const float4 o, const uint32_t otrack, int i, int j,
-                                          const uint32_t* __restrict__ offset, const float4* __restrict__ vis_pos,
-                                          const uint32_t* __restrict__ vis_meta) {
-    const InvDiv sigma(o.w);
-    const int r = f.win_r;
-    const int j0 = max(j - r, 0), j1 = min(j + r, f.W - 1) + 1;
-    const int i0 = max(i - r, 0), i1 = min(i + r, f.H - 1);
-    float acc = 0.f;
-    uint32_t kb = offset[i0 * f.W + j0], ke = offset[i0 * f.W + j1];
-    uint32_t kbn = 0, ken = 0;
-    if (i0 < i1) { kbn = offset[(i0 + 1) * f.W + j0]; ken = offset[(i0 + 1) * f.W + j1]; }
-    VisElem e0{}, e1{};
-    if (kb < ke) e0 = ld_vis(vis_pos, vis_meta, kb);
-    if (kb + 1 < ke) e1 = ld_vis(vis_pos, vis_meta, kb + 1);
-    for (int ni = i0; ni <= i1; ++ni) {
-        VisElem n0{}, n1{};
-        if (kbn < ken) n0 = ld_vis(vis_pos, vis_meta, kbn);
-        if (kbn + 1 < ken) n1 = ld_vis(vis_pos, vis_meta, kbn + 1);
-        uint32_t kbnn = 0, kenn = 0;
-        if (ni + 2 <= i1) { kbnn = offset[(ni + 2) * f.W + j0]; kenn = offset[(ni + 2) * f.W + j1]; }
-        for (uint32_t k = kb; k < ke; ++k) {
-            VisElem nx{};
-            if (k + 2 < ke) nx = ld_vis(vis_pos, vis_meta, k + 2);
-            const uint32_t pm = e0.m;
-            const float4 p = e0.p;
-            e0 = e1; e1 = nx;
-            const bool same = (pm & 0xffffu) == otrack;
-            if (f.indep && !same) continue;
-            float gk = query_pdf<FAST>(p.x, o.x, sigma) * query_pdf<FAST>(p.y, o.y, sigma) * query_pdf<FAST>(p.z, o.z, sigma);
-            if (!f.indep) {
-                gk *= forgetting_factor(f, pm >> 16);
-                if (!same) gk *= f.tau;
-            }
-            acc += p.w * gk;
-        }
-        e0 = n0; e1 = n1;
-        kb = kbn; ke = ken; kbn = kbnn; ken = kenn;
-    }
-    return acc;
-}
-
-__global__ void __launch_bounds__(1024, 1)
-k_ck(const __grid_constant__ FrameParams f, const float* __restrict__ lut, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta,
-     const uint32_t* __restrict__ offset, const float4* __restrict__ vis_pos, const uint32_t* __restrict__ vis_meta,
-     CommView cv, uint32_t seg_stride, Counters* __restrict__ cnt) {
-    stage_lut(lut);
-    const int npix = f.W * f.H;
-    const uint32_t n_seg = (uint32_t)(npix + 31) / 32;
-    // Warps draw 32-pixel segments from a shared counter (the per-pixel work is very uneven).  The drawn index maps to an
-    // image segment through a stride coprime with the segment count, so neighbouring image rows spread over all SMs.
-    // Sharded map: rank r evaluates every size-th segment and writes its values into every rank's ck image.
-    for (;;) {
-        uint32_t c = 0;
-        if (lane_id() == 0) c = atomicAdd(&cnt->ck_next, 1u);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        const uint32_t t = c * (uint32_t)cv.size + (uint32_t)cv.rank;
-        if (t >= n_seg) break;
-        const int q = (int)((uint32_t)(((uint64_t)t * seg_stride) % n_seg) * 32u + lane_id());
-        if (q >= npix) continue;
-        const uint32_t om = cloud_meta[q];
-        if (!pt_valid(om)) { for (int pr = 0; pr < cv.size; ++pr) cv.ck[pr][q] = 0.f; continue; }
-        const float4 o = cloud_pos[q];
-        const int i = q / f.W, j = q - i * f.W;
-        const float ao = fabsf(o.w);
-        const float acc = (ao > 1e-6f && ao < 1e6f) ? ck_pixel<true>(f, o, pt_track(om), i, j, offset, vis_pos, vis_meta)
-                                                    : ck_pixel<false>(f, o, pt_track(om), i, j, offset, vis_pos, vis_meta);
-        const float val = acc * f.Pd + f.kappa;
-        for (int pr = 0; pr < cv.size; ++pr) cv.ck[pr][q] = val;
-    }
-    __threadfence_system();
-}
-
-// =====================================================================================================
-// U3b  weight_update  replaces SemanticDSPMap::updateParticles pass 2 (semantic_dsp_map.h:1041-1119)
-// one thread per listed particle; sigma is the PARTICLE's pixel's sigma (:1047).
-// =====================================================================================================
-template <bool FAST>
-__device__ __forceinline__ float wu_particle(const FrameParams& f, const float4 p, const uint32_t ptrack, const float phi, const float sig,
-                                             int i, int j, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta,
-                                             const float* __restrict__ ck, bool& right_id) {
-    const InvDiv sigma(sig);
-    const int r = f.win_r;
-    float acc = 0.f;
-    for (int ni = max(i - r, 0); ni <= min(i + r, f.H - 1); ++ni) {
-        for (int nj = max(j - r, 0); nj <= min(j + r, f.W - 1); ++nj) {
-            const int oq = ni * f.W + nj;
-            const uint32_t om = cloud_meta[oq];
-            if (!pt_valid(om)) continue;
-            const bool same = pt_track(om) == ptrack;
-            if (f.indep && !same) continue;
-            const float4 o = cloud_pos[oq];
-            float gk = query_pdf<FAST>(p.x, o.x, sigma) * query_pdf<FAST>(p.y, o.y, sigma) * query_pdf<FAST>(p.z, o.z, sigma);
-            if (!f.indep) {
-                if (!same) gk *= f.tau;
-                else if (gk > MIN_RIGHTLY_UPDATED_PDF) right_id = true;
-                gk *= phi;
-            }
-            acc += gk / ck[oq];
-        }
-    }
-    return acc;
-}
-
-__global__ void __launch_bounds__(1024, 2)
-k_weight_update(const __grid_constant__ FrameParams f, const uint32_t* __restrict__ n_visible, const float* __restrict__ lut, const float4* __restrict__ cloud_pos,
-                const uint32_t* __restrict__ cloud_meta, const float* __restrict__ ck, const uint32_t* __restrict__ csr_idx,
-                const uint32_t* __restrict__ vis_pix, const float4* __restrict__ vis_pos, const uint32_t* __restrict__ vis_meta,
-                Store st) {
-    stage_lut(lut);
-    const uint32_t n = *n_visible;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const uint32_t pidx = csr_idx[k];
-        const uint32_t pz = (pidx >> f.Pb) >> (f.Xb + f.Yb);
-        if (pz < f.z_lo || pz >= f.z_hi) continue;          // another shard updates this particle
-        const int q = (int)vis_pix[k];
-        const int i = q / f.W, j = q - i * f.W;
-        const float sig = cloud_pos[q].w;
-        const float4 p = vis_pos[k];
-        const uint32_t pm = vis_meta[k];
-        const uint32_t ptrack = pm & 0xffffu, pforget = pm >> 16;
-        const float phi = f.indep ? 1.f : forgetting_factor(f, pforget);
-        bool right_id = false;
-        const float as = fabsf(sig);
-        const float acc = (as > 1e-6f && as < 1e6f) ? wu_particle<true>(f, p, ptrack, phi, sig, i, j, cloud_pos, cloud_meta, ck, right_id)
-                                                    : wu_particle<false>(f, p, ptrack, phi, sig, i, j, cloud_pos, cloud_meta, ck, right_id);
-        const uint32_t idx = pidx;
-        const uint64_t m = st.meta[idx];
-        uint32_t forget = meta_forget(m);
-        if (!f.indep) {
-            if (right_id) forget = 0;
-            else if (forget < 5) forget += 1;
-        }
-        st.w[idx] = p.w * (acc * f.Pd + 1.f - f.Pd);
-        st.meta[idx] = meta_pack(f.T, meta_track(m), meta_label(m), ST_UPDATED, forget);
-    }
-}
+}  // namespace dspk
+#include "dspmap_stencil.cuh"
+namespace dspk {
 
 // =====================================================================================================
 // ordered insertion of candidates into voxels.
@@ -1422,7 +1266,7 @@ k_occ_emit(const __grid_constant__ FrameParams f, Store st, OccScratch sc, Resul
 // set(T) = { p : status(p) != INVALID and track(p) == T } in ascending particle index (canonical order), read from
 // the movable-particle list the previous frame's occupancy pass left behind (nothing touches the store in between).
 // =====================================================================================================
-constexpr int MAX_MOVES = 64;
+constexpr int MAX_MOVES = 256;           // moved tracks per frame; removals are batched, MAX_MOVES per batch (no limit per frame)
 constexpr uint32_t SEQ_REMOVE = 0xfffffffeu;
 
 struct MoveTable {
@@ -1495,7 +1339,7 @@ k_move_prepare(const MoveTable* __restrict__ mt, const uint16_t* __restrict__ mo
     __syncthreads();
     const uint32_t wid = threadIdx.x >> 5;
     for (uint32_t c = 0; c < n; c += blockDim.x) {
-        for (int i = threadIdx.x; i < 32 * MAX_MOVES; i += blockDim.x) (&s_wcount[0][0])[i] = 0;
+        for (int i = threadIdx.x; i < 32 * n_moves; i += blockDim.x) s_wcount[i / n_moves][i % n_moves] = 0;
         __syncthreads();
         const uint32_t k = c + threadIdx.x;
         int mv = -1;
@@ -1582,7 +1426,8 @@ k_move_bin(const __grid_constant__ FrameParams f, CommView cv, const MovRec* __r
         const MovRec* seg = movs + (size_t)g * cv.mov_cap;
         for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < min(n, cv.mov_cap); k += gridDim.x * blockDim.x) {
             const uint32_t seq = seg[k].seq, v = seg[k].voxel;
-            if (seq < seq_cap) seq_ref[seq] = (uint32_t)g * cv.mov_cap + k;
+            if (seq >= seq_cap) { atomicAdd(&cnt->hash_overflow, 1u); continue; }      // reported as a capacity error by the host
+            seq_ref[seq] = (uint32_t)g * cv.mov_cap + k;
             topk_insert(f, f.hash_cap, f.hash_shift, v, seq, keys, ranks, entry_list, &cnt->n_move_voxels, &cnt->hash_overflow);
         }
     }
@@ -1654,7 +1499,7 @@ k_move_replay(const __grid_constant__ FrameParams f, Store st, const uint32_t* _
 }
 
 __global__ void __launch_bounds__(256)
-k_move_write(const __grid_constant__ FrameParams f, Store st, const MovRec* __restrict__ movs, const uint32_t* __restrict__ seq_ref,
+k_move_write(const __grid_constant__ FrameParams f, Store st, const MovRec* __restrict__ movs, const uint32_t* __restrict__ seq_ref, uint32_t seq_cap,
              uint32_t* __restrict__ ranks, const uint32_t* __restrict__ entry_list, const uint32_t* __restrict__ entry_voxel,
              const Counters* __restrict__ cnt) {
     const uint32_t K = f.topk, n = cnt->n_move_voxels * K;
@@ -1665,6 +1510,7 @@ k_move_write(const __grid_constant__ FrameParams f, Store st, const MovRec* __re
         if (a == NO_RANK) continue;
         *r = NO_RANK;
         const uint32_t s = a >> 24, seq = a & 0xffffffu;
+        if (seq >= seq_cap) continue;                                                  // cannot happen: k_move_bin drops such records
         const size_t idx = ((size_t)entry_voxel[li] << f.Pb) + s;
         const uint4* rec = reinterpret_cast<const uint4*>(movs + seq_ref[seq]);
         const uint4 lo = rec[0], hi = rec[1];
@@ -1706,9 +1552,31 @@ k_count_track(Store st, uint32_t n_voxels, uint32_t slot_bits, uint32_t track, u
     if (lane_id() == 0 && c) atomicAdd(out, c);
 }
 
+// DSPMAP_DUMP_PARTICLES_HASH (include/dspmap_c.h): order-independent digest of the reassembled 24-byte records
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256)
+k_store_hash(Store st, size_t slot_lo, size_t n_slots, uint32_t slot_bits, unsigned long long* __restrict__ out) {
+    const size_t slot_mask = ((size_t)1 << slot_bits) - 1;
+    uint64_t local = 0;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_slots; k += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = slot_lo + k;
+        uint64_t m = st.meta[i];
+        if ((i & slot_mask) == 0) m = (m & ~0xffffull) | hdr_ts(st.hdr[i >> slot_bits]);   // slot 0 = the time particle: its stamp lives in the header
+        const uint64_t a = (uint64_t)__float_as_uint(st.x[i]) | ((uint64_t)__float_as_uint(st.y[i]) << 32);
+        const uint64_t b = (uint64_t)__float_as_uint(st.z[i]) | ((uint64_t)__float_as_uint(st.w[i]) << 32);
+        local += mix64(mix64(mix64((uint64_t)i * 0x9E3779B97F4A7C15ull + a) ^ b) + m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (lane_id() == 0 && local) atomicAdd(out, (unsigned long long)local);
+}
+
 // brute-force check of InvDiv against the compiler's IEEE division (test hook)
 __global__ void k_selftest_invdiv(uint64_t n, uint64_t seed, float b_lo, float b_hi, float a_max, unsigned long long* __restrict__ mismatches) {
     uint64_t local = 0;
+    const bool wide = a_max < 0.f;      // a_max < 0: test div_by_stored (log-uniform divisor in [b_lo, b_hi], dividend 2^-100 .. 2^100)
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t z = seed + i * 0x9E3779B97F4A7C15ull;            // splitmix64
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
@@ -1720,8 +1588,22 @@ __global__ void k_selftest_invdiv(uint64_t n, uint64_t seed, float b_lo, float b
         const int ex = (int)((bits >> 23) & 31u) - 24;            // 2^-24 .. 2^7
         float a = ldexpf(mant, ex) * ((bits >> 28) & 1u ? -1.f : 1.f);
         if (fabsf(a) > a_max) a = a_max * 0.73f;
+        float q1;
+        const float q2 = a / b;
+        if (wide) {                                        // div_by_stored over its whole claimed range
+            const float lb = log2f(b_lo) + ub * (log2f(b_hi) - log2f(b_lo));
+            const float bw = exp2f(lb);
+            const int exw = (int)((bits >> 23) & 255u) % 201 - 100;    // 2^-100 .. 2^100
+            const float aw = ldexpf(mant, exw) * ((bits >> 31) ? -1.f : 1.f);
+            const float2 cy = ck_and_reciprocal(bw);
+            bool exact = true;
+            q1 = div_by_stored(aw, bw, cy.y, exact);
+            const float q2w = aw / bw;
+            if (exact && __float_as_uint(q1) != __float_as_uint(q2w)) ++local;
+            continue;
+        }
         const InvDiv d(b);
-        const float q1 = d.ok ? d.div<true>(a) : d.div<false>(a), q2 = a / b;
+        q1 = d.ok ? d.div<true>(a) : d.div<false>(a);
         if (__float_as_uint(q1) != __float_as_uint(q2)) ++local;
     }
     if (local) atomicAdd(mismatches, (unsigned long long)local);

@@ -9,7 +9,18 @@
 struct dspmap_objects {
     dsp_adapter::ObjectTracker tracker;
     uint32_t step = 0;      // global_time_stamp, semantic_dsp_map.h:173
+    std::vector<dsp_adapter::ObjectTracker::Move> last_moves;   // the plan of the last step (dspmap_objects_last_plan)
+    std::vector<int> last_dropped;
 };
+
+static int copy_plan(const dspmap_objects* o, dspmap_object_move* moves, int32_t moves_cap, int32_t* n_moves, int32_t* dropped, int32_t dropped_cap,
+                     int32_t* n_dropped) {
+    *n_moves = (int32_t)o->last_moves.size();
+    *n_dropped = (int32_t)o->last_dropped.size();
+    for (int32_t i = 0; i < *n_moves && i < moves_cap; ++i) { moves[i].track_id = o->last_moves[(size_t)i].track_id; for (int k = 0; k < 16; ++k) moves[i].t[k] = o->last_moves[(size_t)i].t[k]; }
+    for (int32_t i = 0; i < *n_dropped && i < dropped_cap; ++i) dropped[i] = o->last_dropped[(size_t)i];
+    return (*n_moves > moves_cap || *n_dropped > dropped_cap) ? DSPMAP_ERR_CAPACITY : DSPMAP_OK;
+}
 
 extern "C" {
 
@@ -33,6 +44,7 @@ void dspmap_objects_destroy(dspmap_objects_t* o) { delete o; }
 int dspmap_objects_clear(dspmap_objects_t* o) {
     if (!o) return DSPMAP_ERR_INVALID_ARG;
     o->tracker.clear();
+    o->last_moves.clear(); o->last_dropped.clear();
     o->step = 0;
     return DSPMAP_OK;
 }
@@ -69,14 +81,15 @@ int dspmap_objects_step(dspmap_objects_t* o, const dspmap_object_observation* ob
     }
     ++o->step;
     o->tracker.observe(seen, position, orientation_wxyz, time_stamp, o->step);
-    std::vector<dsp_adapter::ObjectTracker::Move> mv;
-    std::vector<int> gone;
-    o->tracker.plan(o->step, max_lost, mv, gone);
-    *n_moves = (int32_t)mv.size();
-    *n_dropped = (int32_t)gone.size();
-    for (int32_t i = 0; i < *n_moves && i < moves_cap; ++i) { moves[i].track_id = mv[(size_t)i].track_id; for (int k = 0; k < 16; ++k) moves[i].t[k] = mv[(size_t)i].t[k]; }
-    for (int32_t i = 0; i < *n_dropped && i < dropped_cap; ++i) dropped[i] = gone[(size_t)i];
-    return (*n_moves > moves_cap || *n_dropped > dropped_cap) ? DSPMAP_ERR_CAPACITY : DSPMAP_OK;
+    o->last_moves.clear(); o->last_dropped.clear();
+    o->tracker.plan(o->step, max_lost, o->last_moves, o->last_dropped);
+    return copy_plan(o, moves, moves_cap, n_moves, dropped, dropped_cap, n_dropped);
+}
+
+int dspmap_objects_last_plan(dspmap_objects_t* o, dspmap_object_move* moves, int32_t moves_cap, int32_t* n_moves, int32_t* dropped, int32_t dropped_cap,
+                             int32_t* n_dropped) {
+    if (!o || !n_moves || !n_dropped || moves_cap < 0 || dropped_cap < 0 || (moves_cap > 0 && !moves) || (dropped_cap > 0 && !dropped)) return DSPMAP_ERR_INVALID_ARG;
+    return copy_plan(o, moves, moves_cap, n_moves, dropped, dropped_cap, n_dropped);
 }
 
 int dspmap_objects_query(dspmap_objects_t* o, int32_t track_id, int32_t* tracked, int32_t* has_flag, int32_t* moving, double* moved_probability, double* t16) {

@@ -143,7 +143,7 @@ class Engine:
     # numpy mirrors of dspmap_mask / dspmap_object_move (same size and field offsets as the ctypes structures): descriptor
     # arrays are filled with a handful of vectorised assignments instead of one Python attribute store per field
     MASK_DTYPE = np.dtype([("data", "<u8"), ("row_stride", "<i4"), ("is_static", "<i4"), ("track_id", "<i4"), ("label_id", "<i4"),
-                           ("bbox_min", "<f8", (3,)), ("bbox_max", "<f8", (3,))])
+                           ("bbox_min", "<f8", (3,)), ("bbox_max", "<f8", (3,)), ("rows", "<i4"), ("cols", "<i4")])
     MOVE_DTYPE = np.dtype([("track_id", "<i4"), ("t", "<f4", (16,))])
 
     @classmethod
@@ -153,7 +153,8 @@ class Engine:
             return masks
         arr = np.zeros(len(masks), cls.MASK_DTYPE)
         for i, m in enumerate(masks):
-            arr[i] = (m["data"], m["row_stride"], int(m["is_static"]), int(m["track_id"]), int(m["label_id"]), m["bbox_min"], m["bbox_max"])
+            arr[i] = (m["data"], m["row_stride"], int(m["is_static"]), int(m["track_id"]), int(m["label_id"]), m["bbox_min"], m["bbox_max"],
+                      int(m.get("rows", 0)), int(m.get("cols", 0)))
         return arr
 
     @classmethod
@@ -321,6 +322,13 @@ class SemanticDSPMap:
         self._params.depth_noise_first_order, self._params.depth_noise_zero_order = first_order, zero_order
         self.engine.set_params(self._params)
 
+    def followCompiledReferenceSigma(self, on: bool = True, value: float = 0.0):
+        """Not in the reference's API: where the reference reads an uninitialised LabeledPoint::sigma (invalid pixels and
+        pixels its ZED2 bounding-box gate turned into background, pointcloud_tools.h:224-232, 256-272) use ``value`` - a
+        compiled reference reads 0.0 there - instead of the depth-noise model (dspmap_params.uninit_sigma_mode)."""
+        self._params.uninit_sigma_mode, self._params.uninit_sigma_value = int(bool(on)), float(value)
+        self.engine.set_params(self._params)
+
     def setOccupancyThreshold(self, thr):
         self._params.occupancy_threshold = thr
         self.engine.set_params(self._params)
@@ -387,13 +395,15 @@ class SemanticDSPMap:
             if m.label != "static" and m.track_id > max_movable:        # semantic_dsp_map.h:179-186
                 m.track_id = m.track_id % max_movable
             mask = np.ascontiguousarray(m.mask, np.uint8)
+            if mask.ndim != 2:
+                raise TypeError("a mask must be a 2-D uint8 array (CV_8UC1)")
             self._keep.append(mask)
             k = np.asarray(m.kpts_current, np.float64).reshape(-1, 3)                    # pointcloud_tools.h:178-199
             mn = np.minimum(_DBL_MAX, k.min(0)) if len(k) else np.full(3, _DBL_MAX)
             mx = np.maximum(_DBL_MIN, k.max(0)) if len(k) else np.full(3, _DBL_MIN)
             out.append(dict(data=mask.ctypes.data, row_stride=mask.strides[0], is_static=(m.label == "static"),
                             track_id=m.track_id, label_id=self.labels.label_id_of(m.label),
-                            bbox_min=(mn - 1.0).tolist(), bbox_max=(mx + 1.0).tolist()))
+                            bbox_min=(mn - 1.0).tolist(), bbox_max=(mx + 1.0).tolist(), rows=mask.shape[0], cols=mask.shape[1]))
         return out
 
     # -- semantic_dsp_map.h:170-251 -----------------------------------------------------------------------------------------
@@ -416,7 +426,14 @@ class SemanticDSPMap:
             moves, dropped = self._run_object_layer(ins_seg_result, camera_position, camera_orientation, time_stamp_double) if self.config.consider_instance else ([], [])
             self._object_layer()
             remove_tracks = list(remove_tracks) + dropped
+        saved = (set(self._born_tracks), set(self._known_objects), set(self._met_labels))
         remove_tracks = list(remove_tracks) + self._floating_tracks(ins_seg_result, moves, remove_tracks, camera_position, builtin)
-        self.engine.update_raw("update", depth.ctypes.data, depth.shape[0], depth.shape[1], depth.strides[0] // 4, masks,
-                               camera_position, camera_orientation, moves, remove_tracks, if_get_freespace)
+        try:
+            self.engine.update_raw("update", depth.ctypes.data, depth.shape[0], depth.shape[1], depth.strides[0] // 4, masks,
+                                   camera_position, camera_orientation, moves, remove_tracks, if_get_freespace)
+        except _capi.DspMapError:
+            # a refused frame changed nothing in the engine (arguments are validated before any state is touched): the
+            # bookkeeping of which tracks are due for removal goes back to where it was, they go with the next frame
+            self._born_tracks, self._known_objects, self._met_labels = saved
+            raise
         return self.engine.result_arrays(copy_result)

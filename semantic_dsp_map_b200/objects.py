@@ -74,6 +74,10 @@ class ObjectLayer:
         rc = self._lib.dspmap_objects_step(self._h, arr, n, C.cast(pose.ctypes.data, C.POINTER(C.c_double)), C.cast(pose.ctypes.data + 24, C.POINTER(C.c_double)),
                                            float(time_stamp), int(max_lost), self._moves, len(self._moves), C.byref(n_moves), self._dropped, len(self._dropped),
                                            C.byref(n_dropped))
+        if rc == _capi.DSPMAP_ERR_CAPACITY:      # the tracker has stepped; its plan waits in the handle: fetch it into larger arrays
+            cap = 2 * max(n_moves.value, n_dropped.value, 1)
+            self._moves, self._dropped = (_capi.ObjectMove * cap)(), (C.c_int32 * cap)()
+            rc = self._lib.dspmap_objects_last_plan(self._h, self._moves, cap, C.byref(n_moves), self._dropped, cap, C.byref(n_dropped))
         self._check(rc, "dspmap_objects_step")
         moves = [(int(self._moves[i].track_id), np.asarray(self._moves[i].t, np.float32).reshape(4, 4).copy()) for i in range(n_moves.value)]
         return moves, [int(self._dropped[i]) for i in range(n_dropped.value)]

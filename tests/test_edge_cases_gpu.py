@@ -228,3 +228,98 @@ def test_multi_chunk_occupancy_pass_matches_oracle():
         m.enable_colors()
     run_pair(eng, orc, Scene(cfg), 4, make_random_table(cfg.seed, 50_000), want_free=True, stages=False, particles=False)
     assert eng.engine.stats()["n_occupied"] > 0
+
+
+class _QuirkScene:
+    """The seeded scene with the two label quirks of the ZED2 table in the static mask (the patch of
+    tests/golden/make_ref_golden.py's s3_fast_remove_quirks): value 10 = "sky" (the spelling the Sky filter misses or hits through the
+    LUT, pointcloud_tools.h:236) and value 11 = "person", a MOVABLE class in the static mask (its pixels carry track 0 and live one
+    frame: the floating-object rule, semantic_dsp_map.h:712-737)."""
+
+    def __init__(self, cfg):
+        self.scene = Scene(cfg)
+
+    def frame(self, t):
+        fr = self.scene.frame(t)
+        cls = fr.masks[0].mask
+        h, w = cls.shape
+        cls[: h // 6, : w // 3] = 10
+        cls[h // 2:, w // 2: w // 2 + w // 10] = 11
+        return fr
+
+
+@pytest.mark.parametrize("follow_compiled_sigma", [False, True])
+def test_sky_and_person_values_in_the_static_mask(follow_compiled_sigma):
+    # both label quirks on the GPU, every stage, with the ZED2 filters on: "sky" pixels are invalid (pointcloud_tools.h:236), the
+    # "person" pixels (track 0, no bounding box) are turned into background by the bounding-box gate (:256-272).  The second run
+    # also follows a COMPILED reference at its uninitialised-sigma sites (dspmap_params.uninit_sigma_mode: sigma = 0 for invalid
+    # pixels and bbox-gated background pixels, which makes the stencil passes divide by zero the IEEE way)
+    cfg = tiny(BASELINE["B"])
+    eng, orc = _pair(cfg)
+    if follow_compiled_sigma:
+        for m in (eng, orc):
+            m.followCompiledReferenceSigma(True, 0.0)
+    run_pair(eng, orc, _QuirkScene(cfg), 8, make_random_table(cfg.seed, 50_000), want_free=True)
+    pts = eng.engine.dump(_capi.DUMP_POINTS).view(np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("sigma", "<f4"), ("track", "<u2"), ("label", "u1"), ("valid", "u1")]))
+    pts = pts.reshape(cfg.internal_size)
+    h, w = pts.shape
+    assert (pts["valid"][: h // 6 - 1, : w // 3 - 1] == 0).all(), "sky pixels are invalid with the ZED2 filters"
+    gated = pts[h // 2 + 1:, w // 2 + 1: w // 2 + w // 10 - 1]
+    gated = gated[gated["valid"] == 1]
+    assert len(gated) and (gated["track"] == 65535).all() and (gated["label"] == 0).all(), "track-0 pixels are gated into background"
+    if follow_compiled_sigma:
+        assert np.all(pts["sigma"][pts["valid"] == 0] == 0.0) and np.all(gated["sigma"] == 0.0)
+    else:
+        assert np.all(gated["sigma"] > 0.0)
+
+
+@pytest.mark.parametrize("name", ["A", "C"])
+def test_movable_class_in_the_static_mask_lives_one_frame(name):
+    # without the ZED2 filters (static mode A, VKITTI2 camera C) the "person" pixels of the static mask give birth to particles
+    # of track 0, which no object owns: the floating-object rule (semantic_dsp_map.h:712-737) removes them in the next frame;
+    # "sky" pixels are ordinary observations here
+    cfg = tiny(BASELINE[name])
+    eng, orc = _pair(cfg)
+    run_pair(eng, orc, _QuirkScene(cfg), 5, make_random_table(cfg.seed, 50_000), want_free=True)
+    assert eng.engine.stats()["n_removed"] > 0, "the track-0 particles of the 'person' pixels must be removed again"
+
+
+def test_more_removals_than_one_batch_and_too_many_moves():
+    # the reference has no limit on removals per frame (every unregistered detection is one): 300 go in batches; more moves
+    # than the engine's table holds are refused BEFORE anything changes
+    cfg = tiny(BASELINE["B"])
+    eng, orc = _pair(cfg)
+    table = make_random_table(cfg.seed, 50_000)
+    for m in (eng, orc):
+        m.engine.set_random_table(table)
+    scene = Scene(cfg)
+    for t in range(5):
+        outs = []
+        for m in (eng, orc):
+            fr = scene.frame(t)
+            rm = list(range(3, 303)) + [2] if t == 3 else []
+            outs.append(m.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves, remove_tracks=rm))
+        compare_frame(eng, orc, outs[0], outs[1], t)
+    fr = scene.frame(5)
+    before = eng.engine.stats()["time_stamp"]
+    ring = eng.engine.dump(_capi.DUMP_RING, np.uint32).copy()
+    with pytest.raises(_capi.DspMapError) as e:
+        eng.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=[(k + 1, np.eye(4, dtype=np.float32)) for k in range(400)])
+    assert e.value.rc == -5
+    np.testing.assert_array_equal(eng.engine.dump(_capi.DUMP_RING, np.uint32), ring)      # refused before the ring moved
+    fr = scene.frame(5)
+    re = eng.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves)
+    fr = scene.frame(5)
+    ro = orc.update(fr.depth, fr.masks, fr.position, fr.orientation, moves=fr.moves)
+    compare_frame(eng, orc, re, ro, 5)
+    assert eng.engine.stats()["time_stamp"] == before + 1
+
+
+def test_mask_of_another_size_is_refused():
+    cfg = tiny(BASELINE["B"])
+    m = SemanticDSPMap(cfg)
+    depth = np.full((cfg.image_height, cfg.image_width), 2.0, np.float32)
+    short = np.zeros((cfg.image_height - 8, cfg.image_width), np.uint8)
+    with pytest.raises(_capi.DspMapError) as e:
+        m.update(depth, [MaskKpts(65535, "static", short)], np.zeros(3), np.array([1.0, 0, 0, 0]))
+    assert e.value.rc == -3
