@@ -259,14 +259,15 @@ struct dspmap {
     // exchange arena (one allocation, exported over CUDA IPC in sharded maps): barrier flags, counts, visible records,
     // incoming moved particles, the ck image and the (global) result arrays
     DevBuf<uint8_t> arena;
-    struct ArenaLayout { size_t flags, counts, move_counts, recs, movs, ck, r_idx, r_xyz, r_w, r_track, r_label, r_state, r_free_idx, r_free_xyz, r_rgb, total; } lay{};
+    struct ArenaLayout { size_t flags, counts, move_counts, recs, movs, obs_a, obs_b, r_idx, r_xyz, r_w, r_track, r_label, r_state, r_free_idx, r_free_xyz, r_rgb, total; } lay{};
     CommView cv{};
     uint32_t comm_epoch = 0;
     void* peer_base[MAX_RANKS]{};
     bool comm_connected = false;
     uint32_t *r_idx = nullptr, *r_free_idx = nullptr;
     float *r_xyz = nullptr, *r_w = nullptr, *r_free_xyz = nullptr;
-    float2* d_ck = nullptr;           // {ck * Pd + kappa, refined reciprocal} per internal pixel
+    float4* d_obs_a = nullptr;        // observation planes of the stencil passes (padded; dspmap_stencil.cuh)
+    uint2* d_obs_b = nullptr;
     uint16_t* r_track = nullptr;
     uint8_t* r_label = nullptr;
     uint8_t* r_rgb = nullptr;
@@ -383,10 +384,10 @@ struct dspmap {
         for (int p = 0; p < G; ++p) {
             uint8_t* b = (uint8_t*)(peer_base[p] ? peer_base[p] : arena.p);
             cv.flags[p] = (uint32_t*)(b + lay.flags); cv.counts[p] = (uint32_t*)(b + lay.counts); cv.move_counts[p] = (uint32_t*)(b + lay.move_counts);
-            cv.recs[p] = (VisRec*)(b + lay.recs); cv.movs[p] = (MovRec*)(b + lay.movs); cv.ck[p] = (float2*)(b + lay.ck);
+            cv.recs[p] = (VisRec*)(b + lay.recs); cv.movs[p] = (MovRec*)(b + lay.movs); cv.obs_a[p] = (float4*)(b + lay.obs_a); cv.obs_b[p] = (uint2*)(b + lay.obs_b);
         }
         uint8_t* mine = arena.p;
-        d_ck = (float2*)(mine + lay.ck); d_counts = (uint32_t*)(mine + lay.counts);
+        d_obs_a = (float4*)(mine + lay.obs_a); d_obs_b = (uint2*)(mine + lay.obs_b); d_counts = (uint32_t*)(mine + lay.counts);
         uint8_t* r0 = (uint8_t*)(peer_base[0] && have_rank0 >= 0 ? peer_base[0] : arena.p);
         r_idx = (uint32_t*)(r0 + lay.r_idx); r_xyz = (float*)(r0 + lay.r_xyz); r_w = (float*)(r0 + lay.r_w); r_track = (uint16_t*)(r0 + lay.r_track);
         r_label = (uint8_t*)(r0 + lay.r_label); r_state = (int8_t*)(r0 + lay.r_state); r_free_idx = (uint32_t*)(r0 + lay.r_free_idx); r_free_xyz = (float*)(r0 + lay.r_free_xyz);
@@ -560,7 +561,8 @@ int dspmap::init(const dspmap_config& c) {
         auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
         lay.flags = take(64 * 4); lay.counts = take((size_t)MAX_RANKS * COMM_COUNTS * 4); lay.move_counts = take((size_t)MAX_RANKS * MAX_MOVES * 4);
         lay.recs = take((size_t)G * f.vis_cap * sizeof(VisRec)); lay.movs = take((size_t)G * sel_cap * sizeof(MovRec));
-        lay.ck = take(npix * 8);
+        const size_t n_obs = obs_cells(f.W, f.H, f.win_r);
+        lay.obs_a = take(n_obs * 16); lay.obs_b = take(n_obs * 8);
         const size_t Vg = f.V;   // rank 0 receives the global result
         lay.r_idx = take(Vg * 4); lay.r_xyz = take(Vg * 12); lay.r_w = take(Vg * 4); lay.r_track = take(Vg * 2); lay.r_label = take(Vg); lay.r_state = take(Vg);
         lay.r_free_idx = take(Vg * 4); lay.r_free_xyz = take(Vg * 12);
@@ -568,6 +570,7 @@ int dspmap::init(const dspmap_config& c) {
         lay.total = off;
         CU_TRY(this, arena.alloc(lay.total));
         CU_TRY(this, cudaMemset(arena.p, 0, lay.flags + 64 * 4 + (size_t)MAX_RANKS * COMM_COUNTS * 4 + (size_t)MAX_RANKS * MAX_MOVES * 4 + 1024));
+        CU_TRY(this, cudaMemset(arena.p + lay.obs_a, 0, n_obs * 16)); CU_TRY(this, cudaMemset(arena.p + lay.obs_b, 0, n_obs * 8));
         peer_base[c.shard_rank] = arena.p;
         bind_arena(c.shard_rank == 0 ? 0 : -1);
         comm_connected = G == 1;
@@ -894,7 +897,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     DISPATCH_R(f.win_r, (k_ck<RT, INDEP><<<sm_count, CK_WARPS * 32, CK_SMEM_BYTES, stream>>>(fp, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_pix_offset.p, d_vis_pos.p, d_vis_mp.p, d_row_order.p, cv, d_cnt.p)));
     ++launches;
     barrier();   // sharded map: every rank's ck image is complete
-    DISPATCH_R(f.win_r, (k_weight_update<RT, INDEP><<<sm_count, WU_THREADS, WU_SMEM_BYTES, stream>>>(fp, d_pix_offset.p + npix, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_ck, d_csr_idx.p,
+    DISPATCH_R(f.win_r, (k_weight_update<RT, INDEP><<<sm_count, WU_THREADS, WU_SMEM_BYTES, stream>>>(fp, d_pix_offset.p + npix, d_lut.p, d_cloud_pos.p, d_obs_a, d_obs_b, d_csr_idx.p,
                                                                                   d_vis_pos.p, d_vis_mp.p, st)));
     ++launches;
     if (profiling) cudaEventRecord(ev[5], stream);
@@ -1386,8 +1389,20 @@ int dspmap_dump(dspmap_t* h, int32_t what, void* dst, size_t cap, size_t* n_byte
             break;
         }
         case DSPMAP_DUMP_CK:
+        {   // the .w of every pixel's {x, y, z, ck} record of the padded observation plane; 0 where the pixel is invalid
+            const int R = f.win_r, Wp = obs_stride(f.W, R);
+            std::vector<float> plane(obs_cells(f.W, f.H, R) * 4);
+            std::vector<uint32_t> flags(obs_cells(f.W, f.H, R) * 2);
+            CU_TRY(h, pull(plane.data(), h->d_obs_a, plane.size() * 4));
+            CU_TRY(h, pull(flags.data(), h->d_obs_b, flags.size() * 4));
             tmp.resize(npix * 4);
-            CU_TRY(h, cudaMemcpy2D(tmp.data(), 4, h->d_ck, 8, 4, npix, cudaMemcpyDeviceToHost));     // the .x of every {ck, reciprocal} pair
+            float* out = reinterpret_cast<float*>(tmp.data());
+            for (int i = 0; i < f.H; ++i)
+                for (int j = 0; j < f.W; ++j) {
+                    const size_t c = (size_t)(i + R) * Wp + (j + R);
+                    out[(size_t)i * f.W + j] = (flags[2 * c + 1] & OB_VALID) ? plane[4 * c + 3] : 0.f;
+                }
+        }
             break;
         case DSPMAP_DUMP_RING: {
             tmp.resize(4 * (9 + f.NX + f.NY + f.NZ));

@@ -84,7 +84,8 @@ struct CommView {
     uint32_t* counts[MAX_RANKS];       // peer p's counts[source rank][COMM_COUNTS]
     VisRec* recs[MAX_RANKS];           // peer p's visible-record arena: [source rank][rec_cap]
     MovRec* movs[MAX_RANKS];           // peer p's incoming moved particles: [source rank][mov_cap]
-    float2* ck[MAX_RANKS];             // peer p's ck image: {ck * Pd + kappa, its refined reciprocal}
+    float4* obs_a[MAX_RANKS];          // peer p's observation planes (dspmap_stencil.cuh), written by pass 1 of the stencil
+    uint2* obs_b[MAX_RANKS];
     uint32_t* move_counts[MAX_RANKS];  // peer p's per-move particle counts: [source rank][MAX_MOVES]
 };
 
