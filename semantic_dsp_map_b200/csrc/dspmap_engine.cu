@@ -243,6 +243,7 @@ struct dspmap {
     DevBuf<float4> d_vis_pos;
     // ordered insertion
     DevBuf<uint32_t> d_keys, d_ranks, d_birth_flags, d_birth_prefix, d_birth_block;
+    DevBuf<BirthBox> d_birth_box;     // per hash slot of the birth table: bounding rectangle of the voxel's candidate pixels
     // object moves
     DevBuf<uint32_t> d_movl_idx, d_movl_seq;
     DevBuf<uint16_t> d_movl_track, d_mov_mask;
@@ -364,7 +365,7 @@ struct dspmap {
         d_static_track.release(); d_static_label.release(); d_fp.release(); d_cnt.release(); d_persist.release(); d_masks.release(); d_moves.release();
         d_depth_in.release(); d_depth_int.release(); d_mask_in.release(); d_cloud_pos.release(); d_cloud_meta.release();
         d_pix_count.release(); d_pix_offset.release(); d_scan_block.release(); d_vmask.release(); d_csr_key.release(); d_seq_ref.release(); d_mov_out.release(); d_csr_idx.release();
-        d_vis_mp.release(); d_row_order.release(); d_vis_pos.release(); d_keys.release(); d_ranks.release(); d_birth_flags.release(); d_birth_prefix.release(); d_birth_block.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_chunk_tot.release(); d_chunk_base.release(); d_tile_list.release(); d_work.release();
+        d_vis_mp.release(); d_row_order.release(); d_vis_pos.release(); d_keys.release(); d_birth_box.release(); d_ranks.release(); d_birth_flags.release(); d_birth_prefix.release(); d_birth_block.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_chunk_tot.release(); d_chunk_base.release(); d_tile_list.release(); d_work.release();
         for (int p = 0; p < MAX_RANKS; ++p) if (peer_base[p] && p != cfg.shard_rank) { cudaIpcCloseMemHandle(peer_base[p]); peer_base[p] = nullptr; }
         arena.release();
         p_depth.release(); p_masks.release(); p_cnt.release(); p_fp.release(); p_stamps.release(); p_maskdesc.release(); p_moves.release();
@@ -545,6 +546,7 @@ int dspmap::init(const dspmap_config& c) {
         birth_cap1 = bcap; birth_shift1 = 32 - bbits;
     }
     CU_TRY(this, d_keys.alloc(cap)); CU_TRY(this, d_ranks.alloc((size_t)cap * f.topk)); CU_TRY(this, d_entry_list.alloc(cap)); CU_TRY(this, d_entry_voxel.alloc(cap));
+    CU_TRY(this, d_birth_box.alloc(f.birth_hash_cap));
 
     n_occ_blocks = (uint32_t)(v_pad / OCC_TILE);
     CU_TRY(this, d_col_tab.alloc(1024)); CU_TRY(this, cudaMemset(d_col_tab.p, 0, 1024));
@@ -607,6 +609,7 @@ int dspmap::clear_device() {
     ++launches; k_clear_store<<<sm_count * 8, 256, 0, stream>>>(Store{sx.p, sy.p, sz.p, sw.p, smeta.p, shdr.p}, n_slots_local, (uint32_t)fp.Pb);
     ++launches; k_fill_u32<<<sm_count * 4, 256, 0, stream>>>(d_keys.p, d_keys.n, EMPTY_KEY);
     ++launches; k_fill_u32<<<sm_count * 4, 256, 0, stream>>>(d_ranks.p, d_ranks.n, NO_RANK);
+    ++launches; k_fill_birth_boxes<<<sm_count * 4, 256, 0, stream>>>(d_birth_box.p, d_birth_box.n);
     CU_TRY(this, cudaMemsetAsync(d_pix_count.p, 0, d_pix_count.n * sizeof(uint32_t), stream));
     CU_TRY(this, cudaMemsetAsync(d_pix_offset.p, 0, d_pix_offset.n * sizeof(uint32_t), stream));
     CU_TRY(this, cudaMemsetAsync(d_cnt.p, 0, sizeof(Counters), stream));
@@ -881,8 +884,13 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
             ++launches; k_scan_blocksum<<<nb_blocks, SCAN_BLOCK, 0, side_stream>>>(d_birth_flags.p, (uint32_t)n_ranks, d_birth_block.p);
             ++launches; k_scan_apply<<<nb_blocks, SCAN_BLOCK, 0, side_stream>>>(d_birth_flags.p, (uint32_t)n_ranks, d_birth_block.p, d_birth_prefix.p);
         }
-        ++launches; k_birth_bin<<<(n_ranks * f.nb_ptc + 255) / 256, 256, 0, side_stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_entry_list.p, d_cnt.p,
-                                                                                    d_birth_prefix.p, d_randoms.p, d_persist.p);
+        if (f.nb_ptc == 1) {    // one newborn per point: mark the touched voxels, then find every voxel's first candidates in the image
+            ++launches; k_birth_mark<<<(npix + 255) / 256, 256, 0, side_stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_birth_box.p, d_entry_list.p, d_cnt.p);
+            ++launches; k_birth_gather<<<sm_count * 8, 256, 0, side_stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_birth_box.p, d_ranks.p, d_entry_list.p, d_cnt.p);
+        } else {
+            ++launches; k_birth_bin<<<(n_ranks * f.nb_ptc + 255) / 256, 256, 0, side_stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_entry_list.p, d_cnt.p,
+                                                                                        d_birth_prefix.p, d_randoms.p, d_persist.p);
+        }
         CU_TRY(this, cudaEventRecord(ev_join[1], side_stream));
     }
     // ---- U3 weight update --------------------------------------------------------------------------------------------
@@ -898,7 +906,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     ++launches;
     barrier();   // sharded map: every rank's ck image is complete
     DISPATCH_R(f.win_r, (k_weight_update<RT, INDEP><<<sm_count, WU_THREADS, WU_SMEM_BYTES, stream>>>(fp, d_pix_offset.p + npix, d_lut.p, d_cloud_pos.p, d_obs_a, d_obs_b, d_csr_idx.p,
-                                                                                  d_vis_pos.p, d_vis_mp.p, st)));
+                                                                                  d_vis_pos.p, d_vis_mp.p, st, d_cnt.p)));
     ++launches;
     if (profiling) cudaEventRecord(ev[5], stream);
     // ---- B1 birth + resample -----------------------------------------------------------------------------------------

@@ -33,7 +33,8 @@ struct Counters {
     uint32_t n_sweep_work;     // swept voxels with live slots (work list of the slot pass)
     uint32_t n_occ_work;       // voxels whose occupancy needs the slot records
     uint32_t comm_errors;      // barriers that timed out (sharded maps)
-    uint32_t ck_next;          // k_ck: next 32-pixel segment to hand out (dynamic work distribution)
+    uint32_t ck_next;          // k_ck: next pixel tile to hand out (dynamic work distribution)
+    uint32_t wu_next;          // k_weight_update: next 32-particle group to hand out
     uint32_t mov_out[8];       // moved particles sent to each destination rank this frame
 };
 
@@ -634,6 +635,102 @@ k_birth_bin(const __grid_constant__ FrameParams f, const float4* __restrict__ cl
     if (v == INVALID_INDEX) return;
     if (bz < f.z_lo || bz >= f.z_hi) return;   // another shard owns this voxel
     topk_insert(f, f.birth_hash_cap, f.birth_hash_shift, v, cand, keys, ranks, entry_list, &cnt->n_birth_voxels, &cnt->hash_overflow);
+}
+
+// ---- one newborn particle per point (the default): the candidates of a voxel are FOUND instead of being collected ----------
+// mark   : one thread per pixel; the pixels of a warp that fall into the same voxel act as one: a single hash insertion and four
+//          atomic min / max that grow the voxel's bounding rectangle of candidate pixels (a voxel's candidates are a compact patch
+//          of the image).
+// gather : one 8-lane group per touched voxel walks that rectangle in birth-rank order - phase by phase of the 3x3 interleave,
+//          row by row - and keeps the first topk pixels whose point falls into the voxel.  No atomics on the rank lists: a wall
+//          one metre away is hundreds of candidates per voxel, and they all stop after the first rows of phase 0.
+struct BirthBox { uint32_t i_min, i_max, j_min, j_max; };      // idle state: {0xffffffff, 0, 0xffffffff, 0}
+
+__global__ void __launch_bounds__(256)
+k_birth_mark(const __grid_constant__ FrameParams f, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta, uint32_t* __restrict__ keys,
+             BirthBox* __restrict__ boxes, uint32_t* __restrict__ entry_list, Counters* __restrict__ cnt) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t v = INVALID_INDEX, pi = 0, pj = 0;
+    if (q < f.W * f.H && pt_valid(cloud_meta[q])) {
+        const float4 p = cloud_pos[q];
+        uint32_t bx, by, bz;
+        v = global_pos_to_voxel(f, p.x + 0.f, p.y + 0.f, p.z + 0.f, bx, by, bz);
+        if (v != INVALID_INDEX && (bz < f.z_lo || bz >= f.z_hi)) v = INVALID_INDEX;   // another shard owns this voxel
+        pi = (uint32_t)(q / f.W); pj = (uint32_t)(q - (int)pi * f.W);
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, v);
+    const uint32_t i_lo = __reduce_min_sync(peers, pi), i_hi = __reduce_max_sync(peers, pi), j_lo = __reduce_min_sync(peers, pj), j_hi = __reduce_max_sync(peers, pj);
+    if (v == INVALID_INDEX || (uint32_t)(__ffs(peers) - 1) != lane_id()) return;
+    uint32_t h = hash_slot(v, f.birth_hash_shift);
+    for (uint32_t probe = 0;; ++probe) {
+        if (probe >= f.birth_hash_cap) { atomicAdd(&cnt->hash_overflow, 1u); return; }
+        uint32_t old = *(volatile uint32_t*)(keys + h);
+        if (old == EMPTY_KEY) old = atomicCAS(keys + h, EMPTY_KEY, v);
+        if (old == EMPTY_KEY) { entry_list[atomicAdd(&cnt->n_birth_voxels, 1u)] = h; break; }
+        if (old == v) break;
+        h = (h + 1) & (f.birth_hash_cap - 1);
+    }
+    BirthBox* b = boxes + h;
+    atomicMin(&b->i_min, i_lo); atomicMax(&b->i_max, i_hi); atomicMin(&b->j_min, j_lo); atomicMax(&b->j_max, j_hi);
+}
+
+__global__ void k_fill_birth_boxes(BirthBox* __restrict__ boxes, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) boxes[i] = BirthBox{0xffffffffu, 0u, 0xffffffffu, 0u};
+}
+
+constexpr int BG_LANES = 8;      // lanes per touched voxel
+__global__ void __launch_bounds__(256)
+k_birth_gather(const __grid_constant__ FrameParams f, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta, const uint32_t* __restrict__ keys,
+               BirthBox* __restrict__ boxes, uint32_t* __restrict__ ranks, const uint32_t* __restrict__ entry_list, const Counters* __restrict__ cnt) {
+    const uint32_t n_entries = cnt->n_birth_voxels, K = f.topk;
+    const uint32_t sub = lane_id() & (BG_LANES - 1), gmask = ((1u << BG_LANES) - 1u) << (lane_id() & ~(uint32_t)(BG_LANES - 1));
+    const uint32_t n_groups = (gridDim.x * blockDim.x) / BG_LANES;
+    const int hc = (f.H + 2) / 3, wc = (f.W + 2) / 3;
+    for (uint32_t li0 = (blockIdx.x * blockDim.x + threadIdx.x) / BG_LANES;; li0 += n_groups) {
+        // warp-uniform exit (the groups of a warp stay together for the ballots below)
+        if (__all_sync(0xffffffffu, li0 >= n_entries)) break;
+        const bool live = li0 < n_entries;
+        const uint32_t e = live ? entry_list[li0] : 0u, v = live ? keys[e] : INVALID_INDEX;
+        int i0 = 0, i1 = -1, j0 = 0, j1 = -1;
+        if (live) {
+            const BirthBox bb = boxes[e];
+            i0 = (int)bb.i_min; i1 = (int)bb.i_max; j0 = (int)bb.j_min; j1 = (int)bb.j_max;
+        }
+        __syncwarp();
+        if (live && sub == 0) boxes[e] = BirthBox{0xffffffffu, 0u, 0xffffffffu, 0u};     // idle again for the next frame
+        uint32_t found = 0;
+        uint32_t* out = ranks + (size_t)e * K;
+        for (int ph = 0; ph < 9; ++ph) {
+            const int pi = ph / 3, pj = ph - 3 * pi;
+            // cells (a, b) of this phase inside the rectangle: pixel (3a + pi, 3b + pj)
+            const int a0 = (i0 - pi + 2) / 3, a1 = (i1 - pi >= 0) ? (i1 - pi) / 3 : -1, b0 = (j0 - pj + 2) / 3, b1 = (j1 - pj >= 0) ? (j1 - pj) / 3 : -1;
+            const int nb = b1 - b0 + 1, ncell = (live && a1 >= a0 && nb > 0 && found < K) ? (a1 - a0 + 1) * nb : 0;
+            const int ncell_max = (int)__reduce_max_sync(0xffffffffu, (uint32_t)ncell);
+            for (int c0 = 0; c0 < ncell_max; c0 += BG_LANES) {
+                const int c = c0 + (int)sub;
+                bool hit = false;
+                uint32_t rank = 0;
+                if (c < ncell && found < K) {
+                    const int a = a0 + c / nb, b = b0 + c % nb, q = (3 * a + pi) * f.W + 3 * b + pj;
+                    if (pt_valid(cloud_meta[q])) {
+                        const float4 p = cloud_pos[q];
+                        uint32_t bx, by, bz;
+                        hit = global_pos_to_voxel(f, p.x + 0.f, p.y + 0.f, p.z + 0.f, bx, by, bz) == v;
+                        rank = (uint32_t)((ph * hc + a) * wc + b);
+                    }
+                }
+                const uint32_t hits = __ballot_sync(0xffffffffu, hit) & gmask;
+                if (hit) {
+                    const uint32_t pos = found + (uint32_t)__popc(hits & ((1u << lane_id()) - 1u));
+                    if (pos < K) out[pos] = rank;
+                }
+                found += (uint32_t)__popc(hits);
+                if (__all_sync(0xffffffffu, c0 + BG_LANES >= ncell || found >= K)) break;     // every group of the warp is done with this phase
+            }
+        }
+        if (live)
+            for (uint32_t t = min(found, K) + sub; t < K; t += BG_LANES) out[t] = NO_RANK;
+    }
 }
 
 // the map's random cursor moves on by three draws per candidate of every valid pixel (nb > 1 only)
