@@ -274,6 +274,8 @@ public:
 
     dspmap_t* handle() { return h_; }
     // follow a COMPILED reference where it reads an uninitialised sigma (dspmap_params.uninit_sigma_mode); not in the reference's API
+    // pixel lists in the order the reference's breadth-first search visits the voxels in (dspmap_params.reference_iteration_order)
+    void setReferenceIterationOrder(bool on) { prm_.reference_iteration_order = on; pushParams(); }
     void followCompiledReferenceSigma(bool on, float value = 0.f) { prm_.uninit_sigma_mode = on; prm_.uninit_sigma_value = value; pushParams(); }
 
 private:

@@ -90,6 +90,15 @@ typedef struct dspmap_params {
      * oracle/build_ref.sh and of the reference node), so that a replay follows the shipped binary voxel for voxel. */
     int32_t uninit_sigma_mode;
     float   uninit_sigma_value;
+    /* Order of the particles inside a pixel's list, which is the order pass 1 of updateParticles adds their terms in
+     * (semantic_dsp_map.h:995-1031).  0 (default): ascending particle index ("canonical": fastest, independent of the
+     * sweep).  1: the REFERENCE's order - the order in which getIdxOfVisibleParitlces' breadth-first search over the
+     * lattice vertices reaches the voxels (mc_ring/operations.h:1326-1456: FIFO from the vertex in front of the camera,
+     * neighbours pushed +x -x +y -y +z -z, a vertex's eight voxels dx, dy, dz = -1..0 with dz fastest), slot order inside
+     * a voxel; the swept set is then exactly what that search reaches.  The search is replayed level by level on the
+     * device (one cooperative kernel, ~3 grid-wide barriers per level), so a frame costs a few milliseconds more; every
+     * float of a scene without moving objects then equals the reference's bit for bit.  Not available for sharded maps. */
+    int32_t reference_iteration_order;
 } dspmap_params;
 
 /* one segmentation mask: reference MaskKpts (utils/tracking_result_handler.h:15-26),

@@ -46,6 +46,7 @@ class Params(C.Structure):
         ("consider_depth_noise", C.c_int32), ("use_independent_filter", C.c_int32),
         ("zero_center", C.c_int32),
         ("uninit_sigma_mode", C.c_int32), ("uninit_sigma_value", C.c_float),
+        ("reference_iteration_order", C.c_int32),
     ]
 
 

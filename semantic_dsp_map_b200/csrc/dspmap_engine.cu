@@ -194,7 +194,7 @@ struct dspmap {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr, own_stream = nullptr, side_stream = nullptr;   // side: independent kernels run beside the main chain
-    cudaEvent_t ev_fork[2]{}, ev_join[2]{};
+    cudaEvent_t ev_fork[3]{}, ev_join[3]{};
     uint64_t launches = 0;
 
     // host ring state (mc_ring/buffer.h:97-120)
@@ -237,7 +237,9 @@ struct dspmap {
     DevBuf<uint32_t> d_vmask;
     uint32_t words_per_row = 0, n_vwords = 0;
     DevBuf<uint64_t> d_csr_key;
-    DevBuf<uint32_t> d_csr_idx, d_seq_ref, d_mov_out;
+    DevBuf<uint32_t> d_csr_idx, d_seq_ref, d_mov_out, d_mine_list;
+    DevBuf<uint32_t> d_vrank, d_bfs_front[2], d_bfs_blocks, d_work_key;   // reference iteration order (k_bfs_order), allocated on first use
+    int bfs_grid = 0;
     DevBuf<uint32_t> d_row_order;      // image rows by listed particles in their window, descending (k_ck_row_order)
     DevBuf<uint2> d_vis_mp;            // list-ordered {track | forget << 16, pixel}
     DevBuf<float4> d_vis_pos;
@@ -364,8 +366,8 @@ struct dspmap {
         sx.release(); sy.release(); sz.release(); sw.release(); smeta.release(); shdr.release(); d_entry_list.release(); d_entry_voxel.release(); d_stamps.release(); d_lut.release(); d_randoms.release();
         d_static_track.release(); d_static_label.release(); d_fp.release(); d_cnt.release(); d_persist.release(); d_masks.release(); d_moves.release();
         d_depth_in.release(); d_depth_int.release(); d_mask_in.release(); d_cloud_pos.release(); d_cloud_meta.release();
-        d_pix_count.release(); d_pix_offset.release(); d_scan_block.release(); d_vmask.release(); d_csr_key.release(); d_seq_ref.release(); d_mov_out.release(); d_csr_idx.release();
-        d_vis_mp.release(); d_row_order.release(); d_vis_pos.release(); d_keys.release(); d_birth_box.release(); d_ranks.release(); d_birth_flags.release(); d_birth_prefix.release(); d_birth_block.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_chunk_tot.release(); d_chunk_base.release(); d_tile_list.release(); d_work.release();
+        d_pix_count.release(); d_pix_offset.release(); d_scan_block.release(); d_vmask.release(); d_csr_key.release(); d_seq_ref.release(); d_mov_out.release(); d_csr_idx.release(); d_mine_list.release();
+        d_vis_mp.release(); d_row_order.release(); d_vrank.release(); d_bfs_front[0].release(); d_bfs_front[1].release(); d_bfs_blocks.release(); d_work_key.release(); d_vis_pos.release(); d_keys.release(); d_birth_box.release(); d_ranks.release(); d_birth_flags.release(); d_birth_prefix.release(); d_birth_block.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_chunk_tot.release(); d_chunk_base.release(); d_tile_list.release(); d_work.release();
         for (int p = 0; p < MAX_RANKS; ++p) if (peer_base[p] && p != cfg.shard_rank) { cudaIpcCloseMemHandle(peer_base[p]); peer_base[p] = nullptr; }
         arena.release();
         p_depth.release(); p_masks.release(); p_cnt.release(); p_fp.release(); p_stamps.release(); p_maskdesc.release(); p_moves.release();
@@ -526,6 +528,7 @@ int dspmap::init(const dspmap_config& c) {
     f.vis_cap = (uint32_t)std::min<size_t>(usable, c.max_visible ? (size_t)c.max_visible : (size_t)4 << 20);
     const size_t list_cap = (size_t)f.vis_cap * c.shard_count;
     CU_TRY(this, d_csr_key.alloc(list_cap)); CU_TRY(this, d_csr_idx.alloc(list_cap));
+    if (c.shard_count > 1) CU_TRY(this, d_mine_list.alloc(list_cap + 32));
     CU_TRY(this, d_vis_mp.alloc(list_cap)); CU_TRY(this, d_vis_pos.alloc(list_cap)); CU_TRY(this, d_row_order.alloc(f.H));
 
     sel_cap = (uint32_t)std::min<size_t>(usable, (size_t)1 << 20);
@@ -632,6 +635,7 @@ int dspmap::apply_params() {
     f.n0 = prm.depth_noise_zero_order; f.n1 = prm.depth_noise_first_order;
     f.sigma_invalid = prm.uninit_sigma_mode ? prm.uninit_sigma_value : (prm.consider_depth_noise ? prm.depth_noise_zero_order : 0.1f);
     f.sigma_gated_set = prm.uninit_sigma_mode ? 1 : 0;
+    f.ref_order = prm.reference_iteration_order ? 1 : 0;
     f.zero_center = prm.zero_center ? 1 : 0;
     f.col_enabled = colors.enabled ? 1 : 0; f.col_eval = colors.eval_format ? 1 : 0; f.col_scheme = colors.scheme; f.col_background = colors.background_label;
     f.nb_ptc = prm.consider_depth_noise ? prm.nb_ptc_num_per_point : 1;
@@ -742,6 +746,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
         for (int a = 0; a < 3; ++a) {
             sv[a] = static_cast<int>(((sg[a] - map_center[a]) + f.pmax[a]) * f.voxel_recip);
             sv[a] = std::min(std::max(sv[a], 0), (int)axis_n(a));
+            f.start_v[a] = sv[a];
         }
         const float vx = (float)sv[0] * f.voxel + f.vox_off[0], vy = (float)sv[1] * f.voxel + f.vox_off[1], vz = (float)sv[2] * f.voxel + f.vox_off[2];
         const float c0 = ((f.ext[0] * vx + f.ext[1] * vy) + f.ext[2] * vz) + f.ext[3] * 1.0f;
@@ -787,13 +792,29 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     if (profiling) cudaEventRecord(ev[0], stream);
     const bool depth_kernel = !((pre_decimated || !f.boost) && stride == f.W);
     if (late_depth && depth_kernel) { const int rc = (*late_depth)(); if (rc != DSPMAP_OK) return rc; late_depth = nullptr; }
+    if (f.ref_order) {
+        if (cv.size > 1) return fail(DSPMAP_ERR_UNSUPPORTED, "reference_iteration_order is not available for sharded maps");
+        if (!d_vrank.p) {
+            const size_t n_vert = (size_t)(f.NX + 1) * (f.NY + 1) * (f.NZ + 1);
+            CU_TRY(this, cudaStreamSynchronize(stream));
+            CU_TRY(this, d_vrank.alloc(n_vert)); CU_TRY(this, cudaMemset(d_vrank.p, 0xff, n_vert * 4));
+            const size_t fcap = std::min<size_t>(n_vert, (size_t)1 << 22);
+            CU_TRY(this, d_bfs_front[0].alloc(fcap)); CU_TRY(this, d_bfs_front[1].alloc(fcap));
+            CU_TRY(this, d_work_key.alloc(d_work.n));
+            int per_sm = 0;
+            CU_TRY(this, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bfs_order, 1024, 0));
+            if (per_sm < 1) return fail(DSPMAP_ERR_CUDA, "k_bfs_order does not fit an SM");
+            bfs_grid = sm_count;
+            CU_TRY(this, d_bfs_blocks.alloc(bfs_grid + 2));
+        }
+    }
     // ---- U2a vertex mask: depends on the pose only, so it runs on the side stream beside the depth copy and the moves ------
     if (f.start_in) {
         const int y0 = std::max(f.vb_lo[1] - 1, 0), y1 = std::min(f.vb_hi[1] + 1, (int)f.NY);
         const int z0 = std::max(f.vb_lo[2] - 1, 0), z1 = std::min(f.vb_hi[2] + 1, (int)f.NZ);
         CU_TRY(this, cudaEventRecord(ev_fork[0], stream));
         CU_TRY(this, cudaStreamWaitEvent(side_stream, ev_fork[0], 0));
-        ++launches; k_vertex_mask<<<dim3((words_per_row * 32 + 255) / 256, (y1 - y0 + 1) * (z1 - z0 + 1)), 256, 0, side_stream>>>(fp, d_vmask.p, words_per_row, y0, y1 - y0 + 1, z0);
+        ++launches; k_vertex_mask<<<dim3((words_per_row * 32 + 255) / 256, (y1 - y0 + 1) * (z1 - z0 + 1)), 256, 0, side_stream>>>(fp, d_vmask.p, words_per_row, y0, y1 - y0 + 1, z0, f.ref_order ? d_vrank.p : nullptr);
         CU_TRY(this, cudaEventRecord(ev_join[0], side_stream));
     }
     // ---- K1a internal depth image ----------------------------------------------------------------------------------
@@ -837,10 +858,19 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
             const int3 hi = make_int3(std::min(f.vb_hi[0], (int)f.NX - 1), std::min(f.vb_hi[1], (int)f.NY - 1), std::min(f.vb_hi[2], (int)f.NZ - 1));
             const int3 n = make_int3(hi.x - lo.x + 1, hi.y - lo.y + 1, hi.z - lo.z + 1);
             if (n.x > 0 && n.y > 0 && n.z > 0) {
-                ++launches; k_sweep_select<<<dim3((n.x + 255) / 256, n.y * n.z), 256, 0, stream>>>(fp, st, d_vmask.p, words_per_row, depth_int, d_work.p, d_cnt.p, lo, n);
+                if (f.ref_order) {      // the order the reference's search reaches the vertices in (a cooperative launch: grid-wide barriers)
+                    CU_TRY(this, cudaMemsetAsync(d_bfs_blocks.p, 0, (bfs_grid + 2) * sizeof(uint32_t), stream));
+                    BfsScratch bs{d_vrank.p, {d_bfs_front[0].p, d_bfs_front[1].p}, d_bfs_blocks.p, (uint32_t)d_bfs_front[0].n, &d_cnt.p->hash_overflow};
+                    const uint32_t* vm = d_vmask.p;
+                    uint32_t wpr = words_per_row;
+                    void* args[] = {(void*)&fp, (void*)&vm, (void*)&wpr, (void*)&bs};
+                    ++launches; CU_TRY(this, cudaLaunchCooperativeKernel((const void*)k_bfs_order, dim3(bfs_grid), dim3(1024), args, 0, stream));
+                }
+                ++launches; k_sweep_select<<<dim3((n.x + 255) / 256, n.y * n.z), 256, 0, stream>>>(fp, st, d_vmask.p, words_per_row, depth_int, d_work.p, d_cnt.p, lo, n,
+                                                                                       f.ref_order ? d_vrank.p : nullptr, f.ref_order ? d_work_key.p : nullptr);
             }
         }
-        DISPATCH_PB(f.Pb, (k_sweep_slots<PB><<<sm_count * 8, 256, 0, stream>>>(fp, st, stx, sty, stz, d_work.p, depth_int, d_pix_count.p, cv, d_cnt.p)));
+        DISPATCH_PB(f.Pb, (k_sweep_slots<PB><<<sm_count * 8, 256, 0, stream>>>(fp, st, stx, sty, stz, d_work.p, depth_int, d_pix_count.p, cv, d_cnt.p, f.ref_order ? d_work_key.p : nullptr)));
         ++launches;
     }
     // every rank tells every rank how many visible records it wrote into their arenas
@@ -852,7 +882,11 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     const int nsb = (npix + SCAN_BLOCK - 1) / SCAN_BLOCK;
     ++launches; k_scan_blocksum<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p);
     ++launches; k_scan_apply<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p, d_pix_offset.p);
-    ++launches; k_ck_row_order<<<1, 1024, (size_t)f.H * sizeof(uint32_t), stream>>>(fp, d_pix_offset.p, d_row_order.p);
+    // the order in which pass 1 of the stencil takes the image rows needs the offsets only: beside the list building, on the side stream
+    CU_TRY(this, cudaEventRecord(ev_fork[2], stream));
+    CU_TRY(this, cudaStreamWaitEvent(side_stream, ev_fork[2], 0));
+    ++launches; k_ck_row_order<<<1, 1024, (size_t)f.H * sizeof(uint32_t), side_stream>>>(fp, d_pix_offset.p, d_row_order.p);
+    CU_TRY(this, cudaEventRecord(ev_join[2], side_stream));
     ++launches; k_fill<<<sm_count * 4, 256, 0, stream>>>(cv, cv.recs[cv.rank], d_counts, d_cnt.p, d_pix_offset.p, d_pix_count.p, d_csr_key.p);
     ++launches; k_sort_lists<<<(npix + 255) / 256, 256, 0, stream>>>(fp, d_pix_offset.p, d_csr_key.p);
     ++launches; k_gather_visible<<<sm_count * 4, 256, 0, stream>>>(d_pix_offset.p + npix, cv.recs[cv.rank], d_csr_key.p, d_csr_idx.p, d_vis_pos.p, d_vis_mp.p);
@@ -902,11 +936,13 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     }
 #define DISPATCH_R(r, CALL)                                     \
     if (f.indep) { constexpr bool INDEP = true; DISPATCH_R1(r, CALL) } else { constexpr bool INDEP = false; DISPATCH_R1(r, CALL) }
+    CU_TRY(this, cudaStreamWaitEvent(stream, ev_join[2], 0));   // the row order was computed on the side stream
     DISPATCH_R(f.win_r, (k_ck<RT, INDEP><<<sm_count, CK_WARPS * 32, CK_SMEM_BYTES, stream>>>(fp, d_lut.p, d_cloud_pos.p, d_cloud_meta.p, d_pix_offset.p, d_vis_pos.p, d_vis_mp.p, d_row_order.p, cv, d_cnt.p)));
     ++launches;
+    if (cv.size > 1) { ++launches; k_select_mine<<<sm_count * 2, 256, 0, stream>>>(fp, d_pix_offset.p + npix, d_csr_idx.p, d_mine_list.p, d_cnt.p); }
     barrier();   // sharded map: every rank's ck image is complete
     DISPATCH_R(f.win_r, (k_weight_update<RT, INDEP><<<sm_count, WU_THREADS, WU_SMEM_BYTES, stream>>>(fp, d_pix_offset.p + npix, d_lut.p, d_cloud_pos.p, d_obs_a, d_obs_b, d_csr_idx.p,
-                                                                                  d_vis_pos.p, d_vis_mp.p, st, d_cnt.p)));
+                                                                                  d_vis_pos.p, d_vis_mp.p, st, d_cnt.p, cv.size > 1 ? d_mine_list.p : nullptr)));
     ++launches;
     if (profiling) cudaEventRecord(ev[5], stream);
     // ---- B1 birth + resample -----------------------------------------------------------------------------------------

@@ -35,6 +35,7 @@ struct Counters {
     uint32_t comm_errors;      // barriers that timed out (sharded maps)
     uint32_t ck_next;          // k_ck: next pixel tile to hand out (dynamic work distribution)
     uint32_t wu_next;          // k_weight_update: next 32-particle group to hand out
+    uint32_t n_mine;           // sharded map: listed particles this rank owns (k_select_mine)
     uint32_t mov_out[8];       // moved particles sent to each destination rank this frame
 };
 
@@ -67,7 +68,7 @@ struct __align__(16) VisRec {
     float x, y;
     float z, w;
     uint32_t tf;      // track | forget << 16
-    uint32_t pad;
+    uint32_t order;   // sort key inside the pixel's list (the particle index, or the reference's visiting order)
 };
 
 // one moved particle on its way to the rank that owns its destination voxel, 32 bytes
@@ -201,8 +202,10 @@ k_project(const __grid_constant__ FrameParams f, const MaskDesc* __restrict__ ma
 // one warp per 32 consecutive x vertices; blockIdx.y = row (z, y) in MAP coordinates.  Vertices outside the
 // host-computed bounding box of the frustum (conservative, in vertex indices) are written as 0 without the test.
 // =====================================================================================================
+constexpr uint32_t BFS_UNSET = 0xffffffffu, BFS_TENTATIVE = 0x80000000u;
+
 __global__ void __launch_bounds__(256)
-k_vertex_mask(const __grid_constant__ FrameParams f, uint32_t* __restrict__ vmask, uint32_t words_per_row, int y0, int ny, int z0) {
+k_vertex_mask(const __grid_constant__ FrameParams f, uint32_t* __restrict__ vmask, uint32_t words_per_row, int y0, int ny, int z0, uint32_t* __restrict__ vrank) {
     // blockIdx.y enumerates the (y, z) rows of the bounding box grown by one vertex (what k_sweep_select may read)
     const uint32_t xw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (xw >= words_per_row) return;
@@ -214,10 +217,123 @@ k_vertex_mask(const __grid_constant__ FrameParams f, uint32_t* __restrict__ vmas
         in = point_in_frustum(f, (float)(int)x * f.voxel + f.vox_off[0], (float)(int)y * f.voxel + f.vox_off[1], (float)(int)z * f.voxel + f.vox_off[2]);
     const uint32_t bits = __ballot_sync(0xffffffffu, in);
     if (lane_id() == 0) vmask[(size_t)row * words_per_row + xw] = bits;
+    if (vrank && x <= f.NX) vrank[(size_t)row * (f.NX + 1) + x] = BFS_UNSET;      // reference order: no vertex of these rows is reached yet
 }
 
 __device__ __forceinline__ bool vbit(const uint32_t* __restrict__ vmask, uint32_t wpr, uint32_t NYp1, uint32_t x, uint32_t y, uint32_t z) {
     return (__ldg(vmask + (size_t)(z * NYp1 + y) * wpr + (x >> 5)) >> (x & 31u)) & 1u;
+}
+
+// =====================================================================================================
+// U2a' bfs_order      the ORDER of the reference's breadth-first search (mc_ring/operations.h:1326-1456), for
+//                     dspmap_params.reference_iteration_order: rank[vertex] = position of the in-frustum vertex in the order the
+//                     search takes vertices off its queue (vertices outside the frustum are taken off and dropped: they order nothing).
+// A vertex enters the queue when the first of its neighbours (in queue order; +x -x +y -y +z -z within one) pushes it, so level
+// L+1 in queue order = the (parent position, direction) pairs that reach a not-yet-ranked in-frustum vertex FIRST, ascending.
+// One cooperative kernel, level-synchronous: every (frontier vertex, direction) item bids for its target with atomicMin of
+// its item number; the item that won owns the target; an ordered compaction of the owners is the next frontier.
+// Ranks live in one word per lattice vertex: UNSET, TENTATIVE | winning bid, or the final rank.
+// =====================================================================================================
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t val, uint32_t* s_warp, uint32_t& total);
+
+struct BfsScratch {
+    uint32_t* rank;           // (NX+1) x (NY+1) x (NZ+1), indexed like the vertex mask rows: (z * (NY+1) + y) * (NX+1) + x
+    uint32_t* frontier[2];    // vertex ids, in queue order
+    uint32_t* block_count;    // owners per block of the current level
+    uint32_t frontier_cap;
+    uint32_t* overflow;
+};
+
+__global__ void __launch_bounds__(1024, 1)
+k_bfs_order(const __grid_constant__ FrameParams f, const uint32_t* __restrict__ vmask, uint32_t wpr, BfsScratch sc) {
+    __shared__ uint32_t s_warp[33];
+    __shared__ uint32_t s_level[2];
+    const uint32_t NXp = f.NX + 1, NYp = f.NY + 1, NZp = f.NZ + 1;
+    const uint32_t n_threads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    // grid-wide barrier: monotonic counter in block_count[gridDim.x] (the kernel is launched cooperatively: all blocks are resident)
+    uint32_t* bar = sc.block_count + gridDim.x;
+    uint32_t bar_target = 0;
+    auto grid_sync = [&]() {
+        __syncthreads();
+        bar_target += gridDim.x;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(bar, 1u);
+            while (*(volatile uint32_t*)bar < bar_target) {}
+            __threadfence();
+        }
+        __syncthreads();
+    };
+    auto lin = [&](uint32_t x, uint32_t y, uint32_t z) { return (z * NYp + y) * NXp + x; };
+    if (gtid == 0) {
+        const uint32_t s0 = lin((uint32_t)f.start_v[0], (uint32_t)f.start_v[1], (uint32_t)f.start_v[2]);
+        sc.frontier[0][0] = s0;
+        __stcg(sc.rank + s0, 0u);
+    }
+    uint32_t nf = 1, next_rank = 1;
+    int cur = 0;
+    grid_sync();
+    // target vertex of item t = (frontier position t / 6, direction t % 6), or BFS_UNSET
+    auto target = [&](const uint32_t* __restrict__ F, uint32_t t) -> uint32_t {
+        const uint32_t u = __ldcg(F + t / 6u), d = t % 6u;
+        uint32_t x = u % NXp, y = (u / NXp) % NYp, z = u / (NXp * NYp);
+        // dir[6] = {+x, -x, +y, -y, +z, -z}, operations.h:1437
+        if (d == 0) { if (++x >= NXp) return BFS_UNSET; }
+        else if (d == 1) { if (x-- == 0) return BFS_UNSET; }
+        else if (d == 2) { if (++y >= NYp) return BFS_UNSET; }
+        else if (d == 3) { if (y-- == 0) return BFS_UNSET; }
+        else if (d == 4) { if (++z >= NZp) return BFS_UNSET; }
+        else { if (z-- == 0) return BFS_UNSET; }
+        if (!vbit(vmask, wpr, NYp, x, y, z)) return BFS_UNSET;
+        return lin(x, y, z);
+    };
+    while (nf) {
+        const uint32_t* F = sc.frontier[cur];
+        uint32_t* Fn = sc.frontier[cur ^ 1];
+        const uint32_t total = 6u * nf, J = (total + n_threads - 1) / n_threads;     // J consecutive items per thread: thread order = item order
+        const uint32_t t0 = gtid * J;
+        // bids
+        for (uint32_t j = 0; j < J && t0 + j < total; ++j) {
+            const uint32_t n = target(F, t0 + j);
+            if (n != BFS_UNSET && __ldcg(sc.rank + n) >= BFS_TENTATIVE) atomicMin(sc.rank + n, BFS_TENTATIVE | (t0 + j));
+        }
+        grid_sync();
+        // owners of this thread's items, block-wide exclusive scan of the counts
+        uint32_t mine = 0;
+        for (uint32_t j = 0; j < J && t0 + j < total; ++j) {
+            const uint32_t n = target(F, t0 + j);
+            mine += n != BFS_UNSET && __ldcg(sc.rank + n) == (BFS_TENTATIVE | (t0 + j));
+        }
+        uint32_t block_total;
+        const uint32_t off = block_exclusive_scan(mine, s_warp, block_total);
+        if (threadIdx.x == 0) __stcg(sc.block_count + blockIdx.x, block_total);
+        grid_sync();
+        if (threadIdx.x < 32) {          // one warp: owners in the blocks before this one, owners of the whole level
+            uint32_t bsum = 0, tsum = 0;
+            for (uint32_t b = threadIdx.x; b < gridDim.x; b += 32) {
+                const uint32_t c = __ldcg(sc.block_count + b);
+                bsum += b < blockIdx.x ? c : 0u;
+                tsum += c;
+            }
+            bsum = __reduce_add_sync(0xffffffffu, bsum); tsum = __reduce_add_sync(0xffffffffu, tsum);
+            if (threadIdx.x == 0) { s_level[0] = bsum; s_level[1] = tsum; }
+        }
+        __syncthreads();
+        const uint32_t base = s_level[0], level_total = s_level[1];
+        uint32_t pos = base + off;
+        for (uint32_t j = 0; j < J && t0 + j < total; ++j) {
+            const uint32_t n = target(F, t0 + j);
+            if (n != BFS_UNSET && __ldcg(sc.rank + n) == (BFS_TENTATIVE | (t0 + j))) {
+                if (pos < sc.frontier_cap) __stcg(Fn + pos, n); else atomicAdd(sc.overflow, 1u);
+                __stcg(sc.rank + n, next_rank + pos);
+                ++pos;
+            }
+        }
+        next_rank += level_total;
+        nf = min(level_total, sc.frontier_cap);
+        cur ^= 1;
+        grid_sync();
+    }
 }
 
 // ---- warp work queue: P-lane groups take the voxels that need slot-level work ---------------------------------
@@ -261,14 +377,15 @@ __device__ __forceinline__ bool corner_visible(const FrameParams& f, const float
 
 __global__ void __launch_bounds__(256)
 k_sweep_select(const __grid_constant__ FrameParams f, Store st, const uint32_t* __restrict__ vmask, uint32_t words_per_row,
-               const float* __restrict__ depth_int, uint32_t* __restrict__ work, Counters* __restrict__ cnt, int3 box_lo, int3 box_n) {
+               const float* __restrict__ depth_int, uint32_t* __restrict__ work, Counters* __restrict__ cnt, int3 box_lo, int3 box_n,
+               const uint32_t* __restrict__ vrank, uint32_t* __restrict__ work_key) {
     // the grid covers only the voxels of the frustum's bounding box, in MAP coordinates: blockIdx.y = (my, mz) row of the
     // box, x along the threads.  Voxels outside the box touch no in-frustum vertex.
     const int ix = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t mz = (uint32_t)(box_lo.z + (int)(blockIdx.y / (uint32_t)box_n.y)), my = (uint32_t)(box_lo.y + (int)(blockIdx.y % (uint32_t)box_n.y));
     const uint32_t mx = (uint32_t)(box_lo.x + ix);
     bool swept = false;
-    uint32_t v = 0;
+    uint32_t v = 0, visit_key = BFS_UNSET;
     if (ix < box_n.x) {
         uint32_t bx, by, bz;
         map_to_buffer(f, (int)mx, (int)my, (int)mz, bx, by, bz);
@@ -280,7 +397,15 @@ k_sweep_select(const __grid_constant__ FrameParams f, Store st, const uint32_t* 
 #pragma unroll
                 for (int b = 0; b < 2; ++b)
 #pragma unroll
-                    for (int a = 0; a < 2; ++a) swept |= vbit(vmask, words_per_row, nyp, mx + a, my + b, mz + c);
+                    for (int a = 0; a < 2; ++a) {
+                        const bool in = vbit(vmask, words_per_row, nyp, mx + a, my + b, mz + c);
+                        if (!vrank) { swept |= in; continue; }
+                        // reference order: the voxel is visited from the first of its corner vertices the search reaches, as that
+                        // vertex's voxel number (dx, dy, dz) = (-a, -b, -c) of the loops dx, dy, dz = -1..0 (operations.h:1344-1346);
+                        // a corner inside the frustum that the search never reaches visits nothing
+                        const uint32_t r = in ? vrank[((size_t)(mz + c) * nyp + (my + b)) * (f.NX + 1) + (mx + a)] : BFS_UNSET;
+                        if (r < BFS_TENTATIVE) { swept = true; visit_key = min(visit_key, r * 8u + (uint32_t)((1 - a) * 4 + (1 - b) * 2 + (1 - c))); }
+                    }
         }
     }
     __shared__ uint32_t s_swept, s_heavy, s_base;
@@ -305,14 +430,18 @@ k_sweep_select(const __grid_constant__ FrameParams f, Store st, const uint32_t* 
         s_base = s_heavy ? atomicAdd(&cnt->n_sweep_work, s_heavy) : 0u;
     }
     __syncthreads();
-    if (heavy) work[s_base + woff + __popc(b_heavy & ((1u << lane_id()) - 1u))] = v;
+    if (heavy) {
+        const uint32_t pos = s_base + woff + __popc(b_heavy & ((1u << lane_id()) - 1u));
+        work[pos] = v;
+        if (work_key) work_key[pos] = visit_key;
+    }
 }
 
 template <int PB>
 __global__ void __launch_bounds__(256)
 k_sweep_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
               const uint32_t* __restrict__ stamp_z, const uint32_t* __restrict__ work, const float* __restrict__ depth_int,
-              uint32_t* __restrict__ pix_count, CommView cv, Counters* __restrict__ cnt) {
+              uint32_t* __restrict__ pix_count, CommView cv, Counters* __restrict__ cnt, const uint32_t* __restrict__ work_key) {
     constexpr int P = 1 << PB, G = 32 / P;
     const uint32_t n_work = cnt->n_sweep_work;
     const uint32_t s = lane_id() & (P - 1), g = lane_id() / P, gbase = lane_id() & ~(uint32_t)(P - 1);
@@ -320,7 +449,7 @@ k_sweep_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* _
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     uint32_t n_nonempty = 0;
     // the pair list is reserved PAIR_CHUNK entries at a time per warp; unused tails are filled with a sentinel pixel
-    constexpr uint32_t PAIR_CHUNK = 128;
+    constexpr uint32_t PAIR_CHUNK = 32;
     uint32_t chunk_base = 0, chunk_used = PAIR_CHUNK;
     auto put_sentinel = [&](uint32_t pos) {
         for (int pr = 0; pr < cv.size; ++pr) (cv.recs[pr] + (size_t)cv.rank * cv.rec_cap + pos)->pix = 0xffffffffu;
@@ -331,6 +460,9 @@ k_sweep_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* _
         const uint32_t g_v = active ? work[wi] : 0u;
         const uint32_t g_hdr = active ? st.hdr[g_v] : 0u;
         const size_t base = (size_t)g_v << PB;
+        // position of the particle inside its pixel's list: ascending particle index, or (reference order) the order the search
+        // visits the voxels in, slot order inside a voxel
+        const uint32_t order_key = (work_key && active) ? ((work_key[wi] << PB) | s) : (uint32_t)(base + s);
         const bool has = active && s != 0 && ((g_hdr >> (16 + s)) & 1u);
         uint64_t m = 0;
         float x = 0.f, y = 0.f, z = 0.f;
@@ -373,7 +505,7 @@ k_sweep_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* _
                 const uint32_t pos = chunk_base + chunk_used + __popc(b_emit & ((1u << lane_id()) - 1u));
                 if (pos < f.vis_cap) {
                     const uint4 lo = make_uint4(pix, (uint32_t)(base + s), __float_as_uint(x), __float_as_uint(y));
-                    const uint4 hi = make_uint4(__float_as_uint(z), __float_as_uint(st.w[base + s]), meta_track(m) | (meta_forget(m) << 16), 0u);
+                    const uint4 hi = make_uint4(__float_as_uint(z), __float_as_uint(st.w[base + s]), meta_track(m) | (meta_forget(m) << 16), order_key);
                     for (int pr = 0; pr < cv.size; ++pr) {          // every rank builds the full pixel lists
                         uint4* dst = reinterpret_cast<uint4*>(cv.recs[pr] + (size_t)cv.rank * cv.rec_cap + pos);
                         dst[0] = lo; dst[1] = hi;
@@ -501,7 +633,7 @@ k_fill(CommView cv, const VisRec* __restrict__ recs, const uint32_t* __restrict_
             const uint32_t pix = seg[k].pix;
             if (pix == 0xffffffffu) continue;     // unused tail of a reserved chunk
             const uint32_t pos = offset[pix] + (atomicSub(pix_count + pix, 1u) - 1u);   // leaves the counts at zero
-            csr_key[pos] = ((uint64_t)seg[k].idx << 32) | (uint64_t)((uint32_t)g * cv.rec_cap + k);
+            csr_key[pos] = ((uint64_t)seg[k].order << 32) | (uint64_t)((uint32_t)g * cv.rec_cap + k);
         }
     }
 }
@@ -529,7 +661,7 @@ k_gather_visible(const uint32_t* __restrict__ n_visible, const VisRec* __restric
         const uint64_t key = csr_key[k];
         const uint4* r = reinterpret_cast<const uint4*>(recs + (uint32_t)key);
         const uint4 lo = r[0], hi = r[1];
-        csr_idx[k] = (uint32_t)(key >> 32);
+        csr_idx[k] = lo.y;                            // the particle index (the key's upper half is the list order)
         vis_pos[k] = make_float4(__uint_as_float(lo.z), __uint_as_float(lo.w), __uint_as_float(hi.x), __uint_as_float(hi.y));
         vis_mp[k] = make_uint2(hi.z, lo.x);          // {track | forget << 16, pixel}
     }

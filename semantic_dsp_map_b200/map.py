@@ -329,6 +329,13 @@ class SemanticDSPMap:
         self._params.uninit_sigma_mode, self._params.uninit_sigma_value = int(bool(on)), float(value)
         self.engine.set_params(self._params)
 
+    def setReferenceIterationOrder(self, on: bool = True):
+        """Not in the reference's API: build the pixel lists in the order the reference's breadth-first search visits the voxels
+        in (dspmap_params.reference_iteration_order) instead of ascending particle index.  A scene without moving objects then
+        reproduces the reference bit for bit in every float; costs a few milliseconds per frame."""
+        self._params.reference_iteration_order = int(bool(on))
+        self.engine.set_params(self._params)
+
     def setOccupancyThreshold(self, thr):
         self._params.occupancy_threshold = thr
         self.engine.set_params(self._params)

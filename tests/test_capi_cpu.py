@@ -29,7 +29,7 @@ def test_header_symbols_all_exported():
 def test_struct_sizes_match_header_layout():
     # natural alignment, as a C compiler lays the header's structs out
     assert C.sizeof(_capi.Config) == 22 * 4
-    assert C.sizeof(_capi.Params) == 14 * 4
+    assert C.sizeof(_capi.Params) == 15 * 4
     assert C.sizeof(_capi.Mask) == 8 + 4 * 4 + 6 * 8 + 2 * 4
     assert C.sizeof(_capi.ObjectMove) == 4 + 16 * 4
     assert C.sizeof(_capi.FrameStats) == 12 * 4 + 8 * 4

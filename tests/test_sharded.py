@@ -99,3 +99,19 @@ def test_two_shards_of_a_multi_chunk_map_match_oracle():
         cmd.append("--same-gpu")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "sharded_check: PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [4, 8])
+def test_four_and_eight_shards_match_oracle_bit_for_bit(world):
+    """One map over 4 and 8 GPUs (one process per GPU): every slab boundary, every peer arena, the per-rank particle lists of the
+    second stencil pass.  Needs that many GPUs - the device-side barriers of 8 processes time-slicing ONE GPU would run into their
+    own timeout - so the 1-GPU box of the round-end run skips it; profiles/ holds the log of the 8-GPU run."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, this box has {torch.cuda.device_count()}")
+    for config, extra in (("B", []), ("B", ["--grid", "9,6,9", "--frames", "4"])):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+               "--master-port", str(29700 + os.getpid() % 90), os.path.join(ROOT, "tools", "sharded_check.py"), "--config", config, "--frames", "6"] + extra
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0 and "sharded_check: PASS" in r.stdout, f"{config} {extra}: " + r.stdout[-2000:] + r.stderr[-2000:]
