@@ -60,6 +60,16 @@ SCENARIOS = {
     # BASELINE.json's benchmark configuration (the ZED2 preset with 256 x 64 x 256 voxels x 8 slots) -
     # the build bench.py times as the CPU baseline
     "sB_benchmark_config": dict(setting="B", n_frames=2, overrides=dict(), eval_format=False),
+    # ---- scenes WITHOUT object moves: nothing in them depends on std::unordered_set iteration, so the CUDA engine in the reference's
+    # iteration order (dspmap_params.reference_iteration_order) is held to these files DIRECTLY (tests/test_reference_build_gpu.py) ----
+    # the shipped configuration, instance masks present but no object ever moved; a track dropped at frame 4
+    "s3_static_scene": dict(setting=3, n_frames=6, overrides=dict(zero_center=False), eval_format=True, static=True, remove_at={4: [1]}),
+    # display colours, camera-relative output, the label quirks in the static mask, 2 m per frame (sub-stepped ring shift + wrap)
+    "s3_static_fast_quirks": dict(setting=3, n_frames=5, overrides=dict(zero_center=True, speed=2.0), eval_format=False, static=True, quirk_patch=True),
+    # SETTING 2: no BOOST_MODE, 11 x 11 window, 8 slots
+    "s2_static_vkitti2": dict(setting=2, n_frames=3, overrides=dict(zero_center=False), eval_format=True, static=True),
+    # the benchmark configuration (256 x 64 x 256 voxels x 8 slots) over 4 frames
+    "sB_static_benchmark": dict(setting="B", n_frames=4, overrides=dict(), eval_format=False, static=True),
 }
 
 
@@ -82,6 +92,8 @@ def scenario_frame(scene, spec, t):
     fr.remove_tracks = list(spec.get("remove_at", {}).get(t, []))
     if fr.remove_tracks:
         fr.moves = [(k, T) for k, T in fr.moves if k not in fr.remove_tracks]
+    if spec.get("static"):
+        fr.moves = []
     return fr
 
 
@@ -154,18 +166,26 @@ def colour_permutation():
     return np.random.default_rng(7).permutation(256).astype(np.int32)
 
 
-def run_oracle(name, move_orders=None, order=0):
+def run_oracle(name, move_orders=None, order=0, engine=False):
     """The same scenario through the CPU oracle.  move_orders[t] = the order in which the reference visited the moving
-    objects of frame t (std::unordered_map iteration, a host-container artefact the oracle takes as given)."""
-    from oracle_lib import oracle_map
+    objects of frame t (std::unordered_map iteration, a host-container artefact the oracle takes as given).
+    engine=True: through the CUDA engine instead, in the reference's iteration order (static scenarios)."""
     spec = SCENARIOS[name]
     cfg = scenario_config(spec)
-    orc = oracle_map(cfg, order=order)
-    orc.engine.set_random_table(make_random_table(cfg.seed))
     # The reference copies an uninitialised LabeledPoint for invalid pixels (pointcloud_tools.h:224-232) and later reads its
     # sigma (semantic_dsp_map.h:1047).  In oracle/_ref's build that stack slot reads 0 when the depth-noise model is on and
-    # 0.1 when it is off; the oracle takes the value as a parameter so that everything else is compared bit for bit.
-    orc.engine.set_invalid_sigma(0.0 if cfg.consider_depth_noise else 0.1)
+    # 0.1 when it is off; the oracle takes the value as a parameter so that everything else is compared bit for bit (the engine
+    # has the same switch in dspmap_params).
+    if engine:
+        from semantic_dsp_map_b200 import SemanticDSPMap
+        orc = SemanticDSPMap(cfg)
+        orc.setReferenceIterationOrder(True)
+        orc.followCompiledReferenceSigma(True, 0.0 if cfg.consider_depth_noise else 0.1)
+    else:
+        from oracle_lib import oracle_map
+        orc = oracle_map(cfg, order=order)
+        orc.engine.set_invalid_sigma(0.0 if cfg.consider_depth_noise else 0.1)
+    orc.engine.set_random_table(make_random_table(cfg.seed))
     orc.setVisualizeOptions(cfg.zero_center, spec["eval_format"])
     orc.enable_colors(label_bgr=csv_colours(), instance_map=colour_permutation())
     scene = Scene(cfg)
@@ -193,7 +213,10 @@ def run_oracle(name, move_orders=None, order=0):
 
 def main():
     from ref_lib import have_ref, run_scenario_subprocess
+    only = sys.argv[1:]
     for name, spec in SCENARIOS.items():
+        if only and name not in only:
+            continue
         if not have_ref(spec["setting"]):
             print(name, "skipped: oracle/_ref/libdsp_ref_s%s.so not built" % spec["setting"])
             continue
