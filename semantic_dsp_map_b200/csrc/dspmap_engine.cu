@@ -73,6 +73,12 @@ void inverse4f(const float m[16], float o[16]) {
     for (int k = 0; k < 16; ++k) o[k] = adj[k] / det;
 }
 
+static inline void host_pause() {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+}
+
 // A few persistent host threads for the pageable -> pinned staging copies of dspmap_update (row blocks of the depth
 // image and of every mask are independent).  Workers sleep on a condition variable between frames.
 //
@@ -881,7 +887,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     }
     const int nsb = (npix + SCAN_BLOCK - 1) / SCAN_BLOCK;
     ++launches; k_scan_blocksum<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p);
-    ++launches; k_scan_apply<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p, d_pix_offset.p);
+    ++launches; k_scan_apply<<<nsb, SCAN_BLOCK, 0, stream>>>(d_pix_count.p, (uint32_t)npix, d_scan_block.p, d_pix_offset.p, &d_cnt.p->n_visible);
     // the order in which pass 1 of the stencil takes the image rows needs the offsets only: beside the list building, on the side stream
     CU_TRY(this, cudaEventRecord(ev_fork[2], stream));
     CU_TRY(this, cudaStreamWaitEvent(side_stream, ev_fork[2], 0));
@@ -916,7 +922,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
             const int nb_blocks = (n_ranks + SCAN_BLOCK - 1) / SCAN_BLOCK;
             ++launches; k_birth_flags<<<(n_ranks + 255) / 256, 256, 0, side_stream>>>(fp, d_cloud_meta.p, d_birth_flags.p, (uint32_t)n_ranks);
             ++launches; k_scan_blocksum<<<nb_blocks, SCAN_BLOCK, 0, side_stream>>>(d_birth_flags.p, (uint32_t)n_ranks, d_birth_block.p);
-            ++launches; k_scan_apply<<<nb_blocks, SCAN_BLOCK, 0, side_stream>>>(d_birth_flags.p, (uint32_t)n_ranks, d_birth_block.p, d_birth_prefix.p);
+            ++launches; k_scan_apply<<<nb_blocks, SCAN_BLOCK, 0, side_stream>>>(d_birth_flags.p, (uint32_t)n_ranks, d_birth_block.p, d_birth_prefix.p, nullptr);
         }
         if (f.nb_ptc == 1) {    // one newborn per point: mark the touched voxels, then find every voxel's first candidates in the image
             ++launches; k_birth_mark<<<(npix + 255) / 256, 256, 0, side_stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_birth_box.p, d_entry_list.p, d_cnt.p);
@@ -965,7 +971,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     if (profiling) cudaEventRecord(ev[9], stream);
     DISPATCH_PB(f.Pb, (k_occ_slots<PB><<<sm_count * 8, 256, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, d_cnt.p)));
     ++launches;
-    ++launches; k_occ_scan<<<n_occ_chunks, 1024, 0, stream>>>(osc, n_occ_blocks, d_cnt.p, d_persist.p, cv);
+    ++launches; k_occ_scan<<<n_occ_chunks, 1024, 0, stream>>>(osc, n_occ_blocks, d_cnt.p, d_persist.p, cv, T);
     barrier();   // the lower ranks' totals are this rank's base offsets
     {
         const int use_list = n_occ_chunks > 1;
@@ -976,12 +982,23 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     barrier();   // rank 0 holds the whole result
     if (profiling) cudaEventRecord(ev[7], stream);
     CU_TRY(this, cudaMemcpyAsync(p_cnt.p, d_cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-    CU_TRY(this, cudaMemcpyAsync(p_stamps.p + (f.NX + f.NY + f.NZ), d_pix_offset.p + npix, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    CU_TRY(this, cudaMemcpyAsync(p_stamps.p + (f.NX + f.NY + f.NZ) + 1, d_counts, (size_t)MAX_RANKS * COMM_COUNTS * 4, cudaMemcpyDeviceToHost, stream));
+    if (cv.size > 1) CU_TRY(this, cudaMemcpyAsync(p_stamps.p + (f.NX + f.NY + f.NZ) + 1, d_counts, (size_t)MAX_RANKS * COMM_COUNTS * 4, cudaMemcpyDeviceToHost, stream));
     CU_TRY(this, cudaGetLastError());
     static const bool trace_frame = getenv("DSPMAP_TRACE") != nullptr;
     const double t_issued = trace_frame ? host_now_ms() : 0.0;
-    CU_TRY(this, cudaStreamSynchronize(stream));
+    if (cv.size == 1) {
+        // The counter block is the frame's last transfer and carries the frame's stamp at both ends (set by the occupancy scan):
+        // the host polls the pinned copy instead of going through a stream synchronisation - the wake-up is a cache miss, not a
+        // driver call.  The stream is looked at now and then so that a failed launch ends the wait.
+        volatile Counters* pc = p_cnt.p;
+        for (uint32_t spins = 0; pc->seq_head != T || pc->seq_tail != T; ++spins) {
+            host_pause();
+            if ((spins & 0x3fffu) == 0x3fffu && cudaStreamQuery(stream) != cudaErrorNotReady) break;
+        }
+        if (pc->seq_head != T || pc->seq_tail != T) CU_TRY(this, cudaStreamSynchronize(stream));
+    } else {
+        CU_TRY(this, cudaStreamSynchronize(stream));
+    }
     if (trace_frame) {   // host time to issue the frame's launches vs time left waiting for the device afterwards
         trace_issue_ms += t_issued - t_frame_begin; trace_wait_ms += host_now_ms() - t_issued;
         if ((T % 16) == 0) { fprintf(stderr, "[dspmap] frame %u: issue %.3f ms, wait %.3f ms (mean of 16)\n", T, trace_issue_ms / 16, trace_wait_ms / 16); trace_issue_ms = trace_wait_ms = 0; }
@@ -990,11 +1007,12 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
 
     stats.time_stamp = T;
     stats.n_swept_voxels = last.n_swept_voxels; stats.n_swept_nonempty = last.n_swept_nonempty;
-    n_visible_last = p_stamps.p[f.NX + f.NY + f.NZ];
+    n_visible_last = last.n_visible;
     {   // global result size (rank 0 reads the whole list; the other ranks report their own share only)
         const uint32_t* cc = p_stamps.p + (f.NX + f.NY + f.NZ) + 1;
         uint32_t occ = 0, fre = 0;
-        for (int g = 0; g < cv.size; ++g) { occ += cc[g * COMM_COUNTS + CC_OCC]; fre += cc[g * COMM_COUNTS + CC_FREE]; }
+        if (cv.size == 1) { occ = last.n_occupied; fre = last.n_free; }
+        else for (int g = 0; g < cv.size; ++g) { occ += cc[g * COMM_COUNTS + CC_OCC]; fre += cc[g * COMM_COUNTS + CC_FREE]; }
         result_n = cv.rank == 0 ? occ : 0; result_nf = cv.rank == 0 ? fre : 0;
         n_occ_global = occ;
     }

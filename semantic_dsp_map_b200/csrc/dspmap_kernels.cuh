@@ -12,6 +12,7 @@ namespace dspk {
 
 // device-resident per-frame counters (zeroed at frame start)
 struct Counters {
+    uint32_t seq_head;         // = seq_tail = the frame's time stamp once the frame's results are final (host-side completion marker)
     uint32_t n_pairs;          // (pixel, particle) pairs produced by the sweep (may exceed vis_cap -> overflow)
     uint32_t n_valid_points;
     uint32_t n_swept_voxels;
@@ -37,6 +38,8 @@ struct Counters {
     uint32_t wu_next;          // k_weight_update: next 32-particle group to hand out
     uint32_t n_mine;           // sharded map: listed particles this rank owns (k_select_mine)
     uint32_t mov_out[8];       // moved particles sent to each destination rank this frame
+    uint32_t n_visible;        // listed particles (total of the pixel lists)
+    uint32_t seq_tail;
 };
 
 // survives across frames
@@ -582,7 +585,7 @@ k_scan_blocksum(const uint32_t* __restrict__ count, uint32_t n, uint32_t* __rest
 }
 
 __global__ void __launch_bounds__(SCAN_BLOCK)
-k_scan_apply(const uint32_t* __restrict__ count, uint32_t n, const uint32_t* __restrict__ block_sum, uint32_t* __restrict__ offset) {
+k_scan_apply(const uint32_t* __restrict__ count, uint32_t n, const uint32_t* __restrict__ block_sum, uint32_t* __restrict__ offset, uint32_t* __restrict__ total_out) {
     __shared__ uint32_t s_warp[33];
     __shared__ uint32_t s_base;
     // prefix of the preceding blocks' sums
@@ -598,7 +601,7 @@ k_scan_apply(const uint32_t* __restrict__ count, uint32_t n, const uint32_t* __r
     uint32_t total;
     const uint32_t ex = block_exclusive_scan(c, s_warp, total);
     if (i < n) offset[i] = base + ex;
-    if (i == n - 1) offset[n] = base + ex + c;
+    if (i == n - 1) { offset[n] = base + ex + c; if (total_out) *total_out = base + ex + c; }
 }
 
 // this rank's record count goes into every rank's counts table
@@ -1315,7 +1318,7 @@ k_occ_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* __r
 
 // exclusive scan of the per-block (occupied, free, movable) counts; single block, any number of tiles
 __global__ void __launch_bounds__(1024)
-k_occ_scan(OccScratch sc, uint32_t n_blocks, Counters* __restrict__ cnt, Persist* __restrict__ persist, CommView cv) {
+k_occ_scan(OccScratch sc, uint32_t n_blocks, Counters* __restrict__ cnt, Persist* __restrict__ persist, CommView cv, uint32_t frame_stamp) {
     // one block per chunk of OCC_SCAN_CHUNK tiles (a 256 x 64 x 256 map is one chunk, 1024 x 128 x 1024 thirty-two): offsets
     // inside the chunk, the chunk's totals, and the block that finishes last turns the totals into chunk bases
     __shared__ uint32_t s_warp[33];
@@ -1366,6 +1369,7 @@ k_occ_scan(OccScratch sc, uint32_t n_blocks, Counters* __restrict__ cnt, Persist
         tail[0] = 0u;                                             // the ticket counter is ready for the next frame
         tail[1] = run3;                                           // length of the non-empty tile list
         cnt->n_occupied = run0; cnt->n_free = run1; cnt->n_movable = run2; persist->n_movable = run2;
+        cnt->seq_head = frame_stamp; cnt->seq_tail = frame_stamp;    // copied to the host after the last kernel of the frame
         for (int p = 0; p < cv.size; ++p) {   // every rank learns every rank's totals (the emit pass needs the lower ranks')
             uint32_t* row = cv.counts[p] + cv.rank * COMM_COUNTS;
             row[CC_OCC] = run0; row[CC_FREE] = run1;

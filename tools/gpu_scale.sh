@@ -5,13 +5,13 @@ tag=$1; shift
 cfgs=${@:-D}
 mkdir -p gpurun_out
 nvidia-smi -L | head -8
-python -m pytest tests/test_sharded.py -q -m gpu > gpurun_out/${tag}_sharded_pytest.log 2>&1; echo "sharded pytest rc=$?"; tail -4 gpurun_out/${tag}_sharded_pytest.log
+timeout 300 python -m pytest tests/test_sharded.py -q -m gpu > gpurun_out/${tag}_sharded_pytest.log 2>&1; echo "sharded pytest rc=$?"; tail -4 gpurun_out/${tag}_sharded_pytest.log
 for cfg in $cfgs; do
   for n in 1 2 4 8; do
     if [ $n = 1 ]; then
-      python bench.py --config $cfg --steps 40 --warmup 10 --no-cpu-baseline > gpurun_out/${tag}_${cfg}_n1.json 2> gpurun_out/${tag}_${cfg}_n1.err
+      timeout 150 python bench.py --config $cfg --steps 40 --warmup 10 --no-cpu-baseline > gpurun_out/${tag}_${cfg}_n1.json 2> gpurun_out/${tag}_${cfg}_n1.err
     else
-      python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29400 + n)) bench.py --gpus $n --config $cfg --steps 40 --warmup 10 \
+      timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29400 + n)) bench.py --gpus $n --config $cfg --steps 40 --warmup 10 \
           --parallelism sharded --no-cpu-baseline > gpurun_out/${tag}_${cfg}_sharded${n}.json 2> gpurun_out/${tag}_${cfg}_sharded${n}.err
     fi
     echo "$cfg n=$n rc=$?"; tail -c 1200 gpurun_out/${tag}_${cfg}_*${n}.json | python -c "
