@@ -152,6 +152,11 @@ public:
         auto rd = [&seed_source]() { return (uint32_t)seed_source(); };
         std::mt19937 gen(rd());
         for (int i = 255; i > 0; --i) { std::uniform_int_distribution<int> dist(0, i); std::swap(color_map_int_256_[i], color_map_int_256_[dist(gen)]); }
+        // DSPMAP_ADAPTER_REFERENCE_ORDER=1: follow the reference's iteration order and its compiled uninitialised-sigma reads
+        // (setReferenceIterationOrder, followCompiledReferenceSigma): a scene without moving objects is then published voxel for
+        // voxel, colour for colour as the reference node publishes it (regression comparisons against a recorded reference run)
+        const char* exact = std::getenv("DSPMAP_ADAPTER_REFERENCE_ORDER");
+        follow_reference_ = exact && exact[0] == '1';
         pushLabels();
         pushColors();
         setGaussianTableSeed(rd());                                                              // reference :65 -> basic_algorithms.h:394-402
@@ -293,6 +298,10 @@ private:
             std::fprintf(stderr, "max_forget_count %d clamped to 0..5 (size of the forgetting table)\n", p.max_forget_count);
             p.max_forget_count = p.max_forget_count < 0 ? 0 : 5;
         }
+        if (follow_reference_) {      // what a compiled reference reads at its uninitialised-sigma sites: 0 with the depth-noise model, else 0.1
+            p.reference_iteration_order = 1;
+            p.uninit_sigma_mode = 1; p.uninit_sigma_value = p.consider_depth_noise ? 0.f : 0.1f;
+        }
         if (p.nb_ptc_num_per_point < 1) { std::fprintf(stderr, "nb_ptc_num_per_point %d raised to 1\n", p.nb_ptc_num_per_point); p.nb_ptc_num_per_point = 1; }
         checked(dspmap_set_params(h_, &p), "dspmap_set_params");
     }
@@ -389,6 +398,7 @@ private:
         checked(dspmap_set_colors(h_, &c), "dspmap_set_colors");
     }
 
+    bool follow_reference_ = false;
     dspmap_config cfg_;
     DspLabelTables labels_;
     uint8_t color_map_int_256_[256];
