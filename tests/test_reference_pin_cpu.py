@@ -59,6 +59,8 @@ def test_live_reference_reproduces_the_committed_fixtures(name):
     spec = G.SCENARIOS[name]
     if spec["setting"] == 0 and not os.environ.get("DSPMAP_SLOW_TESTS"):
         pytest.skip("SETTING 0 keeps a 3.2 GB particle array: the live re-run takes over a minute (set DSPMAP_SLOW_TESTS=1)")
+    if spec.get("static") and name != "s3_static_scene" and not os.environ.get("DSPMAP_SLOW_TESTS"):
+        pytest.skip("live re-run of the larger static scenarios takes over a minute (set DSPMAP_SLOW_TESTS=1); s3_static_scene is re-run")
     if not have_ref(spec["setting"]):
         pytest.skip("oracle/_ref/libdsp_ref_s%s.so not built (needs /root/reference at build time)" % spec["setting"])
     want = load(name)
