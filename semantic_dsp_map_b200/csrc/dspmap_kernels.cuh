@@ -395,6 +395,18 @@ k_sweep_select(const __grid_constant__ FrameParams f, Store st, const uint32_t* 
         if (bz >= f.z_lo && bz < f.z_hi) {        // this shard's slabs
             v = buffer_to_voxel(f, bx, by, bz);
             const uint32_t nyp = f.NY + 1;
+            if (!vrank) {
+                // the eight corner bits: vertices mx, mx + 1 of the four vertex rows (my + b, mz + c) = two adjacent bits of one or two words per row
+                const uint32_t w = mx >> 5, sh = mx & 31u;
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        const uint32_t* row = vmask + (size_t)((mz + c) * nyp + (my + b)) * words_per_row;
+                        const uint32_t w0 = __ldg(row + w), w1 = (sh == 31u && w + 1 < words_per_row) ? __ldg(row + w + 1) : 0u;
+                        swept |= (__funnelshift_r(w0, w1, sh) & 3u) != 0u;
+                    }
+            } else
 #pragma unroll
             for (int c = 0; c < 2; ++c)
 #pragma unroll
