@@ -241,6 +241,37 @@ int dspmap_update_device(dspmap_t* h, const float* d_depth, int32_t rows, int32_
                          const int32_t* remove_tracks, int32_t n_remove,
                          int32_t want_freespace);
 
+/* ---- pipelined frames ---------------------------------------------------------------------------------
+ * The reference's update() returns with the clouds filled (semantic_dsp_map.h:170-251), so a caller's frame costs
+ * staging + host->device copy + kernels + device->host copy, one after the other.  A camera STREAM does not need that:
+ * dspmap_update_async stages and enqueues frame t and returns while it runs; the call that enqueues frame t+1 reads
+ * frame t's counters once it has finished and starts the transfer of its result on a copy stream, where it overlaps
+ * frame t+1's kernels; dspmap_wait_result(t) returns when that transfer is done.  Same arguments, same arithmetic, same
+ * results as dspmap_update - only the hand-over is deferred (mapping.cpp would publish frame t's clouds while frame t+1
+ * is being computed).  Loop:   update_async(0,&k0); for t = 1..: { update_async(t,&k); wait_result(k_prev,&r); use r; }
+ *   *ticket   names the frame (its time stamp; never 0 for an accepted frame).
+ *   errors    a frame's capacity / communication errors are found when its counters are read: they are returned by the
+ *             NEXT dspmap_update_async (whose own frame is enqueued all the same) and by dspmap_wait_result(ticket).
+ *   lifetime  the views of dspmap_wait_result(t) stay valid until dspmap_wait_result(t+2) is called or frame t+3 is
+ *             submitted, whichever comes first.
+ *   mixing    every other entry point first waits for the frames in flight.  With profiling on, and for sharded maps,
+ *             the async calls run the frame synchronously (the ticket works the same).
+ * dspmap_update_device_async: the same for images resident in device memory; its result stays on the device
+ * (dspmap_wait_result then returns device pointers, as dspmap_get_result_device does). */
+int dspmap_update_async(dspmap_t* h, const float* depth, int32_t rows, int32_t cols,
+                        int32_t row_stride, const dspmap_mask* masks, int32_t n_masks,
+                        const double position[3], const double orientation_wxyz[4],
+                        const dspmap_object_move* moves, int32_t n_moves,
+                        const int32_t* remove_tracks, int32_t n_remove,
+                        int32_t want_freespace, uint32_t* ticket);
+int dspmap_update_device_async(dspmap_t* h, const float* d_depth, int32_t rows, int32_t cols,
+                               int32_t row_stride, const dspmap_mask* masks, int32_t n_masks,
+                               const double position[3], const double orientation_wxyz[4],
+                               const dspmap_object_move* moves, int32_t n_moves,
+                               const int32_t* remove_tracks, int32_t n_remove,
+                               int32_t want_freespace, uint32_t* ticket);
+int dspmap_wait_result(dspmap_t* h, uint32_t ticket, dspmap_result* out);
+
 /* result of the last update: host view (pinned buffers owned by the handle, valid until
  * the next update) — what the reference push_backs into the caller's clouds */
 int dspmap_get_result(dspmap_t* h, dspmap_result* out);

@@ -7,7 +7,7 @@
 #
 # The name "B" builds BASELINE.json's benchmark configuration (ZED2 preset with 256 x 64 x 256 voxels and 8 slots per voxel,
 # SURVEY.md section 8 config B): SETTING 3 with the four grid-size constants of that block changed - what docs/parameter_table.md
-# tells a user to edit.  bench.py times it as the CPU baseline (cpu_baseline.kind = "reference").
+# tells a user to edit.  bench.py times it as the CPU baseline (cpu_baseline.kind = "reference").  "BV" is "B" with VERBOSE_MODE 1.
 #
 # SETTING 3 compiles the tree exactly as it is.  The reference selects its grid / camera preset with a hard
 # "#define SETTING 3" (include/settings/settings.h:22) that no -D can override, so for another preset the headers are
@@ -38,14 +38,18 @@ for S in "$@"; do
         (cd "$REF/include" && find . -type d) | while read -r d; do mkdir -p "$TMP/$d"; done
         (cd "$REF/include" && find . -type f) | while read -r f; do ln -s "$REF/include/$f" "$TMP/$f"; done
         rm "$TMP/settings/settings.h"
-        if [ "$S" = "B" ]; then
-            sed -e '/^#elif SETTING == 3/,/^#else/ s/C_VOXEL_NUM_AXIS_X_N = 7;/C_VOXEL_NUM_AXIS_X_N = 8;/' \
+        if [ "$S" = "B" ] || [ "$S" = "BV" ]; then
+            # BV: config B with the reference's own stage timers on (VERBOSE_MODE 1, settings.h:20; semantic_dsp_map.h:912-953
+            # prints the six "Time used for ..." lines per frame): bench.py reads the CPU baseline's per-stage split from them
+            VERB=0; [ "$S" != "BV" ] || VERB=1
+            sed -e "s/^#define VERBOSE_MODE 0 /#define VERBOSE_MODE $VERB /" -e '/^#elif SETTING == 3/,/^#else/ s/C_VOXEL_NUM_AXIS_X_N = 7;/C_VOXEL_NUM_AXIS_X_N = 8;/' \
                 -e '/^#elif SETTING == 3/,/^#else/ s/C_VOXEL_NUM_AXIS_Y_N = 5;/C_VOXEL_NUM_AXIS_Y_N = 6;/' \
                 -e '/^#elif SETTING == 3/,/^#else/ s/C_VOXEL_NUM_AXIS_Z_N = 7;/C_VOXEL_NUM_AXIS_Z_N = 8;/' \
                 -e '/^#elif SETTING == 3/,/^#else/ s/C_MAX_PARTICLE_NUM_PER_VOXEL_N = 2;/C_MAX_PARTICLE_NUM_PER_VOXEL_N = 3;/' \
                 "$REF/include/settings/settings.h" > "$TMP/settings/settings.h"
             [ "$(grep -c 'C_VOXEL_NUM_AXIS_Y_N = 6;' "$TMP/settings/settings.h")" = "1" ]
             [ "$(grep -c 'C_MAX_PARTICLE_NUM_PER_VOXEL_N = 3;' "$TMP/settings/settings.h")" = "3" ]
+            grep -q "^#define VERBOSE_MODE $VERB " "$TMP/settings/settings.h"
         else
             sed "s/^#define SETTING 3 /#define SETTING $S /" "$REF/include/settings/settings.h" > "$TMP/settings/settings.h"
             grep -q "^#define SETTING $S " "$TMP/settings/settings.h"

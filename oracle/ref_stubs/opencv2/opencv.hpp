@@ -137,7 +137,7 @@ enum { COLORMAP_JET = 2 };
 enum { COLOR_BGR2RGB = 4, COLOR_RGB2HSV = 41, COLOR_HSV2RGB = 55 };
 
 inline void resize(const Mat&, Mat&, Size, double = 0, double = 0, int = INTER_LINEAR) { stub_unreachable("cv::resize"); }
-inline void applyColorMap(const Mat&, Mat&, int) { stub_unreachable("cv::applyColorMap"); }
+inline void applyColorMap(const Mat&, Mat&, int) {}   // display only (the VERBOSE_MODE debug windows, semantic_dsp_map.h:1562-1569), like imshow
 inline void imshow(const std::string&, const Mat&) {}
 inline int waitKey(int = 0) { return -1; }
 

@@ -118,6 +118,13 @@ SYMBOLS = {
     "dspmap_update_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Mask), C.c_int32,
                                        C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(ObjectMove), C.c_int32,
                                        C.POINTER(C.c_int32), C.c_int32, C.c_int32]),
+    "dspmap_update_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Mask), C.c_int32,
+                                      C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(ObjectMove), C.c_int32,
+                                      C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(C.c_uint32)]),
+    "dspmap_update_device_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Mask), C.c_int32,
+                                             C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(ObjectMove), C.c_int32,
+                                             C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(C.c_uint32)]),
+    "dspmap_wait_result": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(Result)]),
     "dspmap_get_result": (C.c_int, [C.c_void_p, C.POINTER(Result)]),
     "dspmap_get_result_device": (C.c_int, [C.c_void_p, C.POINTER(Result)]),
     "dspmap_get_stats": (C.c_int, [C.c_void_p, C.POINTER(FrameStats)]),

@@ -273,37 +273,55 @@ struct dspmap {
     uint32_t comm_epoch = 0;
     void* peer_base[MAX_RANKS]{};
     bool comm_connected = false;
-    uint32_t *r_idx = nullptr, *r_free_idx = nullptr;
-    float *r_xyz = nullptr, *r_w = nullptr, *r_free_xyz = nullptr;
     float4* d_obs_a = nullptr;        // observation planes of the stencil passes (padded; dspmap_stencil.cuh)
     uint2* d_obs_b = nullptr;
-    uint16_t* r_track = nullptr;
-    uint8_t* r_label = nullptr;
-    uint8_t* r_rgb = nullptr;
+    DevBuf<uint8_t> result2;           // second set of result arrays (unsharded maps; allocated by the first pipelined frame)
     dspmap_colors colors{};            // dspmap_set_colors
     DevBuf<uint8_t> d_col_tab;         // 768 B label colours (b, g, r) + 256 B instance map
-    int8_t* r_state = nullptr;
     uint32_t* d_counts = nullptr;      // this rank's counts[source rank][COMM_COUNTS]
 
-    // pinned staging
-    PinBuf<float> p_depth;
-    PinBuf<uint8_t> p_masks;
-    PinBuf<Counters> p_cnt;
-    PinBuf<FrameParams> p_fp;
-    PinBuf<uint32_t> p_stamps;
-    PinBuf<MaskDesc> p_maskdesc;
-    PinBuf<MoveTable> p_moves;
-    PinBuf<uint32_t> hr_idx, hr_free_idx;
-    PinBuf<float> hr_xyz, hr_w, hr_free_xyz;
-    PinBuf<uint16_t> hr_track;
-    PinBuf<uint8_t> hr_label, hr_rgb;
-    PinBuf<int8_t> hr_state;
-    bool host_result_valid = false;
+    // Frame slots.  Everything the host writes for ONE frame and the device reads later (pinned staging of the images,
+    // descriptor tables, slab stamps), everything the device writes for one frame and the host reads later (the counter
+    // block, the result arrays and their pinned host copies) exists twice, indexed by the parity of the frame's time stamp:
+    // frame t+1 can be staged and enqueued while frame t still runs and frame t-1's result is on its way to the host
+    // (dspmap_update_async).  The synchronous calls use the same slots, one frame at a time.
+    struct FrameSlot {
+        PinBuf<float> p_depth;
+        PinBuf<uint8_t> p_masks;
+        PinBuf<Counters> p_cnt;
+        PinBuf<uint32_t> p_stamps;
+        PinBuf<MaskDesc> p_maskdesc;
+        PinBuf<MoveTable> p_moves;
+        PinBuf<uint32_t> hr_idx, hr_free_idx;
+        PinBuf<float> hr_xyz, hr_w, hr_free_xyz;
+        PinBuf<uint16_t> hr_track;
+        PinBuf<uint8_t> hr_label, hr_rgb;
+        PinBuf<int8_t> hr_state;
+        ResultArrays dres{};               // this slot's result arrays on the device
+        cudaEvent_t copy_done = nullptr;   // the device->host transfer of this slot's result
+        bool copy_issued = false;          // ... has been enqueued since the slot's frame finished
+        bool host_result_valid = false;    // ... and has completed
+        bool inflight = false;             // the slot's frame is enqueued, its counters have not been read yet
+        bool want_host = false;            // the frame came through dspmap_update_async: its result goes to the host
+        int want_free = 0, col_enabled = 0;
+        uint32_t T = 0;                    // time stamp of the slot's frame (the ticket of dspmap_update_async)
+        uint32_t result_n = 0, result_nf = 0, n_occ_global = 0;
+        int rc = DSPMAP_OK;                // what finishing the frame returned
+        double t_issued = 0;
+        void release() {
+            p_depth.release(); p_masks.release(); p_cnt.release(); p_stamps.release(); p_maskdesc.release(); p_moves.release();
+            hr_idx.release(); hr_free_idx.release(); hr_xyz.release(); hr_w.release(); hr_free_xyz.release(); hr_track.release();
+            hr_label.release(); hr_rgb.release(); hr_state.release();
+            if (copy_done) { cudaEventDestroy(copy_done); copy_done = nullptr; }
+        }
+    } slot[2];
+    int cur = 0;                           // slot of the most recent frame
+    cudaStream_t copy_stream = nullptr;    // result transfers of pipelined frames
     double t_frame_begin = 0, trace_issue_ms = 0, trace_wait_ms = 0;   // DSPMAP_TRACE
     std::unique_ptr<StagePool> stage_pool;
 
-    Counters last{};
-    uint32_t n_visible_last = 0, result_n = 0, result_nf = 0, n_occ_global = 0;
+    Counters last{};                       // of the most recent FINISHED frame
+    uint32_t n_visible_last = 0;
     dspmap_frame_stats stats{};
     bool profiling = false;
     cudaEvent_t ev[10]{};
@@ -376,8 +394,9 @@ struct dspmap {
         d_vis_mp.release(); d_row_order.release(); d_vrank.release(); d_bfs_front[0].release(); d_bfs_front[1].release(); d_bfs_blocks.release(); d_work_key.release(); d_vis_pos.release(); d_keys.release(); d_birth_box.release(); d_ranks.release(); d_birth_flags.release(); d_birth_prefix.release(); d_birth_block.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_chunk_tot.release(); d_chunk_base.release(); d_tile_list.release(); d_work.release();
         for (int p = 0; p < MAX_RANKS; ++p) if (peer_base[p] && p != cfg.shard_rank) { cudaIpcCloseMemHandle(peer_base[p]); peer_base[p] = nullptr; }
         arena.release();
-        p_depth.release(); p_masks.release(); p_cnt.release(); p_fp.release(); p_stamps.release(); p_maskdesc.release(); p_moves.release();
-        hr_idx.release(); hr_free_idx.release(); hr_xyz.release(); hr_w.release(); hr_free_xyz.release(); hr_track.release(); hr_label.release(); hr_state.release(); hr_rgb.release();
+        result2.release();
+        for (auto& sl : slot) sl.release();
+        if (copy_stream) { cudaStreamDestroy(copy_stream); copy_stream = nullptr; }
         for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (own_stream) { cudaStreamDestroy(own_stream); own_stream = nullptr; }
         if (side_stream) { cudaStreamDestroy(side_stream); side_stream = nullptr; }
@@ -398,9 +417,14 @@ struct dspmap {
         uint8_t* mine = arena.p;
         d_obs_a = (float4*)(mine + lay.obs_a); d_obs_b = (uint2*)(mine + lay.obs_b); d_counts = (uint32_t*)(mine + lay.counts);
         uint8_t* r0 = (uint8_t*)(peer_base[0] && have_rank0 >= 0 ? peer_base[0] : arena.p);
-        r_idx = (uint32_t*)(r0 + lay.r_idx); r_xyz = (float*)(r0 + lay.r_xyz); r_w = (float*)(r0 + lay.r_w); r_track = (uint16_t*)(r0 + lay.r_track);
-        r_label = (uint8_t*)(r0 + lay.r_label); r_state = (int8_t*)(r0 + lay.r_state); r_free_idx = (uint32_t*)(r0 + lay.r_free_idx); r_free_xyz = (float*)(r0 + lay.r_free_xyz);
-        r_rgb = r0 + lay.r_rgb;
+        slot[0].dres = result_arrays_at(r0, 0);
+        slot[1].dres = result2.p ? result_arrays_at(result2.p, lay.r_idx) : slot[0].dres;
+    }
+    // the nine result arrays inside a block laid out like the arena's result part (`bias` = offset of that part's first array)
+    ResultArrays result_arrays_at(uint8_t* b, size_t bias) const {
+        b -= bias;
+        return ResultArrays{(uint32_t*)(b + lay.r_idx), (float*)(b + lay.r_xyz), (float*)(b + lay.r_w), (uint16_t*)(b + lay.r_track), (uint8_t*)(b + lay.r_label),
+                            (int8_t*)(b + lay.r_state), (uint32_t*)(b + lay.r_free_idx), (float*)(b + lay.r_free_xyz), b + lay.r_rgb};
     }
     int barrier() {
         if (cfg.shard_count == 1) return DSPMAP_OK;
@@ -414,8 +438,15 @@ struct dspmap {
     int frame(const float* d_depth, int rows, int cols, int stride, const dspmap_mask* masks, int n_masks, const double pos[3],
               const double quat[4], const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove,
               int want_free, int pre_decimated, const std::function<int(dspmap_mask*)>* late_masks = nullptr,
-              const std::function<int()>* late_depth = nullptr);
-    int fetch_result_to_host();
+              const std::function<int()>* late_depth = nullptr, bool pipelined = false, bool want_host = false);
+    int frame_enqueue(const float* d_depth, int rows, int cols, int stride, const dspmap_mask* masks, int n_masks, const double pos[3],
+                      const double quat[4], const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove,
+                      int want_free, int pre_decimated, const std::function<int(dspmap_mask*)>* late_masks, const std::function<int()>* late_depth);
+    int frame_finish(int s);
+    int issue_result_copy(int s, cudaStream_t on);
+    int fetch_result_to_host(int s);
+    int drain();
+    int next_slot() const { return (int)((T + 1) & 1u); }
 };
 
 // kernels templated on the slot-count bits
@@ -587,8 +618,13 @@ int dspmap::init(const dspmap_config& c) {
         comm_connected = G == 1;
     }
 
-    CU_TRY(this, p_cnt.reserve(1)); CU_TRY(this, p_fp.reserve(1)); CU_TRY(this, p_stamps.reserve(f.NX + f.NY + f.NZ + 1 + MAX_RANKS * COMM_COUNTS));
-    CU_TRY(this, p_maskdesc.reserve(64)); CU_TRY(this, p_moves.reserve(1));
+    for (auto& sl : slot) {
+        CU_TRY(this, sl.p_cnt.reserve(1)); CU_TRY(this, sl.p_stamps.reserve(f.NX + f.NY + f.NZ + 1 + MAX_RANKS * COMM_COUNTS));
+        CU_TRY(this, sl.p_maskdesc.reserve(64)); CU_TRY(this, sl.p_moves.reserve(1));
+        memset(sl.p_cnt.p, 0, sizeof(Counters));
+        CU_TRY(this, cudaEventCreateWithFlags(&sl.copy_done, cudaEventDisableTiming));
+    }
+    CU_TRY(this, cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
 
     // Gaussian PDF LUT (utils/basic_algorithms.h:403-407, 455-459): (1/sqrt(2*M_PI_2f32)) * exp(-v^2/2), v=(i-10000)*0.001
     {
@@ -629,7 +665,8 @@ int dspmap::clear_device() {
     CU_TRY(this, cudaStreamSynchronize(stream));
     memset(&last, 0, sizeof last);
     memset(&stats, 0, sizeof stats);
-    host_result_valid = false;
+    for (auto& sl : slot) { memset(sl.p_cnt.p, 0, sizeof(Counters)); sl.host_result_valid = false; sl.inflight = false; sl.copy_issued = false; sl.result_n = sl.result_nf = sl.n_occ_global = 0; sl.T = 0; sl.rc = DSPMAP_OK; }
+    n_visible_last = 0;
     return DSPMAP_OK;
 }
 
@@ -654,7 +691,7 @@ int dspmap::apply_params() {
 // scan_remove: the movable list no longer describes the store (second phase of a move-then-remove frame)
 int dspmap::run_moves(const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove, bool scan_remove, int slot) {
     // one staging table per call of a frame (slot): nothing waits for an earlier table's copy to finish
-    MoveTable& mt = p_moves.p[slot];
+    MoveTable& mt = this->slot[cur].p_moves.p[slot];
     mt.n_moves = n_moves; mt.n_remove = n_remove;
     for (int i = 0; i < n_moves; ++i) { mt.move_track[i] = moves[i].track_id; memcpy(mt.t[i], moves[i].t, 12 * sizeof(float)); }
     for (int i = 0; i < n_remove; ++i) mt.remove_track[i] = remove_tracks[i];
@@ -699,7 +736,36 @@ static double host_now_ms() {
 // SemanticDSPMap::update (semantic_dsp_map.h:170-251) -> subObjectLevelUpdate (:576-955)
 int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const dspmap_mask* masks, int n_masks, const double pos[3],
                   const double quat[4], const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove,
-                  int want_free, int pre_decimated, const std::function<int(dspmap_mask*)>* late_masks, const std::function<int()>* late_depth) {
+                  int want_free, int pre_decimated, const std::function<int(dspmap_mask*)>* late_masks, const std::function<int()>* late_depth,
+                  bool pipelined, bool want_host) {
+    // Synchronous call: enqueue the frame, wait for its counters.  Pipelined call (dspmap_update_async): enqueue frame t, THEN
+    // wait for frame t-1 - which ran while the host staged and enqueued this one - and start the transfer of its result.
+    const int prev = cur;
+    if (!pipelined || profiling || cv.size > 1) { const int rc = drain(); if (rc != DSPMAP_OK) return rc; }
+    if (slot[next_slot()].inflight) { const int rc = frame_finish(next_slot()); if (rc != DSPMAP_OK) return rc; }   // (protocol: cannot happen)
+    int rc = frame_enqueue(d_depth, rows, cols, stride, masks, n_masks, pos, quat, moves, n_moves, remove_tracks, n_remove, want_free, pre_decimated, late_masks, late_depth);
+    if (rc != DSPMAP_OK) return rc;
+    slot[cur].want_host = want_host;
+    if (!pipelined || profiling || cv.size > 1) return frame_finish(cur);
+    if (prev != cur && slot[prev].inflight) {
+        rc = frame_finish(prev);
+        if (rc == DSPMAP_OK && slot[prev].want_host) rc = issue_result_copy(prev, copy_stream);
+        if (rc != DSPMAP_OK) { err = "frame " + std::to_string(slot[prev].T) + " (reported by the call that enqueued frame " + std::to_string(T) + "): " + err; return rc; }
+    }
+    return DSPMAP_OK;
+}
+
+int dspmap::drain() {
+    for (int k = 0; k < 2; ++k) {
+        const int s = (cur + 1 + k) & 1;      // older frame first
+        if (slot[s].inflight) { const int rc = frame_finish(s); if (rc != DSPMAP_OK) return rc; }
+    }
+    return DSPMAP_OK;
+}
+
+int dspmap::frame_enqueue(const float* d_depth, int rows, int cols, int stride, const dspmap_mask* masks, int n_masks, const double pos[3],
+                          const double quat[4], const dspmap_object_move* moves, int n_moves, const int32_t* remove_tracks, int n_remove,
+                          int want_free, int pre_decimated, const std::function<int(dspmap_mask*)>* late_masks, const std::function<int()>* late_depth) {
     // late_depth: the depth image is not on the device yet; the callback (host staging + H2D enqueue) runs after the vertex
     // mask and the object moves - which need the pose only - have been launched, so the GPU works while the host stages.
     // late_masks: the mask images are not on the device yet; the callback (host staging + H2D enqueue) runs after the
@@ -716,10 +782,16 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     // everything that can refuse the frame is checked BEFORE the time stamp, the ring or the store are touched
     if (n_moves > MAX_MOVES) return fail(DSPMAP_ERR_CAPACITY, "%d object moves in one frame (limit %d); nothing was changed", n_moves, MAX_MOVES);
     if (!comm_connected) return fail(DSPMAP_ERR_COMM, "sharded map: call dspmap_comm_connect on every rank before the first update");
-    host_result_valid = false;
     t_frame_begin = host_now_ms();
     T += 1;                                                       // :173
     f.T = T;
+    cur = (int)(T & 1u);
+    FrameSlot& sl = slot[cur];
+    sl.T = T; sl.host_result_valid = false; sl.want_host = false; sl.rc = DSPMAP_OK;
+    sl.want_free = want_free ? 1 : 0;
+    // the slot's result arrays may still be on their way to the host (frame T-2, pipelined): the emit pass waits for that copy
+    const bool wait_copy = sl.copy_issued;
+    sl.copy_issued = false;
     apply_params();
     if (!forgetting_init) {                                       // utils/basic_algorithms.h:32-48, built once
         for (int i = 0; i < 5; ++i) forget_tab[i] = (float)pow(2.5, -i / prm.forgetting_rate);
@@ -784,9 +856,9 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
 
     // ---- uploads -------------------------------------------------------------------------------------------
     if (stamps_dirty) {
-        uint32_t* s = p_stamps.p;
+        uint32_t* s = sl.p_stamps.p;
         for (int a = 0; a < 3; ++a) { memcpy(s, stamps[a].data(), stamps[a].size() * 4); s += stamps[a].size(); }
-        CU_TRY(this, cudaMemcpyAsync(d_stamps.p, p_stamps.p, (f.NX + f.NY + f.NZ) * 4, cudaMemcpyHostToDevice, stream));
+        CU_TRY(this, cudaMemcpyAsync(d_stamps.p, sl.p_stamps.p, (f.NX + f.NY + f.NZ) * 4, cudaMemcpyHostToDevice, stream));
         stamps_dirty = false;
     }
     CU_TRY(this, cudaMemsetAsync(d_cnt.p, 0, sizeof(Counters), stream));
@@ -840,7 +912,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
         // the reference has no limit on removals per frame (every unregistered detection is one): they are independent, so
         // they go MAX_MOVES at a time, the first batch together with the moves
         const int nb_now = std::max(1, ((int)rm_now.size() + MAX_MOVES - 1) / MAX_MOVES), nb_after = ((int)rm_after.size() + MAX_MOVES - 1) / MAX_MOVES;
-        CU_TRY(this, p_moves.reserve(nb_now + nb_after));
+        CU_TRY(this, sl.p_moves.reserve(nb_now + nb_after));
         if (d_moves.n < (size_t)(nb_now + nb_after)) { CU_TRY(this, cudaStreamSynchronize(stream)); CU_TRY(this, d_moves.alloc(nb_now + nb_after)); }
         int slot = 0;
         for (int b = 0; b < nb_now; ++b, ++slot) {
@@ -901,14 +973,14 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     std::vector<dspmap_mask> mask_copy(masks, masks + n_masks);
     if (late_masks) { const int rc = (*late_masks)(mask_copy.data()); if (rc != DSPMAP_OK) return rc; }
     if ((size_t)n_masks > d_masks.n) { CU_TRY(this, d_masks.alloc(n_masks)); }
-    CU_TRY(this, p_maskdesc.reserve(std::max(n_masks, 1)));
+    CU_TRY(this, sl.p_maskdesc.reserve(std::max(n_masks, 1)));
     for (int m = 0; m < n_masks; ++m) {
-        MaskDesc& md = p_maskdesc.p[m];
+        MaskDesc& md = sl.p_maskdesc.p[m];
         md.data = mask_copy[m].data; md.row_stride = mask_copy[m].row_stride; md.is_static = mask_copy[m].is_static;
         md.track_id = mask_copy[m].track_id; md.label_id = mask_copy[m].label_id;
         for (int a = 0; a < 3; ++a) { md.bbox_min[a] = mask_copy[m].bbox_min[a]; md.bbox_max[a] = mask_copy[m].bbox_max[a]; }
     }
-    if (n_masks) CU_TRY(this, cudaMemcpyAsync(d_masks.p, p_maskdesc.p, n_masks * sizeof(MaskDesc), cudaMemcpyHostToDevice, stream));
+    if (n_masks) CU_TRY(this, cudaMemcpyAsync(d_masks.p, sl.p_maskdesc.p, n_masks * sizeof(MaskDesc), cudaMemcpyHostToDevice, stream));
     ++launches; k_project<<<(npix + 255) / 256, 256, 0, stream>>>(fp, d_masks.p, d_static_track.p, d_static_label.p,
                                                      depth_int, d_cloud_pos.p, d_cloud_meta.p, d_cnt.p);
     if (profiling) cudaEventRecord(ev[4], stream);
@@ -962,7 +1034,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     }
     if (profiling) cudaEventRecord(ev[6], stream);
     // ---- O1 occupancy -------------------------------------------------------------------------------------------------
-    ResultArrays out{r_idx, r_xyz, r_w, r_track, r_label, r_state, r_free_idx, r_free_xyz, r_rgb};
+    const ResultArrays out = sl.dres;
     OccScratch osc{d_vstate.p, d_res_w.p - (slot_lo >> f.Pb), d_res_tl.p - (slot_lo >> f.Pb), d_mov_mask.p - (slot_lo >> f.Pb), d_blk_cnt.p, d_blk_off.p, d_chunk_tot.p, d_chunk_base.p, d_tile_list.p};
     CU_TRY(this, cudaMemsetAsync(d_blk_cnt.p, 0, (size_t)n_occ_blocks * sizeof(uint4), stream));
     if (profiling) cudaEventRecord(ev[8], stream);
@@ -973,6 +1045,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     ++launches;
     ++launches; k_occ_scan<<<n_occ_chunks, 1024, 0, stream>>>(osc, n_occ_blocks, d_cnt.p, d_persist.p, cv, T);
     barrier();   // the lower ranks' totals are this rank's base offsets
+    if (wait_copy) CU_TRY(this, cudaStreamWaitEvent(stream, sl.copy_done, 0));
     {
         const int use_list = n_occ_chunks > 1;
         const uint32_t emit_grid = use_list ? std::min<uint32_t>(n_occ_blocks, (uint32_t)sm_count * 8) : n_occ_blocks;
@@ -981,16 +1054,29 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     ++launches;
     barrier();   // rank 0 holds the whole result
     if (profiling) cudaEventRecord(ev[7], stream);
-    CU_TRY(this, cudaMemcpyAsync(p_cnt.p, d_cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-    if (cv.size > 1) CU_TRY(this, cudaMemcpyAsync(p_stamps.p + (f.NX + f.NY + f.NZ) + 1, d_counts, (size_t)MAX_RANKS * COMM_COUNTS * 4, cudaMemcpyDeviceToHost, stream));
+    CU_TRY(this, cudaMemcpyAsync(sl.p_cnt.p, d_cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+    if (cv.size > 1) CU_TRY(this, cudaMemcpyAsync(sl.p_stamps.p + (f.NX + f.NY + f.NZ) + 1, d_counts, (size_t)MAX_RANKS * COMM_COUNTS * 4, cudaMemcpyDeviceToHost, stream));
     CU_TRY(this, cudaGetLastError());
     static const bool trace_frame = getenv("DSPMAP_TRACE") != nullptr;
-    const double t_issued = trace_frame ? host_now_ms() : 0.0;
+    sl.t_issued = trace_frame ? host_now_ms() : 0.0;
+    sl.col_enabled = f.col_enabled;
+    sl.inflight = true;
+    if (trace_frame) trace_issue_ms += sl.t_issued - t_frame_begin;
+    return DSPMAP_OK;
+}
+
+// the end of a frame on the host: wait for its counter block, derive the statistics and the result size, report overflows
+int dspmap::frame_finish(int s) {
+    FrameSlot& sl = slot[s];
+    const FrameParams& f = fp;
+    const uint32_t T = sl.T;
+    static const bool trace_frame = getenv("DSPMAP_TRACE") != nullptr;
+    sl.inflight = false;
     if (cv.size == 1) {
         // The counter block is the frame's last transfer and carries the frame's stamp at both ends (set by the occupancy scan):
         // the host polls the pinned copy instead of going through a stream synchronisation - the wake-up is a cache miss, not a
         // driver call.  The stream is looked at now and then so that a failed launch ends the wait.
-        volatile Counters* pc = p_cnt.p;
+        volatile Counters* pc = sl.p_cnt.p;
         for (uint32_t spins = 0; pc->seq_head != T || pc->seq_tail != T; ++spins) {
             host_pause();
             if ((spins & 0x3fffu) == 0x3fffu && cudaStreamQuery(stream) != cudaErrorNotReady) break;
@@ -1000,26 +1086,26 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
         CU_TRY(this, cudaStreamSynchronize(stream));
     }
     if (trace_frame) {   // host time to issue the frame's launches vs time left waiting for the device afterwards
-        trace_issue_ms += t_issued - t_frame_begin; trace_wait_ms += host_now_ms() - t_issued;
+        trace_wait_ms += host_now_ms() - sl.t_issued;
         if ((T % 16) == 0) { fprintf(stderr, "[dspmap] frame %u: issue %.3f ms, wait %.3f ms (mean of 16)\n", T, trace_issue_ms / 16, trace_wait_ms / 16); trace_issue_ms = trace_wait_ms = 0; }
     }
-    last = *p_cnt.p;
+    last = *sl.p_cnt.p;
 
     stats.time_stamp = T;
     stats.n_swept_voxels = last.n_swept_voxels; stats.n_swept_nonempty = last.n_swept_nonempty;
     n_visible_last = last.n_visible;
     {   // global result size (rank 0 reads the whole list; the other ranks report their own share only)
-        const uint32_t* cc = p_stamps.p + (f.NX + f.NY + f.NZ) + 1;
+        const uint32_t* cc = sl.p_stamps.p + (f.NX + f.NY + f.NZ) + 1;
         uint32_t occ = 0, fre = 0;
         if (cv.size == 1) { occ = last.n_occupied; fre = last.n_free; }
         else for (int g = 0; g < cv.size; ++g) { occ += cc[g * COMM_COUNTS + CC_OCC]; fre += cc[g * COMM_COUNTS + CC_FREE]; }
-        result_n = cv.rank == 0 ? occ : 0; result_nf = cv.rank == 0 ? fre : 0;
-        n_occ_global = occ;
+        sl.result_n = cv.rank == 0 ? occ : 0; sl.result_nf = cv.rank == 0 ? fre : 0;
+        sl.n_occ_global = occ;
     }
-    if (last.comm_errors) return fail(DSPMAP_ERR_COMM, "a peer did not reach a barrier within the timeout");
+    if (last.comm_errors) return sl.rc = fail(DSPMAP_ERR_COMM, "a peer did not reach a barrier within the timeout");
     stats.n_visible = n_visible_last; stats.n_valid_points = last.n_valid_points;
     stats.n_born = last.n_born; stats.n_birth_voxels = last.n_birth_voxels; stats.n_resampled = last.n_resampled;
-    stats.n_occupied = n_occ_global; stats.n_nonempty_voxels = last.n_nonempty_voxels;
+    stats.n_occupied = sl.n_occ_global; stats.n_nonempty_voxels = last.n_nonempty_voxels;
     stats.n_moved = last.n_moved; stats.n_removed = last.n_removed;
     if (profiling) {
         // events: 0 start | 1 depth | 2 moves | 3 visibility | 4 project | 5 update | 6 birth | 7 occupancy
@@ -1032,40 +1118,52 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
         stats.ms_stage[4] = d45; stats.ms_stage[5] = d56; stats.ms_stage[6] = d67;
         cudaEventElapsedTime(&stats.ms_stage[7], ev[0], ev[7]);
     }
-    if (last.n_pairs > f.vis_cap) return fail(DSPMAP_ERR_CAPACITY, "visible-particle list overflow: %u > max_visible %u", last.n_pairs, f.vis_cap);
-    if (last.n_movable > sel_cap) return fail(DSPMAP_ERR_CAPACITY, "movable-particle list overflow: %u > %u", last.n_movable, sel_cap);
-    if (last.hash_overflow) return fail(DSPMAP_ERR_CAPACITY, "insertion hash table overflow");
+    if (last.n_pairs > f.vis_cap) return sl.rc = fail(DSPMAP_ERR_CAPACITY, "visible-particle list overflow: %u > max_visible %u", last.n_pairs, f.vis_cap);
+    if (last.n_movable > sel_cap) return sl.rc = fail(DSPMAP_ERR_CAPACITY, "movable-particle list overflow: %u > %u", last.n_movable, sel_cap);
+    if (last.hash_overflow) return sl.rc = fail(DSPMAP_ERR_CAPACITY, "insertion hash table overflow");
     return DSPMAP_OK;
 }
 
-int dspmap::fetch_result_to_host() {
-    if (host_result_valid) return DSPMAP_OK;
+// enqueues the device->host transfer of slot s's result (its frame has finished) on `on` and records the slot's copy_done event
+int dspmap::issue_result_copy(int s, cudaStream_t on) {
+    FrameSlot& sl = slot[s];
+    if (sl.copy_issued || sl.host_result_valid) return DSPMAP_OK;
     // pinned result buffers grow in big steps (cudaMallocHost takes milliseconds: not something to do every few frames)
     const size_t grain = (size_t)1 << 18;
-    const size_t n = result_n, nf = fp.want_free ? result_nf : 0;
+    const size_t n = sl.result_n, nf = sl.want_free ? sl.result_nf : 0;
     const size_t n_cap = (std::max<size_t>(n, 1) + grain - 1) / grain * grain;
-    CU_TRY(this, hr_idx.reserve(n_cap)); CU_TRY(this, hr_xyz.reserve(3 * n_cap));
-    CU_TRY(this, hr_w.reserve(n_cap)); CU_TRY(this, hr_track.reserve(n_cap));
-    CU_TRY(this, hr_label.reserve(n_cap)); CU_TRY(this, hr_state.reserve(n_cap));
-    CU_TRY(this, hr_rgb.reserve(3 * n_cap));
+    CU_TRY(this, sl.hr_idx.reserve(n_cap)); CU_TRY(this, sl.hr_xyz.reserve(3 * n_cap));
+    CU_TRY(this, sl.hr_w.reserve(n_cap)); CU_TRY(this, sl.hr_track.reserve(n_cap));
+    CU_TRY(this, sl.hr_label.reserve(n_cap)); CU_TRY(this, sl.hr_state.reserve(n_cap));
+    CU_TRY(this, sl.hr_rgb.reserve(3 * n_cap));
+    const ResultArrays& r = sl.dres;
     if (n) {
-        CU_TRY(this, cudaMemcpyAsync(hr_idx.p, r_idx, n * 4, cudaMemcpyDeviceToHost, stream));
-        CU_TRY(this, cudaMemcpyAsync(hr_xyz.p, r_xyz, n * 12, cudaMemcpyDeviceToHost, stream));
-        CU_TRY(this, cudaMemcpyAsync(hr_w.p, r_w, n * 4, cudaMemcpyDeviceToHost, stream));
-        CU_TRY(this, cudaMemcpyAsync(hr_track.p, r_track, n * 2, cudaMemcpyDeviceToHost, stream));
-        CU_TRY(this, cudaMemcpyAsync(hr_label.p, r_label, n, cudaMemcpyDeviceToHost, stream));
-        CU_TRY(this, cudaMemcpyAsync(hr_state.p, r_state, n, cudaMemcpyDeviceToHost, stream));
-        if (fp.col_enabled) CU_TRY(this, cudaMemcpyAsync(hr_rgb.p, r_rgb, 3 * n, cudaMemcpyDeviceToHost, stream));
-        else memset(hr_rgb.p, 0, 3 * n);
+        CU_TRY(this, cudaMemcpyAsync(sl.hr_idx.p, r.voxel_index, n * 4, cudaMemcpyDeviceToHost, on));
+        CU_TRY(this, cudaMemcpyAsync(sl.hr_xyz.p, r.xyz, n * 12, cudaMemcpyDeviceToHost, on));
+        CU_TRY(this, cudaMemcpyAsync(sl.hr_w.p, r.weight_sum, n * 4, cudaMemcpyDeviceToHost, on));
+        CU_TRY(this, cudaMemcpyAsync(sl.hr_track.p, r.track_id, n * 2, cudaMemcpyDeviceToHost, on));
+        CU_TRY(this, cudaMemcpyAsync(sl.hr_label.p, r.label_id, n, cudaMemcpyDeviceToHost, on));
+        CU_TRY(this, cudaMemcpyAsync(sl.hr_state.p, r.state, n, cudaMemcpyDeviceToHost, on));
+        if (sl.col_enabled) CU_TRY(this, cudaMemcpyAsync(sl.hr_rgb.p, r.rgb, 3 * n, cudaMemcpyDeviceToHost, on));
+        else memset(sl.hr_rgb.p, 0, 3 * n);
     }
     if (nf) {
         const size_t nf_cap = (nf + grain - 1) / grain * grain;
-        CU_TRY(this, hr_free_idx.reserve(nf_cap)); CU_TRY(this, hr_free_xyz.reserve(3 * nf_cap));
-        CU_TRY(this, cudaMemcpyAsync(hr_free_idx.p, r_free_idx, nf * 4, cudaMemcpyDeviceToHost, stream));
-        CU_TRY(this, cudaMemcpyAsync(hr_free_xyz.p, r_free_xyz, nf * 12, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(this, sl.hr_free_idx.reserve(nf_cap)); CU_TRY(this, sl.hr_free_xyz.reserve(3 * nf_cap));
+        CU_TRY(this, cudaMemcpyAsync(sl.hr_free_idx.p, r.free_voxel_index, nf * 4, cudaMemcpyDeviceToHost, on));
+        CU_TRY(this, cudaMemcpyAsync(sl.hr_free_xyz.p, r.free_xyz, nf * 12, cudaMemcpyDeviceToHost, on));
     }
-    CU_TRY(this, cudaStreamSynchronize(stream));
-    host_result_valid = true;
+    CU_TRY(this, cudaEventRecord(sl.copy_done, on));
+    sl.copy_issued = true;
+    return DSPMAP_OK;
+}
+
+int dspmap::fetch_result_to_host(int s) {
+    FrameSlot& sl = slot[s];
+    if (sl.host_result_valid) return DSPMAP_OK;
+    if (!sl.copy_issued) { const int rc = issue_result_copy(s, stream); if (rc != DSPMAP_OK) return rc; }
+    CU_TRY(this, cudaEventSynchronize(sl.copy_done));
+    sl.host_result_valid = true;
     return DSPMAP_OK;
 }
 
@@ -1093,7 +1191,9 @@ int dspmap_create(const dspmap_config* cfg, dspmap_t** out) {
 void dspmap_destroy(dspmap_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    h->drain();
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     h->release_all();
     delete h;
 }
@@ -1101,6 +1201,8 @@ void dspmap_destroy(dspmap_t* h) {
 int dspmap_clear(dspmap_t* h) {
     if (!h) return DSPMAP_ERR_INVALID_ARG;
     CU_TRY(h, cudaSetDevice(h->device));
+    h->drain();          // a frame that failed is cleared like any other
+    CU_TRY(h, cudaStreamSynchronize(h->copy_stream));
     return h->clear_device();
 }
 
@@ -1118,6 +1220,7 @@ int dspmap_set_label_luts(dspmap_t* h, const uint16_t static_value_to_track[256]
                           const uint8_t* static_labels, int32_t n_static, uint16_t max_movable_track, uint16_t sky_track) {
     if (!h || !static_value_to_track || n_static < 0 || (n_static > 0 && (!static_tracks || !static_labels))) return DSPMAP_ERR_INVALID_ARG;
     CU_TRY(h, cudaSetDevice(h->device));
+    { const int rc = h->drain(); if (rc != DSPMAP_OK) return rc; }      // a pipelined frame may still read the tables
     memcpy(h->h_static_track, static_value_to_track, 256 * sizeof(uint16_t));
     std::fill(h->h_static_label.begin(), h->h_static_label.end(), (uint8_t)0);
     for (int i = 0; i < n_static; ++i) h->h_static_label[static_tracks[i]] = static_labels[i];
@@ -1131,6 +1234,7 @@ int dspmap_set_label_luts(dspmap_t* h, const uint16_t static_value_to_track[256]
 int dspmap_set_random_table(dspmap_t* h, const float* table, uint32_t n) {
     if (!h || !table || n < 1) return DSPMAP_ERR_INVALID_ARG;
     CU_TRY(h, cudaSetDevice(h->device));
+    { const int rc = h->drain(); if (rc != DSPMAP_OK) return rc; }
     CU_TRY(h, h->d_randoms.alloc(n));
     CU_TRY(h, cudaMemcpy(h->d_randoms.p, table, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
     h->rand_n = n;
@@ -1141,6 +1245,7 @@ int dspmap_set_colors(dspmap_t* h, const dspmap_colors* c) {
     if (!h || !c) return DSPMAP_ERR_INVALID_ARG;
     if (c->scheme != 0 && c->scheme != 1 && c->scheme != 3) return h->fail(DSPMAP_ERR_INVALID_ARG, "colour scheme %d (0, 1 or 3)", c->scheme);
     CU_TRY(h, cudaSetDevice(h->device));
+    { const int rc = h->drain(); if (rc != DSPMAP_OK) return rc; }
     h->colors = *c;
     uint8_t tab[1024];
     memcpy(tab, c->label_bgr, 768);
@@ -1167,24 +1272,56 @@ static int check_frame_args(dspmap_t* h, const float* depth, int32_t rows, int32
     return DSPMAP_OK;
 }
 
-int dspmap_update_device(dspmap_t* h, const float* d_depth, int32_t rows, int32_t cols, int32_t row_stride, const dspmap_mask* masks,
-                         int32_t n_masks, const double position[3], const double orientation_wxyz[4], const dspmap_object_move* moves,
-                         int32_t n_moves, const int32_t* remove_tracks, int32_t n_remove, int32_t want_freespace) {
+// pipelined frames need a second set of result arrays: frame t's emit pass must not write where frame t-1's transfer reads
+static int ensure_pipelined(dspmap_t* h) {
+    if (h->cfg.shard_count > 1 || h->result2.p) return DSPMAP_OK;      // sharded maps run their frames synchronously
+    CU_TRY(h, h->result2.alloc(h->lay.total - h->lay.r_idx));
+    h->slot[1].dres = h->result_arrays_at(h->result2.p, h->lay.r_idx);
+    return DSPMAP_OK;
+}
+
+static int update_device_impl(dspmap_t* h, const float* d_depth, int32_t rows, int32_t cols, int32_t row_stride, const dspmap_mask* masks,
+                              int32_t n_masks, const double position[3], const double orientation_wxyz[4], const dspmap_object_move* moves,
+                              int32_t n_moves, const int32_t* remove_tracks, int32_t n_remove, int32_t want_freespace, bool pipelined, uint32_t* ticket) {
     int rc = check_frame_args(h, d_depth, rows, cols, row_stride, masks, n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove);
     if (rc != DSPMAP_OK) return rc;
     CU_TRY(h, cudaSetDevice(h->device));
-    return h->frame(d_depth, rows, cols, row_stride, masks, n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove, want_freespace, 0);
+    if (pipelined && (rc = ensure_pipelined(h)) != DSPMAP_OK) return rc;
+    const uint32_t t_before = h->T;
+    rc = h->frame(d_depth, rows, cols, row_stride, masks, n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove, want_freespace, 0,
+                  nullptr, nullptr, pipelined, false);
+    if (ticket) *ticket = h->T != t_before ? h->T : 0;
+    return rc;
 }
 
+int dspmap_update_device(dspmap_t* h, const float* d_depth, int32_t rows, int32_t cols, int32_t row_stride, const dspmap_mask* masks,
+                         int32_t n_masks, const double position[3], const double orientation_wxyz[4], const dspmap_object_move* moves,
+                         int32_t n_moves, const int32_t* remove_tracks, int32_t n_remove, int32_t want_freespace) {
+    return update_device_impl(h, d_depth, rows, cols, row_stride, masks, n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove, want_freespace, false, nullptr);
+}
 
-int dspmap_update(dspmap_t* h, const float* depth, int32_t rows, int32_t cols, int32_t row_stride, const dspmap_mask* masks,
-                  int32_t n_masks, const double position[3], const double orientation_wxyz[4], const dspmap_object_move* moves,
-                  int32_t n_moves, const int32_t* remove_tracks, int32_t n_remove, int32_t want_freespace) {
+int dspmap_update_device_async(dspmap_t* h, const float* d_depth, int32_t rows, int32_t cols, int32_t row_stride, const dspmap_mask* masks,
+                               int32_t n_masks, const double position[3], const double orientation_wxyz[4], const dspmap_object_move* moves,
+                               int32_t n_moves, const int32_t* remove_tracks, int32_t n_remove, int32_t want_freespace, uint32_t* ticket) {
+    if (!ticket) return DSPMAP_ERR_INVALID_ARG;
+    *ticket = 0;
+    return update_device_impl(h, d_depth, rows, cols, row_stride, masks, n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove, want_freespace, true, ticket);
+}
+
+static int update_host_impl(dspmap_t* h, const float* depth, int32_t rows, int32_t cols, int32_t row_stride, const dspmap_mask* masks,
+                            int32_t n_masks, const double position[3], const double orientation_wxyz[4], const dspmap_object_move* moves,
+                            int32_t n_moves, const int32_t* remove_tracks, int32_t n_remove, int32_t want_freespace, bool pipelined, uint32_t* ticket) {
     static const bool trace = getenv("DSPMAP_TRACE") != nullptr;
     const double t_a = trace ? host_now_ms() : 0.0;
     int rc = check_frame_args(h, depth, rows, cols, row_stride, masks, n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove);
     if (rc != DSPMAP_OK) return rc;
     CU_TRY(h, cudaSetDevice(h->device));
+    if (pipelined && (rc = ensure_pipelined(h)) != DSPMAP_OK) return rc;
+    if (!pipelined || h->profiling || h->cfg.shard_count > 1) { if ((rc = h->drain()) != DSPMAP_OK) return rc; }
+    // the pinned staging buffers of the frame's slot: free since the frame two back finished
+    dspmap::FrameSlot& sl = h->slot[h->next_slot()];
+    if (sl.inflight && (rc = h->frame_finish(h->next_slot())) != DSPMAP_OK) return rc;
+    const uint32_t t_before = h->T;
     // Stage the caller's (pageable) images through pinned memory.  Under BOOST_MODE the nearest 1/2 resize of
     // manualResize (pointcloud_tools.h:1104-1133: src = (int)(i * 2.0f), clamped) is applied while staging, so only the
     // quarter of the pixels the map will read crosses PCIe; K1 then reads the staged image 1:1 (same source pixels).
@@ -1193,10 +1330,10 @@ int dspmap_update(dspmap_t* h, const float* depth, int32_t rows, int32_t cols, i
     const size_t npix = (size_t)srows * scols;
     std::vector<int> src_col(scols);
     for (int j = 0; j < scols; ++j) src_col[j] = f.boost ? std::min((int)((float)j * 2.0f), cols - 1) : j;
-    CU_TRY(h, h->p_depth.reserve(npix));
+    CU_TRY(h, sl.p_depth.reserve(npix));
     std::vector<dspmap_mask> dm(masks, masks + n_masks);
     if (n_masks) {
-        CU_TRY(h, h->p_masks.reserve(npix * n_masks));
+        CU_TRY(h, sl.p_masks.reserve(npix * n_masks));
         if (h->d_mask_in.n < npix * n_masks) CU_TRY(h, h->d_mask_in.alloc(npix * n_masks));
     }
     if (!h->stage_pool) {
@@ -1242,8 +1379,8 @@ int dspmap_update(dspmap_t* h, const float* depth, int32_t rows, int32_t cols, i
     // and even the depth is staged only after the pose-only work (vertex mask, object moves) has been launched
     const std::function<int()> late_depth = [&]() -> int {
         const int depth_parts = 8;
-        h->stage_pool->run(depth_parts, [&](int t) { stage_rows(h->p_depth.p, depth, row_stride, srows * t / depth_parts, srows * (t + 1) / depth_parts); });
-        CU_TRY(h, cudaMemcpyAsync(h->d_depth_in.p, h->p_depth.p, npix * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        h->stage_pool->run(depth_parts, [&](int t) { stage_rows(sl.p_depth.p, depth, row_stride, srows * t / depth_parts, srows * (t + 1) / depth_parts); });
+        CU_TRY(h, cudaMemcpyAsync(h->d_depth_in.p, sl.p_depth.p, npix * sizeof(float), cudaMemcpyHostToDevice, h->stream));
         return DSPMAP_OK;
     };
     const std::function<int(dspmap_mask*)> late_masks = [&](dspmap_mask* dmv) -> int {
@@ -1251,49 +1388,100 @@ int dspmap_update(dspmap_t* h, const float* depth, int32_t rows, int32_t cols, i
         const int parts = 2;   // row blocks per mask: enough tasks to keep every helper busy
         h->stage_pool->run(n_masks * parts, [&](int t) {
             const int m = t / parts, b = t % parts;
-            stage_rows(h->p_masks.p + (size_t)m * npix, masks[m].data, masks[m].row_stride, srows * b / parts, srows * (b + 1) / parts);
+            stage_rows(sl.p_masks.p + (size_t)m * npix, masks[m].data, masks[m].row_stride, srows * b / parts, srows * (b + 1) / parts);
         });
         for (int m = 0; m < n_masks; ++m) { dmv[m].data = h->d_mask_in.p + (size_t)m * npix; dmv[m].row_stride = scols; }
-        CU_TRY(h, cudaMemcpyAsync(h->d_mask_in.p, h->p_masks.p, npix * n_masks, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaMemcpyAsync(h->d_mask_in.p, sl.p_masks.p, npix * n_masks, cudaMemcpyHostToDevice, h->stream));
         return DSPMAP_OK;
     };
     const double t_b = trace ? host_now_ms() : 0.0;
     rc = h->frame(h->d_depth_in.p, rows, cols, scols, dm.data(), n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove,
-                  want_freespace, f.boost ? 1 : 0, &late_masks, &late_depth);
+                  want_freespace, f.boost ? 1 : 0, &late_masks, &late_depth, pipelined, true);
+    if (ticket) *ticket = h->T != t_before ? h->T : 0;
     if (rc != DSPMAP_OK) return rc;
     const double t_c = trace ? host_now_ms() : 0.0;
-    rc = h->fetch_result_to_host();
+    if (!h->slot[h->cur].inflight) rc = h->fetch_result_to_host(h->cur);      // synchronous frame: the result is on the host on return
     if (trace && (h->T % 16) == 0)
         fprintf(stderr, "[dspmap] frame %u: stage+h2d-enqueue %.3f ms, frame (launch+sync) %.3f ms, result d2h %.3f ms\n", h->T, t_b - t_a, t_c - t_b,
                 host_now_ms() - t_c);
     return rc;
 }
 
+int dspmap_update(dspmap_t* h, const float* depth, int32_t rows, int32_t cols, int32_t row_stride, const dspmap_mask* masks,
+                  int32_t n_masks, const double position[3], const double orientation_wxyz[4], const dspmap_object_move* moves,
+                  int32_t n_moves, const int32_t* remove_tracks, int32_t n_remove, int32_t want_freespace) {
+    return update_host_impl(h, depth, rows, cols, row_stride, masks, n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove, want_freespace, false, nullptr);
+}
+
+int dspmap_update_async(dspmap_t* h, const float* depth, int32_t rows, int32_t cols, int32_t row_stride, const dspmap_mask* masks,
+                        int32_t n_masks, const double position[3], const double orientation_wxyz[4], const dspmap_object_move* moves,
+                        int32_t n_moves, const int32_t* remove_tracks, int32_t n_remove, int32_t want_freespace, uint32_t* ticket) {
+    if (!ticket) return DSPMAP_ERR_INVALID_ARG;
+    *ticket = 0;
+    return update_host_impl(h, depth, rows, cols, row_stride, masks, n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove, want_freespace, true, ticket);
+}
+
+static void fill_result(const dspmap::FrameSlot& sl, bool host, dspmap_result* out) {
+    out->count = sl.result_n;
+    out->free_count = sl.want_free ? sl.result_nf : 0;
+    if (host) {
+        out->voxel_index = sl.hr_idx.p; out->xyz = sl.hr_xyz.p; out->weight_sum = sl.hr_w.p; out->track_id = sl.hr_track.p;
+        out->label_id = sl.hr_label.p; out->state = sl.hr_state.p; out->free_voxel_index = sl.hr_free_idx.p; out->free_xyz = sl.hr_free_xyz.p;
+        out->rgb = sl.hr_rgb.p;
+    } else {
+        const ResultArrays& r = sl.dres;
+        out->voxel_index = r.voxel_index; out->xyz = r.xyz; out->weight_sum = r.weight_sum; out->track_id = r.track_id;
+        out->label_id = r.label_id; out->state = r.state; out->free_voxel_index = r.free_voxel_index; out->free_xyz = r.free_xyz;
+        out->rgb = r.rgb;
+    }
+}
+
+int dspmap_wait_result(dspmap_t* h, uint32_t ticket, dspmap_result* out) {
+    if (!h || !out) return DSPMAP_ERR_INVALID_ARG;
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int s = (int)(ticket & 1u);
+    dspmap::FrameSlot& sl = h->slot[s];
+    if (ticket == 0 || sl.T != ticket) return h->fail(DSPMAP_ERR_INVALID_ARG, "frame %u is not held any more (a result lives until two more frames have been submitted)", ticket);
+    if (sl.inflight) {
+        if (s == h->cur && h->slot[s ^ 1].inflight) { const int rc = h->frame_finish(s ^ 1); if (rc != DSPMAP_OK) return rc; }   // older frame first
+        const int rc = h->frame_finish(s);
+        if (rc != DSPMAP_OK) return rc;
+    }
+    if (sl.rc != DSPMAP_OK) return h->fail(sl.rc, "frame %u failed (reported when it finished)", ticket);
+    if (sl.want_host) {
+        if (!sl.copy_issued && !sl.host_result_valid) { const int rc = h->issue_result_copy(s, h->copy_stream); if (rc != DSPMAP_OK) return rc; }
+        const int rc = h->fetch_result_to_host(s);
+        if (rc != DSPMAP_OK) return rc;
+    }
+    fill_result(sl, sl.want_host, out);
+    return DSPMAP_OK;
+}
+
 int dspmap_get_result(dspmap_t* h, dspmap_result* out) {
     if (!h || !out) return DSPMAP_ERR_INVALID_ARG;
     CU_TRY(h, cudaSetDevice(h->device));
-    const int rc = h->fetch_result_to_host();
+    int rc = h->drain();
     if (rc != DSPMAP_OK) return rc;
-    out->count = h->result_n;
-    out->free_count = h->fp.want_free ? h->result_nf : 0;
-    out->voxel_index = h->hr_idx.p; out->xyz = h->hr_xyz.p; out->weight_sum = h->hr_w.p; out->track_id = h->hr_track.p;
-    out->label_id = h->hr_label.p; out->state = h->hr_state.p; out->free_voxel_index = h->hr_free_idx.p; out->free_xyz = h->hr_free_xyz.p;
-    out->rgb = h->hr_rgb.p;
+    rc = h->fetch_result_to_host(h->cur);
+    if (rc != DSPMAP_OK) return rc;
+    fill_result(h->slot[h->cur], true, out);
     return DSPMAP_OK;
 }
 
 int dspmap_get_result_device(dspmap_t* h, dspmap_result* out) {
     if (!h || !out) return DSPMAP_ERR_INVALID_ARG;
-    out->count = h->result_n;
-    out->free_count = h->fp.want_free ? h->result_nf : 0;
-    out->voxel_index = h->r_idx; out->xyz = h->r_xyz; out->weight_sum = h->r_w; out->track_id = h->r_track;
-    out->label_id = h->r_label; out->state = h->r_state; out->free_voxel_index = h->r_free_idx; out->free_xyz = h->r_free_xyz;
-    out->rgb = h->r_rgb;
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int rc = h->drain();
+    if (rc != DSPMAP_OK) return rc;
+    fill_result(h->slot[h->cur], false, out);
     return DSPMAP_OK;
 }
 
 int dspmap_get_stats(dspmap_t* h, dspmap_frame_stats* out) {
     if (!h || !out) return DSPMAP_ERR_INVALID_ARG;
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int rc = h->drain();
+    if (rc != DSPMAP_OK) return rc;
     *out = h->stats;
     return DSPMAP_OK;
 }
@@ -1307,6 +1495,7 @@ int dspmap_set_profiling(dspmap_t* h, int32_t on) {
 int dspmap_set_stream(dspmap_t* h, void* cuda_stream) {
     if (!h) return DSPMAP_ERR_INVALID_ARG;
     CU_TRY(h, cudaSetDevice(h->device));
+    { const int rc = h->drain(); if (rc != DSPMAP_OK) return rc; }
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
     return DSPMAP_OK;
@@ -1321,6 +1510,7 @@ int dspmap_get_launch_count(dspmap_t* h, uint64_t* count) {
 int dspmap_object_particle_count(dspmap_t* h, int32_t track_id, uint32_t* count) {
     if (!h || !count) return DSPMAP_ERR_INVALID_ARG;
     CU_TRY(h, cudaSetDevice(h->device));
+    { const int rc = h->drain(); if (rc != DSPMAP_OK) return rc; }
     CU_TRY(h, cudaMemsetAsync(&h->d_cnt.p->scratch, 0, sizeof(uint32_t), h->stream));
     ++h->launches; k_count_track<<<h->sm_count * 8, 256, 0, h->stream>>>(Store{h->sx.p, h->sy.p, h->sz.p, h->sw.p, h->smeta.p, h->shdr.p}, h->v_local, (uint32_t)h->fp.Pb, (uint32_t)track_id & 0xffffu, &h->d_cnt.p->scratch);
     CU_TRY(h, cudaMemcpyAsync(count, &h->d_cnt.p->scratch, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -1390,6 +1580,7 @@ int dspmap_selftest_colour(dspmap_t* h, uint32_t* rgb_to_hsv, uint32_t* hsv_to_r
 int dspmap_dump(dspmap_t* h, int32_t what, void* dst, size_t cap, size_t* n_bytes) {
     if (!h) return DSPMAP_ERR_INVALID_ARG;
     CU_TRY(h, cudaSetDevice(h->device));
+    { const int rc = h->drain(); if (rc != DSPMAP_OK) return rc; }
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     const FrameParams& f = h->fp;
     const size_t npix = (size_t)f.W * f.H;

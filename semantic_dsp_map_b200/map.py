@@ -173,20 +173,35 @@ class Engine:
         rm = np.asarray(remove_tracks if len(remove_tracks) else (0,), np.int32)
         pose = np.empty(7, np.float64)
         pose[:3], pose[3:] = position, orientation
-        rc = self._fn(fn_name)(self._h, depth_ptr, rows, cols, stride, C.cast(marr.ctypes.data, C.POINTER(_capi.Mask)), n_masks,
-                               C.cast(pose.ctypes.data, C.POINTER(C.c_double)), C.cast(pose.ctypes.data + 24, C.POINTER(C.c_double)),
-                               C.cast(mvarr.ctypes.data, C.POINTER(_capi.ObjectMove)), n_moves,
-                               C.cast(rm.ctypes.data, C.POINTER(C.c_int32)), len(remove_tracks), int(bool(want_freespace)))
-        self.check(rc, "dspmap_" + fn_name)
+        args = (self._h, depth_ptr, rows, cols, stride, C.cast(marr.ctypes.data, C.POINTER(_capi.Mask)), n_masks,
+                C.cast(pose.ctypes.data, C.POINTER(C.c_double)), C.cast(pose.ctypes.data + 24, C.POINTER(C.c_double)),
+                C.cast(mvarr.ctypes.data, C.POINTER(_capi.ObjectMove)), n_moves,
+                C.cast(rm.ctypes.data, C.POINTER(C.c_int32)), len(remove_tracks), int(bool(want_freespace)))
+        if fn_name.endswith("_async"):      # pipelined frame (dspmap_c.h): returns the frame's ticket
+            ticket = C.c_uint32()
+            self.pending_ticket = 0
+            rc = self._fn(fn_name)(*args, C.byref(ticket))
+            if rc != _capi.DSPMAP_OK and ticket.value:
+                # this frame IS enqueued; the error belongs to the frame before it (found when its counters were read)
+                self.pending_ticket = ticket.value
+            self.check(rc, "dspmap_" + fn_name)
+            return ticket.value
+        self.check(self._fn(fn_name)(*args), "dspmap_" + fn_name)
 
     def result(self, device=False) -> _capi.Result:
         r = _capi.Result()
         self.check(self._fn("get_result_device" if device else "get_result")(self._h, C.byref(r)), "dspmap_get_result")
         return r
 
-    def result_arrays(self, copy=True) -> OccupancyResult:
+    def wait_result(self, ticket, copy=True) -> OccupancyResult:
+        """Result of the pipelined frame `ticket` (dspmap_wait_result); copy=False: views valid until two more frames."""
+        r = _capi.Result()
+        self.check(self._fn("wait_result")(self._h, ticket, C.byref(r)), "dspmap_wait_result")
+        return self.result_arrays(copy, r)
+
+    def result_arrays(self, copy=True, r=None) -> OccupancyResult:
         """copy=False returns views of the handle's pinned host buffers, valid until the next update (dspmap_c.h)."""
-        r = self.result()
+        r = r or self.result()
         n, nf = r.count, r.free_count
         return OccupancyResult(
             _as_array(r.voxel_index, n, np.uint32, None, copy), _as_array(r.xyz, n, np.float32, (n, 3), copy),
@@ -413,14 +428,9 @@ class SemanticDSPMap:
                             bbox_min=(mn - 1.0).tolist(), bbox_max=(mx + 1.0).tolist(), rows=mask.shape[0], cols=mask.shape[1]))
         return out
 
-    # -- semantic_dsp_map.h:170-251 -----------------------------------------------------------------------------------------
-    def update(self, depth_value_mat: np.ndarray, ins_seg_result: Sequence[MaskKpts], camera_position, camera_orientation,
-               if_get_freespace: bool = False, time_stamp_double: float = 0.0, moves=None, remove_tracks=(),
-               copy_result: bool = True) -> OccupancyResult:
-        """One frame.  ``camera_orientation`` is (w, x, y, z).  With ``moves=None`` (default) the object layer of the
-        reference (objectLevelUpdate) runs on the host from the masks' key points and ``time_stamp_double``, like in the
-        reference.  A caller with an object layer of their own passes ``moves`` = [(track_id, 4x4)] and ``remove_tracks`` =
-        [track_id] instead (an empty list = "no object moves this frame")."""
+    def _prepare_frame(self, depth_value_mat, ins_seg_result, camera_position, camera_orientation, time_stamp_double, moves, remove_tracks):
+        """The host part of update() before the engine call: argument checks, mask descriptors, the object layer, the
+        floating-object rule (semantic_dsp_map.h:176-190, 306-566, 712-737)."""
         depth = np.asarray(depth_value_mat)
         if depth.dtype != np.float32 or depth.ndim != 2:
             raise TypeError("depth must be a 2-D float32 array (CV_32FC1, metres)")
@@ -435,6 +445,18 @@ class SemanticDSPMap:
             remove_tracks = list(remove_tracks) + dropped
         saved = (set(self._born_tracks), set(self._known_objects), set(self._met_labels))
         remove_tracks = list(remove_tracks) + self._floating_tracks(ins_seg_result, moves, remove_tracks, camera_position, builtin)
+        return depth, masks, moves, remove_tracks, saved
+
+    # -- semantic_dsp_map.h:170-251 -----------------------------------------------------------------------------------------
+    def update(self, depth_value_mat: np.ndarray, ins_seg_result: Sequence[MaskKpts], camera_position, camera_orientation,
+               if_get_freespace: bool = False, time_stamp_double: float = 0.0, moves=None, remove_tracks=(),
+               copy_result: bool = True) -> OccupancyResult:
+        """One frame.  ``camera_orientation`` is (w, x, y, z).  With ``moves=None`` (default) the object layer of the
+        reference (objectLevelUpdate) runs on the host from the masks' key points and ``time_stamp_double``, like in the
+        reference.  A caller with an object layer of their own passes ``moves`` = [(track_id, 4x4)] and ``remove_tracks`` =
+        [track_id] instead (an empty list = "no object moves this frame")."""
+        depth, masks, moves, remove_tracks, saved = self._prepare_frame(depth_value_mat, ins_seg_result, camera_position, camera_orientation,
+                                                                        time_stamp_double, moves, remove_tracks)
         try:
             self.engine.update_raw("update", depth.ctypes.data, depth.shape[0], depth.shape[1], depth.strides[0] // 4, masks,
                                    camera_position, camera_orientation, moves, remove_tracks, if_get_freespace)
@@ -444,3 +466,22 @@ class SemanticDSPMap:
             self._born_tracks, self._known_objects, self._met_labels = saved
             raise
         return self.engine.result_arrays(copy_result)
+
+    def update_async(self, depth_value_mat: np.ndarray, ins_seg_result: Sequence[MaskKpts], camera_position, camera_orientation,
+                     if_get_freespace: bool = False, time_stamp_double: float = 0.0, moves=None, remove_tracks=()) -> int:
+        """Not in the reference's API: update() with a deferred hand-over (dspmap_update_async, include/dspmap_c.h).  Stages
+        and enqueues this frame and returns its ticket while it runs; ``wait_result(ticket)`` gives what ``update()`` would
+        have returned.  Calling it for frame t+1 before ``wait_result(t)`` lets frame t's device->host transfer overlap
+        frame t+1's kernels.  Results, order of operations on the map and the host object layer are those of update()."""
+        depth, masks, moves, remove_tracks, saved = self._prepare_frame(depth_value_mat, ins_seg_result, camera_position, camera_orientation,
+                                                                        time_stamp_double, moves, remove_tracks)
+        try:
+            return self.engine.update_raw("update_async", depth.ctypes.data, depth.shape[0], depth.shape[1], depth.strides[0] // 4, masks,
+                                          camera_position, camera_orientation, moves, remove_tracks, if_get_freespace)
+        except _capi.DspMapError:
+            if not getattr(self.engine, "pending_ticket", 0):      # the frame itself was refused (not: an earlier frame failed)
+                self._born_tracks, self._known_objects, self._met_labels = saved
+            raise
+
+    def wait_result(self, ticket: int, copy_result: bool = True) -> OccupancyResult:
+        return self.engine.wait_result(ticket, copy_result)
