@@ -235,8 +235,7 @@ struct dspmap {
     DevBuf<MaskDesc> d_masks;
     DevBuf<MoveTable> d_moves;
     // images
-    DevBuf<float> d_depth_in, d_depth_int;
-    DevBuf<uint8_t> d_mask_in;
+    DevBuf<float> d_depth_int;
     DevBuf<float4> d_cloud_pos;
     DevBuf<uint32_t> d_cloud_meta, d_pix_count, d_pix_offset, d_scan_block;
     // visibility
@@ -297,6 +296,10 @@ struct dspmap {
         PinBuf<uint16_t> hr_track;
         PinBuf<uint8_t> hr_label, hr_rgb;
         PinBuf<int8_t> hr_state;
+        DevBuf<float> d_depth_in;          // where dspmap_update uploads the frame's images (on the upload stream, so that
+        DevBuf<uint8_t> d_mask_in;         // frame t+1's images travel while frame t's kernels run)
+        cudaEvent_t up_depth = nullptr, up_masks = nullptr;
+        cudaEvent_t tr_begin = nullptr, tr_end = nullptr;   // DSPMAP_TRACE: the frame's first and last operation on the main stream
         ResultArrays dres{};               // this slot's result arrays on the device
         cudaEvent_t copy_done = nullptr;   // the device->host transfer of this slot's result
         bool copy_issued = false;          // ... has been enqueued since the slot's frame finished
@@ -312,12 +315,14 @@ struct dspmap {
             p_depth.release(); p_masks.release(); p_cnt.release(); p_stamps.release(); p_maskdesc.release(); p_moves.release();
             hr_idx.release(); hr_free_idx.release(); hr_xyz.release(); hr_w.release(); hr_free_xyz.release(); hr_track.release();
             hr_label.release(); hr_rgb.release(); hr_state.release();
-            if (copy_done) { cudaEventDestroy(copy_done); copy_done = nullptr; }
+            d_depth_in.release(); d_mask_in.release();
+            for (cudaEvent_t* e : {&copy_done, &up_depth, &up_masks, &tr_begin, &tr_end}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
         }
     } slot[2];
     int cur = 0;                           // slot of the most recent frame
     cudaStream_t copy_stream = nullptr;    // result transfers of pipelined frames
-    double t_frame_begin = 0, trace_issue_ms = 0, trace_wait_ms = 0;   // DSPMAP_TRACE
+    cudaStream_t upload_stream = nullptr;  // image uploads of dspmap_update
+    double t_frame_begin = 0, trace_issue_ms = 0, trace_wait_ms = 0, trace_prev_ms = 0, trace_copy_issue_ms = 0, trace_result_ms = 0, trace_gpu_ms = 0, trace_gap_ms = 0;   // DSPMAP_TRACE
     std::unique_ptr<StagePool> stage_pool;
 
     Counters last{};                       // of the most recent FINISHED frame
@@ -389,7 +394,7 @@ struct dspmap {
     void release_all() {
         sx.release(); sy.release(); sz.release(); sw.release(); smeta.release(); shdr.release(); d_entry_list.release(); d_entry_voxel.release(); d_stamps.release(); d_lut.release(); d_randoms.release();
         d_static_track.release(); d_static_label.release(); d_fp.release(); d_cnt.release(); d_persist.release(); d_masks.release(); d_moves.release();
-        d_depth_in.release(); d_depth_int.release(); d_mask_in.release(); d_cloud_pos.release(); d_cloud_meta.release();
+        d_depth_int.release(); d_cloud_pos.release(); d_cloud_meta.release();
         d_pix_count.release(); d_pix_offset.release(); d_scan_block.release(); d_vmask.release(); d_csr_key.release(); d_seq_ref.release(); d_mov_out.release(); d_csr_idx.release(); d_mine_list.release();
         d_vis_mp.release(); d_row_order.release(); d_vrank.release(); d_bfs_front[0].release(); d_bfs_front[1].release(); d_bfs_blocks.release(); d_work_key.release(); d_vis_pos.release(); d_keys.release(); d_birth_box.release(); d_ranks.release(); d_birth_flags.release(); d_birth_prefix.release(); d_birth_block.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_chunk_tot.release(); d_chunk_base.release(); d_tile_list.release(); d_work.release();
         for (int p = 0; p < MAX_RANKS; ++p) if (peer_base[p] && p != cfg.shard_rank) { cudaIpcCloseMemHandle(peer_base[p]); peer_base[p] = nullptr; }
@@ -397,6 +402,7 @@ struct dspmap {
         result2.release();
         for (auto& sl : slot) sl.release();
         if (copy_stream) { cudaStreamDestroy(copy_stream); copy_stream = nullptr; }
+        if (upload_stream) { cudaStreamDestroy(upload_stream); upload_stream = nullptr; }
         for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (own_stream) { cudaStreamDestroy(own_stream); own_stream = nullptr; }
         if (side_stream) { cudaStreamDestroy(side_stream); side_stream = nullptr; }
@@ -552,7 +558,8 @@ int dspmap::init(const dspmap_config& c) {
     CU_TRY(this, d_fp.alloc(1)); CU_TRY(this, d_cnt.alloc(1)); CU_TRY(this, d_persist.alloc(1)); CU_TRY(this, d_moves.alloc(1));
     CU_TRY(this, cudaMemset(d_persist.p, 0, sizeof(Persist)));
     CU_TRY(this, d_masks.alloc(64));
-    CU_TRY(this, d_depth_in.alloc(npix_in)); CU_TRY(this, d_depth_int.alloc(npix));
+    for (auto& sl : slot) CU_TRY(this, sl.d_depth_in.alloc(npix_in));
+    CU_TRY(this, d_depth_int.alloc(npix));
     CU_TRY(this, d_cloud_pos.alloc(npix)); CU_TRY(this, d_cloud_meta.alloc(npix));
     CU_TRY(this, d_pix_count.alloc(npix)); CU_TRY(this, d_pix_offset.alloc(npix + 1));
     CU_TRY(this, d_scan_block.alloc((npix + SCAN_BLOCK - 1) / SCAN_BLOCK));
@@ -623,8 +630,12 @@ int dspmap::init(const dspmap_config& c) {
         CU_TRY(this, sl.p_maskdesc.reserve(64)); CU_TRY(this, sl.p_moves.reserve(1));
         memset(sl.p_cnt.p, 0, sizeof(Counters));
         CU_TRY(this, cudaEventCreateWithFlags(&sl.copy_done, cudaEventDisableTiming));
+        CU_TRY(this, cudaEventCreateWithFlags(&sl.up_depth, cudaEventDisableTiming));
+        CU_TRY(this, cudaEventCreateWithFlags(&sl.up_masks, cudaEventDisableTiming));
+        CU_TRY(this, cudaEventCreate(&sl.tr_begin)); CU_TRY(this, cudaEventCreate(&sl.tr_end));
     }
     CU_TRY(this, cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    CU_TRY(this, cudaStreamCreateWithFlags(&upload_stream, cudaStreamNonBlocking));
 
     // Gaussian PDF LUT (utils/basic_algorithms.h:403-407, 455-459): (1/sqrt(2*M_PI_2f32)) * exp(-v^2/2), v=(i-10000)*0.001
     {
@@ -748,8 +759,19 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     slot[cur].want_host = want_host;
     if (!pipelined || profiling || cv.size > 1) return frame_finish(cur);
     if (prev != cur && slot[prev].inflight) {
+        static const bool trace = getenv("DSPMAP_TRACE") != nullptr;
+        const double ta = trace ? host_now_ms() : 0.0;
         rc = frame_finish(prev);
+        const double tb = trace ? host_now_ms() : 0.0;
         if (rc == DSPMAP_OK && slot[prev].want_host) rc = issue_result_copy(prev, copy_stream);
+        if (trace) {
+            trace_prev_ms += tb - ta; trace_copy_issue_ms += host_now_ms() - tb;
+            if ((T % 16) == 0) {
+                fprintf(stderr, "[dspmap] pipelined, mean of 16: enqueue %.3f ms, then waited %.3f ms for the previous frame, result copy issue %.3f ms, wait_result blocked %.3f ms\n",
+                        trace_issue_ms / 16, trace_prev_ms / 16, trace_copy_issue_ms / 16, trace_result_ms / 16);
+                trace_issue_ms = trace_prev_ms = trace_copy_issue_ms = trace_result_ms = trace_wait_ms = 0;
+            }
+        }
         if (rc != DSPMAP_OK) { err = "frame " + std::to_string(slot[prev].T) + " (reported by the call that enqueued frame " + std::to_string(T) + "): " + err; return rc; }
     }
     return DSPMAP_OK;
@@ -862,6 +884,8 @@ int dspmap::frame_enqueue(const float* d_depth, int rows, int cols, int stride, 
         stamps_dirty = false;
     }
     CU_TRY(this, cudaMemsetAsync(d_cnt.p, 0, sizeof(Counters), stream));
+    static const bool trace_gpu = getenv("DSPMAP_TRACE") != nullptr;
+    if (trace_gpu) cudaEventRecord(sl.tr_begin, stream);
     const uint32_t* stx = d_stamps.p;
     const uint32_t* sty = d_stamps.p + f.NX;
     const uint32_t* stz = d_stamps.p + f.NX + f.NY;
@@ -1056,6 +1080,7 @@ int dspmap::frame_enqueue(const float* d_depth, int rows, int cols, int stride, 
     if (profiling) cudaEventRecord(ev[7], stream);
     CU_TRY(this, cudaMemcpyAsync(sl.p_cnt.p, d_cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
     if (cv.size > 1) CU_TRY(this, cudaMemcpyAsync(sl.p_stamps.p + (f.NX + f.NY + f.NZ) + 1, d_counts, (size_t)MAX_RANKS * COMM_COUNTS * 4, cudaMemcpyDeviceToHost, stream));
+    if (trace_gpu) cudaEventRecord(sl.tr_end, stream);
     CU_TRY(this, cudaGetLastError());
     static const bool trace_frame = getenv("DSPMAP_TRACE") != nullptr;
     sl.t_issued = trace_frame ? host_now_ms() : 0.0;
@@ -1087,9 +1112,15 @@ int dspmap::frame_finish(int s) {
     }
     if (trace_frame) {   // host time to issue the frame's launches vs time left waiting for the device afterwards
         trace_wait_ms += host_now_ms() - sl.t_issued;
-        if ((T % 16) == 0) { fprintf(stderr, "[dspmap] frame %u: issue %.3f ms, wait %.3f ms (mean of 16)\n", T, trace_issue_ms / 16, trace_wait_ms / 16); trace_issue_ms = trace_wait_ms = 0; }
+        if ((T % 16) == 0 && s == cur) { fprintf(stderr, "[dspmap] frame %u: issue %.3f ms, wait %.3f ms (mean of 16)\n", T, trace_issue_ms / 16, trace_wait_ms / 16); trace_issue_ms = trace_wait_ms = 0; }
     }
     last = *sl.p_cnt.p;
+    if (trace_frame && T > 2) {
+        float gpu_ms = 0.f, gap_ms = 0.f;
+        if (cudaEventSynchronize(sl.tr_end) == cudaSuccess && cudaEventElapsedTime(&gpu_ms, sl.tr_begin, sl.tr_end) == cudaSuccess) trace_gpu_ms += gpu_ms;
+        if (cudaEventElapsedTime(&gap_ms, slot[s ^ 1].tr_end, sl.tr_begin) == cudaSuccess) trace_gap_ms += gap_ms;
+        if ((T % 16) == 0) { fprintf(stderr, "[dspmap] device, mean of 16: frame %.3f ms first to last operation, %.3f ms between the previous frame's last and this frame's first\n", trace_gpu_ms / 16, trace_gap_ms / 16); trace_gpu_ms = trace_gap_ms = 0; }
+    }
 
     stats.time_stamp = T;
     stats.n_swept_voxels = last.n_swept_voxels; stats.n_swept_nonempty = last.n_swept_nonempty;
@@ -1334,7 +1365,7 @@ static int update_host_impl(dspmap_t* h, const float* depth, int32_t rows, int32
     std::vector<dspmap_mask> dm(masks, masks + n_masks);
     if (n_masks) {
         CU_TRY(h, sl.p_masks.reserve(npix * n_masks));
-        if (h->d_mask_in.n < npix * n_masks) CU_TRY(h, h->d_mask_in.alloc(npix * n_masks));
+        if (sl.d_mask_in.n < npix * n_masks) CU_TRY(h, sl.d_mask_in.alloc(npix * n_masks));
     }
     if (!h->stage_pool) {
         const char* env = getenv("DSPMAP_STAGE_THREADS");
@@ -1380,7 +1411,10 @@ static int update_host_impl(dspmap_t* h, const float* depth, int32_t rows, int32
     const std::function<int()> late_depth = [&]() -> int {
         const int depth_parts = 8;
         h->stage_pool->run(depth_parts, [&](int t) { stage_rows(sl.p_depth.p, depth, row_stride, srows * t / depth_parts, srows * (t + 1) / depth_parts); });
-        CU_TRY(h, cudaMemcpyAsync(h->d_depth_in.p, sl.p_depth.p, npix * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        // the slot's device buffers were last read by the frame two back, which has finished: no wait before the upload
+        CU_TRY(h, cudaMemcpyAsync(sl.d_depth_in.p, sl.p_depth.p, npix * sizeof(float), cudaMemcpyHostToDevice, h->upload_stream));
+        CU_TRY(h, cudaEventRecord(sl.up_depth, h->upload_stream));
+        CU_TRY(h, cudaStreamWaitEvent(h->stream, sl.up_depth, 0));
         return DSPMAP_OK;
     };
     const std::function<int(dspmap_mask*)> late_masks = [&](dspmap_mask* dmv) -> int {
@@ -1390,12 +1424,14 @@ static int update_host_impl(dspmap_t* h, const float* depth, int32_t rows, int32
             const int m = t / parts, b = t % parts;
             stage_rows(sl.p_masks.p + (size_t)m * npix, masks[m].data, masks[m].row_stride, srows * b / parts, srows * (b + 1) / parts);
         });
-        for (int m = 0; m < n_masks; ++m) { dmv[m].data = h->d_mask_in.p + (size_t)m * npix; dmv[m].row_stride = scols; }
-        CU_TRY(h, cudaMemcpyAsync(h->d_mask_in.p, sl.p_masks.p, npix * n_masks, cudaMemcpyHostToDevice, h->stream));
+        for (int m = 0; m < n_masks; ++m) { dmv[m].data = sl.d_mask_in.p + (size_t)m * npix; dmv[m].row_stride = scols; }
+        CU_TRY(h, cudaMemcpyAsync(sl.d_mask_in.p, sl.p_masks.p, npix * n_masks, cudaMemcpyHostToDevice, h->upload_stream));
+        CU_TRY(h, cudaEventRecord(sl.up_masks, h->upload_stream));
+        CU_TRY(h, cudaStreamWaitEvent(h->stream, sl.up_masks, 0));
         return DSPMAP_OK;
     };
     const double t_b = trace ? host_now_ms() : 0.0;
-    rc = h->frame(h->d_depth_in.p, rows, cols, scols, dm.data(), n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove,
+    rc = h->frame(sl.d_depth_in.p, rows, cols, scols, dm.data(), n_masks, position, orientation_wxyz, moves, n_moves, remove_tracks, n_remove,
                   want_freespace, f.boost ? 1 : 0, &late_masks, &late_depth, pipelined, true);
     if (ticket) *ticket = h->T != t_before ? h->T : 0;
     if (rc != DSPMAP_OK) return rc;
@@ -1450,7 +1486,10 @@ int dspmap_wait_result(dspmap_t* h, uint32_t ticket, dspmap_result* out) {
     if (sl.rc != DSPMAP_OK) return h->fail(sl.rc, "frame %u failed (reported when it finished)", ticket);
     if (sl.want_host) {
         if (!sl.copy_issued && !sl.host_result_valid) { const int rc = h->issue_result_copy(s, h->copy_stream); if (rc != DSPMAP_OK) return rc; }
+        static const bool trace = getenv("DSPMAP_TRACE") != nullptr;
+        const double ta = trace ? host_now_ms() : 0.0;
         const int rc = h->fetch_result_to_host(s);
+        if (trace) h->trace_result_ms += host_now_ms() - ta;
         if (rc != DSPMAP_OK) return rc;
     }
     fill_result(sl, sl.want_host, out);

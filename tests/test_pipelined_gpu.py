@@ -163,4 +163,4 @@ class _DevArray:
     """__cuda_array_interface__ over a raw device pointer."""
 
     def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (int(ptr), True), "version": 2}
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
