@@ -210,7 +210,6 @@ struct dspmap {
     uint32_t T = 0;
     bool forgetting_init = false;
     float forget_tab[5]{};
-    bool stamps_dirty = true;
 
     // label tables
     uint16_t h_static_track[256];
@@ -225,15 +224,12 @@ struct dspmap {
     Store st{};
     size_t n_slots_local = 0, slot_lo = 0;
     uint32_t v_local = 0;
-    DevBuf<uint32_t> d_stamps;  // x | y | z
     DevBuf<float> d_lut, d_randoms;
     DevBuf<uint16_t> d_static_track;
     DevBuf<uint8_t> d_static_label;
     DevBuf<FrameParams> d_fp;
     DevBuf<Counters> d_cnt;
     DevBuf<Persist> d_persist;
-    DevBuf<MaskDesc> d_masks;
-    DevBuf<MoveTable> d_moves;
     // images
     DevBuf<float> d_depth_int;
     DevBuf<float4> d_cloud_pos;
@@ -298,7 +294,11 @@ struct dspmap {
         PinBuf<int8_t> hr_state;
         DevBuf<float> d_depth_in;          // where dspmap_update uploads the frame's images (on the upload stream, so that
         DevBuf<uint8_t> d_mask_in;         // frame t+1's images travel while frame t's kernels run)
-        cudaEvent_t up_depth = nullptr, up_masks = nullptr;
+        DevBuf<uint32_t> d_stamps;         // x | y | z slab stamps, mask descriptors, move tables of the slot's frame: uploaded on
+        DevBuf<MaskDesc> d_masks;          // the upload stream as well - a copy-engine operation IN the kernels' stream costs
+        DevBuf<MoveTable> d_moves;         // the stream several microseconds each time, a wait for a finished upload next to nothing
+        bool stamps_stale = true;          // the slot's device copy of the stamps is older than the host's
+        cudaEvent_t up_depth = nullptr, up_masks = nullptr, up_tab = nullptr, frame_done = nullptr;
         cudaEvent_t tr_begin = nullptr, tr_end = nullptr;   // DSPMAP_TRACE: the frame's first and last operation on the main stream
         ResultArrays dres{};               // this slot's result arrays on the device
         cudaEvent_t copy_done = nullptr;   // the device->host transfer of this slot's result
@@ -315,8 +315,8 @@ struct dspmap {
             p_depth.release(); p_masks.release(); p_cnt.release(); p_stamps.release(); p_maskdesc.release(); p_moves.release();
             hr_idx.release(); hr_free_idx.release(); hr_xyz.release(); hr_w.release(); hr_free_xyz.release(); hr_track.release();
             hr_label.release(); hr_rgb.release(); hr_state.release();
-            d_depth_in.release(); d_mask_in.release();
-            for (cudaEvent_t* e : {&copy_done, &up_depth, &up_masks, &tr_begin, &tr_end}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+            d_depth_in.release(); d_mask_in.release(); d_stamps.release(); d_masks.release(); d_moves.release();
+            for (cudaEvent_t* e : {&copy_done, &up_depth, &up_masks, &up_tab, &frame_done, &tr_begin, &tr_end}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
         }
     } slot[2];
     int cur = 0;                           // slot of the most recent frame
@@ -356,8 +356,8 @@ struct dspmap {
         }
         for (int a = 0; a < 3; ++a) {
             const int n = (int)axis_n(a), d = center[a] - moved[a];
-            for (int i = 0; i < d; ++i) { stamps[a][wrap(i + equiv[a], a)] = T; stamps_dirty = true; }
-            for (int i = 0; i < -d; ++i) { stamps[a][wrap(n - 1 - i + equiv[a], a)] = T; stamps_dirty = true; }
+            for (int i = 0; i < d; ++i) { stamps[a][wrap(i + equiv[a], a)] = T; stamps_changed(); }
+            for (int i = 0; i < -d; ++i) { stamps[a][wrap(n - 1 - i + equiv[a], a)] = T; stamps_changed(); }
         }
         for (int a = 0; a < 3; ++a) {
             const int n = (int)axis_n(a);
@@ -385,15 +385,23 @@ struct dspmap {
         for (int a = 0; a < 3; ++a) last_pos[a] = pos[a];
     }
 
+    void stamps_changed() { slot[0].stamps_stale = slot[1].stamps_stale = true; }
     void reset_host_state() {
         T = 0;
         for (int a = 0; a < 3; ++a) std::fill(stamps[a].begin(), stamps[a].end(), 0u);
-        stamps_dirty = true;
+        stamps_changed();
+    }
+    // host table -> the slot's device copy, on the upload stream; the kernels' stream waits for it (cheap once the copy is done)
+    cudaError_t upload_table(FrameSlot& sl, void* dst, const void* src, size_t bytes) {
+        cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, upload_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(sl.up_tab, upload_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, sl.up_tab, 0);
+        return e;
     }
 
     void release_all() {
-        sx.release(); sy.release(); sz.release(); sw.release(); smeta.release(); shdr.release(); d_entry_list.release(); d_entry_voxel.release(); d_stamps.release(); d_lut.release(); d_randoms.release();
-        d_static_track.release(); d_static_label.release(); d_fp.release(); d_cnt.release(); d_persist.release(); d_masks.release(); d_moves.release();
+        sx.release(); sy.release(); sz.release(); sw.release(); smeta.release(); shdr.release(); d_entry_list.release(); d_entry_voxel.release(); d_lut.release(); d_randoms.release();
+        d_static_track.release(); d_static_label.release(); d_fp.release(); d_cnt.release(); d_persist.release();
         d_depth_int.release(); d_cloud_pos.release(); d_cloud_meta.release();
         d_pix_count.release(); d_pix_offset.release(); d_scan_block.release(); d_vmask.release(); d_csr_key.release(); d_seq_ref.release(); d_mov_out.release(); d_csr_idx.release(); d_mine_list.release();
         d_vis_mp.release(); d_row_order.release(); d_vrank.release(); d_bfs_front[0].release(); d_bfs_front[1].release(); d_bfs_blocks.release(); d_work_key.release(); d_vis_pos.release(); d_keys.release(); d_birth_box.release(); d_ranks.release(); d_birth_flags.release(); d_birth_prefix.release(); d_birth_block.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_chunk_tot.release(); d_chunk_base.release(); d_tile_list.release(); d_work.release();
@@ -451,7 +459,7 @@ struct dspmap {
     int frame_finish(int s);
     int issue_result_copy(int s, cudaStream_t on);
     int fetch_result_to_host(int s);
-    int drain();
+    int drain(bool whole_frame = true);
     int next_slot() const { return (int)((T + 1) & 1u); }
 };
 
@@ -545,7 +553,7 @@ int dspmap::init(const dspmap_config& c) {
     st.hdr = shdr.p - (slot_lo >> f.Pb);
 
     for (int a = 0; a < 3; ++a) stamps[a].assign(axis_n(a), 0u);
-    CU_TRY(this, d_stamps.alloc(f.NX + f.NY + f.NZ));
+    for (auto& sl : slot) CU_TRY(this, sl.d_stamps.alloc(f.NX + f.NY + f.NZ));
     CU_TRY(this, d_lut.alloc(PDF_NUM));
     CU_TRY(this, d_randoms.alloc(1));
     CU_TRY(this, cudaMemset(d_randoms.p, 0, sizeof(float)));
@@ -555,9 +563,9 @@ int dspmap::init(const dspmap_config& c) {
     h_static_label.assign(65536, 0);
     CU_TRY(this, cudaMemcpy(d_static_track.p, h_static_track, sizeof h_static_track, cudaMemcpyHostToDevice));
     CU_TRY(this, cudaMemset(d_static_label.p, 0, 65536));
-    CU_TRY(this, d_fp.alloc(1)); CU_TRY(this, d_cnt.alloc(1)); CU_TRY(this, d_persist.alloc(1)); CU_TRY(this, d_moves.alloc(1));
+    CU_TRY(this, d_fp.alloc(1)); CU_TRY(this, d_cnt.alloc(1)); CU_TRY(this, d_persist.alloc(1));
+    for (auto& sl : slot) { CU_TRY(this, sl.d_moves.alloc(1)); CU_TRY(this, sl.d_masks.alloc(64)); }
     CU_TRY(this, cudaMemset(d_persist.p, 0, sizeof(Persist)));
-    CU_TRY(this, d_masks.alloc(64));
     for (auto& sl : slot) CU_TRY(this, sl.d_depth_in.alloc(npix_in));
     CU_TRY(this, d_depth_int.alloc(npix));
     CU_TRY(this, d_cloud_pos.alloc(npix)); CU_TRY(this, d_cloud_meta.alloc(npix));
@@ -632,6 +640,8 @@ int dspmap::init(const dspmap_config& c) {
         CU_TRY(this, cudaEventCreateWithFlags(&sl.copy_done, cudaEventDisableTiming));
         CU_TRY(this, cudaEventCreateWithFlags(&sl.up_depth, cudaEventDisableTiming));
         CU_TRY(this, cudaEventCreateWithFlags(&sl.up_masks, cudaEventDisableTiming));
+        CU_TRY(this, cudaEventCreateWithFlags(&sl.up_tab, cudaEventDisableTiming));
+        CU_TRY(this, cudaEventCreateWithFlags(&sl.frame_done, cudaEventDisableTiming));
         CU_TRY(this, cudaEventCreate(&sl.tr_begin)); CU_TRY(this, cudaEventCreate(&sl.tr_end));
     }
     CU_TRY(this, cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
@@ -672,6 +682,7 @@ int dspmap::clear_device() {
     // the movable-particle list is empty again; the random-table cursors survive a clear, as in the reference
     CU_TRY(this, cudaMemsetAsync(&d_persist.p->n_movable, 0, sizeof(uint32_t), stream));
     CU_TRY(this, cudaMemsetAsync(d_vstate.p, 0, d_vstate.n, stream));
+    CU_TRY(this, cudaMemsetAsync(d_blk_cnt.p, 0, (size_t)n_occ_blocks * sizeof(uint4), stream));   // from here on k_occ_scan re-zeroes it every frame
     CU_TRY(this, cudaGetLastError());
     CU_TRY(this, cudaStreamSynchronize(stream));
     memset(&last, 0, sizeof last);
@@ -706,11 +717,13 @@ int dspmap::run_moves(const dspmap_object_move* moves, int n_moves, const int32_
     mt.n_moves = n_moves; mt.n_remove = n_remove;
     for (int i = 0; i < n_moves; ++i) { mt.move_track[i] = moves[i].track_id; memcpy(mt.t[i], moves[i].t, 12 * sizeof(float)); }
     for (int i = 0; i < n_remove; ++i) mt.remove_track[i] = remove_tracks[i];
-    MoveTable* d_mt = d_moves.p + slot;
-    CU_TRY(this, cudaMemcpyAsync(d_mt, &mt, sizeof mt, cudaMemcpyHostToDevice, stream));
-    const uint32_t* stx = d_stamps.p;
-    const uint32_t* sty = d_stamps.p + fp.NX;
-    const uint32_t* stz = d_stamps.p + fp.NX + fp.NY;
+    MoveTable* d_mt = this->slot[cur].d_moves.p + slot;
+    // only the used part of the table travels (the rigid transforms are its tail)
+    const size_t mt_bytes = n_moves > 0 ? offsetof(MoveTable, t) + (size_t)n_moves * sizeof(mt.t[0]) : offsetof(MoveTable, t);
+    CU_TRY(this, upload_table(this->slot[cur], d_mt, &mt, mt_bytes));
+    const uint32_t* stx = this->slot[cur].d_stamps.p;
+    const uint32_t* sty = stx + fp.NX;
+    const uint32_t* stz = sty + fp.NY;
     if (scan_remove) {
         ++launches; k_remove_tracks_scan<<<sm_count * 8, 256, 0, stream>>>(fp, st, d_mt, d_cnt.p);
     } else {
@@ -752,7 +765,7 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     // Synchronous call: enqueue the frame, wait for its counters.  Pipelined call (dspmap_update_async): enqueue frame t, THEN
     // wait for frame t-1 - which ran while the host staged and enqueued this one - and start the transfer of its result.
     const int prev = cur;
-    if (!pipelined || profiling || cv.size > 1) { const int rc = drain(); if (rc != DSPMAP_OK) return rc; }
+    if (!pipelined || profiling || cv.size > 1) { const int rc = drain(false); if (rc != DSPMAP_OK) return rc; }
     if (slot[next_slot()].inflight) { const int rc = frame_finish(next_slot()); if (rc != DSPMAP_OK) return rc; }   // (protocol: cannot happen)
     int rc = frame_enqueue(d_depth, rows, cols, stride, masks, n_masks, pos, quat, moves, n_moves, remove_tracks, n_remove, want_free, pre_decimated, late_masks, late_depth);
     if (rc != DSPMAP_OK) return rc;
@@ -777,11 +790,14 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     return DSPMAP_OK;
 }
 
-int dspmap::drain() {
+// Waits for the frames in flight.  A frame has "finished" for the host when its counters have arrived, which is before its emit
+// pass has written the last result entry: whole_frame also waits for that (callers that touch device memory outside the stream).
+int dspmap::drain(bool whole_frame) {
     for (int k = 0; k < 2; ++k) {
         const int s = (cur + 1 + k) & 1;      // older frame first
         if (slot[s].inflight) { const int rc = frame_finish(s); if (rc != DSPMAP_OK) return rc; }
     }
+    if (whole_frame && T > 0) CU_TRY(this, cudaEventSynchronize(slot[cur].frame_done));
     return DSPMAP_OK;
 }
 
@@ -877,18 +893,19 @@ int dspmap::frame_enqueue(const float* d_depth, int rows, int cols, int stride, 
     f.rand_n = rand_n;
 
     // ---- uploads -------------------------------------------------------------------------------------------
-    if (stamps_dirty) {
+    if (sl.stamps_stale) {
         uint32_t* s = sl.p_stamps.p;
         for (int a = 0; a < 3; ++a) { memcpy(s, stamps[a].data(), stamps[a].size() * 4); s += stamps[a].size(); }
-        CU_TRY(this, cudaMemcpyAsync(d_stamps.p, sl.p_stamps.p, (f.NX + f.NY + f.NZ) * 4, cudaMemcpyHostToDevice, stream));
-        stamps_dirty = false;
+        CU_TRY(this, upload_table(sl, sl.d_stamps.p, sl.p_stamps.p, (f.NX + f.NY + f.NZ) * 4));
+        sl.stamps_stale = false;
     }
-    CU_TRY(this, cudaMemsetAsync(d_cnt.p, 0, sizeof(Counters), stream));
+    // unsharded maps: k_occ_scan hands the counters to the host and leaves them zero; sharded maps still copy and clear them
+    if (cv.size > 1) CU_TRY(this, cudaMemsetAsync(d_cnt.p, 0, sizeof(Counters), stream));
     static const bool trace_gpu = getenv("DSPMAP_TRACE") != nullptr;
     if (trace_gpu) cudaEventRecord(sl.tr_begin, stream);
-    const uint32_t* stx = d_stamps.p;
-    const uint32_t* sty = d_stamps.p + f.NX;
-    const uint32_t* stz = d_stamps.p + f.NX + f.NY;
+    const uint32_t* stx = sl.d_stamps.p;
+    const uint32_t* sty = stx + f.NX;
+    const uint32_t* stz = sty + f.NY;
     const int npix = f.W * f.H;
 
     if (profiling) cudaEventRecord(ev[0], stream);
@@ -937,7 +954,7 @@ int dspmap::frame_enqueue(const float* d_depth, int rows, int cols, int stride, 
         // they go MAX_MOVES at a time, the first batch together with the moves
         const int nb_now = std::max(1, ((int)rm_now.size() + MAX_MOVES - 1) / MAX_MOVES), nb_after = ((int)rm_after.size() + MAX_MOVES - 1) / MAX_MOVES;
         CU_TRY(this, sl.p_moves.reserve(nb_now + nb_after));
-        if (d_moves.n < (size_t)(nb_now + nb_after)) { CU_TRY(this, cudaStreamSynchronize(stream)); CU_TRY(this, d_moves.alloc(nb_now + nb_after)); }
+        if (sl.d_moves.n < (size_t)(nb_now + nb_after)) { CU_TRY(this, cudaStreamSynchronize(stream)); CU_TRY(this, sl.d_moves.alloc(nb_now + nb_after)); }
         int slot = 0;
         for (int b = 0; b < nb_now; ++b, ++slot) {
             const int lo = b * MAX_MOVES, n = std::min((int)rm_now.size() - lo, MAX_MOVES);
@@ -996,7 +1013,7 @@ int dspmap::frame_enqueue(const float* d_depth, int rows, int cols, int stride, 
     // ---- K1 projection + labels (needs the masks) -----------------------------------------------------------------------
     std::vector<dspmap_mask> mask_copy(masks, masks + n_masks);
     if (late_masks) { const int rc = (*late_masks)(mask_copy.data()); if (rc != DSPMAP_OK) return rc; }
-    if ((size_t)n_masks > d_masks.n) { CU_TRY(this, d_masks.alloc(n_masks)); }
+    if ((size_t)n_masks > sl.d_masks.n) { CU_TRY(this, cudaStreamSynchronize(stream)); CU_TRY(this, sl.d_masks.alloc(n_masks)); }
     CU_TRY(this, sl.p_maskdesc.reserve(std::max(n_masks, 1)));
     for (int m = 0; m < n_masks; ++m) {
         MaskDesc& md = sl.p_maskdesc.p[m];
@@ -1004,8 +1021,8 @@ int dspmap::frame_enqueue(const float* d_depth, int rows, int cols, int stride, 
         md.track_id = mask_copy[m].track_id; md.label_id = mask_copy[m].label_id;
         for (int a = 0; a < 3; ++a) { md.bbox_min[a] = mask_copy[m].bbox_min[a]; md.bbox_max[a] = mask_copy[m].bbox_max[a]; }
     }
-    if (n_masks) CU_TRY(this, cudaMemcpyAsync(d_masks.p, sl.p_maskdesc.p, n_masks * sizeof(MaskDesc), cudaMemcpyHostToDevice, stream));
-    ++launches; k_project<<<(npix + 255) / 256, 256, 0, stream>>>(fp, d_masks.p, d_static_track.p, d_static_label.p,
+    if (n_masks) CU_TRY(this, upload_table(sl, sl.d_masks.p, sl.p_maskdesc.p, n_masks * sizeof(MaskDesc)));
+    ++launches; k_project<<<(npix + 255) / 256, 256, 0, stream>>>(fp, sl.d_masks.p, d_static_track.p, d_static_label.p,
                                                      depth_int, d_cloud_pos.p, d_cloud_meta.p, d_cnt.p);
     if (profiling) cudaEventRecord(ev[4], stream);
     // ---- B1a birth binning: needs only the labelled points, so it runs on the side stream beside the two stencil passes ----
@@ -1060,14 +1077,13 @@ int dspmap::frame_enqueue(const float* d_depth, int rows, int cols, int stride, 
     // ---- O1 occupancy -------------------------------------------------------------------------------------------------
     const ResultArrays out = sl.dres;
     OccScratch osc{d_vstate.p, d_res_w.p - (slot_lo >> f.Pb), d_res_tl.p - (slot_lo >> f.Pb), d_mov_mask.p - (slot_lo >> f.Pb), d_blk_cnt.p, d_blk_off.p, d_chunk_tot.p, d_chunk_base.p, d_tile_list.p};
-    CU_TRY(this, cudaMemsetAsync(d_blk_cnt.p, 0, (size_t)n_occ_blocks * sizeof(uint4), stream));
     if (profiling) cudaEventRecord(ev[8], stream);
     DISPATCH_PB(f.Pb, (k_occ_headers<PB><<<sm_count * 8, OCC_BLOCK, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, n_occ_blocks, d_cnt.p)));
     ++launches;
     if (profiling) cudaEventRecord(ev[9], stream);
     DISPATCH_PB(f.Pb, (k_occ_slots<PB><<<sm_count * 8, 256, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, d_cnt.p)));
     ++launches;
-    ++launches; k_occ_scan<<<n_occ_chunks, 1024, 0, stream>>>(osc, n_occ_blocks, d_cnt.p, d_persist.p, cv, T);
+    ++launches; k_occ_scan<<<n_occ_chunks, 1024, 0, stream>>>(osc, n_occ_blocks, d_cnt.p, d_persist.p, cv, T, cv.size == 1 ? sl.p_cnt.p : nullptr);
     barrier();   // the lower ranks' totals are this rank's base offsets
     if (wait_copy) CU_TRY(this, cudaStreamWaitEvent(stream, sl.copy_done, 0));
     {
@@ -1078,7 +1094,8 @@ int dspmap::frame_enqueue(const float* d_depth, int rows, int cols, int stride, 
     ++launches;
     barrier();   // rank 0 holds the whole result
     if (profiling) cudaEventRecord(ev[7], stream);
-    CU_TRY(this, cudaMemcpyAsync(sl.p_cnt.p, d_cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+    CU_TRY(this, cudaEventRecord(sl.frame_done, stream));      // the result arrays are complete
+    if (cv.size > 1) CU_TRY(this, cudaMemcpyAsync(sl.p_cnt.p, d_cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
     if (cv.size > 1) CU_TRY(this, cudaMemcpyAsync(sl.p_stamps.p + (f.NX + f.NY + f.NZ) + 1, d_counts, (size_t)MAX_RANKS * COMM_COUNTS * 4, cudaMemcpyDeviceToHost, stream));
     if (trace_gpu) cudaEventRecord(sl.tr_end, stream);
     CU_TRY(this, cudaGetLastError());
@@ -1139,6 +1156,7 @@ int dspmap::frame_finish(int s) {
     stats.n_occupied = sl.n_occ_global; stats.n_nonempty_voxels = last.n_nonempty_voxels;
     stats.n_moved = last.n_moved; stats.n_removed = last.n_removed;
     if (profiling) {
+        cudaEventSynchronize(ev[7]);      // the counters arrive before the emit pass has ended
         // events: 0 start | 1 depth | 2 moves | 3 visibility | 4 project | 5 update | 6 birth | 7 occupancy
         float d01, d12, d23, d34, d45, d56, d67;
         cudaEventElapsedTime(&d01, ev[0], ev[1]); cudaEventElapsedTime(&d12, ev[1], ev[2]); cudaEventElapsedTime(&d23, ev[2], ev[3]);
@@ -1168,6 +1186,8 @@ int dspmap::issue_result_copy(int s, cudaStream_t on) {
     CU_TRY(this, sl.hr_label.reserve(n_cap)); CU_TRY(this, sl.hr_state.reserve(n_cap));
     CU_TRY(this, sl.hr_rgb.reserve(3 * n_cap));
     const ResultArrays& r = sl.dres;
+    // the counters reach the host before the emit pass has written the result arrays: another stream waits for that pass
+    if (on != stream) CU_TRY(this, cudaStreamWaitEvent(on, sl.frame_done, 0));
     if (n) {
         CU_TRY(this, cudaMemcpyAsync(sl.hr_idx.p, r.voxel_index, n * 4, cudaMemcpyDeviceToHost, on));
         CU_TRY(this, cudaMemcpyAsync(sl.hr_xyz.p, r.xyz, n * 12, cudaMemcpyDeviceToHost, on));
@@ -1348,7 +1368,7 @@ static int update_host_impl(dspmap_t* h, const float* depth, int32_t rows, int32
     if (rc != DSPMAP_OK) return rc;
     CU_TRY(h, cudaSetDevice(h->device));
     if (pipelined && (rc = ensure_pipelined(h)) != DSPMAP_OK) return rc;
-    if (!pipelined || h->profiling || h->cfg.shard_count > 1) { if ((rc = h->drain()) != DSPMAP_OK) return rc; }
+    if (!pipelined || h->profiling || h->cfg.shard_count > 1) { if ((rc = h->drain(false)) != DSPMAP_OK) return rc; }
     // the pinned staging buffers of the frame's slot: free since the frame two back finished
     dspmap::FrameSlot& sl = h->slot[h->next_slot()];
     if (sl.inflight && (rc = h->frame_finish(h->next_slot())) != DSPMAP_OK) return rc;
@@ -1492,6 +1512,7 @@ int dspmap_wait_result(dspmap_t* h, uint32_t ticket, dspmap_result* out) {
         if (trace) h->trace_result_ms += host_now_ms() - ta;
         if (rc != DSPMAP_OK) return rc;
     }
+    else CU_TRY(h, cudaEventSynchronize(sl.frame_done));      // device view: the emit pass has written the arrays
     fill_result(sl, sl.want_host, out);
     return DSPMAP_OK;
 }

@@ -8,6 +8,8 @@
 #pragma once
 #include "dspmap_device.cuh"
 
+#include <cstddef>
+
 namespace dspk {
 
 // device-resident per-frame counters (zeroed at frame start)
@@ -1176,7 +1178,7 @@ struct OccScratch {
 };
 
 // persistent warps, each streaming 128-voxel pieces (32 lanes x one 16-byte load) of the header plane with the next
-// piece's load already in flight; no block-level synchronisation.  blk_cnt must be zero on entry.
+// piece's load already in flight; no block-level synchronisation.  blk_cnt must be zero on entry (k_occ_scan leaves it so).
 template <int PB>
 __global__ void __launch_bounds__(OCC_BLOCK)
 k_occ_headers(const __grid_constant__ FrameParams f, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
@@ -1330,7 +1332,8 @@ k_occ_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* __r
 
 // exclusive scan of the per-block (occupied, free, movable) counts; single block, any number of tiles
 __global__ void __launch_bounds__(1024)
-k_occ_scan(OccScratch sc, uint32_t n_blocks, Counters* __restrict__ cnt, Persist* __restrict__ persist, CommView cv, uint32_t frame_stamp) {
+k_occ_scan(OccScratch sc, uint32_t n_blocks, Counters* __restrict__ cnt, Persist* __restrict__ persist, CommView cv, uint32_t frame_stamp,
+           Counters* __restrict__ host_cnt) {
     // one block per chunk of OCC_SCAN_CHUNK tiles (a 256 x 64 x 256 map is one chunk, 1024 x 128 x 1024 thirty-two): offsets
     // inside the chunk, the chunk's totals, and the block that finishes last turns the totals into chunk bases
     __shared__ uint32_t s_warp[33];
@@ -1342,6 +1345,7 @@ k_occ_scan(OccScratch sc, uint32_t n_blocks, Counters* __restrict__ cnt, Persist
 #pragma unroll
     for (int i = 0; i < TPT; ++i) {
         v[i] = (b0 + i) < n_blocks ? sc.blk_cnt[b0 + i] : make_uint4(0, 0, 0, 0);
+        if ((b0 + i) < n_blocks) sc.blk_cnt[b0 + i] = make_uint4(0, 0, 0, 0);      // read once per frame, here: zero again for the next frame's header pass
         s0 += v[i].x; s1 += v[i].y; s2 += v[i].z; s3 += (v[i].x | v[i].y | v[i].z) != 0;
     }
     uint32_t t0, t1, t2, t3;
@@ -1354,7 +1358,7 @@ k_occ_scan(OccScratch sc, uint32_t n_blocks, Counters* __restrict__ cnt, Persist
     if (multi) e3 = block_exclusive_scan(s3, s_warp, t3);
 #pragma unroll
     for (int i = 0; i < TPT; ++i) {
-        if ((b0 + i) < n_blocks) sc.blk_off[b0 + i] = make_uint4(e0, e1, e2, 0u);
+        if ((b0 + i) < n_blocks) sc.blk_off[b0 + i] = make_uint4(e0, e1, e2, (v[i].x | v[i].y | v[i].z) != 0);   // .w: the tile emits something
         if (multi && (v[i].x | v[i].y | v[i].z) != 0) sc.tile_list[blockIdx.x * OCC_SCAN_CHUNK + e3++] = b0 + i;   // the emit pass visits only these
         e0 += v[i].x; e1 += v[i].y; e2 += v[i].z;
     }
@@ -1381,10 +1385,23 @@ k_occ_scan(OccScratch sc, uint32_t n_blocks, Counters* __restrict__ cnt, Persist
         tail[0] = 0u;                                             // the ticket counter is ready for the next frame
         tail[1] = run3;                                           // length of the non-empty tile list
         cnt->n_occupied = run0; cnt->n_free = run1; cnt->n_movable = run2; persist->n_movable = run2;
-        cnt->seq_head = frame_stamp; cnt->seq_tail = frame_stamp;    // copied to the host after the last kernel of the frame
+        cnt->seq_head = frame_stamp; cnt->seq_tail = frame_stamp;    // sharded maps: copied to the host after the last kernel of the frame
         for (int p = 0; p < cv.size; ++p) {   // every rank learns every rank's totals (the emit pass needs the lower ranks')
             uint32_t* row = cv.counts[p] + cv.rank * COMM_COUNTS;
             row[CC_OCC] = run0; row[CC_FREE] = run1;
+        }
+        if (host_cnt) {
+            // Unsharded map: nothing after this point changes a counter (the emit pass reads the scan's tables only), so the block
+            // goes to the host from here - plain stores into the handle's pinned copy, body first, the two stamps the host polls
+            // for last - and is zeroed for the next frame.  No copy-engine operation at either end of a frame.
+            constexpr int NW = sizeof(Counters) / 4;
+            static_assert(offsetof(Counters, seq_head) == 0 && offsetof(Counters, seq_tail) == (NW - 1) * 4, "stamps at both ends");
+            volatile uint32_t* src = reinterpret_cast<volatile uint32_t*>(cnt);      // other kernels' atomics live in L2: bypass L1
+            volatile uint32_t* dst = reinterpret_cast<volatile uint32_t*>(host_cnt);
+            for (int i = 1; i < NW - 1; ++i) dst[i] = src[i];
+            __threadfence_system();
+            dst[0] = frame_stamp; dst[NW - 1] = frame_stamp;
+            for (int i = 0; i < NW; ++i) src[i] = 0u;
         }
     }
     __threadfence_system();
@@ -1489,8 +1506,7 @@ k_occ_emit(const __grid_constant__ FrameParams f, Store st, OccScratch sc, Resul
     uint32_t base_occ = 0, base_free = 0;
     for (int g = 0; g < cv.rank; ++g) { base_occ += counts[g * COMM_COUNTS + CC_OCC]; base_free += counts[g * COMM_COUNTS + CC_FREE]; }
     if (!use_list) {
-        const uint4 cntb = sc.blk_cnt[blockIdx.x];
-        if ((cntb.x | cntb.y | cntb.z) == 0) return;          // nothing to emit from this tile
+        if (sc.blk_off[blockIdx.x].w == 0) return;            // nothing to emit from this tile
         occ_emit_tile<PB>(f, st, sc, out, movl_idx, movl_track, movl_cap, col_tab, blockIdx.x, base_occ, base_free, s_warp, false);
         __threadfence_system();
         return;
