@@ -157,6 +157,8 @@ public:
         // voxel, colour for colour as the reference node publishes it (regression comparisons against a recorded reference run)
         const char* exact = std::getenv("DSPMAP_ADAPTER_REFERENCE_ORDER");
         follow_reference_ = exact && exact[0] == '1';
+        const char* piped = std::getenv("DSPMAP_ADAPTER_PIPELINED");      // = setPipelinedOutput(true), for callers that cannot be edited
+        pipelined_ = piped && piped[0] == '1';
         pushLabels();
         pushColors();
         setGaussianTableSeed(rd());                                                              // reference :65 -> basic_algorithms.h:394-402
@@ -253,6 +255,21 @@ public:
             for (const MaskKpts& m : ins_seg_result)   // non-static mask is known from the next frame on, with id 0
                 if (m.label != "static") labels_.label_id.emplace(m.label, 0);
         appendFloatingTracks(ins_seg_result);
+        dspmap_result r;
+        if (pipelined_) {
+            // setPipelinedOutput: this frame is staged and enqueued, the clouds handed back are those of the PREVIOUS call, whose
+            // device->host transfer ran under this frame's kernels (dspmap_update_async / dspmap_wait_result, include/dspmap_c.h)
+            uint32_t ticket = 0;
+            const int rc = dspmap_update_async(h_, reinterpret_cast<const float*>(depth_value_mat.data), depth_value_mat.rows, depth_value_mat.cols,
+                                               (int32_t)(depth_value_mat.step / sizeof(float)), masks.data(), (int32_t)masks.size(), pos, quat,
+                                               moves_.data(), (int32_t)moves_.size(), remove_.data(), (int32_t)remove_.size(), if_get_freespace, &ticket);
+            moves_.clear();
+            if (rc != DSPMAP_OK) std::fprintf(stderr, "dspmap_update_async: %s\n", dspmap_last_error(h_));
+            if (ticket) remove_.clear();                      // this frame was accepted (an error then belongs to the frame before it)
+            const uint32_t due = pending_ticket_;
+            pending_ticket_ = ticket;
+            if (!due || dspmap_wait_result(h_, due, &r) != DSPMAP_OK) return;
+        } else {
         const int rc = dspmap_update(h_, reinterpret_cast<const float*>(depth_value_mat.data), depth_value_mat.rows, depth_value_mat.cols,
                                      (int32_t)(depth_value_mat.step / sizeof(float)), masks.data(), (int32_t)masks.size(), pos, quat,
                                      moves_.data(), (int32_t)moves_.size(), remove_.data(), (int32_t)remove_.size(), if_get_freespace);
@@ -261,8 +278,25 @@ public:
         // is touched), so the tracks that were due for removal stay queued and go with the next frame.
         if (rc != DSPMAP_OK) { std::fprintf(stderr, "dspmap_update: %s\n", dspmap_last_error(h_)); return; }
         remove_.clear();
-        dspmap_result r;
         if (dspmap_get_result(h_, &r) != DSPMAP_OK) return;
+        }
+        appendClouds(r, occupied_point_cloud, freespace_point_cloud);
+    }
+
+    // Not in the reference's API.  on: update() returns as soon as its frame is enqueued and fills the clouds with the result of
+    // the PREVIOUS update() (empty on the first call); flush() hands out the last frame's.  Same map, same clouds, one call later -
+    // the host->device copy, the kernels and the device->host copy of consecutive frames overlap (a camera stream, not a request).
+    void setPipelinedOutput(bool on) { pipelined_ = on; }
+    void flush(pcl::PointCloud<pcl::PointXYZRGB>::Ptr& occupied_point_cloud, pcl::PointCloud<pcl::PointXYZRGB>::Ptr& freespace_point_cloud) {
+        dspmap_result r;
+        const uint32_t due = pending_ticket_;
+        pending_ticket_ = 0;
+        if (due && dspmap_wait_result(h_, due, &r) == DSPMAP_OK) appendClouds(r, occupied_point_cloud, freespace_point_cloud);
+    }
+
+private:
+    void appendClouds(const dspmap_result& r, pcl::PointCloud<pcl::PointXYZRGB>::Ptr& occupied_point_cloud,
+                      pcl::PointCloud<pcl::PointXYZRGB>::Ptr& freespace_point_cloud) {
         for (uint32_t i = 0; i < r.count; ++i) {                                                  // reference :1274-1351
             pcl::PointXYZRGB pt;
             pt.x = r.xyz[3 * i]; pt.y = r.xyz[3 * i + 1]; pt.z = r.xyz[3 * i + 2];
@@ -277,6 +311,7 @@ public:
         }
     }
 
+public:
     dspmap_t* handle() { return h_; }
     // follow a COMPILED reference where it reads an uninitialised sigma (dspmap_params.uninit_sigma_mode); not in the reference's API
     // pixel lists in the order the reference's breadth-first search visits the voxels in (dspmap_params.reference_iteration_order)
@@ -399,6 +434,8 @@ private:
     }
 
     bool follow_reference_ = false;
+    bool pipelined_ = false;            // setPipelinedOutput
+    uint32_t pending_ticket_ = 0;       // the frame whose clouds the next update() / flush() hands out
     dspmap_config cfg_;
     DspLabelTables labels_;
     uint8_t color_map_int_256_[256];

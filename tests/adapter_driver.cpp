@@ -7,6 +7,7 @@
 
 int main(int argc, char** argv) {
     const int frames = argc > 1 ? std::atoi(argv[1]) : 3;
+    const bool pipelined = argc > 2 && std::strcmp(argv[2], "pipelined") == 0;      // clouds come out one call later (setPipelinedOutput)
     dspmap_config cfg{};
     cfg.voxel_bits_x = 6; cfg.voxel_bits_y = 5; cfg.voxel_bits_z = 6; cfg.slot_bits = 3; cfg.voxel_size = 0.15f;
     cfg.fx = cfg.fy = 66.f; cfg.cx = 79.5f; cfg.cy = 47.5f; cfg.image_width = 160; cfg.image_height = 96; cfg.boost_mode = 0;
@@ -19,6 +20,12 @@ int main(int argc, char** argv) {
     dsp_map_.setVisualizeOptions(false, true);
     dsp_map_.setBeyesianMovementParameters(0.1, 0.9, 0.3, 0.1);
     dsp_map_.setDepthNoiseModelParameters(0.02f, 0.3f);
+    dsp_map_.setPipelinedOutput(pipelined);
+    auto print = [](int t, const pcl::PointCloud<pcl::PointXYZRGB>::Ptr& occ) {
+        uint64_t h = 1469598103934665603ull;
+        for (const auto& p : occ->points) { uint32_t b[3]; std::memcpy(b, &p.x, 12); for (uint32_t w : b) { h ^= w; h *= 1099511628211ull; } h ^= p.r; h *= 1099511628211ull; }
+        std::printf("%d %zu %016llx\n", t, occ->size(), (unsigned long long)h);
+    };
     for (int t = 0; t < frames; ++t) {
         cv::Mat depth(96, 160, CV_32FC1);
         float* d = reinterpret_cast<float*>(depth.data);
@@ -36,9 +43,13 @@ int main(int argc, char** argv) {
         Eigen::Quaterniond q(1.0, 0.0, 0.0, 0.0);
         pcl::PointCloud<pcl::PointXYZRGB>::Ptr occ(new pcl::PointCloud<pcl::PointXYZRGB>), fre(new pcl::PointCloud<pcl::PointXYZRGB>);
         dsp_map_.update(depth, ins_seg, pos, q, occ, fre, false, 0.1 * t);
-        uint64_t h = 1469598103934665603ull;
-        for (const auto& p : occ->points) { uint32_t b[3]; std::memcpy(b, &p.x, 12); for (uint32_t w : b) { h ^= w; h *= 1099511628211ull; } h ^= p.r; h *= 1099511628211ull; }
-        std::printf("%d %zu %016llx\n", t, occ->size(), (unsigned long long)h);
+        if (!pipelined) print(t, occ);
+        else if (t > 0) print(t - 1, occ);          // the previous frame's clouds
+    }
+    if (pipelined) {
+        pcl::PointCloud<pcl::PointXYZRGB>::Ptr occ(new pcl::PointCloud<pcl::PointXYZRGB>), fre(new pcl::PointCloud<pcl::PointXYZRGB>);
+        dsp_map_.flush(occ, fre);
+        print(frames - 1, occ);
     }
     return 0;
 }

@@ -62,6 +62,16 @@ def test_adapter_matches_python_mirror():
     assert int(out[-1].split()[1]) > 0
 
 
+@pytest.mark.gpu
+def test_adapter_pipelined_output_is_the_same_clouds_one_call_later():
+    """setPipelinedOutput(true): update() hands out the previous frame's clouds (dspmap_update_async / dspmap_wait_result), flush()
+    the last one's - frame for frame what the synchronous adapter publishes."""
+    build_driver()
+    sync = subprocess.run([EXE, "6"], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    piped = subprocess.run([EXE, "6", "pipelined"], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    assert len(sync) == 6 and piped == sync and int(sync[-1].split()[1]) > 0
+
+
 def _compare_static(clouds, want, G, exact):
     """Clouds of a scene without moving objects against the reference's.  exact: the adapter follows the reference's iteration
     order (DSPMAP_ADAPTER_REFERENCE_ORDER=1) - every frame the same count, the last frame the same voxels with the same colours.
