@@ -1038,7 +1038,7 @@ int dspmap::frame_enqueue(const float* d_depth, int rows, int cols, int stride, 
             ++launches; k_scan_apply<<<nb_blocks, SCAN_BLOCK, 0, side_stream>>>(d_birth_flags.p, (uint32_t)n_ranks, d_birth_block.p, d_birth_prefix.p, nullptr);
         }
         if (f.nb_ptc == 1) {    // one newborn per point: mark the touched voxels, then find every voxel's first candidates in the image
-            ++launches; k_birth_mark<<<(npix + 255) / 256, 256, 0, side_stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_birth_box.p, d_entry_list.p, d_cnt.p);
+            ++launches; k_birth_mark<<<(npix + 255) / 256, 256, 0, side_stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_birth_box.p, d_ranks.p, d_entry_list.p, d_cnt.p);
             ++launches; k_birth_gather<<<sm_count * 8, 256, 0, side_stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_birth_box.p, d_ranks.p, d_entry_list.p, d_cnt.p);
         } else {
             ++launches; k_birth_bin<<<(n_ranks * f.nb_ptc + 255) / 256, 256, 0, side_stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_entry_list.p, d_cnt.p,

@@ -549,7 +549,7 @@ k_sweep_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* _
     }
     for (uint32_t k = chunk_used + lane_id(); k < PAIR_CHUNK; k += 32)          // retire the last chunk
         if (chunk_base + k < f.vis_cap) put_sentinel(chunk_base + k);
-    __threadfence_system();
+    if (cv.size > 1) __threadfence_system();      // sharded map: peers read what this kernel wrote after the next barrier
     n_nonempty = __reduce_add_sync(0xffffffffu, n_nonempty);
     if (lane_id() == 0 && n_nonempty) atomicAdd(&cnt->n_swept_nonempty, n_nonempty);
 }
@@ -790,14 +790,18 @@ k_birth_bin(const __grid_constant__ FrameParams f, const float4* __restrict__ cl
 // mark   : one thread per pixel; the pixels of a warp that fall into the same voxel act as one: a single hash insertion and four
 //          atomic min / max that grow the voxel's bounding rectangle of candidate pixels (a voxel's candidates are a compact patch
 //          of the image).
-// gather : one 8-lane group per touched voxel walks that rectangle in birth-rank order - phase by phase of the 3x3 interleave,
-//          row by row - and keeps the first topk pixels whose point falls into the voxel.  No atomics on the rank lists: a wall
-//          one metre away is hundreds of candidates per voxel, and they all stop after the first rows of phase 0.
-struct BirthBox { uint32_t i_min, i_max, j_min, j_max; };      // idle state: {0xffffffff, 0, 0xffffffff, 0}
+//          The pixels also count themselves per voxel, and the first topk to arrive leave their birth ranks in the voxel's rank
+//          list (arrival order, i.e. no order).
+// gather : one 8-lane group per touched voxel.  A voxel with at most topk candidates - nine in ten: everything but near
+//          surfaces - has them all in its rank list already and only sorts them.  The others walk the rectangle in birth-rank
+//          order - phase by phase of the 3x3 interleave, row by row - and keep the first topk pixels whose point falls into the
+//          voxel: a wall one metre away is hundreds of candidates per voxel, and they all stop after the first rows of phase 0.
+//          (Walking the rectangle of a voxel with three candidates far apart in the image was the tail of this kernel.)
+struct BirthBox { uint32_t i_min, i_max, j_min, j_max, count; };      // idle state: {0xffffffff, 0, 0xffffffff, 0, 0}
 
 __global__ void __launch_bounds__(256)
 k_birth_mark(const __grid_constant__ FrameParams f, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta, uint32_t* __restrict__ keys,
-             BirthBox* __restrict__ boxes, uint32_t* __restrict__ entry_list, Counters* __restrict__ cnt) {
+             BirthBox* __restrict__ boxes, uint32_t* __restrict__ ranks, uint32_t* __restrict__ entry_list, Counters* __restrict__ cnt) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t v = INVALID_INDEX, pi = 0, pj = 0;
     if (q < f.W * f.H && pt_valid(cloud_meta[q])) {
@@ -809,25 +813,38 @@ k_birth_mark(const __grid_constant__ FrameParams f, const float4* __restrict__ c
     }
     const uint32_t peers = __match_any_sync(0xffffffffu, v);
     const uint32_t i_lo = __reduce_min_sync(peers, pi), i_hi = __reduce_max_sync(peers, pi), j_lo = __reduce_min_sync(peers, pj), j_hi = __reduce_max_sync(peers, pj);
-    if (v == INVALID_INDEX || (uint32_t)(__ffs(peers) - 1) != lane_id()) return;
-    uint32_t h = hash_slot(v, f.birth_hash_shift);
-    for (uint32_t probe = 0;; ++probe) {
-        if (probe >= f.birth_hash_cap) { atomicAdd(&cnt->hash_overflow, 1u); return; }
-        uint32_t old = *(volatile uint32_t*)(keys + h);
-        if (old == EMPTY_KEY) old = atomicCAS(keys + h, EMPTY_KEY, v);
-        if (old == EMPTY_KEY) { entry_list[atomicAdd(&cnt->n_birth_voxels, 1u)] = h; break; }
-        if (old == v) break;
-        h = (h + 1) & (f.birth_hash_cap - 1);
+    const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
+    uint32_t h = EMPTY_KEY, base = 0;
+    if (v != INVALID_INDEX && leader == lane_id()) {
+        h = hash_slot(v, f.birth_hash_shift);
+        for (uint32_t probe = 0;; ++probe) {
+            if (probe >= f.birth_hash_cap) { atomicAdd(&cnt->hash_overflow, 1u); h = EMPTY_KEY; break; }
+            uint32_t old = *(volatile uint32_t*)(keys + h);
+            if (old == EMPTY_KEY) old = atomicCAS(keys + h, EMPTY_KEY, v);
+            if (old == EMPTY_KEY) { entry_list[atomicAdd(&cnt->n_birth_voxels, 1u)] = h; break; }
+            if (old == v) break;
+            h = (h + 1) & (f.birth_hash_cap - 1);
+        }
+        if (h != EMPTY_KEY) {
+            BirthBox* b = boxes + h;
+            atomicMin(&b->i_min, i_lo); atomicMax(&b->i_max, i_hi); atomicMin(&b->j_min, j_lo); atomicMax(&b->j_max, j_hi);
+            base = atomicAdd(&b->count, (uint32_t)__popc(peers));
+        }
     }
-    BirthBox* b = boxes + h;
-    atomicMin(&b->i_min, i_lo); atomicMax(&b->i_max, i_hi); atomicMin(&b->j_min, j_lo); atomicMax(&b->j_max, j_hi);
+    __syncwarp();
+    h = __shfl_sync(0xffffffffu, h, leader);
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (v == INVALID_INDEX || h == EMPTY_KEY) return;
+    const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane_id()) - 1u));
+    if (pos < f.topk) ranks[(size_t)h * f.topk + pos] = birth_rank(f, (int)pi, (int)pj);
 }
 
 __global__ void k_fill_birth_boxes(BirthBox* __restrict__ boxes, size_t n) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) boxes[i] = BirthBox{0xffffffffu, 0u, 0xffffffffu, 0u};
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) boxes[i] = BirthBox{0xffffffffu, 0u, 0xffffffffu, 0u, 0u};
 }
 
 constexpr int BG_LANES = 8;      // lanes per touched voxel
+constexpr int BG_VALS = 4;       // rank-list entries per lane: topk = 2 * MAX_P - 1 = 31 at most (static_assert below MAX_P)
 __global__ void __launch_bounds__(256)
 k_birth_gather(const __grid_constant__ FrameParams f, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta, const uint32_t* __restrict__ keys,
                BirthBox* __restrict__ boxes, uint32_t* __restrict__ ranks, const uint32_t* __restrict__ entry_list, const Counters* __restrict__ cnt) {
@@ -841,14 +858,43 @@ k_birth_gather(const __grid_constant__ FrameParams f, const float4* __restrict__
         const bool live = li0 < n_entries;
         const uint32_t e = live ? entry_list[li0] : 0u, v = live ? keys[e] : INVALID_INDEX;
         int i0 = 0, i1 = -1, j0 = 0, j1 = -1;
+        uint32_t n_cand = 0;
         if (live) {
             const BirthBox bb = boxes[e];
-            i0 = (int)bb.i_min; i1 = (int)bb.i_max; j0 = (int)bb.j_min; j1 = (int)bb.j_max;
+            i0 = (int)bb.i_min; i1 = (int)bb.i_max; j0 = (int)bb.j_min; j1 = (int)bb.j_max; n_cand = bb.count;
         }
         __syncwarp();
-        if (live && sub == 0) boxes[e] = BirthBox{0xffffffffu, 0u, 0xffffffffu, 0u};     // idle again for the next frame
-        uint32_t found = 0;
+        if (live && sub == 0) boxes[e] = BirthBox{0xffffffffu, 0u, 0xffffffffu, 0u, 0u};     // idle again for the next frame
         uint32_t* out = ranks + (size_t)e * K;
+        // at most topk candidates: they are all in the list (k_birth_mark), in arrival order - every value finds its place by
+        // counting the smaller ones (ranks are distinct); the lists of the warp's four groups are sorted side by side
+        const bool listed = live && n_cand <= K;
+        {
+            uint32_t mine[BG_VALS];
+#pragma unroll
+            for (int t = 0; t < BG_VALS; ++t) { const uint32_t k = sub + (uint32_t)t * BG_LANES; mine[t] = (listed && k < n_cand) ? out[k] : NO_RANK; }
+            uint32_t place[BG_VALS] = {};
+            const uint32_t lane0 = lane_id() & ~(uint32_t)(BG_LANES - 1);
+#pragma unroll
+            for (int t2 = 0; t2 < BG_VALS; ++t2)
+#pragma unroll
+                for (int src = 0; src < BG_LANES; ++src) {
+                    const uint32_t other = __shfl_sync(0xffffffffu, mine[t2], lane0 + src);
+#pragma unroll
+                    for (int t = 0; t < BG_VALS; ++t) place[t] += other < mine[t];
+                }
+            __syncwarp();
+            if (listed) {
+#pragma unroll
+                for (int t = 0; t < BG_VALS; ++t) {
+                    const uint32_t k = sub + (uint32_t)t * BG_LANES;
+                    if (k < n_cand) out[place[t]] = mine[t];
+                }
+                for (uint32_t t = n_cand + sub; t < K; t += BG_LANES) out[t] = NO_RANK;
+            }
+        }
+        const bool scan = live && !listed;
+        uint32_t found = scan ? 0u : K;
         for (int ph = 0; ph < 9; ++ph) {
             const int pi = ph / 3, pj = ph - 3 * pi;
             // cells (a, b) of this phase inside the rectangle: pixel (3a + pi, 3b + pj)
@@ -877,7 +923,7 @@ k_birth_gather(const __grid_constant__ FrameParams f, const float4* __restrict__
                 if (__all_sync(0xffffffffu, c0 + BG_LANES >= ncell || found >= K)) break;     // every group of the warp is done with this phase
             }
         }
-        if (live)
+        if (scan)
             for (uint32_t t = min(found, K) + sub; t < K; t += BG_LANES) out[t] = NO_RANK;
     }
 }
@@ -1072,6 +1118,7 @@ constexpr int OCC_TILE = OCC_BLOCK * OCC_VPT;
 constexpr int OCC_SCAN_TPT = 4;                  // tiles per thread of the tile-count scan
 constexpr int OCC_SCAN_CHUNK = 1024 * OCC_SCAN_TPT;   // tiles per scan block
 constexpr int MAX_P = 16;
+static_assert(2 * MAX_P - 1 <= BG_LANES * BG_VALS, "k_birth_gather sorts a voxel's rank list in BG_VALS registers per lane");
 // state byte: bits 0..1 = state + 1 (0 unknown, 1 free, 2 occupied, 3 guessed occupied), bit 2 = holds movable particles
 constexpr uint32_t VS_MOVABLE = 4u;
 constexpr uint32_t VS_ASSIGNS = 8u;     // the voxel's label histogram had a positive entry: it assigned (label, track), res_tl holds them
@@ -1404,7 +1451,7 @@ k_occ_scan(OccScratch sc, uint32_t n_blocks, Counters* __restrict__ cnt, Persist
             for (int i = 0; i < NW; ++i) src[i] = 0u;
         }
     }
-    __threadfence_system();
+    if (cv.size > 1) __threadfence_system();      // sharded map: peers read what this kernel wrote after the next barrier
 }
 
 // one tile (OCC_TILE voxels) of the ordered emission; every thread of the block takes part in the two scans
@@ -1508,7 +1555,7 @@ k_occ_emit(const __grid_constant__ FrameParams f, Store st, OccScratch sc, Resul
     if (!use_list) {
         if (sc.blk_off[blockIdx.x].w == 0) return;            // nothing to emit from this tile
         occ_emit_tile<PB>(f, st, sc, out, movl_idx, movl_track, movl_cap, col_tab, blockIdx.x, base_occ, base_free, s_warp, false);
-        __threadfence_system();
+        if (cv.size > 1) __threadfence_system();      // sharded map: peers read what this kernel wrote after the next barrier
         return;
     }
     const uint32_t n_list = reinterpret_cast<const uint32_t*>(sc.chunk_tot + n_chunks)[1];
@@ -1519,7 +1566,7 @@ k_occ_emit(const __grid_constant__ FrameParams f, Store st, OccScratch sc, Resul
         occ_emit_tile<PB>(f, st, sc, out, movl_idx, movl_track, movl_cap, col_tab, tile, base_occ, base_free, s_warp, true);
         __syncthreads();      // s_warp is reused by the next tile
     }
-    __threadfence_system();
+    if (cv.size > 1) __threadfence_system();      // sharded map: peers read what this kernel wrote after the next barrier
 }
 
 // =====================================================================================================
@@ -1667,7 +1714,7 @@ k_move_apply(const __grid_constant__ FrameParams f, Counters* __restrict__ cnt, 
         }
     }
     if (n_removed) atomicAdd(&cnt->n_removed, n_removed);
-    __threadfence_system();
+    if (cv.size > 1) __threadfence_system();      // sharded map: peers read what this kernel wrote after the next barrier
 }
 
 // tell every destination rank how many moved particles this rank sent it
