@@ -187,7 +187,7 @@ def run_reference(args, cfg_name):
     }))
 
 
-def measure_engine(m, frames, warmup, steps, stream, dev, barrier, n_prof, torch):
+def measure_engine(m, frames, warmup, steps, stream, dev, barrier, n_prof, torch, device_arm_only=False):
     """All engine-arm measurements of one map over one frame sequence.  Returns a dict of raw numbers (per rank)."""
     from semantic_dsp_map_b200 import Engine, _capi
     eng = m.engine
@@ -264,6 +264,9 @@ def measure_engine(m, frames, warmup, steps, stream, dev, barrier, n_prof, torch
         acc["n_listed"] += st["n_nonempty_voxels"]
     eng.check(eng.lib.dspmap_set_profiling(eng._h, 0), "dspmap_set_profiling")
     out["stage_ms"], out["acc"] = stage_ms, acc
+    if device_arm_only:
+        out.update(ms_device_sync=out["ms_device"], ms_e2e=out["ms_device"], ms_e2e_sync=out["ms_device"], h2d=0, d2h=0)
+        return out
     # synchronous calls on the same frames (every update returns after its frame has finished): what round 1 reported as `value`
     eng.clear()
     for k in range(warmup):
@@ -348,6 +351,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--config", default="B")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-arm-only", action="store_true", help="profiling runs (ncu): only the device-resident pipelined arm and the per-stage frames")
     ap.add_argument("--no-sharded-d", action="store_true", help="N > 1: skip the extra measurement of ONE config-D map sharded over the N GPUs")
     ap.add_argument("--parallelism", default="replicas", choices=["replicas", "sharded"],
                     help="N > 1: independent map replicas (weak scaling, default) or ONE map sharded by storage-z slabs over the GPUs (strong)")
@@ -368,7 +372,7 @@ def main():
     sharded = world > 1 and args.parallelism == "sharded"
     # N > 1, default run: besides the N replicas of the metric's configuration, ONE config-D map (512 x 128 x 512 voxels x 16 slots,
     # 2 m per frame: BASELINE.json's multi-GPU configuration) sharded over the same N GPUs
-    extra_d = world > 1 and not sharded and args.config == "B" and not args.no_sharded_d
+    extra_d = world > 1 and not sharded and args.config == "B" and not args.no_sharded_d and not args.device_arm_only
     d_warm, d_steps = 8, 24
     frames_d = generate_frames("D", d_warm + d_steps + 8) if extra_d else None
 
@@ -407,7 +411,7 @@ def main():
 
     m, stream = make_map(cfg, sharded)
     units = 1 if sharded else world          # maps updated per step by the whole job
-    r = measure_engine(m, frames, args.warmup, args.steps, stream, dev, barrier, n_prof, torch)
+    r = measure_engine(m, frames, args.warmup, args.steps, stream, dev, barrier, n_prof, torch, args.device_arm_only)
     ms_device, ms_e2e, ms_device_sync, ms_e2e_sync = reduce_max([r["ms_device"], r["ms_e2e"], r["ms_device_sync"], r["ms_e2e_sync"]])
     barrier()
     m.engine.close()
@@ -490,12 +494,14 @@ def main():
         }
         if sharded_d is not None:
             out["sharded_D"] = sharded_d
-        if world == 1 and not sharded:
+        if world == 1 and not sharded and not args.device_arm_only:
             try:
                 out["parity_vs_reference"] = order_parity(cfg, frames, min(40, n_frames), local)
             except Exception as exc:      # a measurement beside the bench line, never a reason to lose it
                 out["parity_vs_reference"] = {"error": str(exc)[:200]}
-        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is a rank-0, N = 1 measurement
+        if args.device_arm_only:
+            out["note"] = "--device-arm-only: e2e and synchronous fields repeat the device arm (profiling run, not a bench line)"
+        if not args.no_cpu_baseline and world == 1 and not args.device_arm_only:      # the CPU baseline is a rank-0, N = 1 measurement
             out["cpu_baseline"] = cpu_baseline(args.config, frames)
         print(json.dumps(out))
     if world > 1:

@@ -256,7 +256,7 @@ struct dspmap {
     DevBuf<uint4> d_blk_cnt, d_blk_off, d_chunk_tot, d_chunk_base;
     DevBuf<uint32_t> d_tile_list;
     uint32_t n_occ_chunks = 0;
-    DevBuf<uint32_t> d_work;
+    DevBuf<uint32_t> d_work, d_work_hdr;      // work lists of the per-voxel passes; header words beside the sweep's list
     uint32_t n_occ_blocks = 0, birth_cap1 = 0, birth_shift1 = 0;
     uint32_t sel_cap = 0, seq_cap = 0;
     // occupancy
@@ -404,7 +404,7 @@ struct dspmap {
         d_static_track.release(); d_static_label.release(); d_fp.release(); d_cnt.release(); d_persist.release();
         d_depth_int.release(); d_cloud_pos.release(); d_cloud_meta.release();
         d_pix_count.release(); d_pix_offset.release(); d_scan_block.release(); d_vmask.release(); d_csr_key.release(); d_seq_ref.release(); d_mov_out.release(); d_csr_idx.release(); d_mine_list.release();
-        d_vis_mp.release(); d_row_order.release(); d_vrank.release(); d_bfs_front[0].release(); d_bfs_front[1].release(); d_bfs_blocks.release(); d_work_key.release(); d_vis_pos.release(); d_keys.release(); d_birth_box.release(); d_ranks.release(); d_birth_flags.release(); d_birth_prefix.release(); d_birth_block.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_chunk_tot.release(); d_chunk_base.release(); d_tile_list.release(); d_work.release();
+        d_vis_mp.release(); d_row_order.release(); d_vrank.release(); d_bfs_front[0].release(); d_bfs_front[1].release(); d_bfs_blocks.release(); d_work_key.release(); d_vis_pos.release(); d_keys.release(); d_birth_box.release(); d_ranks.release(); d_birth_flags.release(); d_birth_prefix.release(); d_birth_block.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_chunk_tot.release(); d_chunk_base.release(); d_tile_list.release(); d_work.release(); d_work_hdr.release();
         for (int p = 0; p < MAX_RANKS; ++p) if (peer_base[p] && p != cfg.shard_rank) { cudaIpcCloseMemHandle(peer_base[p]); peer_base[p] = nullptr; }
         arena.release();
         result2.release();
@@ -611,6 +611,7 @@ int dspmap::init(const dspmap_config& c) {
     CU_TRY(this, cudaMemset(d_chunk_tot.p, 0, (n_occ_chunks + 1) * sizeof(uint4))); CU_TRY(this, cudaMemset(d_chunk_base.p, 0, n_occ_chunks * sizeof(uint4)));
     CU_TRY(this, d_tile_list.alloc((size_t)n_occ_chunks * OCC_SCAN_CHUNK));
     CU_TRY(this, d_blk_cnt.alloc(n_occ_blocks)); CU_TRY(this, d_blk_off.alloc(n_occ_blocks)); CU_TRY(this, d_work.alloc(v_pad + (size_t)sm_count * 8 * 8 * 512 + 512));
+    CU_TRY(this, d_work_hdr.alloc(v_pad));
     CU_TRY(this, cudaMemset(d_vstate.p, 0, v_pad));
     {   // exchange arena
         const int G = c.shard_count;
@@ -985,11 +986,11 @@ int dspmap::frame_enqueue(const float* d_depth, int rows, int cols, int stride, 
                     void* args[] = {(void*)&fp, (void*)&vm, (void*)&wpr, (void*)&bs};
                     ++launches; CU_TRY(this, cudaLaunchCooperativeKernel((const void*)k_bfs_order, dim3(bfs_grid), dim3(1024), args, 0, stream));
                 }
-                ++launches; k_sweep_select<<<dim3((n.x + 255) / 256, n.y * n.z), 256, 0, stream>>>(fp, st, d_vmask.p, words_per_row, depth_int, d_work.p, d_cnt.p, lo, n,
+                ++launches; k_sweep_select<<<dim3((n.x + 255) / 256, n.y * n.z), 256, 0, stream>>>(fp, st, d_vmask.p, words_per_row, depth_int, d_work.p, d_work_hdr.p, d_cnt.p, lo, n,
                                                                                        f.ref_order ? d_vrank.p : nullptr, f.ref_order ? d_work_key.p : nullptr);
             }
         }
-        DISPATCH_PB(f.Pb, (k_sweep_slots<PB><<<sm_count * 8, 256, 0, stream>>>(fp, st, stx, sty, stz, d_work.p, depth_int, d_pix_count.p, cv, d_cnt.p, f.ref_order ? d_work_key.p : nullptr)));
+        DISPATCH_PB(f.Pb, (k_sweep_slots<PB><<<sm_count * 8, 256, 0, stream>>>(fp, st, stx, sty, stz, d_work.p, d_work_hdr.p, depth_int, d_pix_count.p, cv, d_cnt.p, f.ref_order ? d_work_key.p : nullptr)));
         ++launches;
     }
     // every rank tells every rank how many visible records it wrote into their arenas

@@ -382,7 +382,7 @@ __device__ __forceinline__ bool corner_visible(const FrameParams& f, const float
 
 __global__ void __launch_bounds__(256)
 k_sweep_select(const __grid_constant__ FrameParams f, Store st, const uint32_t* __restrict__ vmask, uint32_t words_per_row,
-               const float* __restrict__ depth_int, uint32_t* __restrict__ work, Counters* __restrict__ cnt, int3 box_lo, int3 box_n,
+               const float* __restrict__ depth_int, uint32_t* __restrict__ work, uint32_t* __restrict__ work_hdr, Counters* __restrict__ cnt, int3 box_lo, int3 box_n,
                const uint32_t* __restrict__ vrank, uint32_t* __restrict__ work_key) {
     // the grid covers only the voxels of the frustum's bounding box, in MAP coordinates: blockIdx.y = (my, mz) row of the
     // box, x along the threads.  Voxels outside the box touch no in-frustum vertex.
@@ -450,6 +450,7 @@ k_sweep_select(const __grid_constant__ FrameParams f, Store st, const uint32_t* 
     if (heavy) {
         const uint32_t pos = s_base + woff + __popc(b_heavy & ((1u << lane_id()) - 1u));
         work[pos] = v;
+        work_hdr[pos] = hdr;              // nothing changes a listed voxel's header before the slot pass reads it: one gather less there
         if (work_key) work_key[pos] = visit_key;
     }
 }
@@ -457,7 +458,7 @@ k_sweep_select(const __grid_constant__ FrameParams f, Store st, const uint32_t* 
 template <int PB>
 __global__ void __launch_bounds__(256)
 k_sweep_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
-              const uint32_t* __restrict__ stamp_z, const uint32_t* __restrict__ work, const float* __restrict__ depth_int,
+              const uint32_t* __restrict__ stamp_z, const uint32_t* __restrict__ work, const uint32_t* __restrict__ work_hdr, const float* __restrict__ depth_int,
               uint32_t* __restrict__ pix_count, CommView cv, Counters* __restrict__ cnt, const uint32_t* __restrict__ work_key) {
     constexpr int P = 1 << PB, G = 32 / P;
     const uint32_t n_work = cnt->n_sweep_work;
@@ -471,19 +472,27 @@ k_sweep_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* _
     auto put_sentinel = [&](uint32_t pos) {
         for (int pr = 0; pr < cv.size; ++pr) (cv.recs[pr] + (size_t)cv.rank * cv.rec_cap + pos)->pix = 0xffffffffu;
     };
+    // the voxel and its header word come from the work list (coalesced); the next iteration's pair is requested before this
+    // iteration's slot records, so the list is never on the chain of dependent loads (list -> slots -> depth pixel)
+    uint32_t nx_v = 0, nx_hdr = 0;
+    if (warp * G + g < n_work) { nx_v = work[warp * G + g]; nx_hdr = work_hdr[warp * G + g]; }
     for (uint32_t w0 = warp * G; w0 < n_work; w0 += n_warps * G) {     // warp-uniform trip count
         const uint32_t wi = w0 + g;
         const bool active = wi < n_work;
-        const uint32_t g_v = active ? work[wi] : 0u;
-        const uint32_t g_hdr = active ? st.hdr[g_v] : 0u;
+        const uint32_t g_v = nx_v, g_hdr = nx_hdr;
+        {
+            const uint32_t wn = wi + n_warps * G;
+            nx_v = 0; nx_hdr = 0;
+            if (wn < n_work) { nx_v = work[wn]; nx_hdr = work_hdr[wn]; }
+        }
         const size_t base = (size_t)g_v << PB;
         // position of the particle inside its pixel's list: ascending particle index, or (reference order) the order the search
         // visits the voxels in, slot order inside a voxel
         const uint32_t order_key = (work_key && active) ? ((work_key[wi] << PB) | s) : (uint32_t)(base + s);
         const bool has = active && s != 0 && ((g_hdr >> (16 + s)) & 1u);
         uint64_t m = 0;
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (has) { m = st.meta[base + s]; x = st.x[base + s]; y = st.y[base + s]; z = st.z[base + s]; }
+        float x = 0.f, y = 0.f, z = 0.f, wgt = 0.f;
+        if (has) { m = st.meta[base + s]; x = st.x[base + s]; y = st.y[base + s]; z = st.z[base + s]; wgt = st.w[base + s]; }
         uint32_t bx, by, bz;
         voxel_to_buffer(f, g_v, bx, by, bz);
         const uint32_t stamp = slab_stamp(stamp_x, stamp_y, stamp_z, bx, by, bz);
@@ -522,7 +531,7 @@ k_sweep_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* _
                 const uint32_t pos = chunk_base + chunk_used + __popc(b_emit & ((1u << lane_id()) - 1u));
                 if (pos < f.vis_cap) {
                     const uint4 lo = make_uint4(pix, (uint32_t)(base + s), __float_as_uint(x), __float_as_uint(y));
-                    const uint4 hi = make_uint4(__float_as_uint(z), __float_as_uint(st.w[base + s]), meta_track(m) | (meta_forget(m) << 16), order_key);
+                    const uint4 hi = make_uint4(__float_as_uint(z), __float_as_uint(wgt), meta_track(m) | (meta_forget(m) << 16), order_key);
                     for (int pr = 0; pr < cv.size; ++pr) {          // every rank builds the full pixel lists
                         uint4* dst = reinterpret_cast<uint4*>(cv.recs[pr] + (size_t)cv.rank * cv.rec_cap + pos);
                         dst[0] = lo; dst[1] = hi;
