@@ -246,6 +246,7 @@ struct dspmap {
     DevBuf<float4> d_vis_pos;
     // ordered insertion
     DevBuf<uint32_t> d_keys, d_ranks, d_birth_flags, d_birth_prefix, d_birth_block;
+    DevBuf<BirthBig> d_birth_big;     // touched voxels whose candidate search runs block-wide
     DevBuf<BirthBox> d_birth_box;     // per hash slot of the birth table: bounding rectangle of the voxel's candidate pixels
     // object moves
     DevBuf<uint32_t> d_movl_idx, d_movl_seq;
@@ -404,7 +405,7 @@ struct dspmap {
         d_static_track.release(); d_static_label.release(); d_fp.release(); d_cnt.release(); d_persist.release();
         d_depth_int.release(); d_cloud_pos.release(); d_cloud_meta.release();
         d_pix_count.release(); d_pix_offset.release(); d_scan_block.release(); d_vmask.release(); d_csr_key.release(); d_seq_ref.release(); d_mov_out.release(); d_csr_idx.release(); d_mine_list.release();
-        d_vis_mp.release(); d_row_order.release(); d_vrank.release(); d_bfs_front[0].release(); d_bfs_front[1].release(); d_bfs_blocks.release(); d_work_key.release(); d_vis_pos.release(); d_keys.release(); d_birth_box.release(); d_ranks.release(); d_birth_flags.release(); d_birth_prefix.release(); d_birth_block.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_chunk_tot.release(); d_chunk_base.release(); d_tile_list.release(); d_work.release(); d_work_hdr.release();
+        d_vis_mp.release(); d_row_order.release(); d_vrank.release(); d_bfs_front[0].release(); d_bfs_front[1].release(); d_bfs_blocks.release(); d_work_key.release(); d_vis_pos.release(); d_keys.release(); d_birth_box.release(); d_birth_big.release(); d_ranks.release(); d_birth_flags.release(); d_birth_prefix.release(); d_birth_block.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_chunk_tot.release(); d_chunk_base.release(); d_tile_list.release(); d_work.release(); d_work_hdr.release();
         for (int p = 0; p < MAX_RANKS; ++p) if (peer_base[p] && p != cfg.shard_rank) { cudaIpcCloseMemHandle(peer_base[p]); peer_base[p] = nullptr; }
         arena.release();
         result2.release();
@@ -601,7 +602,7 @@ int dspmap::init(const dspmap_config& c) {
         birth_cap1 = bcap; birth_shift1 = 32 - bbits;
     }
     CU_TRY(this, d_keys.alloc(cap)); CU_TRY(this, d_ranks.alloc((size_t)cap * f.topk)); CU_TRY(this, d_entry_list.alloc(cap)); CU_TRY(this, d_entry_voxel.alloc(cap));
-    CU_TRY(this, d_birth_box.alloc(f.birth_hash_cap));
+    CU_TRY(this, d_birth_box.alloc(f.birth_hash_cap)); CU_TRY(this, d_birth_big.alloc(f.birth_hash_cap));
 
     n_occ_blocks = (uint32_t)(v_pad / OCC_TILE);
     CU_TRY(this, d_col_tab.alloc(1024)); CU_TRY(this, cudaMemset(d_col_tab.p, 0, 1024));
@@ -1040,7 +1041,8 @@ int dspmap::frame_enqueue(const float* d_depth, int rows, int cols, int stride, 
         }
         if (f.nb_ptc == 1) {    // one newborn per point: mark the touched voxels, then find every voxel's first candidates in the image
             ++launches; k_birth_mark<<<(npix + 255) / 256, 256, 0, side_stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_birth_box.p, d_ranks.p, d_entry_list.p, d_cnt.p);
-            ++launches; k_birth_gather<<<sm_count * 8, 256, 0, side_stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_birth_box.p, d_ranks.p, d_entry_list.p, d_cnt.p);
+            ++launches; k_birth_gather<<<sm_count * 8, 256, 0, side_stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_birth_box.p, d_ranks.p, d_entry_list.p, d_cnt.p, d_birth_big.p);
+            ++launches; k_birth_gather_big<<<sm_count * 4, 256, 0, side_stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_birth_big.p, d_cnt.p);
         } else {
             ++launches; k_birth_bin<<<(n_ranks * f.nb_ptc + 255) / 256, 256, 0, side_stream>>>(fp, d_cloud_pos.p, d_cloud_meta.p, d_keys.p, d_ranks.p, d_entry_list.p, d_cnt.p,
                                                                                         d_birth_prefix.p, d_randoms.p, d_persist.p);

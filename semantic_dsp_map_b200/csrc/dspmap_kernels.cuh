@@ -41,6 +41,7 @@ struct Counters {
     uint32_t n_mine;           // sharded map: listed particles this rank owns (k_select_mine)
     uint32_t mov_out[8];       // moved particles sent to each destination rank this frame
     uint32_t n_visible;        // listed particles (total of the pixel lists)
+    uint32_t n_birth_big;      // touched voxels whose candidate search was handed to whole blocks (k_birth_gather_big)
     uint32_t seq_tail;
 };
 
@@ -852,11 +853,13 @@ __global__ void k_fill_birth_boxes(BirthBox* __restrict__ boxes, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) boxes[i] = BirthBox{0xffffffffu, 0u, 0xffffffffu, 0u, 0u};
 }
 
+struct BirthBig { uint32_t e, i_min, i_max, j_min, j_max; };      // a voxel handed to k_birth_gather_big: hash slot + rectangle
 constexpr int BG_LANES = 8;      // lanes per touched voxel
 constexpr int BG_VALS = 4;       // rank-list entries per lane: topk = 2 * MAX_P - 1 = 31 at most (static_assert below MAX_P)
 __global__ void __launch_bounds__(256)
 k_birth_gather(const __grid_constant__ FrameParams f, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta, const uint32_t* __restrict__ keys,
-               BirthBox* __restrict__ boxes, uint32_t* __restrict__ ranks, const uint32_t* __restrict__ entry_list, const Counters* __restrict__ cnt) {
+               BirthBox* __restrict__ boxes, uint32_t* __restrict__ ranks, const uint32_t* __restrict__ entry_list, Counters* __restrict__ cnt,
+               BirthBig* __restrict__ big_list) {
     const uint32_t n_entries = cnt->n_birth_voxels, K = f.topk;
     const uint32_t sub = lane_id() & (BG_LANES - 1), gmask = ((1u << BG_LANES) - 1u) << (lane_id() & ~(uint32_t)(BG_LANES - 1));
     const uint32_t n_groups = (gridDim.x * blockDim.x) / BG_LANES;
@@ -902,7 +905,13 @@ k_birth_gather(const __grid_constant__ FrameParams f, const float4* __restrict__
                 for (uint32_t t = n_cand + sub; t < K; t += BG_LANES) out[t] = NO_RANK;
             }
         }
-        const bool scan = live && !listed;
+        // More candidates than the list holds: walk the rectangle.  The walk ends after about  area * topk / candidates  cells (the
+        // hits are spread over the nine phases like the cells) - a few for a near surface, hundreds for a voxel with thirty
+        // candidates scattered over a large rectangle; those go to whole blocks (k_birth_gather_big) instead of eight lanes.
+        const uint32_t area = live ? (uint32_t)((i1 - i0 + 1) * (j1 - j0 + 1)) : 0u;
+        const bool big = live && !listed && (uint64_t)area * K > (uint64_t)n_cand * (8u * BG_LANES);
+        if (big && sub == 0) big_list[atomicAdd(&cnt->n_birth_big, 1u)] = BirthBig{e, (uint32_t)i0, (uint32_t)i1, (uint32_t)j0, (uint32_t)j1};
+        const bool scan = live && !listed && !big;
         uint32_t found = scan ? 0u : K;
         for (int ph = 0; ph < 9; ++ph) {
             const int pi = ph / 3, pj = ph - 3 * pi;
@@ -934,6 +943,54 @@ k_birth_gather(const __grid_constant__ FrameParams f, const float4* __restrict__
         }
         if (scan)
             for (uint32_t t = min(found, K) + sub; t < K; t += BG_LANES) out[t] = NO_RANK;
+    }
+}
+
+// the rectangle walk of k_birth_gather for one voxel per BLOCK: 256 cells of a phase at a time, ordered compaction of the hits
+__global__ void __launch_bounds__(256)
+k_birth_gather_big(const __grid_constant__ FrameParams f, const float4* __restrict__ cloud_pos, const uint32_t* __restrict__ cloud_meta, const uint32_t* __restrict__ keys,
+                   uint32_t* __restrict__ ranks, const BirthBig* __restrict__ big_list, const Counters* __restrict__ cnt) {
+    __shared__ uint32_t s_wcnt[8];
+    const uint32_t n_big = cnt->n_birth_big, K = f.topk, wid = threadIdx.x >> 5;
+    const int hc = (f.H + 2) / 3, wc = (f.W + 2) / 3;
+    for (uint32_t bi = blockIdx.x; bi < n_big; bi += gridDim.x) {
+        const BirthBig bb = big_list[bi];
+        const uint32_t v = keys[bb.e];
+        const int i0 = (int)bb.i_min, i1 = (int)bb.i_max, j0 = (int)bb.j_min, j1 = (int)bb.j_max;
+        uint32_t* out = ranks + (size_t)bb.e * K;
+        uint32_t found = 0;                                      // the same in every thread of the block
+        for (int ph = 0; ph < 9 && found < K; ++ph) {
+            const int pi = ph / 3, pj = ph - 3 * pi;
+            const int a0 = (i0 - pi + 2) / 3, a1 = (i1 - pi >= 0) ? (i1 - pi) / 3 : -1, b0 = (j0 - pj + 2) / 3, b1 = (j1 - pj >= 0) ? (j1 - pj) / 3 : -1;
+            const int nb = b1 - b0 + 1, ncell = (a1 >= a0 && nb > 0) ? (a1 - a0 + 1) * nb : 0;
+            for (int c0 = 0; c0 < ncell && found < K; c0 += 256) {
+                const int c = c0 + (int)threadIdx.x;
+                bool hit = false;
+                uint32_t rank = 0;
+                if (c < ncell) {
+                    const int a = a0 + c / nb, b = b0 + c % nb, q = (3 * a + pi) * f.W + 3 * b + pj;
+                    if (pt_valid(cloud_meta[q])) {
+                        const float4 p = cloud_pos[q];
+                        uint32_t bx, by, bz;
+                        hit = global_pos_to_voxel(f, p.x + 0.f, p.y + 0.f, p.z + 0.f, bx, by, bz) == v;
+                        rank = (uint32_t)((ph * hc + a) * wc + b);
+                    }
+                }
+                const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+                if (lane_id() == 0) s_wcnt[wid] = (uint32_t)__popc(hits);
+                __syncthreads();
+                uint32_t before = 0, total = 0;
+#pragma unroll
+                for (uint32_t w = 0; w < 8; ++w) { const uint32_t t = s_wcnt[w]; before += w < wid ? t : 0u; total += t; }
+                if (hit) {
+                    const uint32_t pos = found + before + (uint32_t)__popc(hits & ((1u << lane_id()) - 1u));
+                    if (pos < K) out[pos] = rank;
+                }
+                found += total;
+                __syncthreads();
+            }
+        }
+        for (uint32_t t = min(found, K) + threadIdx.x; t < K; t += 256) out[t] = NO_RANK;
     }
 }
 
@@ -1446,18 +1503,26 @@ k_occ_scan(OccScratch sc, uint32_t n_blocks, Counters* __restrict__ cnt, Persist
             uint32_t* row = cv.counts[p] + cv.rank * COMM_COUNTS;
             row[CC_OCC] = run0; row[CC_FREE] = run1;
         }
-        if (host_cnt) {
-            // Unsharded map: nothing after this point changes a counter (the emit pass reads the scan's tables only), so the block
-            // goes to the host from here - plain stores into the handle's pinned copy, body first, the two stamps the host polls
-            // for last - and is zeroed for the next frame.  No copy-engine operation at either end of a frame.
+    }
+    if (host_cnt) {
+        // Unsharded map: nothing after this point changes a counter (the emit pass reads the scan's tables only), so the block goes
+        // to the host from here - plain stores into the handle's pinned copy, body first, the two stamps the host polls for
+        // last - and is zeroed for the next frame.  No copy-engine operation at either end of a frame.  (One warp, two words
+        // per lane: the loads come from L2 - other kernels' atomics live there - and should not queue up behind one thread.)
+        __syncthreads();                                          // thread 0 has written its totals (the branch is block-uniform)
+        if (threadIdx.x < 32) {
             constexpr int NW = sizeof(Counters) / 4;
-            static_assert(offsetof(Counters, seq_head) == 0 && offsetof(Counters, seq_tail) == (NW - 1) * 4, "stamps at both ends");
-            volatile uint32_t* src = reinterpret_cast<volatile uint32_t*>(cnt);      // other kernels' atomics live in L2: bypass L1
+            static_assert(offsetof(Counters, seq_head) == 0 && offsetof(Counters, seq_tail) == (NW - 1) * 4 && NW - 2 <= 64, "stamps at both ends, body of at most 64 words");
+            volatile uint32_t* src = reinterpret_cast<volatile uint32_t*>(cnt);
             volatile uint32_t* dst = reinterpret_cast<volatile uint32_t*>(host_cnt);
-            for (int i = 1; i < NW - 1; ++i) dst[i] = src[i];
+            const int k0 = 1 + (int)threadIdx.x, k1 = 33 + (int)threadIdx.x;
+            const uint32_t w0 = k0 < NW - 1 ? src[k0] : 0u, w1 = k1 < NW - 1 ? src[k1] : 0u;
+            if (k0 < NW - 1) dst[k0] = w0;
+            if (k1 < NW - 1) dst[k1] = w1;
             __threadfence_system();
-            dst[0] = frame_stamp; dst[NW - 1] = frame_stamp;
-            for (int i = 0; i < NW; ++i) src[i] = 0u;
+            __syncwarp();
+            if (threadIdx.x == 0) { dst[0] = frame_stamp; dst[NW - 1] = frame_stamp; }
+            for (int i = (int)threadIdx.x; i < NW; i += 32) src[i] = 0u;
         }
     }
     if (cv.size > 1) __threadfence_system();      // sharded map: peers read what this kernel wrote after the next barrier
