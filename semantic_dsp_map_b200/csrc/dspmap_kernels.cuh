@@ -1720,6 +1720,47 @@ k_move_prepare(const MoveTable* __restrict__ mt, const uint16_t* __restrict__ mo
         persist->cursor_ring = (uint32_t)(((uint64_t)persist->cursor_ring + 3ull * acc) % rand_n);   // basic_algorithms.h:426-433
     }
     __syncthreads();
+    if (n_moves <= 4 && blockDim.x == SCAN_BLOCK) {
+        // The usual frame moves a handful of objects: every thread takes MP_EPT consecutive list entries (thread order = list
+        // order), the counts of two moved tracks share one word of a block scan (16 bits each: a chunk holds 4096 entries), and
+        // a chunk of 4096 entries costs one scan per pair of tracks instead of four barriers per 1024 entries.
+        constexpr int MP_EPT = 4;
+        uint32_t* s_scan = &s_wcount[0][0];                        // (33 words of it)
+        uint32_t run[4] = {0u, 0u, 0u, 0u};                        // entries of each moved track in the chunks before this one
+        for (uint32_t c = 0; c < n; c += SCAN_BLOCK * MP_EPT) {
+            int mvv[MP_EPT];
+            bool rmv[MP_EPT];
+            uint32_t pk01 = 0, pk23 = 0;
+#pragma unroll
+            for (int i = 0; i < MP_EPT; ++i) {
+                const uint32_t k = c + threadIdx.x * MP_EPT + i;
+                mvv[i] = -1; rmv[i] = false;
+                if (k < n) {
+                    const int tr = (int)movl_track[k];
+                    mvv[i] = find_track(mt->move_track, n_moves, tr);
+                    if (mvv[i] < 0) rmv[i] = find_track(mt->remove_track, mt->n_remove, tr) >= 0;
+                }
+                pk01 += (mvv[i] == 0) + ((uint32_t)(mvv[i] == 1) << 16);
+                pk23 += (mvv[i] == 2) + ((uint32_t)(mvv[i] == 3) << 16);
+            }
+            uint32_t tot01 = 0, tot23 = 0, ex23 = 0;
+            const uint32_t ex01 = block_exclusive_scan(pk01, s_scan, tot01);
+            if (n_moves > 2) ex23 = block_exclusive_scan(pk23, s_scan, tot23);
+            uint32_t before[4] = {run[0] + (ex01 & 0xffffu), run[1] + (ex01 >> 16), run[2] + (ex23 & 0xffffu), run[3] + (ex23 >> 16)};
+#pragma unroll
+            for (int i = 0; i < MP_EPT; ++i) {
+                const uint32_t k = c + threadIdx.x * MP_EPT + i;
+                if (k >= n) continue;
+                uint32_t seq = rmv[i] ? SEQ_REMOVE : NO_RANK;
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+                    if (mvv[i] == m) seq = s_offset[m] + before[m]++;
+                movl_seq[k] = seq;
+            }
+            run[0] += tot01 & 0xffffu; run[1] += tot01 >> 16; run[2] += tot23 & 0xffffu; run[3] += tot23 >> 16;
+        }
+        return;
+    }
     const uint32_t wid = threadIdx.x >> 5;
     for (uint32_t c = 0; c < n; c += blockDim.x) {
         for (int i = threadIdx.x; i < 32 * n_moves; i += blockDim.x) s_wcount[i / n_moves][i % n_moves] = 0;
