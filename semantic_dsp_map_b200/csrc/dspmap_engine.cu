@@ -1081,7 +1081,13 @@ int dspmap::frame_enqueue(const float* d_depth, int rows, int cols, int stride, 
     const ResultArrays out = sl.dres;
     OccScratch osc{d_vstate.p, d_res_w.p - (slot_lo >> f.Pb), d_res_tl.p - (slot_lo >> f.Pb), d_mov_mask.p - (slot_lo >> f.Pb), d_blk_cnt.p, d_blk_off.p, d_chunk_tot.p, d_chunk_base.p, d_tile_list.p};
     if (profiling) cudaEventRecord(ev[8], stream);
-    DISPATCH_PB(f.Pb, (k_occ_headers<PB><<<sm_count * 8, OCC_BLOCK, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, n_occ_blocks, d_cnt.p)));
+    // DSPMAP_OCC_HEADERS=bulk: the header plane staged through shared memory by the bulk-copy unit (k_occ_headers_bulk).  Measured
+    // at configs B / D / E: 18.4 / 63.1 / 137.9 us against 17.1 / 57.7 / 134.7 us for a 16-byte load per thread with one prefetch -
+    // the pass already runs at the copy peak on the margin (504 MB more from D to E in 77 us = 6.5 TB/s); what is left at the
+    // smaller sizes is start-up, not bytes in flight.  Kept for comparisons, not the default.
+    static const bool headers_by_loads = !(getenv("DSPMAP_OCC_HEADERS") && !strcmp(getenv("DSPMAP_OCC_HEADERS"), "bulk"));
+    if (headers_by_loads) { DISPATCH_PB(f.Pb, (k_occ_headers<PB><<<sm_count * 8, OCC_BLOCK, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, n_occ_blocks, d_cnt.p))); }
+    else { DISPATCH_PB(f.Pb, (k_occ_headers_bulk<PB><<<sm_count * 4, OHB_BLOCK, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, n_occ_blocks, d_cnt.p))); }
     ++launches;
     if (profiling) cudaEventRecord(ev[9], stream);
     DISPATCH_PB(f.Pb, (k_occ_slots<PB><<<sm_count * 8, 256, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, d_cnt.p)));

@@ -1355,6 +1355,119 @@ k_occ_headers(const __grid_constant__ FrameParams f, Store st, const uint32_t* _
     }
 }
 
+// ---- the same pass with the header plane staged through shared memory by the bulk-copy (TMA) unit ----------------------
+// The plane is the one thing the engine streams whole from HBM (4 B per voxel, 134 MB at 512 x 128 x 512), and a load per
+// thread with one prefetch keeps 64 KB per SM in flight - short of what HBM3e needs at full rate.  Here every CTA runs a ring of
+// OHB_STAGES chunks of OHB_CHUNK voxels: one elected thread issues cp.async.bulk global -> shared for the chunk OHB_STAGES ahead,
+// completion is counted in bytes on the stage's mbarrier, the CTA's threads wait on the barrier's phase and read their header
+// words from shared memory (16-byte, conflict-free).  Four CTAs per SM x 32 KB = 128 KB per SM in flight, issued by four threads.
+constexpr int OHB_STAGES = 4;
+constexpr int OHB_CHUNK = 2048;                  // voxels per stage (8 KB)
+constexpr int OHB_BLOCK = 256;
+static_assert(OCC_TILE % OHB_CHUNK == 0 || OHB_CHUNK % OCC_TILE == 0, "chunks and tiles nest");
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_global_to_shared(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_BAR:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_BAR;\n"
+        "bra WAIT_BAR;\n"
+        "DONE_BAR:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+template <int PB>
+__global__ void __launch_bounds__(OHB_BLOCK)
+k_occ_headers_bulk(const __grid_constant__ FrameParams f, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
+                   const uint32_t* __restrict__ stamp_z, OccScratch sc, uint32_t* __restrict__ work, uint32_t n_tiles, Counters* __restrict__ cnt) {
+    __shared__ __align__(128) uint32_t s_hdr[OHB_STAGES][OHB_CHUNK];
+    __shared__ __align__(8) uint64_t s_bar[OHB_STAGES];
+    const uint32_t v_lo = f.z_lo << (f.Xb + f.Yb);
+    const uint32_t n_vox = n_tiles * OCC_TILE;                               // the plane is padded to whole tiles
+    const uint32_t n_chunks = (n_vox + OHB_CHUNK - 1) / OHB_CHUNK;
+    const uint32_t my_chunks = blockIdx.x < n_chunks ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(s_bar), buf0 = (uint32_t)__cvta_generic_to_shared(s_hdr);
+    auto issue = [&](uint32_t k) {       // chunk number k of this CTA into its stage (one thread)
+        const uint32_t chunk = blockIdx.x + k * gridDim.x, stage = k % OHB_STAGES;
+        const uint32_t vox0 = chunk * OHB_CHUNK, bytes = min((uint32_t)OHB_CHUNK, n_vox - vox0) * 4u;
+        mbar_expect_tx(bar0 + 8 * stage, bytes);
+        bulk_global_to_shared(buf0 + stage * (OHB_CHUNK * 4), st.hdr + v_lo + vox0, bytes, bar0 + 8 * stage);
+    };
+    if (threadIdx.x == 0) {
+        for (int s2 = 0; s2 < OHB_STAGES; ++s2) mbar_init(bar0 + 8 * s2, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (uint32_t k = 0; k < min(my_chunks, (uint32_t)OHB_STAGES); ++k) issue(k);
+    for (uint32_t k = 0; k < my_chunks; ++k) {
+        const uint32_t chunk = blockIdx.x + k * gridDim.x, stage = k % OHB_STAGES;
+        const uint32_t vox0 = chunk * OHB_CHUNK, n_here = min((uint32_t)OHB_CHUNK, n_vox - vox0);
+        mbar_wait(bar0 + 8 * stage, (k / OHB_STAGES) & 1u);
+#pragma unroll
+        for (int j = 0; j < OHB_CHUNK / (OHB_BLOCK * OCC_VPT); ++j) {
+            const uint32_t q = (uint32_t)j * OHB_BLOCK + threadIdx.x;        // 16-byte group inside the chunk (whole warps in or out)
+            if (q * OCC_VPT >= n_here) break;
+            const uint4 h4 = *reinterpret_cast<const uint4*>(&s_hdr[stage][q * OCC_VPT]);
+            const uint32_t v0 = v_lo + vox0 + q * OCC_VPT;
+            const uint32_t hdrs[OCC_VPT] = {h4.x, h4.y, h4.z, h4.w};
+            // never-observed voxels (header 0: no time stamp, no live slot) are unknown whatever the slab stamps say
+            const bool any_set = (hdrs[0] | hdrs[1] | hdrs[2] | hdrs[3]) != 0;
+            if (!__any_sync(0xffffffffu, any_set)) {
+                *reinterpret_cast<uint32_t*>(sc.vstate + (v0 - v_lo)) = 0u;
+                continue;
+            }
+            uint32_t sb4 = 0, heavy = 0, n_free = 0;
+            if (any_set) {
+                uint32_t bx0, by, bz;
+                voxel_to_buffer(f, v0, bx0, by, bz);
+                const uint32_t stamp_yz = max(__ldg(stamp_y + by), __ldg(stamp_z + bz));
+#pragma unroll
+                for (int u = 0; u < OCC_VPT; ++u) {
+                    const uint32_t hdr = hdrs[u];
+                    const uint32_t stamp = max(stamp_yz, __ldg(stamp_x + bx0 + u));
+                    const uint32_t ts0 = hdr_ts(hdr);
+                    const bool known = ts0 != 0 && !(ts0 < stamp);                  // isVoxelValid, operations.h:824-837
+                    const bool hv = hdr_live(hdr) != 0 && (known || (hdr & HDR_MOVABLE));
+                    sb4 |= (known ? 1u : 0u) << (8 * u);
+                    heavy |= (hv ? 1u : 0u) << u;
+                    n_free += known && !hv;
+                }
+            }
+            *reinterpret_cast<uint32_t*>(sc.vstate + (v0 - v_lo)) = sb4;
+            if (f.want_free) {
+                n_free = __reduce_add_sync(0xffffffffu, n_free);
+                if (lane_id() == 0 && n_free) atomicAdd(reinterpret_cast<uint32_t*>(sc.blk_cnt + (v0 - v_lo) / OCC_TILE) + 1, n_free);
+            }
+            if (!__any_sync(0xffffffffu, heavy != 0)) continue;
+            const uint32_t nh = __popc(heavy);
+            uint32_t inc = nh;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane_id() >= (uint32_t)o) inc += n;
+            }
+            const uint32_t warp_total = __shfl_sync(0xffffffffu, inc, 31);
+            uint32_t base = 0;
+            if (lane_id() == 31) base = atomicAdd(&cnt->n_occ_work, warp_total);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            uint32_t pos = base + inc - nh;
+#pragma unroll
+            for (int u = 0; u < OCC_VPT; ++u)
+                if ((heavy >> u) & 1u) work[pos++] = v0 + u;
+        }
+        __syncthreads();                                                     // the stage has been read by everyone
+        if (threadIdx.x == 0 && k + OHB_STAGES < my_chunks) issue(k + OHB_STAGES);
+    }
+}
+
 template <int PB>
 __global__ void __launch_bounds__(256)
 k_occ_slots(const __grid_constant__ FrameParams f, Store st, const uint32_t* __restrict__ stamp_x, const uint32_t* __restrict__ stamp_y,
