@@ -264,7 +264,7 @@ struct dspmap {
     // exchange arena (one allocation, exported over CUDA IPC in sharded maps): barrier flags, counts, visible records,
     // incoming moved particles, the ck image and the (global) result arrays
     DevBuf<uint8_t> arena;
-    struct ArenaLayout { size_t flags, counts, move_counts, recs, movs, obs_a, obs_b, r_idx, r_xyz, r_w, r_track, r_label, r_state, r_free_idx, r_free_xyz, r_rgb, total; } lay{};
+    struct ArenaLayout { size_t flags, counts, move_counts, recs, movs, obs_a, obs_b, r_idx, r_xyz, r_w, r_track, r_label, r_state, r_free_idx, r_free_xyz, r_rgb, total, res2; } lay{};
     CommView cv{};
     uint32_t comm_epoch = 0;
     void* peer_base[MAX_RANKS]{};
@@ -433,7 +433,7 @@ struct dspmap {
         d_obs_a = (float4*)(mine + lay.obs_a); d_obs_b = (uint2*)(mine + lay.obs_b); d_counts = (uint32_t*)(mine + lay.counts);
         uint8_t* r0 = (uint8_t*)(peer_base[0] && have_rank0 >= 0 ? peer_base[0] : arena.p);
         slot[0].dres = result_arrays_at(r0, 0);
-        slot[1].dres = result2.p ? result_arrays_at(result2.p, lay.r_idx) : slot[0].dres;
+        slot[1].dres = lay.res2 ? result_arrays_at(r0 + lay.res2, lay.r_idx) : (result2.p ? result_arrays_at(result2.p, lay.r_idx) : slot[0].dres);
     }
     // the nine result arrays inside a block laid out like the arena's result part (`bias` = offset of that part's first array)
     ResultArrays result_arrays_at(uint8_t* b, size_t bias) const {
@@ -627,7 +627,10 @@ int dspmap::init(const dspmap_config& c) {
         lay.r_free_idx = take(Vg * 4); lay.r_free_xyz = take(Vg * 12);
         lay.r_rgb = take(Vg * 3);
         lay.total = off;
-        CU_TRY(this, arena.alloc(lay.total));
+        // a sharded map's result arrays live in rank 0's arena (the peers write into them): both sets of a pipelined map are part
+        // of every rank's arena, so that the layout is the same everywhere; an unsharded map allocates its second set on demand
+        lay.res2 = G > 1 ? lay.total : 0;
+        CU_TRY(this, arena.alloc(lay.total + (G > 1 ? lay.total - lay.r_idx : 0)));
         CU_TRY(this, cudaMemset(arena.p, 0, lay.flags + 64 * 4 + (size_t)MAX_RANKS * COMM_COUNTS * 4 + (size_t)MAX_RANKS * MAX_MOVES * 4 + 1024));
         CU_TRY(this, cudaMemset(arena.p + lay.obs_a, 0, n_obs * 16)); CU_TRY(this, cudaMemset(arena.p + lay.obs_b, 0, n_obs * 8));
         peer_base[c.shard_rank] = arena.p;
@@ -767,12 +770,12 @@ int dspmap::frame(const float* d_depth, int rows, int cols, int stride, const ds
     // Synchronous call: enqueue the frame, wait for its counters.  Pipelined call (dspmap_update_async): enqueue frame t, THEN
     // wait for frame t-1 - which ran while the host staged and enqueued this one - and start the transfer of its result.
     const int prev = cur;
-    if (!pipelined || profiling || cv.size > 1) { const int rc = drain(false); if (rc != DSPMAP_OK) return rc; }
+    if (!pipelined || profiling) { const int rc = drain(false); if (rc != DSPMAP_OK) return rc; }
     if (slot[next_slot()].inflight) { const int rc = frame_finish(next_slot()); if (rc != DSPMAP_OK) return rc; }   // (protocol: cannot happen)
     int rc = frame_enqueue(d_depth, rows, cols, stride, masks, n_masks, pos, quat, moves, n_moves, remove_tracks, n_remove, want_free, pre_decimated, late_masks, late_depth);
     if (rc != DSPMAP_OK) return rc;
     slot[cur].want_host = want_host;
-    if (!pipelined || profiling || cv.size > 1) return frame_finish(cur);
+    if (!pipelined || profiling) return frame_finish(cur);
     if (prev != cur && slot[prev].inflight) {
         static const bool trace = getenv("DSPMAP_TRACE") != nullptr;
         const double ta = trace ? host_now_ms() : 0.0;
@@ -901,8 +904,7 @@ int dspmap::frame_enqueue(const float* d_depth, int rows, int cols, int stride, 
         CU_TRY(this, upload_table(sl, sl.d_stamps.p, sl.p_stamps.p, (f.NX + f.NY + f.NZ) * 4));
         sl.stamps_stale = false;
     }
-    // unsharded maps: k_occ_scan hands the counters to the host and leaves them zero; sharded maps still copy and clear them
-    if (cv.size > 1) CU_TRY(this, cudaMemsetAsync(d_cnt.p, 0, sizeof(Counters), stream));
+    // (the counters are zero: k_occ_scan - sharded maps: k_publish_counters - hands them to the host and clears them)
     static const bool trace_gpu = getenv("DSPMAP_TRACE") != nullptr;
     if (trace_gpu) cudaEventRecord(sl.tr_begin, stream);
     const uint32_t* stx = sl.d_stamps.p;
@@ -1093,8 +1095,10 @@ int dspmap::frame_enqueue(const float* d_depth, int rows, int cols, int stride, 
     DISPATCH_PB(f.Pb, (k_occ_slots<PB><<<sm_count * 8, 256, 0, stream>>>(fp, st, stx, sty, stz, osc, d_work.p, d_cnt.p)));
     ++launches;
     ++launches; k_occ_scan<<<n_occ_chunks, 1024, 0, stream>>>(osc, n_occ_blocks, d_cnt.p, d_persist.p, cv, T, cv.size == 1 ? sl.p_cnt.p : nullptr);
-    barrier();   // the lower ranks' totals are this rank's base offsets
+    // before the barrier: on a sharded map the PEERS' emit passes write into rank 0's arrays too, and they pass this barrier only
+    // when rank 0 has
     if (wait_copy) CU_TRY(this, cudaStreamWaitEvent(stream, sl.copy_done, 0));
+    barrier();   // the lower ranks' totals are this rank's base offsets
     {
         const int use_list = n_occ_chunks > 1;
         const uint32_t emit_grid = use_list ? std::min<uint32_t>(n_occ_blocks, (uint32_t)sm_count * 8) : n_occ_blocks;
@@ -1104,8 +1108,9 @@ int dspmap::frame_enqueue(const float* d_depth, int rows, int cols, int stride, 
     barrier();   // rank 0 holds the whole result
     if (profiling) cudaEventRecord(ev[7], stream);
     CU_TRY(this, cudaEventRecord(sl.frame_done, stream));      // the result arrays are complete
-    if (cv.size > 1) CU_TRY(this, cudaMemcpyAsync(sl.p_cnt.p, d_cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-    if (cv.size > 1) CU_TRY(this, cudaMemcpyAsync(sl.p_stamps.p + (f.NX + f.NY + f.NZ) + 1, d_counts, (size_t)MAX_RANKS * COMM_COUNTS * 4, cudaMemcpyDeviceToHost, stream));
+    if (cv.size > 1) {
+        ++launches; k_publish_counters<<<1, 64, 0, stream>>>(d_cnt.p, d_counts, sl.p_cnt.p, sl.p_stamps.p + (f.NX + f.NY + f.NZ) + 1, (uint32_t)(MAX_RANKS * COMM_COUNTS), T);
+    }
     if (trace_gpu) cudaEventRecord(sl.tr_end, stream);
     CU_TRY(this, cudaGetLastError());
     static const bool trace_frame = getenv("DSPMAP_TRACE") != nullptr;
@@ -1123,18 +1128,16 @@ int dspmap::frame_finish(int s) {
     const uint32_t T = sl.T;
     static const bool trace_frame = getenv("DSPMAP_TRACE") != nullptr;
     sl.inflight = false;
-    if (cv.size == 1) {
-        // The counter block is the frame's last transfer and carries the frame's stamp at both ends (set by the occupancy scan):
-        // the host polls the pinned copy instead of going through a stream synchronisation - the wake-up is a cache miss, not a
-        // driver call.  The stream is looked at now and then so that a failed launch ends the wait.
+    {
+        // The counter block arrives in the handle's pinned copy with the frame's stamp at both ends (written by k_occ_scan, on a
+        // sharded map by k_publish_counters): the host polls it instead of going through a stream synchronisation - the wake-up
+        // is a cache miss, not a driver call.  The stream is looked at now and then so that a failed launch ends the wait.
         volatile Counters* pc = sl.p_cnt.p;
         for (uint32_t spins = 0; pc->seq_head != T || pc->seq_tail != T; ++spins) {
             host_pause();
             if ((spins & 0x3fffu) == 0x3fffu && cudaStreamQuery(stream) != cudaErrorNotReady) break;
         }
         if (pc->seq_head != T || pc->seq_tail != T) CU_TRY(this, cudaStreamSynchronize(stream));
-    } else {
-        CU_TRY(this, cudaStreamSynchronize(stream));
     }
     if (trace_frame) {   // host time to issue the frame's launches vs time left waiting for the device afterwards
         trace_wait_ms += host_now_ms() - sl.t_issued;
@@ -1334,7 +1337,7 @@ static int check_frame_args(dspmap_t* h, const float* depth, int32_t rows, int32
 
 // pipelined frames need a second set of result arrays: frame t's emit pass must not write where frame t-1's transfer reads
 static int ensure_pipelined(dspmap_t* h) {
-    if (h->cfg.shard_count > 1 || h->result2.p) return DSPMAP_OK;      // sharded maps run their frames synchronously
+    if (h->cfg.shard_count > 1 || h->result2.p) return DSPMAP_OK;      // sharded maps carry both sets in their arenas
     CU_TRY(h, h->result2.alloc(h->lay.total - h->lay.r_idx));
     h->slot[1].dres = h->result_arrays_at(h->result2.p, h->lay.r_idx);
     return DSPMAP_OK;
@@ -1377,7 +1380,7 @@ static int update_host_impl(dspmap_t* h, const float* depth, int32_t rows, int32
     if (rc != DSPMAP_OK) return rc;
     CU_TRY(h, cudaSetDevice(h->device));
     if (pipelined && (rc = ensure_pipelined(h)) != DSPMAP_OK) return rc;
-    if (!pipelined || h->profiling || h->cfg.shard_count > 1) { if ((rc = h->drain(false)) != DSPMAP_OK) return rc; }
+    if (!pipelined || h->profiling) { if ((rc = h->drain(false)) != DSPMAP_OK) return rc; }
     // the pinned staging buffers of the frame's slot: free since the frame two back finished
     dspmap::FrameSlot& sl = h->slot[h->next_slot()];
     if (sl.inflight && (rc = h->frame_finish(h->next_slot())) != DSPMAP_OK) return rc;

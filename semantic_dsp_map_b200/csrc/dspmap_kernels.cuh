@@ -111,6 +111,25 @@ __global__ void k_comm_barrier(CommView c, uint32_t epoch, uint32_t* __restrict_
     __threadfence_system();
 }
 
+// Sharded map, end of a frame (after the last barrier): this rank's counter block and its table of per-rank counts go to the
+// host - plain stores into the handle's pinned copies, the block's two stamps last - and the counters are zeroed for the next
+// frame.  (An unsharded map does this from k_occ_scan; here the barriers after the scan still count their time-outs.)
+__global__ void __launch_bounds__(64)
+k_publish_counters(Counters* __restrict__ cnt, const uint32_t* __restrict__ counts, Counters* __restrict__ host_cnt, uint32_t* __restrict__ host_counts,
+                   uint32_t n_counts, uint32_t frame_stamp) {
+    constexpr int NW = sizeof(Counters) / 4;
+    volatile uint32_t* src = reinterpret_cast<volatile uint32_t*>(cnt);
+    volatile uint32_t* dst = reinterpret_cast<volatile uint32_t*>(host_cnt);
+    const volatile uint32_t* csrc = counts;
+    volatile uint32_t* cdst = host_counts;
+    for (uint32_t i = threadIdx.x; i < n_counts; i += blockDim.x) cdst[i] = csrc[i];
+    for (int i = 1 + (int)threadIdx.x; i < NW - 1; i += (int)blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) { dst[0] = frame_stamp; dst[NW - 1] = frame_stamp; }
+    for (int i = (int)threadIdx.x; i < NW; i += (int)blockDim.x) src[i] = 0u;
+}
+
 // =====================================================================================================
 // K1a depth_int       the internal-resolution depth image (manualResize of the depth Mat, pointcloud_tools.h:1104-1133):
 //                     everything up to the pixel lists needs only this, so it runs before the masks have arrived.

@@ -89,6 +89,19 @@ def test_two_shards_match_oracle_bit_for_bit(config):
 
 
 @pytest.mark.gpu
+def test_two_shards_pipelined_match_oracle_bit_for_bit():
+    """The same through update_async / wait_result: every rank enqueues frame t+1 while frame t runs; both result sets live in the
+    ranks' arenas and the peers' emit passes wait (through rank 0's barrier) for rank 0's transfer out of the set they overwrite."""
+    import torch
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + os.getpid() % 90), os.path.join(ROOT, "tools", "sharded_check.py"), "--config", "B", "--frames", "8", "--pipelined"]
+    if torch.cuda.device_count() < 2:
+        cmd.append("--same-gpu")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "sharded_check: PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
 def test_two_shards_of_a_multi_chunk_map_match_oracle():
     """512 x 64 x 512 voxels: every shard has 8192 occupancy tiles = two scan chunks, so the tile-count scan hands over between
     blocks and the emit pass runs from the non-empty-tile list (the large-map path) on both ranks."""

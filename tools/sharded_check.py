@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--same-gpu", action="store_true")
     ap.add_argument("--full", action="store_true", help="full-size config instead of the tiny variant")
+    ap.add_argument("--pipelined", action="store_true", help="frames through update_async / wait_result (frame t+1 enqueued while frame t runs)")
     ap.add_argument("--grid", default="", help="voxel bits x,y,z overriding the (tiny) config's grid, e.g. 9,6,9")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -53,20 +54,33 @@ def main():
         orc.engine.set_random_table(table)
     scene = Scene(cfg)
     ok = True
+    def check(t, r):
+        nonlocal ok
+        if rank != 0:
+            return
+        fr = scene.frame(t)
+        ro = orc.update(fr.depth, fr.masks, fr.position, fr.orientation, if_get_freespace=True, moves=fr.moves, remove_tracks=[2] if t == 5 else [])
+        for name in ("voxel_index", "xyz", "weight_sum", "track_id", "label_id", "state", "free_voxel_index", "free_xyz"):
+            a, b = getattr(r, name), getattr(ro, name)
+            same = a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+            if not same:
+                ok = False
+                print(f"frame {t}: {name} differs: engine {a.shape} oracle {b.shape}", flush=True)
+        print(f"frame {t}: occupied {len(r.voxel_index)} free {len(r.free_voxel_index)} {'OK' if ok else 'MISMATCH'}", flush=True)
+
+    prev = None
     for t in range(args.frames):
         fr = scene.frame(t)
         rm = [2] if t == 5 else []
-        r = m.update(fr.depth, fr.masks, fr.position, fr.orientation, if_get_freespace=True, moves=fr.moves, remove_tracks=rm)
-        if rank == 0:
-            fr = scene.frame(t)
-            ro = orc.update(fr.depth, fr.masks, fr.position, fr.orientation, if_get_freespace=True, moves=fr.moves, remove_tracks=rm)
-            for name in ("voxel_index", "xyz", "weight_sum", "track_id", "label_id", "state", "free_voxel_index", "free_xyz"):
-                a, b = getattr(r, name), getattr(ro, name)
-                same = a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
-                if not same:
-                    ok = False
-                    print(f"frame {t}: {name} differs: engine {a.shape} oracle {b.shape}", flush=True)
-            print(f"frame {t}: occupied {len(r.voxel_index)} free {len(r.free_voxel_index)} {'OK' if ok else 'MISMATCH'}", flush=True)
+        if args.pipelined:      # every rank submits frame t, then collects frame t-1 (rank 0 holds the whole result)
+            k = m.update_async(fr.depth, fr.masks, fr.position, fr.orientation, if_get_freespace=True, moves=fr.moves, remove_tracks=rm)
+            if prev is not None:
+                check(t - 1, m.wait_result(prev))
+            prev = k
+        else:
+            check(t, m.update(fr.depth, fr.masks, fr.position, fr.orientation, if_get_freespace=True, moves=fr.moves, remove_tracks=rm))
+    if args.pipelined:
+        check(args.frames - 1, m.wait_result(prev))
     flag = torch.tensor([1 if ok else 0])
     dist.broadcast(flag, 0)
     dist.barrier()
