@@ -249,6 +249,7 @@ struct dspmap {
     DevBuf<BirthBig> d_birth_big;     // touched voxels whose candidate search runs block-wide
     DevBuf<BirthBox> d_birth_box;     // per hash slot of the birth table: bounding rectangle of the voxel's candidate pixels
     // object moves
+    DevBuf<uint4> d_move_blk;           // per-block counts of the moved tracks' list entries (k_move_count_blocks)
     DevBuf<uint32_t> d_movl_idx, d_movl_seq;
     DevBuf<uint16_t> d_movl_track, d_mov_mask;
     DevBuf<uint8_t> d_vstate;
@@ -405,7 +406,7 @@ struct dspmap {
         d_static_track.release(); d_static_label.release(); d_fp.release(); d_cnt.release(); d_persist.release();
         d_depth_int.release(); d_cloud_pos.release(); d_cloud_meta.release();
         d_pix_count.release(); d_pix_offset.release(); d_scan_block.release(); d_vmask.release(); d_csr_key.release(); d_seq_ref.release(); d_mov_out.release(); d_csr_idx.release(); d_mine_list.release();
-        d_vis_mp.release(); d_row_order.release(); d_vrank.release(); d_bfs_front[0].release(); d_bfs_front[1].release(); d_bfs_blocks.release(); d_work_key.release(); d_vis_pos.release(); d_keys.release(); d_birth_box.release(); d_birth_big.release(); d_ranks.release(); d_birth_flags.release(); d_birth_prefix.release(); d_birth_block.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_chunk_tot.release(); d_chunk_base.release(); d_tile_list.release(); d_work.release(); d_work_hdr.release();
+        d_vis_mp.release(); d_row_order.release(); d_vrank.release(); d_bfs_front[0].release(); d_bfs_front[1].release(); d_bfs_blocks.release(); d_work_key.release(); d_vis_pos.release(); d_keys.release(); d_birth_box.release(); d_birth_big.release(); d_ranks.release(); d_birth_flags.release(); d_birth_prefix.release(); d_birth_block.release(); d_move_blk.release(); d_movl_idx.release(); d_movl_seq.release(); d_movl_track.release(); d_mov_mask.release(); d_vstate.release(); d_res_w.release(); d_res_tl.release(); d_blk_cnt.release(); d_blk_off.release(); d_chunk_tot.release(); d_chunk_base.release(); d_tile_list.release(); d_work.release(); d_work_hdr.release();
         for (int p = 0; p < MAX_RANKS; ++p) if (peer_base[p] && p != cfg.shard_rank) { cudaIpcCloseMemHandle(peer_base[p]); peer_base[p] = nullptr; }
         arena.release();
         result2.release();
@@ -585,6 +586,7 @@ int dspmap::init(const dspmap_config& c) {
     CU_TRY(this, d_vis_mp.alloc(list_cap)); CU_TRY(this, d_vis_pos.alloc(list_cap)); CU_TRY(this, d_row_order.alloc(f.H));
 
     sel_cap = (uint32_t)std::min<size_t>(usable, (size_t)1 << 20);
+    CU_TRY(this, d_move_blk.alloc((sel_cap + MPB_CHUNK - 1) / MPB_CHUNK));
     CU_TRY(this, d_movl_idx.alloc(sel_cap)); CU_TRY(this, d_movl_seq.alloc(sel_cap)); CU_TRY(this, d_movl_track.alloc(sel_cap));
     seq_cap = (size_t)sel_cap * c.shard_count >= ((size_t)1 << 24) ? (1u << 24) : sel_cap * (uint32_t)c.shard_count;   // sequence numbers are global (and 24 bits in the rank lists)
     CU_TRY(this, d_seq_ref.alloc(seq_cap)); CU_TRY(this, d_mov_out.alloc(MAX_RANKS));
@@ -736,8 +738,15 @@ int dspmap::run_moves(const dspmap_object_move* moves, int n_moves, const int32_
             ++launches; k_move_count<<<1, 1024, 0, stream>>>(d_mt, d_movl_track.p, sel_cap, d_persist.p, cv);
             barrier();   // every rank knows how many particles of each moved track the lower ranks hold
         }
-        ++launches; k_move_prepare<<<1, 1024, 0, stream>>>(d_mt, d_movl_track.p, d_movl_seq.p, sel_cap, rand_n, d_cnt.p, d_persist.p, cv,
-                                                         cv.move_counts[cv.rank]);
+        if (n_moves <= 4) {      // the usual frame: numbering over the whole GPU
+            const uint32_t nb = (sel_cap + MPB_CHUNK - 1) / MPB_CHUNK;          // <= SCAN_BLOCK blocks (sel_cap <= 2^20)
+            ++launches; k_move_count_blocks<<<nb, SCAN_BLOCK, 0, stream>>>(d_mt, d_movl_track.p, sel_cap, d_persist.p, d_move_blk.p);
+            ++launches; k_move_number<<<nb, SCAN_BLOCK, 0, stream>>>(d_mt, d_movl_track.p, d_movl_seq.p, sel_cap, rand_n, d_cnt.p, d_persist.p, cv,
+                                                                     cv.move_counts[cv.rank], d_move_blk.p);
+        } else {
+            ++launches; k_move_prepare<<<1, 1024, 0, stream>>>(d_mt, d_movl_track.p, d_movl_seq.p, sel_cap, rand_n, d_cnt.p, d_persist.p, cv,
+                                                             cv.move_counts[cv.rank]);
+        }
         ++launches; k_move_apply<<<sm_count * 2, 256, 0, stream>>>(fp, d_cnt.p, st, d_mt, d_randoms.p, d_persist.p, d_movl_idx.p, d_movl_track.p,
                                                              d_movl_seq.p, sel_cap, cv);
         if (n_moves > 0) {

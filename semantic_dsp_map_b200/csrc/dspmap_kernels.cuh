@@ -1852,47 +1852,6 @@ k_move_prepare(const MoveTable* __restrict__ mt, const uint16_t* __restrict__ mo
         persist->cursor_ring = (uint32_t)(((uint64_t)persist->cursor_ring + 3ull * acc) % rand_n);   // basic_algorithms.h:426-433
     }
     __syncthreads();
-    if (n_moves <= 4 && blockDim.x == SCAN_BLOCK) {
-        // The usual frame moves a handful of objects: every thread takes MP_EPT consecutive list entries (thread order = list
-        // order), the counts of two moved tracks share one word of a block scan (16 bits each: a chunk holds 4096 entries), and
-        // a chunk of 4096 entries costs one scan per pair of tracks instead of four barriers per 1024 entries.
-        constexpr int MP_EPT = 4;
-        uint32_t* s_scan = &s_wcount[0][0];                        // (33 words of it)
-        uint32_t run[4] = {0u, 0u, 0u, 0u};                        // entries of each moved track in the chunks before this one
-        for (uint32_t c = 0; c < n; c += SCAN_BLOCK * MP_EPT) {
-            int mvv[MP_EPT];
-            bool rmv[MP_EPT];
-            uint32_t pk01 = 0, pk23 = 0;
-#pragma unroll
-            for (int i = 0; i < MP_EPT; ++i) {
-                const uint32_t k = c + threadIdx.x * MP_EPT + i;
-                mvv[i] = -1; rmv[i] = false;
-                if (k < n) {
-                    const int tr = (int)movl_track[k];
-                    mvv[i] = find_track(mt->move_track, n_moves, tr);
-                    if (mvv[i] < 0) rmv[i] = find_track(mt->remove_track, mt->n_remove, tr) >= 0;
-                }
-                pk01 += (mvv[i] == 0) + ((uint32_t)(mvv[i] == 1) << 16);
-                pk23 += (mvv[i] == 2) + ((uint32_t)(mvv[i] == 3) << 16);
-            }
-            uint32_t tot01 = 0, tot23 = 0, ex23 = 0;
-            const uint32_t ex01 = block_exclusive_scan(pk01, s_scan, tot01);
-            if (n_moves > 2) ex23 = block_exclusive_scan(pk23, s_scan, tot23);
-            uint32_t before[4] = {run[0] + (ex01 & 0xffffu), run[1] + (ex01 >> 16), run[2] + (ex23 & 0xffffu), run[3] + (ex23 >> 16)};
-#pragma unroll
-            for (int i = 0; i < MP_EPT; ++i) {
-                const uint32_t k = c + threadIdx.x * MP_EPT + i;
-                if (k >= n) continue;
-                uint32_t seq = rmv[i] ? SEQ_REMOVE : NO_RANK;
-#pragma unroll
-                for (int m = 0; m < 4; ++m)
-                    if (mvv[i] == m) seq = s_offset[m] + before[m]++;
-                movl_seq[k] = seq;
-            }
-            run[0] += tot01 & 0xffffu; run[1] += tot01 >> 16; run[2] += tot23 & 0xffffu; run[3] += tot23 >> 16;
-        }
-        return;
-    }
     const uint32_t wid = threadIdx.x >> 5;
     for (uint32_t c = 0; c < n; c += blockDim.x) {
         for (int i = threadIdx.x; i < 32 * n_moves; i += blockDim.x) s_wcount[i / n_moves][i % n_moves] = 0;
@@ -1917,6 +1876,99 @@ k_move_prepare(const MoveTable* __restrict__ mt, const uint16_t* __restrict__ mo
         __syncthreads();
         if (k < n) movl_seq[k] = mv >= 0 ? s_offset[mv] + s_wcount[wid][mv] + rank_in_warp : (rm ? SEQ_REMOVE : NO_RANK);
         __syncthreads();
+    }
+}
+
+// ---- the same numbering for the usual frame (at most four moved objects), over the whole GPU -------------------------------
+// The movable list of a large map is long (every live particle of every movable track: 3 x 10^5 entries at 512 x 128 x 512), and
+// one block walking it twice was 66 us there.  Two launches of MPB_BLOCKS blocks, block b owning entries [b, b + 1) * MPB_CHUNK
+// (thread order = list order, MPB_EPT consecutive entries per thread):
+//   k_move_count_blocks : per block, the number of entries of each moved track (two tracks share one word of a block scan);
+//   k_move_number       : every block adds up the counts of the blocks before it (its base per track) and all of them (the
+//                         rank's totals; sharded maps: this rank's row of the published counts), numbers its own entries, and
+//                         block 0 does the bookkeeping of k_move_prepare's thread 0.
+constexpr int MPB_EPT = 4, MPB_CHUNK = SCAN_BLOCK * MPB_EPT;
+
+__device__ __forceinline__ void move_classify(const MoveTable* __restrict__ mt, int n_moves, const uint16_t* __restrict__ movl_track, uint32_t n, uint32_t k0,
+                                              int (&mvv)[MPB_EPT], bool (&rmv)[MPB_EPT], uint32_t& pk01, uint32_t& pk23) {
+    pk01 = 0; pk23 = 0;
+#pragma unroll
+    for (int i = 0; i < MPB_EPT; ++i) {
+        const uint32_t k = k0 + i;
+        mvv[i] = -1; rmv[i] = false;
+        if (k < n) {
+            const int tr = (int)movl_track[k];
+            mvv[i] = find_track(mt->move_track, n_moves, tr);
+            if (mvv[i] < 0) rmv[i] = find_track(mt->remove_track, mt->n_remove, tr) >= 0;
+        }
+        pk01 += (mvv[i] == 0) + ((uint32_t)(mvv[i] == 1) << 16);
+        pk23 += (mvv[i] == 2) + ((uint32_t)(mvv[i] == 3) << 16);
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK)
+k_move_count_blocks(const MoveTable* __restrict__ mt, const uint16_t* __restrict__ movl_track, uint32_t movl_cap, const Persist* __restrict__ persist,
+                    uint4* __restrict__ blk_counts) {
+    __shared__ uint32_t s_scan[33];
+    const uint32_t n = min(persist->n_movable, movl_cap);
+    const uint32_t k0 = blockIdx.x * MPB_CHUNK;
+    if (k0 >= n) { if (threadIdx.x == 0) blk_counts[blockIdx.x] = make_uint4(0, 0, 0, 0); return; }      // (block-uniform)
+    int mvv[MPB_EPT];
+    bool rmv[MPB_EPT];
+    uint32_t pk01, pk23, tot01 = 0, tot23 = 0;
+    move_classify(mt, mt->n_moves, movl_track, n, k0 + threadIdx.x * MPB_EPT, mvv, rmv, pk01, pk23);
+    block_exclusive_scan(pk01, s_scan, tot01);
+    block_exclusive_scan(pk23, s_scan, tot23);
+    if (threadIdx.x == 0) blk_counts[blockIdx.x] = make_uint4(tot01 & 0xffffu, tot01 >> 16, tot23 & 0xffffu, tot23 >> 16);
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK)
+k_move_number(const MoveTable* __restrict__ mt, const uint16_t* __restrict__ movl_track, uint32_t* __restrict__ movl_seq, uint32_t movl_cap, uint32_t rand_n,
+              Counters* __restrict__ cnt, Persist* __restrict__ persist, CommView cv, const uint32_t* __restrict__ move_counts, const uint4* __restrict__ blk_counts) {
+    __shared__ uint32_t s_scan[33];
+    __shared__ uint32_t s_base[4], s_offset[4];
+    const uint32_t n = min(persist->n_movable, movl_cap);
+    const int n_moves = mt->n_moves;
+    // counts of the blocks before this one, and of all blocks (gridDim.x <= SCAN_BLOCK: thread t looks at block t)
+    const uint4 c4 = threadIdx.x < gridDim.x ? blk_counts[threadIdx.x] : make_uint4(0, 0, 0, 0);
+    const uint32_t cs[4] = {c4.x, c4.y, c4.z, c4.w};
+    uint32_t total[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const uint32_t ex = block_exclusive_scan(cs[m], s_scan, total[m]);
+        if (threadIdx.x == blockIdx.x) s_base[m] = ex;
+    }
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int m = 0; m < n_moves; ++m) {      // offset of a track = everything of the tracks before it + this track on the lower ranks
+            uint32_t below = 0, all = 0;
+            for (int g = 0; g < cv.size; ++g) { const uint32_t c = cv.size == 1 ? total[m] : move_counts[g * MAX_MOVES + m]; if (g < cv.rank) below += c; all += c; }
+            s_offset[m] = acc + below;
+            acc += all;
+        }
+        if (blockIdx.x == 0) {
+            cnt->n_selected = acc;
+            cnt->move_cursor0 = persist->cursor_ring;
+            persist->cursor_ring = (uint32_t)(((uint64_t)persist->cursor_ring + 3ull * acc) % rand_n);   // basic_algorithms.h:426-433
+        }
+    }
+    __syncthreads();
+    const uint32_t k0 = blockIdx.x * MPB_CHUNK + threadIdx.x * MPB_EPT;
+    if (blockIdx.x * MPB_CHUNK >= n) return;                                                             // (block-uniform)
+    int mvv[MPB_EPT];
+    bool rmv[MPB_EPT];
+    uint32_t pk01, pk23, tot01 = 0, tot23 = 0;
+    move_classify(mt, n_moves, movl_track, n, k0, mvv, rmv, pk01, pk23);
+    const uint32_t ex01 = block_exclusive_scan(pk01, s_scan, tot01), ex23 = block_exclusive_scan(pk23, s_scan, tot23);
+    uint32_t before[4] = {s_base[0] + (ex01 & 0xffffu), s_base[1] + (ex01 >> 16), s_base[2] + (ex23 & 0xffffu), s_base[3] + (ex23 >> 16)};
+#pragma unroll
+    for (int i = 0; i < MPB_EPT; ++i) {
+        if (k0 + i >= n) continue;
+        uint32_t seq = rmv[i] ? SEQ_REMOVE : NO_RANK;
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+            if (mvv[i] == m) seq = s_offset[m] + before[m]++;
+        movl_seq[k0 + i] = seq;
     }
 }
 
