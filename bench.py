@@ -373,7 +373,7 @@ def main():
     # N > 1, default run: besides the N replicas of the metric's configuration, ONE config-D map (512 x 128 x 512 voxels x 16 slots,
     # 2 m per frame: BASELINE.json's multi-GPU configuration) sharded over the same N GPUs
     extra_d = world > 1 and not sharded and args.config == "B" and not args.no_sharded_d and not args.device_arm_only
-    d_warm, d_steps = 8, 24
+    d_warm, d_steps = 10, 40
     frames_d = generate_frames("D", d_warm + d_steps + 8) if extra_d else None
 
     import torch
@@ -409,14 +409,6 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.tolist()
 
-    m, stream = make_map(cfg, sharded)
-    units = 1 if sharded else world          # maps updated per step by the whole job
-    r = measure_engine(m, frames, args.warmup, args.steps, stream, dev, barrier, n_prof, torch, args.device_arm_only)
-    ms_device, ms_e2e, ms_device_sync, ms_e2e_sync = reduce_max([r["ms_device"], r["ms_e2e"], r["ms_device_sync"], r["ms_e2e_sync"]])
-    barrier()
-    m.engine.close()
-    del m
-
     sharded_d = None
     if extra_d:
         cfg_d = BASELINE["D"]
@@ -428,10 +420,20 @@ def main():
         del md
         sharded_d = {"config": dict(config_strings(cfg_d), parallelism="sharded: one map, storage-z slabs over %d GPUs, NVLink peer-memory exchange, no collective library in the data path" % world),
                      "scaling": "strong", "steps": d_steps, "warmup": d_warm, "value": d_steps / (v[0] * 1e-3), "unit": UNIT, "ms_per_step": v[0] / d_steps,
-                     "e2e": {"value": d_steps / (v[1] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": rd["h2d"], "d2h_bytes_per_step": rd["d2h"]},
+                     "e2e": {"value": d_steps / (v[1] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": rd["h2d"], "d2h_bytes_per_step": rd["d2h"],
+                             "synchronous_value": d_steps / (v[3] * 1e-3)},
+                     "synchronous": {"value": d_steps / (v[2] * 1e-3), "ms_per_step": v[2] / d_steps},
                      "stage_ms_rank0": {n: float(x / 8) for n, x in zip(_capi.STAGE_NAMES, rd["stage_ms"])},
-                     "note": "sharded frames run synchronously (every rank meets the others at device-side barriers inside the frame); "
-                             "compare with profiles/r02_scale_D_1gpu.json for the same map on one GPU"}
+                     "note": "every rank submits the same frame (pipelined calls) and meets the others at device-side barriers inside the frame; "
+                             "the same map on one GPU: profiles/r02b_scale_D.md"}
+
+    m, stream = make_map(cfg, sharded)
+    units = 1 if sharded else world          # maps updated per step by the whole job
+    r = measure_engine(m, frames, args.warmup, args.steps, stream, dev, barrier, n_prof, torch, args.device_arm_only)
+    ms_device, ms_e2e, ms_device_sync, ms_e2e_sync = reduce_max([r["ms_device"], r["ms_e2e"], r["ms_device_sync"], r["ms_e2e_sync"]])
+    barrier()
+    m.engine.close()
+    del m
 
     if rank == 0:
         peak, peak_src = load_peaks()
